@@ -1,0 +1,384 @@
+"""CPU oracle: a functional restatement of the reference diffusion hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``diffusionmodel_b200/`` may import this
+module; only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` use it, and only as the checker or the
+timed CPU baseline -- never as the product path.
+
+What it restates (file:line under /root/reference):
+  * ``ddpm_schedules``                         new_scripy.py:358-384 == MNIST_script.py:190-216
+  * enhanced ``ContextUnet.forward``           new_scripy.py:317-356  (variant "rdd")
+  * original ``ContextUnet.forward``           MNIST_script.py:155-187 (variant "mnist")
+  * ``DDPM.forward`` (weighted loss / MSE)     new_scripy.py:401-439 / MNIST_script.py:234-252
+  * ``DDPM.sample`` CFG reverse loop           new_scripy.py:441-477 / MNIST_script.py:254-300
+
+All arithmetic lives in PyTorch (un-pinned dependency of the reference; this
+container has torch 2.11.0).  The port is written as plain functions over a
+``state_dict`` (reference key names) using the same ``torch.nn.functional`` calls
+the reference's ``nn.Module``s dispatch to, so on CPU it is bit-identical to the
+imported reference; ``oracle/make_golden.py`` asserts exactly that and writes the
+fixtures under ``tests/golden/`` (the reference ships no tests or golden vectors
+of its own -- parity is pinned by those generated fixtures).
+
+The one deliberate deviation: ``new_scripy.py:353`` passes ``ctx_mask`` where an
+attention map is intended (it only broadcasts for degenerate shapes and then
+contributes exactly +0).  ``attn_map=None`` reproduces the shipped behaviour
+(LocalEnhancer adds 0); passing a ``[B,H,W]`` map exercises the intended path.
+
+``operand_dtype=torch.bfloat16`` rounds the inputs and weights of every
+conv / conv-transpose / linear to bf16 (fp32 accumulate, everything else fp32):
+the precision-matched oracle of SURVEY.md Appendix D.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+HIGH_THRESH = 1.2   # new_scripy.py:31
+MID_THRESH = 0.8    # new_scripy.py:32
+HIGH_WEIGHT = 3.0   # new_scripy.py:33
+MID_WEIGHT = 1.0    # new_scripy.py:34
+LOW_WEIGHT = 0.5    # new_scripy.py:35
+FEAT_CONSIST_WEIGHT = 2.0  # new_scripy.py:36
+
+
+# --------------------------------------------------------------------------- schedules
+def ddpm_schedules(beta1: float, beta2: float, T: int) -> dict:
+    """new_scripy.py:358-384 -- seven fp32 tables with T+1 entries."""
+    assert beta1 < beta2 < 1.0
+    beta_t = (beta2 - beta1) * torch.arange(0, T + 1, dtype=torch.float32) / T + beta1
+    alpha_t = 1 - beta_t
+    alphabar_t = torch.cumsum(torch.log(alpha_t), dim=0).exp()
+    sqrtmab = torch.sqrt(1 - alphabar_t)
+    return {
+        "alpha_t": alpha_t,
+        "oneover_sqrta": 1 / torch.sqrt(alpha_t),
+        "sqrt_beta_t": torch.sqrt(beta_t),
+        "alphabar_t": alphabar_t,
+        "sqrtab": torch.sqrt(alphabar_t),
+        "sqrtmab": sqrtmab,
+        "mab_over_sqrtmab": (1 - alpha_t) / sqrtmab,
+    }
+
+
+# --------------------------------------------------------------------------- primitives
+class _Ctx:
+    """Carries the state dict, train/eval flag and operand rounding through the port."""
+
+    def __init__(self, sd, training, operand_dtype=None, tap=None):
+        self.sd = sd
+        self.training = training
+        self.od = operand_dtype
+        self.tap = tap  # optional dict: name -> intermediate tensor
+
+    def rnd(self, t):
+        return t if self.od is None else t.to(self.od).to(torch.float32)
+
+    def p(self, name):
+        return self.sd[name]
+
+    def record(self, name, t):
+        if self.tap is not None:
+            self.tap[name] = t
+        return t
+
+
+def _conv(cx, pre, x, stride=1, padding=0):
+    return F.conv2d(cx.rnd(x), cx.rnd(cx.p(pre + ".weight")), cx.p(pre + ".bias"), stride, padding)
+
+
+def _convT(cx, pre, x, stride):
+    return F.conv_transpose2d(cx.rnd(x), cx.rnd(cx.p(pre + ".weight")), cx.p(pre + ".bias"), stride)
+
+
+def _linear(cx, pre, x, bias=True):
+    return F.linear(cx.rnd(x), cx.rnd(cx.p(pre + ".weight")), cx.p(pre + ".bias") if bias else None)
+
+
+def _bn(cx, pre, x):
+    """nn.BatchNorm2d: eps 1e-5, momentum 0.1; train mode updates the running buffers in ``sd``."""
+    sd = cx.sd
+    if cx.training and (pre + ".num_batches_tracked") in sd:
+        sd[pre + ".num_batches_tracked"] += 1
+    return F.batch_norm(x, sd[pre + ".running_mean"], sd[pre + ".running_var"],
+                        sd[pre + ".weight"], sd[pre + ".bias"], cx.training, 0.1, 1e-5)
+
+
+def _gn(cx, pre, x, groups=8):
+    return F.group_norm(x, groups, cx.p(pre + ".weight"), cx.p(pre + ".bias"), 1e-5)
+
+
+def _conv_bn_gelu(cx, pre, x):
+    """Sequential(Conv2d 3x3 p1, BatchNorm2d, GELU): new_scripy.py:183-187."""
+    return F.gelu(_bn(cx, pre + ".1", _conv(cx, pre + ".0", x, 1, 1)))
+
+
+# --------------------------------------------------------------------------- blocks
+def se_block(cx, pre, x):
+    """new_scripy.py:143-158."""
+    b, c = x.shape[:2]
+    y = F.adaptive_avg_pool2d(x, 1).squeeze(-1).squeeze(-1)
+    y = torch.sigmoid(_linear(cx, pre + ".fc.2", F.gelu(_linear(cx, pre + ".fc.0", y, False)), False))
+    return x * y.view(b, c, 1, 1)
+
+
+def res_conv_block(cx, pre, x, is_res, has_se):
+    """new_scripy.py:176-209 (has_se=True) / MNIST_script.py:31-65 (has_se=False)."""
+    x1 = _conv_bn_gelu(cx, pre + ".conv1", x)
+    x2 = _conv_bn_gelu(cx, pre + ".conv2", x1)
+    if not is_res:
+        return x2
+    if has_se:
+        x2 = se_block(cx, pre + ".se", x2)
+    same = cx.p(pre + ".conv1.0.weight").shape[0] == cx.p(pre + ".conv1.0.weight").shape[1]
+    out = (x + x2) if same else (x1 + x2)
+    return out / 1.414
+
+
+def coord_attn(cx, pre, x):
+    """new_scripy.py:97-140."""
+    n, c, h, w = x.shape
+    x_h = F.adaptive_avg_pool2d(x, (None, 1))
+    x_w = F.adaptive_avg_pool2d(x, (1, None))
+    x_h = F.gelu(_bn(cx, pre + ".bn1_h", _conv(cx, pre + ".conv1_h", x_h)))
+    x_w = F.gelu(_bn(cx, pre + ".bn1_w", _conv(cx, pre + ".conv1_w", x_w)))
+    h2w = _conv(cx, pre + ".h2w_proj", x_h).permute(0, 1, 3, 2)
+    w2h = _conv(cx, pre + ".w2h_proj", x_w).permute(0, 1, 3, 2)
+    h2w = F.adaptive_avg_pool2d(h2w, (1, w))
+    w2h = F.adaptive_avg_pool2d(w2h, (h, 1))
+    x_h = x_h + torch.sigmoid(cx.p(pre + ".gamma_h")) * w2h
+    x_w = x_w + torch.sigmoid(cx.p(pre + ".gamma_w")) * h2w
+    a_h = torch.sigmoid(_conv(cx, pre + ".conv_h", x_h))
+    a_w = torch.sigmoid(_conv(cx, pre + ".conv_w", x_w))
+    alpha = torch.sigmoid(cx.p(pre + ".alpha"))
+    beta = torch.sigmoid(cx.p(pre + ".beta"))
+    wsum = alpha + beta + 1e-8
+    return x * ((alpha / wsum) * a_h + (beta / wsum) * a_w)
+
+
+def local_enhancer(cx, pre, x, mask, high_thresh=HIGH_THRESH):
+    """new_scripy.py:161-174 with a [B,H,W] attention map."""
+    high = (mask > high_thresh).float().unsqueeze(1)
+    y = _conv(cx, pre + ".conv.0", x, 1, 1)
+    y = F.gelu(_gn(cx, pre + ".conv.1", y))
+    y = _conv(cx, pre + ".conv.3", y, 1, 1)
+    return x + y * high
+
+
+def unet_down_rdd(cx, pre, x):
+    """new_scripy.py:211-235."""
+    x = F.gelu(_bn(cx, pre + ".channel_compress.1", _conv(cx, pre + ".channel_compress.0", x)))
+    x = _conv(cx, pre + ".ch_adjust", x)
+    x = F.gelu(_bn(cx, pre + ".down.1", _conv(cx, pre + ".down.0", x, 1, 1)))
+    x = res_conv_block(cx, pre + ".down.3", x, True, True)
+    return _conv(cx, pre + ".down.4", x, 2, 1)
+
+
+def unet_up_rdd(cx, pre, x, skip):
+    """new_scripy.py:237-253."""
+    x = torch.cat((x, skip), 1)
+    x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+    x = _conv(cx, pre + ".model.0.1", x, 1, 1)
+    x = res_conv_block(cx, pre + ".model.1", x, False, False)
+    return res_conv_block(cx, pre + ".model.2", x, False, False)
+
+
+def unet_down_mnist(cx, pre, x):
+    """MNIST_script.py:68-78."""
+    return F.max_pool2d(res_conv_block(cx, pre + ".model.0", x, False, False), 2)
+
+
+def unet_up_mnist(cx, pre, x, skip):
+    """MNIST_script.py:81-97."""
+    x = _convT(cx, pre + ".model.0", torch.cat((x, skip), 1), 2)
+    x = res_conv_block(cx, pre + ".model.1", x, False, False)
+    return res_conv_block(cx, pre + ".model.2", x, False, False)
+
+
+def embed_fc(cx, pre, x, input_dim):
+    """new_scripy.py:255-268."""
+    x = x.view(-1, input_dim)
+    return _linear(cx, pre + ".model.2", F.gelu(_linear(cx, pre + ".model.0", x)))
+
+
+def up0(cx, pre, hidden, k):
+    """ConvTranspose2d(k, k) + GroupNorm(8) + ReLU: new_scripy.py:297-301 / MNIST_script.py:139-144."""
+    return F.relu(_gn(cx, pre + ".1", _convT(cx, pre + ".0", hidden, k)))
+
+
+def out_head(cx, pre, x):
+    """conv3x3 + GroupNorm(8) + ReLU + conv3x3: new_scripy.py:310-315."""
+    y = F.relu(_gn(cx, pre + ".1", _conv(cx, pre + ".0", x, 1, 1)))
+    return _conv(cx, pre + ".3", y, 1, 1)
+
+
+# --------------------------------------------------------------------------- denoisers
+def unet_forward(sd, x, c, t, ctx_mask, *, variant, training, attn_map=None,
+                 operand_dtype=None, prefix="", tap=None):
+    """ContextUnet.forward.  ``sd`` uses the reference's parameter names (optionally under
+    ``prefix``, e.g. "nn_model.").  In train mode the BatchNorm running buffers in ``sd`` are
+    updated in place exactly as the reference's modules would."""
+    if prefix:
+        sd = _PrefixView(sd, prefix)
+    cx = _Ctx(sd, training, operand_dtype, tap)
+    if variant == "rdd":
+        return _unet_rdd(cx, x, c, t, ctx_mask, attn_map)
+    if variant == "mnist":
+        return _unet_mnist(cx, x, c, t, ctx_mask)
+    raise ValueError(variant)
+
+
+class _PrefixView(dict):
+    def __init__(self, sd, prefix):
+        super().__init__()
+        self._sd, self._p = sd, prefix
+
+    def __getitem__(self, k):
+        return self._sd[self._p + k]
+
+    def __setitem__(self, k, v):
+        self._sd[self._p + k] = v
+
+    def __contains__(self, k):
+        return (self._p + k) in self._sd
+
+
+def _unet_rdd(cx, x, c, t, ctx_mask, attn_map):
+    """new_scripy.py:317-356."""
+    n_feat = cx.p("init_conv.conv1.0.weight").shape[0]
+    n_classes = cx.p("ctx_emb1.model.0.weight").shape[1]
+    x0 = cx.record("init_conv", res_conv_block(cx, "init_conv", x, True, True))
+    d1 = cx.record("down1", coord_attn(cx, "ca1", unet_down_rdd(cx, "down1", x0)))
+    d2 = cx.record("down2", coord_attn(cx, "ca2", unet_down_rdd(cx, "down2", d1)))
+    d3 = cx.record("down3", coord_attn(cx, "ca3", unet_down_rdd(cx, "down3", d2)))
+    d4 = cx.record("down4", coord_attn(cx, "ca4", unet_down_rdd(cx, "down4", d3)))
+    hidden = F.gelu(F.avg_pool2d(d4, 8))
+    c1h = F.one_hot(c.long(), num_classes=n_classes).type(torch.float)
+    c1h = c1h * ctx_mask[:, None].repeat(1, n_classes)          # :337-340, no flip
+    cemb1 = embed_fc(cx, "ctx_emb1", c1h, n_classes).view(-1, n_feat * 8, 1, 1)
+    temb1 = embed_fc(cx, "time_emb1", t, 1).view(-1, n_feat * 8, 1, 1)
+    cemb2 = embed_fc(cx, "ctx_emb2", c1h, n_classes).view(-1, n_feat * 4, 1, 1)
+    temb2 = embed_fc(cx, "time_emb2", t, 1).view(-1, n_feat * 4, 1, 1)
+    u1 = cx.record("up0", up0(cx, "up0", hidden, 8))
+    u2 = cx.record("up1", unet_up_rdd(cx, "up1", cemb1 * u1 + temb1, d4))
+    u3 = cx.record("up2", unet_up_rdd(cx, "up2", cemb2 * u2 + temb2, d3))
+    u4 = cx.record("up3", unet_up_rdd(cx, "up3", u3, d2))
+    u5 = cx.record("up4", unet_up_rdd(cx, "up4", u4, d1))
+    if attn_map is None:
+        # shipped call site (:353) contributes exactly +0 wherever it runs at all
+        attn_map = torch.zeros(x.shape[0], x.shape[2], x.shape[3], dtype=x.dtype, device=x.device)
+    u5 = cx.record("local_enhance", local_enhancer(cx, "local_enhance", u5, attn_map))
+    return out_head(cx, "out", torch.cat((u5, x0), 1))
+
+
+def _unet_mnist(cx, x, c, t, context_mask):
+    """MNIST_script.py:155-187."""
+    n_feat = cx.p("init_conv.conv1.0.weight").shape[0]
+    n_classes = cx.p("contextembed1.model.0.weight").shape[1]
+    x0 = cx.record("init_conv", res_conv_block(cx, "init_conv", x, True, False))
+    d1 = cx.record("down1", unet_down_mnist(cx, "down1", x0))
+    d2 = cx.record("down2", unet_down_mnist(cx, "down2", d1))
+    hidden = F.gelu(F.avg_pool2d(d2, 7))
+    c1h = F.one_hot(c, num_classes=n_classes).type(torch.float)
+    m = context_mask[:, None].repeat(1, n_classes)
+    m = (-1 * (1 - m))                                          # :170 flip and negate
+    c1h = c1h * m
+    cemb1 = embed_fc(cx, "contextembed1", c1h, n_classes).view(-1, n_feat * 2, 1, 1)
+    temb1 = embed_fc(cx, "timeembed1", t, 1).view(-1, n_feat * 2, 1, 1)
+    cemb2 = embed_fc(cx, "contextembed2", c1h, n_classes).view(-1, n_feat, 1, 1)
+    temb2 = embed_fc(cx, "timeembed2", t, 1).view(-1, n_feat, 1, 1)
+    u1 = cx.record("up0", up0(cx, "up0", hidden, 7))
+    u2 = cx.record("up1", unet_up_mnist(cx, "up1", cemb1 * u1 + temb1, d2))
+    u3 = cx.record("up2", unet_up_mnist(cx, "up2", cemb2 * u2 + temb2, d1))
+    return out_head(cx, "out", torch.cat((u3, x0), 1))
+
+
+# --------------------------------------------------------------------------- DDPM
+def draw_train_randoms(x, c, n_T, drop_prob, variant):
+    """The reference's RNG draw order inside DDPM.forward (new_scripy.py:405-413,
+    MNIST_script.py:239-249): randint on the CPU generator, randn_like(x), bernoulli."""
+    ts = torch.randint(1, n_T + 1, (x.shape[0],))
+    noise = torch.randn_like(x)
+    if variant == "rdd":
+        ctx_mask = torch.bernoulli(torch.ones_like(c, dtype=torch.float) * (1 - drop_prob))
+    else:
+        ctx_mask = torch.bernoulli(torch.zeros_like(c) + drop_prob)
+    return ts, noise, ctx_mask
+
+
+def q_sample(sched, x, ts, noise):
+    """x_t = sqrtab[t] x + sqrtmab[t] eps: new_scripy.py:408-411."""
+    return sched["sqrtab"][ts, None, None, None] * x + sched["sqrtmab"][ts, None, None, None] * noise
+
+
+def weighted_loss(noise, pred, attn_mask):
+    """new_scripy.py:417-437 (mask repeated to exactly 3 channels, :418)."""
+    m = attn_mask.unsqueeze(1).repeat(1, 3, 1, 1)
+    w = torch.where(m > HIGH_THRESH, torch.tensor(HIGH_WEIGHT),
+                    torch.where(m > MID_THRESH, torch.tensor(MID_WEIGHT), torch.tensor(LOW_WEIGHT)))
+    loss = (noise - pred) ** 2
+    high = (m > HIGH_THRESH).float()
+    feat = torch.mean(torch.abs(pred * high - noise * high)) * FEAT_CONSIST_WEIGHT
+    return (loss * w).mean() + feat
+
+
+def ddpm_loss(sd, sched, x, c, attn_mask, ts, noise, ctx_mask, *, variant, n_T, training=True,
+              attn_map=None, operand_dtype=None, prefix="nn_model."):
+    """DDPM.forward with the random draws passed in (see draw_train_randoms)."""
+    x_t = q_sample(sched, x, ts, noise)
+    pred = unet_forward(sd, x_t, c, ts / n_T, ctx_mask, variant=variant, training=training,
+                        attn_map=attn_map, operand_dtype=operand_dtype, prefix=prefix)
+    if variant == "rdd":
+        return weighted_loss(noise, pred, attn_mask)
+    return F.mse_loss(noise, pred)                               # MNIST_script.py:252 (arg order kept)
+
+
+def reverse_step(sched, x_i, eps1, eps2, z, i, guide_w):
+    """new_scripy.py:468-475."""
+    eps = (1 + guide_w) * eps1 - guide_w * eps2
+    return sched["oneover_sqrta"][i] * (x_i - eps * sched["mab_over_sqrtmab"][i]) + sched["sqrt_beta_t"][i] * z
+
+
+def ddpm_sample(sd, sched, x_T, zs, guide_w, *, variant, n_T, n_classes, steps=None,
+                operand_dtype=None, prefix="nn_model.", store=None):
+    """CFG reverse loop (new_scripy.py:441-477 / MNIST_script.py:254-300) with x_T and the
+    per-step noises ``zs[i]`` (i = n_T .. 2) supplied by the caller.  ``steps`` truncates the
+    loop to the first ``steps`` iterations (for tests)."""
+    n = x_T.shape[0]
+    ncls = 10 if variant == "mnist" else n_classes              # MNIST_script.py:262 hard-codes 10
+    c_i = torch.arange(0, ncls).repeat(int(n / ncls)).repeat(2)
+    ctx_mask = torch.zeros_like(c_i)
+    ctx_mask[n:] = 1.0
+    x_i = x_T
+    done = 0
+    for i in range(n_T, 0, -1):
+        t_is = torch.tensor([i / n_T]).repeat(n, 1, 1, 1).repeat(2, 1, 1, 1)
+        z = zs[i] if i > 1 else 0
+        eps = unet_forward(sd, x_i.repeat(2, 1, 1, 1), c_i, t_is, ctx_mask, variant=variant,
+                           training=False, operand_dtype=operand_dtype, prefix=prefix)
+        x_i = reverse_step(sched, x_i, eps[:n], eps[n:], z, i, guide_w)
+        if store is not None and (i % 20 == 0 or i == n_T or i < 8):
+            store.append(x_i.detach().clone())
+        done += 1
+        if steps is not None and done >= steps:
+            break
+    return x_i
+
+
+# --------------------------------------------------------------------------- synthetic inputs
+def synth_attn_mask(batch, size, gen):
+    """Attention map as CrackDataset.__getitem__ builds it (new_scripy.py:535-546): 0.5, lower
+    half 1.0, one random bbox 3.0."""
+    m = torch.full((batch, size, size), 0.5)
+    m[:, size // 2:, :] = MID_WEIGHT
+    for b in range(batch):
+        xs = torch.randint(0, size, (2,), generator=gen).sort().values
+        ys = torch.randint(0, size, (2,), generator=gen).sort().values
+        m[b, int(ys[0]):int(ys[1]), int(xs[0]):int(xs[1])] = HIGH_WEIGHT
+    return m
+
+
+def rel_l2(a, b):
+    a = a.detach().double().flatten()
+    b = b.detach().double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
