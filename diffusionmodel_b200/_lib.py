@@ -1,0 +1,118 @@
+"""ctypes binding of libdm_b200.so (the C-ABI declared in include/dm_b200.h).
+
+There is no CPU fallback: importing the package works without a GPU (so the CPU test-suite can
+check the exported symbols), but any compute call without the library or without a CUDA device
+raises immediately.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libdm_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "dm_b200.h")
+
+_lib = None
+
+
+class DmB200Error(RuntimeError):
+    pass
+
+
+def declared_symbols() -> list:
+    """Every function name declared in include/dm_b200.h."""
+    with open(HEADER_PATH) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dm_[a-z0-9_]+)\s*\(", src)))
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DmB200Error(
+                f"{LIB_PATH} is missing: build it with `python -m diffusionmodel_b200.build` "
+                "(there is no CPU or PyTorch fallback for the hot path)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.dm_last_error.restype = ctypes.c_char_p
+        _lib.dm_debug_set.argtypes = [ctypes.c_int, ctypes.c_longlong]
+        _lib.dm_debug_set.restype = None
+    return _lib
+
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_longlong
+_F = ctypes.c_float
+_D = ctypes.c_double
+
+# argument signatures, in header order (p = pointer, i = int, l = long long, f = float, d = double)
+_SIGS = {
+    "dm_conv2d_fwd": "pii pii p p pii pi iiiiiiii p",
+    "dm_conv2d_fwd_mtiles": "iii",
+    "dm_conv2d_s2_dgrad": "pii p pii iii p",
+    "dm_convt_fwd": "pii p p pi iiiii p",
+    "dm_conv2d_wgrad": "pii pii pi p iiiiiiii p",
+    "dm_pack_weight": "p p iii p ll iil i p",
+    "dm_unpack_wgrad": "p p iii p ll iil i p",
+    "dm_nchw_to_nhwc": "p pi i iiii p",
+    "dm_cast_nhwc": "pi pi l i p",
+    "dm_nhwc_to_nchw": "pii p iiii p",
+    "dm_space_to_depth": "pi pi iiiii p",
+    "dm_bn_finalize": "p iii d pp pp ff p",
+    "dm_bn_act_fwd": "pi pppp pi l ii p",
+    "dm_bn_act_bwd": "pi pi pppp pi pp p l iii p",
+    "dm_gn_act_fwd": "pi pp pi pp p iiii f i p",
+    "dm_gn_act_bwd": "pi pi pppp pi pp p iiii i p",
+    "dm_pool_nhw": "pi p iii f p",
+    "dm_pool_prod_nhw": "pi pi p iii f p",
+    "dm_se_apply_fwd": "pi p pi pi iii f p",
+    "dm_se_apply_bwd": "pi p p pi pi iii f p",
+    "dm_ca_pool": "pi pi pp iiii ff p",
+    "dm_ca_gate_fwd": "pi pp pi iiii p",
+    "dm_ca_gate_bwd": "pi pp pp pi iiii p",
+    "dm_upcat_fwd": "pii pii pi iii p",
+    "dm_upcat_bwd": "pi pii pii iii p",
+    "dm_film_fwd": "pi pp pi iii p",
+    "dm_film_bwd": "pi pi p pi pp iii p",
+    "dm_avgpool_act_fwd": "pi pi iiiii i p",
+    "dm_avgpool_act_bwd": "pi pi pi iiiii i p",
+    "dm_maxpool2_fwd": "pi pi iiii p",
+    "dm_maxpool2_bwd": "pi pi pi iiii p",
+    "dm_mask_fma": "pi pi p f pi l i p",
+    "dm_axpby": "pi pi pi l i ff p",
+    "dm_colsum": "pi p l i p",
+    "dm_q_sample": "pp pp p pi iiii p",
+    "dm_ddpm_loss_fwd": "pi p p p p iiii ffffff p",
+    "dm_ddpm_loss_bwd": "pi p p p pi iiii ffffff p",
+    "dm_cfg_reverse_step": "pi p p p pi ffff iiii p",
+    "dm_sumsq": "p l p p",
+    "dm_adamw": "pppp l fffffff p f p",
+}
+_CT = {"p": _P, "i": _I, "l": _L, "f": _F, "d": _D}
+_bound = {}
+
+
+def fn(name):
+    f = _bound.get(name)
+    if f is None:
+        f = getattr(lib(), name)
+        f.argtypes = [_CT[ch] for ch in _SIGS[name].replace(" ", "")]
+        f.restype = _I
+        _bound[name] = f
+    return f
+
+
+def call(name, *args):
+    rc = fn(name)(*args)
+    if rc != 0:
+        msg = lib().dm_last_error().decode(errors="replace")
+        raise DmB200Error(f"{name} failed (rc={rc}): {msg}")
+    return rc
+
+
+def debug_set(key: int, value: int) -> None:
+    lib().dm_debug_set(key, value)

@@ -1,0 +1,831 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernels for the U-Net convolutions (sm_100a only).
+//
+//   kernel A  conv_gemm_kernel   D[pixels, Cout] = im2col(X)[pixels, taps*Cin] * Wp[Cout, taps*Cin]^T
+//             forward conv (3x3 s1, 1x1, 4x4 s2 through four parity views), data-gradient (same
+//             kernel with the flipped/transposed weight pack), conv-transpose k==s (scatter epilogue).
+//             M tile = 128 output pixels laid out as a (bn x bh x bw) patch, so one 4-D TMA box per
+//             filter tap (shifted by the tap offset, out-of-bounds zero-filled = the conv padding)
+//             lands in shared memory already in the K-major SWIZZLE_128B layout tcgen05.mma wants.
+//   kernel B  wgrad_gemm_kernel  dWp[Cout, tap, Cin] += dY[pixels, Cout]^T * im2col(X)[pixels, tap*Cin]
+//             both operands MN-major (channels contiguous), K = pixels, split-K with fp32 red.add.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> bias / BN partial statistics -> bf16 -> global).
+// Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), double-buffered TMEM accumulator
+// full/empty mbarriers (MMA <-> epilogue), static persistent tile schedule (grid <= #SMs).
+//
+// Replaces (reference, all through cuDNN): nn.Conv2d call sites new_scripy.py:166,169,184,188,217,222,
+// 225,229,243,311,314 and nn.ConvTranspose2d new_scripy.py:298 / MNIST_script.py:88,141.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "dm_b200.h"
+
+namespace {
+
+using dm::bf16;
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;        // bf16 elements = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kAStage = kBlockM * kBlockK * 2;       // 16 KB
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kAuxBytes = 4096 + 512;                // stats staging + barriers
+constexpr int kMaxStages = 8;
+
+struct TapInfo { int8_t dy, dx, map, pad_; };
+
+struct ConvParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  TapInfo taps[16];
+  int num_taps, chunks0, chunks1, dual;
+  int log_bw, log_bh, log_bn;
+  int tiles_w, tiles_h, tiles_b, m_tiles, n_tiles, block_n;
+  int N, H, W;
+  int stages, b_stage_bytes;
+  void* out;
+  int out_f32;
+  long long sN, sH, sW;
+  int Cout, ldc_pad;
+  int convt_k;
+  long long sKy, sKx;
+  const float* bias;
+  float* stats;
+  int stats_ld;
+  unsigned idesc;
+  unsigned long long desc_hi;   // upper 32 bits of the smem descriptors (SBO / version / layout)
+};
+
+struct WgradParams {
+  CUtensorMap tmX[4];
+  CUtensorMap tmDY;
+  TapInfo taps[16];
+  int num_taps, chunks0, chunks1, dual;
+  int log_bw, log_bh, log_bn;       // 64-pixel patch
+  int tiles_w, tiles_h, tiles_b, patches;
+  int co_tiles, ci_tiles, block_n, splits, patches_per_split;
+  int Cout, cin_k;                  // cin_k = padded K columns per tap in dWp
+  int stages, b_stage_bytes;
+  float* dwp;
+  unsigned idesc;
+  unsigned long long desc_hi_a, desc_hi_b;
+  unsigned lbo_a, lbo_b;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  printf("dm_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_alloc(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Column sums across the 32 lanes of a warp for 32 per-lane values: after the call lane L holds
+// sum over lanes of v[L] (in v[0]).  31 shuffles instead of 160.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      float send = up ? v[j] : v[j + s];
+      float keep = up ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+struct SmemLayout {
+  uint32_t base;        // 1024-aligned start of the stage ring
+  uint32_t full, empty, tfull, tempty, tmem_slot, stat;
+};
+
+__device__ __forceinline__ SmemLayout carve(uint8_t* raw, int stages, int stage_bytes) {
+  SmemLayout L;
+  uint32_t b = (smem_u32(raw) + 1023u) & ~1023u;
+  L.base = b;
+  uint32_t aux = b + (uint32_t)stages * (uint32_t)stage_bytes;
+  L.stat = aux;                       // 4096 B: [2 accum stages][4 warps][2][64]... see epilogue
+  L.full = aux + 4096;
+  L.empty = L.full + 8 * kMaxStages;
+  L.tfull = L.empty + 8 * kMaxStages;
+  L.tempty = L.tfull + 16;
+  L.tmem_slot = L.tempty + 16;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------ kernel A
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stage_bytes = kAStage + p.b_stage_bytes;
+  const SmemLayout L = carve(smem_raw, p.stages, stage_bytes);
+  const int num_kb = p.num_taps * (p.chunks0 + p.chunks1);
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(L.full + 8 * s, 1); mbar_init(L.empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(L.tfull + 8 * s, 1); mbar_init(L.tempty + 8 * s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  {
+    float* slab0 = reinterpret_cast<float*>(smem_raw + (L.stat - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < 1024; i += kThreads) slab0[i] = 0.0f;
+  }
+  if (warp == 1) tc_alloc(L.tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(L.tmem_slot));
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const int chunks = p.chunks0 + p.chunks1;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw << p.log_bw, h0 = th << p.log_bh, n0 = tb << p.log_bn;
+        const int n_base = nt * p.block_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(L.empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = L.base + stage * stage_bytes, sb = sa + kAStage;
+          const uint32_t fb = L.full + 8 * stage;
+          mbar_expect_tx(fb, kAStage + p.b_stage_bytes);
+          const int tap = kb / chunks, ch = kb - tap * chunks;
+          const TapInfo t = p.taps[tap];
+          int map = t.map, c0 = ch * kBlockK;
+          if (p.dual && ch >= p.chunks0) { map = 1; c0 = (ch - p.chunks0) * kBlockK; }
+          tma_load_4d(sa, &p.tmA[map], c0, w0 + t.dx, h0 + t.dy, n0, fb);
+          tma_load_2d(sb, &p.tmB, kb * kBlockK, n_base, fb);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(L.tempty + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(L.full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = L.base + stage * stage_bytes, sb = sa + kAStage;
+          const uint64_t adesc = p.desc_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
+          const uint64_t bdesc = p.desc_hi | (uint64_t)((sb & 0x3FFFFu) >> 4);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
+          tc_commit(L.empty + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(L.tfull + 8 * as);
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // row of the 128-pixel tile
+    const int bw = 1 << p.log_bw, bh = 1 << p.log_bh;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+      const int w = (tw << p.log_bw) + (row & (bw - 1));
+      const int h = (th << p.log_bh) + ((row >> p.log_bw) & (bh - 1));
+      const int n = (tb << p.log_bn) + (row >> (p.log_bw + p.log_bh));
+      const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
+      const int n_base = nt * p.block_n;
+      int co0 = n_base;
+      long long off = (long long)n * p.sN + (long long)h * p.sH + (long long)w * p.sW;
+      if (p.convt_k) {
+        const int tap = n_base / p.Cout;
+        co0 = n_base - tap * p.Cout;
+        off += (long long)(tap / p.convt_k) * p.sKy + (long long)(tap % p.convt_k) * p.sKx;
+      }
+      mbar_wait(L.tfull + 8 * as, aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+      for (int cc = 0; cc < p.block_n; cc += 32) {
+        float v[32];
+        tc_ld32(t_row + (uint32_t)cc, v);
+        const int cbase = co0 + cc;         // first output channel of this chunk
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = cbase + j;
+          const float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.0f;
+          v[j] = (c < p.Cout && cc + j < p.block_n) ? v[j] + b : 0.0f;
+        }
+        if (valid) {
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + off + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (cbase + j < p.ldc_pad && cc + j < p.block_n)
+                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + off + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              if (cbase + j < p.ldc_pad && cc + j < p.block_n) {
+                uint4 u;
+                u.x = dm::pack2(v[j], v[j + 1]); u.y = dm::pack2(v[j + 2], v[j + 3]);
+                u.z = dm::pack2(v[j + 4], v[j + 5]); u.w = dm::pack2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = u;
+              }
+          }
+        }
+        if (p.stats != nullptr) {
+          // per-channel sum and sum of squares over this warp's 32 rows -> combined over the 4 warps below
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float x = valid ? v[j] : 0.0f; s1[j] = x; s2[j] = x * x; }
+          const float a = warp_colsum32(s1, lane), b2 = warp_colsum32(s2, lane);
+          // the four warps accumulate through shared-memory atomics into a [2][block_n] slab
+          float* slab = reinterpret_cast<float*>(smem_raw + (L.stat - smem_u32(smem_raw))) + as * 512;
+          atomicAdd(slab + cc + lane, a);
+          atomicAdd(slab + 256 + cc + lane, b2);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(L.tempty + 8 * as);
+      if (p.stats != nullptr) {
+        // all four epilogue warps have added their partials: flush the slab and re-zero it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float* slab = reinterpret_cast<float*>(smem_raw + (L.stat - smem_u32(smem_raw))) + as * 512;
+        const int e = threadIdx.x - 64;     // 0..127
+        float* g = p.stats + (long long)mt * 2 * p.stats_ld;
+        for (int c = e; c < p.block_n; c += 128) {
+          if (co0 + c < p.Cout) {
+            g[co0 + c] = slab[c];
+            g[p.stats_ld + co0 + c] = slab[256 + c];
+          }
+          slab[c] = 0.0f; slab[256 + c] = 0.0f;   // re-armed for tile it+2; ordered by the next tile's bar.sync
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tc_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------ kernel B
+__global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stage_bytes = kAStage + p.b_stage_bytes;   // A: 2 boxes of [64 px][64 co]; B: block_n/64 boxes
+  const SmemLayout L = carve(smem_raw, p.stages, stage_bytes);
+  const int chunks = p.chunks0 + p.chunks1;            // 64-channel chunks of Cin
+  const int cpt = p.block_n / 64;                      // chunks per ci tile
+  const int total_tiles = p.co_tiles * p.num_taps * p.ci_tiles * p.splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(L.full + 8 * s, 1); mbar_init(L.empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(L.tfull + 8 * s, 1); mbar_init(L.tempty + 8 * s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tc_alloc(L.tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(L.tmem_slot));
+
+  // tile -> (split, ci tile, tap, co tile); co fastest so concurrent CTAs share the X patches in L2
+  auto decode = [&](int tile, int& cot, int& tap, int& cit, int& sp) {
+    cot = tile % p.co_tiles; tile /= p.co_tiles;
+    tap = tile % p.num_taps; tile /= p.num_taps;
+    cit = tile % p.ci_tiles; sp = tile / p.ci_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int cot, tap, cit, sp; decode(tile, cot, tap, cit, sp);
+        const TapInfo t = p.taps[tap];
+        const int p0 = sp * p.patches_per_split;
+        const int p1 = min(p.patches, p0 + p.patches_per_split);
+        const int nch = min(cpt, chunks - cit * cpt);   // live 64-channel boxes of this ci tile
+        for (int pp = p0; pp < p1; ++pp) {
+          const int tw = pp % p.tiles_w, th = (pp / p.tiles_w) % p.tiles_h, tb = pp / (p.tiles_w * p.tiles_h);
+          const int w0 = tw << p.log_bw, h0 = th << p.log_bh, n0 = tb << p.log_bn;
+          mbar_wait(L.empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = L.base + stage * stage_bytes, sb = sa + kAStage;
+          const uint32_t fb = L.full + 8 * stage;
+          mbar_expect_tx(fb, 2 * 8192 + nch * 8192);
+          tma_load_4d(sa, &p.tmDY, cot * 128, w0, h0, n0, fb);
+          tma_load_4d(sa + 8192, &p.tmDY, cot * 128 + 64, w0, h0, n0, fb);
+          for (int j = 0; j < nch; ++j) {
+            const int ch = cit * cpt + j;
+            int map = t.map, c0 = ch * 64;
+            if (p.dual && ch >= p.chunks0) { map = 1; c0 = (ch - p.chunks0) * 64; }
+            tma_load_4d(sb + j * 8192, &p.tmX[map], c0, w0 + t.dx, h0 + t.dy, n0, fb);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        int cot, tap, cit, sp; decode(tile, cot, tap, cit, sp);
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        const int p0 = sp * p.patches_per_split;
+        const int p1 = min(p.patches, p0 + p.patches_per_split);
+        mbar_wait(L.tempty + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+        for (int pp = p0; pp < p1; ++pp) {
+          mbar_wait(L.full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = L.base + stage * stage_bytes, sb = sa + kAStage;
+          const uint64_t adesc = p.desc_hi_a | ((uint64_t)p.lbo_a << 16) | (uint64_t)((sa & 0x3FFFFu) >> 4);
+          const uint64_t bdesc = p.desc_hi_b | ((uint64_t)p.lbo_b << 16) | (uint64_t)((sb & 0x3FFFFu) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)      // 16 pixels per MMA = two 8-row swizzle groups = 2048 B
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc, (pp != p0) | (k != 0));
+          tc_commit(L.empty + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(L.tfull + 8 * as);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int cot, tap, cit, sp; decode(tile, cot, tap, cit, sp);
+      const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+      const int co = cot * 128 + q * 32 + lane;
+      const int ci0 = cit * p.block_n;
+      const int ncols = min(p.block_n, p.cin_k - ci0);
+      mbar_wait(L.tfull + 8 * as, aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+      float* dst = p.dwp + ((long long)co * p.num_taps + tap) * p.cin_k + ci0;
+      for (int cc = 0; cc < ncols; cc += 32) {
+        float v[32];
+        tc_ld32(t_row + (uint32_t)cc, v);
+        if (co < p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (cc + j < ncols)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + cc + j), "f"(v[j]), "f"(v[j + 1]),
+                           "f"(v[j + 2]), "f"(v[j + 3])
+                           : "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(L.tempty + 8 * as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tc_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+long long g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+int ensure_encode() {
+  if (g_encode) return DM_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr) { dm_set_error("cuTensorMapEncodeTiled entry point not found"); return DM_ERR_TMA; }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return DM_OK;
+}
+
+// 4-D map over an NHWC bf16 activation view: dims (C, W, H, N), element strides (1, sw, sh, sn).
+int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sw, long long sh, long long sn,
+                 int bw, int bh, int bn) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(act) failed: %d (C=%d W=%d H=%d N=%d sw=%lld sh=%lld sn=%lld box=%d,%d,%d ptr=%p)",
+             (int)r, C, W, H, N, sw, sh, sn, bw, bh, bn, base);
+    dm_set_error(buf);
+    return DM_ERR_TMA;
+  }
+  return DM_OK;
+}
+
+// 2-D map over the packed weight matrix [rows, ktot] (K contiguous).
+int make_w_map(CUtensorMap* m, const void* base, long long rows, long long ktot, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(weights) failed: %d (rows=%lld ktot=%lld box=%d)", (int)r, rows, ktot, box_rows);
+    dm_set_error(buf);
+    return DM_ERR_TMA;
+  }
+  return DM_OK;
+}
+
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+int pow2ceil(int v) { return 1 << ilog2(v); }
+
+void pick_patch(int W, int H, int rows, int& lbw, int& lbh, int& lbn) {
+  int bw = pow2ceil(W); if (bw > rows) bw = rows;
+  int bh = pow2ceil(H); if (bh > rows / bw) bh = rows / bw;
+  int bn = rows / (bw * bh);
+  lbw = ilog2(bw); lbh = ilog2(bh); lbn = ilog2(bn);
+}
+
+int pick_block_n(int cout) {
+  int c16 = (cout + 15) / 16 * 16;
+  int nt = (c16 + 255) / 256;
+  int bn = ((c16 + nt - 1) / nt + 15) / 16 * 16;
+  return bn;
+}
+
+unsigned make_idesc(int n, bool a_mn, bool b_mn) {
+  // kind::f16: c=f32 (1<<4), a=bf16 (1<<7), b=bf16 (1<<10), a_major<<15, b_major<<16, N>>3 <<17, M>>4 <<24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((unsigned)(n >> 3) << 17) | ((unsigned)(kBlockM >> 4) << 24);
+}
+
+// SBO = 1024 B (8 rows x 128 B), descriptor version 1 (sm_100), SWIZZLE_128B
+constexpr unsigned long long kDescHiKMajor = (64ull << 32) | (1ull << 46) | (2ull << 61) | (1ull << 16);
+constexpr unsigned long long kDescHiMN = (64ull << 32) | (1ull << 46) | (2ull << 61);
+
+bool g_attr_a = false, g_attr_b = false;
+
+struct ConvGeom {
+  // one launch of kernel A
+  const void* src[4]; int srcC[4]; long long src_sw[4], src_sh[4], src_sn[4]; int src_W[4], src_H[4];
+  int num_src;
+};
+
+}  // namespace
+
+extern "C" void dm_debug_set(int key, long long value) { if (key >= 0 && key < 8) g_debug[key] = value; }
+
+// Generic launcher for kernel A.  All geometry is resolved by the typed entry points below.
+static int launch_conv(ConvParams& P, cudaStream_t st) {
+  int stage_bytes = kAStage + P.b_stage_bytes;
+  int stages = (kSmemBudget - 1024 - kAuxBytes) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (g_debug[0] > 0 && g_debug[0] < stages) stages = (int)g_debug[0];
+  if (stages < 2) { dm_set_error("conv_gemm: not enough shared memory for 2 stages"); return DM_ERR_ARG; }
+  P.stages = stages;
+  size_t smem = 1024 + (size_t)stages * stage_bytes + kAuxBytes;
+  if (!g_attr_a) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
+    g_attr_a = true;
+  }
+  int tiles = P.m_tiles * P.n_tiles;
+  int grid = tiles < DM_NUM_SMS ? tiles : DM_NUM_SMS;
+  if (g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
+  conv_gemm_kernel<<<grid, kThreads, smem, st>>>(P);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
+static void fill_common(ConvParams& P, int N, int H, int W, int Cout_rows, int block_n) {
+  pick_patch(W, H, kBlockM, P.log_bw, P.log_bh, P.log_bn);
+  P.tiles_w = dm::cdiv(W, 1 << P.log_bw);
+  P.tiles_h = dm::cdiv(H, 1 << P.log_bh);
+  P.tiles_b = dm::cdiv(N, 1 << P.log_bn);
+  P.m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
+  P.block_n = block_n;
+  P.n_tiles = dm::cdiv(Cout_rows, block_n);
+  P.N = N; P.H = H; P.W = W;
+  P.b_stage_bytes = block_n * 128;
+  P.idesc = make_idesc(block_n, false, false);
+  P.desc_hi = kDescHiKMajor;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dm_conv2d_fwd: y[N,Ho,Wo,Cout] = conv(x0 (++ x1 on channels), Wp) + bias    (bf16 NHWC in, bf16/fp32 out)
+// stride 1: any kh,kw,pad.  stride 2: even Hin,Win (parity views), single source.
+// stats (optional): per-M-tile partial sums [m_tiles][2][stats_ld] of y and y^2 for train-mode BatchNorm.
+extern "C" int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, int C1, int ld1, const void* wpk,
+                             const float* bias, void* y, int ldy, int y_f32, float* stats, int stats_ld, int N, int Hin,
+                             int Win, int Cout, int kh, int kw, int stride, int pad, void* stream) {
+  if (ensure_encode() != DM_OK) return DM_ERR_TMA;
+  if (kh * kw > 16 || (stride != 1 && stride != 2)) { dm_set_error("dm_conv2d_fwd: unsupported kernel/stride"); return DM_ERR_ARG; }
+  if (stride == 2 && (x1 != nullptr || (Hin & 1) || (Win & 1))) { dm_set_error("dm_conv2d_fwd: stride 2 needs one source, even H/W"); return DM_ERR_ARG; }
+  if ((ld0 & 7) || (x1 && (ld1 & 7)) || (ldy & (y_f32 ? 3 : 7))) { dm_set_error("dm_conv2d_fwd: channel pitch must be a multiple of 8"); return DM_ERR_ARG; }
+  const int Ho = (Hin + 2 * pad - kh) / stride + 1, Wo = (Win + 2 * pad - kw) / stride + 1;
+  ConvParams P;
+  memset(&P, 0, sizeof P);
+  const int block_n = pick_block_n(Cout);
+  fill_common(P, N, Ho, Wo, Cout, block_n);
+  P.chunks0 = dm::cdiv(C0, 64);
+  P.chunks1 = x1 ? dm::cdiv(C1, 64) : 0;
+  P.dual = x1 ? 1 : 0;
+  P.num_taps = kh * kw;
+  const int bw = 1 << P.log_bw, bh = 1 << P.log_bh, bn = 1 << P.log_bn;
+  int rc;
+  if (stride == 1) {
+    for (int r = 0; r < kh; ++r)
+      for (int s = 0; s < kw; ++s) { TapInfo t = {(int8_t)(r - pad), (int8_t)(s - pad), 0, 0}; P.taps[r * kw + s] = t; }
+    rc = make_act_map(&P.tmA[0], x0, C0, Win, Hin, N, ld0, (long long)Win * ld0, (long long)Hin * Win * ld0, bw, bh, bn);
+    if (rc) return rc;
+    if (x1) {
+      rc = make_act_map(&P.tmA[1], x1, C1, Win, Hin, N, ld1, (long long)Win * ld1, (long long)Hin * Win * ld1, bw, bh, bn);
+      if (rc) return rc;
+    }
+  } else {
+    // input row = 2*y - pad + r = 2*(y + floor((r-pad)/2)) + ((r-pad) mod 2): parity view + integer offset
+    for (int r = 0; r < kh; ++r)
+      for (int s = 0; s < kw; ++s) {
+        const int a = r - pad, b = s - pad;
+        const int pa = ((a % 2) + 2) % 2, pb = ((b % 2) + 2) % 2;
+        TapInfo t = {(int8_t)((a - pa) / 2), (int8_t)((b - pb) / 2), (int8_t)(pa * 2 + pb), 0};
+        P.taps[r * kw + s] = t;
+      }
+    for (int pa = 0; pa < 2; ++pa)
+      for (int pb = 0; pb < 2; ++pb) {
+        const bf16* base = reinterpret_cast<const bf16*>(x0) + ((long long)pa * Win + pb) * ld0;
+        rc = make_act_map(&P.tmA[pa * 2 + pb], base, C0, Win / 2, Hin / 2, N, 2LL * ld0, 2LL * Win * ld0,
+                          (long long)Hin * Win * ld0, bw, bh, bn);
+        if (rc) return rc;
+      }
+  }
+  const long long ktot = (long long)P.num_taps * (P.chunks0 + P.chunks1) * 64;
+  rc = make_w_map(&P.tmB, wpk, Cout, ktot, block_n);
+  if (rc) return rc;
+  P.out = y; P.out_f32 = y_f32;
+  P.sN = (long long)Ho * Wo * ldy; P.sH = (long long)Wo * ldy; P.sW = ldy;
+  P.Cout = Cout; P.ldc_pad = ldy;
+  P.bias = bias; P.stats = stats; P.stats_ld = stats_ld;
+  return launch_conv(P, (cudaStream_t)stream);
+}
+
+extern "C" int dm_conv2d_fwd_mtiles(int N, int Ho, int Wo) {
+  int a, b, c; pick_patch(Wo, Ho, kBlockM, a, b, c);
+  return dm::cdiv(Wo, 1 << a) * dm::cdiv(Ho, 1 << b) * dm::cdiv(N, 1 << c);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dm_conv2d_s2_dgrad: data gradient of a k=4, stride 2, pad 1 convolution.
+// dy [N,Ho,Wo,Cout] -> dx [N,2Ho,2Wo,Cin].  Four launches, one per output parity (ph,pw); each is a
+// 2x2-tap conv over dy.  wpk: [4 phases][Cin][4 taps][Cout_k] (see dm_pack_weights mode 2).
+extern "C" int dm_conv2d_s2_dgrad(const void* dy, int Cout, int lddy, const void* wpk, void* dx, int Cin, int lddx,
+                                  int N, int Ho, int Wo, void* stream) {
+  if (ensure_encode() != DM_OK) return DM_ERR_TMA;
+  if ((lddy & 7) || (lddx & 7)) { dm_set_error("dm_conv2d_s2_dgrad: channel pitch must be a multiple of 8"); return DM_ERR_ARG; }
+  const int H = 2 * Ho, W = 2 * Wo;
+  const int chunks = dm::cdiv(Cout, 64);
+  const long long ktot = 4LL * chunks * 64;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      ConvParams P;
+      memset(&P, 0, sizeof P);
+      const int block_n = pick_block_n(Cin);
+      fill_common(P, N, Ho, Wo, Cin, block_n);
+      P.chunks0 = chunks; P.num_taps = 4;
+      // row i = 2Y+ph gets dy rows y with r = i + 1 - 2y in [0,3]:  ph=0: (y=Y, r=1), (y=Y-1, r=3);  ph=1: (y=Y+1, r=0), (y=Y, r=2)
+      const int dyo[2][2] = {{0, -1}, {1, 0}};
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) { TapInfo t = {(int8_t)dyo[ph][a], (int8_t)dyo[pw][b], 0, 0}; P.taps[a * 2 + b] = t; }
+      int rc = make_act_map(&P.tmA[0], dy, Cout, Wo, Ho, N, lddy, (long long)Wo * lddy, (long long)Ho * Wo * lddy,
+                            1 << P.log_bw, 1 << P.log_bh, 1 << P.log_bn);
+      if (rc) return rc;
+      const bf16* wbase = reinterpret_cast<const bf16*>(wpk) + (long long)(ph * 2 + pw) * Cin * ktot;
+      rc = make_w_map(&P.tmB, wbase, Cin, ktot, block_n);
+      if (rc) return rc;
+      P.out = reinterpret_cast<bf16*>(dx) + ((long long)ph * W + pw) * lddx;
+      P.out_f32 = 0;
+      P.sN = (long long)H * W * lddx; P.sH = 2LL * W * lddx; P.sW = 2LL * lddx;
+      P.Cout = Cin; P.ldc_pad = lddx;
+      rc = launch_conv(P, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+  return DM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dm_convt_fwd: ConvTranspose2d with kernel == stride == k (non-overlapping): a GEMM
+// [N*Hin*Win, Cin] x [Cin, k*k*Cout] with a pixel-shuffle scatter epilogue.  wpk: [k*k*Cout][Cin_k].
+extern "C" int dm_convt_fwd(const void* x, int Cin, int ldx, const void* wpk, const float* bias, void* y, int ldy, int N,
+                            int Hin, int Win, int Cout, int k, void* stream) {
+  if (ensure_encode() != DM_OK) return DM_ERR_TMA;
+  if ((ldx & 7) || (ldy & 7) || (Cout & 15)) { dm_set_error("dm_convt_fwd: Cout must be a multiple of 16, pitches of 8"); return DM_ERR_ARG; }
+  int block_n = 256;
+  while (Cout % block_n) block_n -= 16;
+  ConvParams P;
+  memset(&P, 0, sizeof P);
+  fill_common(P, N, Hin, Win, k * k * Cout, block_n);
+  P.chunks0 = dm::cdiv(Cin, 64); P.num_taps = 1;
+  TapInfo t = {0, 0, 0, 0}; P.taps[0] = t;
+  int rc = make_act_map(&P.tmA[0], x, Cin, Win, Hin, N, ldx, (long long)Win * ldx, (long long)Hin * Win * ldx,
+                        1 << P.log_bw, 1 << P.log_bh, 1 << P.log_bn);
+  if (rc) return rc;
+  rc = make_w_map(&P.tmB, wpk, (long long)k * k * Cout, (long long)P.chunks0 * 64, block_n);
+  if (rc) return rc;
+  const int Ho = Hin * k, Wo = Win * k;
+  P.out = y; P.out_f32 = 0;
+  P.sN = (long long)Ho * Wo * ldy; P.sH = (long long)k * Wo * ldy; P.sW = (long long)k * ldy;
+  P.sKy = (long long)Wo * ldy; P.sKx = ldy; P.convt_k = k;
+  P.Cout = Cout; P.ldc_pad = ldy;
+  P.bias = bias;
+  return launch_conv(P, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dm_conv2d_wgrad: dWp[Cout][taps][Cin_k] (fp32, accumulated with red.add) += dY^T * im2col(X).
+// Same geometry arguments as dm_conv2d_fwd; dy is [N,Ho,Wo,Cout] bf16 with pitch lddy.
+extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, int C1, int ld1, const void* dy, int lddy,
+                               float* dwp, int N, int Hin, int Win, int Cout, int kh, int kw, int stride, int pad,
+                               void* stream) {
+  if (ensure_encode() != DM_OK) return DM_ERR_TMA;
+  if (kh * kw > 16 || (stride != 1 && stride != 2)) { dm_set_error("dm_conv2d_wgrad: unsupported kernel/stride"); return DM_ERR_ARG; }
+  if (stride == 2 && (x1 != nullptr || (Hin & 1) || (Win & 1))) { dm_set_error("dm_conv2d_wgrad: stride 2 needs one source, even H/W"); return DM_ERR_ARG; }
+  if ((ld0 & 7) || (x1 && (ld1 & 7)) || (lddy & 7)) { dm_set_error("dm_conv2d_wgrad: channel pitch must be a multiple of 8"); return DM_ERR_ARG; }
+  const int Ho = (Hin + 2 * pad - kh) / stride + 1, Wo = (Win + 2 * pad - kw) / stride + 1;
+  WgradParams P;
+  memset(&P, 0, sizeof P);
+  pick_patch(Wo, Ho, 64, P.log_bw, P.log_bh, P.log_bn);
+  const int bw = 1 << P.log_bw, bh = 1 << P.log_bh, bn = 1 << P.log_bn;
+  P.tiles_w = dm::cdiv(Wo, bw); P.tiles_h = dm::cdiv(Ho, bh); P.tiles_b = dm::cdiv(N, bn);
+  P.patches = P.tiles_w * P.tiles_h * P.tiles_b;
+  P.chunks0 = dm::cdiv(C0, 64);
+  P.chunks1 = x1 ? dm::cdiv(C1, 64) : 0;
+  P.dual = x1 ? 1 : 0;
+  P.num_taps = kh * kw;
+  const int chunks = P.chunks0 + P.chunks1;
+  P.cin_k = chunks * 64;
+  P.block_n = chunks >= 4 ? 256 : chunks * 64;
+  P.ci_tiles = dm::cdiv(P.cin_k, P.block_n);
+  P.co_tiles = dm::cdiv(Cout, 128);
+  P.Cout = Cout;
+  const int base_tiles = P.co_tiles * P.num_taps * P.ci_tiles;
+  // split-K over pixel patches: aim for >= 2 waves of CTAs, keep >= 8 patches per split
+  int splits = 1;
+  if (base_tiles < 2 * DM_NUM_SMS) {
+    splits = dm::cdiv(2 * DM_NUM_SMS, base_tiles);
+    int max_splits = P.patches / 8; if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = max_splits;
+  }
+  if (g_debug[2] > 0) splits = (int)g_debug[2];
+  P.patches_per_split = dm::cdiv(P.patches, splits);
+  P.splits = dm::cdiv(P.patches, P.patches_per_split);
+  P.b_stage_bytes = (P.block_n / 64) * 8192;
+  P.dwp = dwp;
+  P.idesc = make_idesc(P.block_n, true, true);
+  P.desc_hi_a = kDescHiMN; P.desc_hi_b = kDescHiMN;
+  P.lbo_a = 8192 >> 4; P.lbo_b = 8192 >> 4;
+  if (g_debug[3] == 1) {   // probe: swap the roles of LBO / SBO
+    P.desc_hi_a = (512ull << 32) | (1ull << 46) | (2ull << 61); P.desc_hi_b = P.desc_hi_a;
+    P.lbo_a = 64; P.lbo_b = 64;
+  }
+  int rc;
+  if (stride == 1) {
+    for (int r = 0; r < kh; ++r)
+      for (int s = 0; s < kw; ++s) { TapInfo t = {(int8_t)(r - pad), (int8_t)(s - pad), 0, 0}; P.taps[r * kw + s] = t; }
+    rc = make_act_map(&P.tmX[0], x0, C0, Win, Hin, N, ld0, (long long)Win * ld0, (long long)Hin * Win * ld0, bw, bh, bn);
+    if (rc) return rc;
+    if (x1) {
+      rc = make_act_map(&P.tmX[1], x1, C1, Win, Hin, N, ld1, (long long)Win * ld1, (long long)Hin * Win * ld1, bw, bh, bn);
+      if (rc) return rc;
+    }
+  } else {
+    for (int r = 0; r < kh; ++r)
+      for (int s = 0; s < kw; ++s) {
+        const int a = r - pad, b = s - pad;
+        const int pa = ((a % 2) + 2) % 2, pb = ((b % 2) + 2) % 2;
+        TapInfo t = {(int8_t)((a - pa) / 2), (int8_t)((b - pb) / 2), (int8_t)(pa * 2 + pb), 0};
+        P.taps[r * kw + s] = t;
+      }
+    for (int pa = 0; pa < 2; ++pa)
+      for (int pb = 0; pb < 2; ++pb) {
+        const bf16* base = reinterpret_cast<const bf16*>(x0) + ((long long)pa * Win + pb) * ld0;
+        rc = make_act_map(&P.tmX[pa * 2 + pb], base, C0, Win / 2, Hin / 2, N, 2LL * ld0, 2LL * Win * ld0,
+                          (long long)Hin * Win * ld0, bw, bh, bn);
+        if (rc) return rc;
+      }
+  }
+  rc = make_act_map(&P.tmDY, dy, Cout, Wo, Ho, N, lddy, (long long)Wo * lddy, (long long)Ho * Wo * lddy, bw, bh, bn);
+  if (rc) return rc;
+  int stage_bytes = kAStage + P.b_stage_bytes;
+  int stages = (kSmemBudget - 1024 - kAuxBytes) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (g_debug[0] > 0 && g_debug[0] < stages) stages = (int)g_debug[0];
+  P.stages = stages;
+  size_t smem = 1024 + (size_t)stages * stage_bytes + kAuxBytes;
+  if (!g_attr_b) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
+    g_attr_b = true;
+  }
+  int tiles = base_tiles * P.splits;
+  int grid = tiles < DM_NUM_SMS ? tiles : DM_NUM_SMS;
+  if (g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
+  wgrad_gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}

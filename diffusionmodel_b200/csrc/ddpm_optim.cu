@@ -1,0 +1,295 @@
+// DDPM-side kernels (q-sample, weighted loss fwd/bwd, CFG combine + reverse step), weight packing for
+// the implicit-GEMM kernels, and the optimizer pass (global grad-norm + clipped AdamW).
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "dm_b200.h"
+
+using dm::bf16;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+void dm_set_error(const char* msg) { strncpy(g_err, msg, sizeof(g_err) - 1); g_err[sizeof(g_err) - 1] = 0; }
+extern "C" const char* dm_last_error(void) { return g_err; }
+extern "C" int dm_version(void) { return 100; }
+
+#define ST ((cudaStream_t)stream)
+
+namespace {
+
+inline int grid_for(long long total, int threads = 256) {
+  long long b = (total + threads - 1) / threads;
+  long long cap = (long long)DM_NUM_SMS * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ------------------------------------------------------------------------------------------ packing
+struct PackArgs {
+  long long tap_off[16];
+  int rows, cols, ntaps, c_split, cols_k, tap_major_rows;
+  long long s_row, s_col, row_len;
+};
+
+__device__ __forceinline__ bool pack_decode(const PackArgs& A, long long i, long long& src) {
+  // i indexes the packed buffer: [row][k] with k in [0,row_len) (tap_major_rows=0) or [tap*rows+row][k]
+  const long long k = i % A.row_len;
+  long long r = i / A.row_len;
+  int tap, col_k;
+  if (A.tap_major_rows) { tap = (int)(r / A.rows); r = r % A.rows; col_k = (int)k; if (k >= A.cols_k) return false; }
+  else { tap = (int)(k / A.cols_k); col_k = (int)(k % A.cols_k); if (tap >= A.ntaps) return false; }
+  int col = col_k;
+  if (A.c_split > 0) {
+    const int s64 = (A.c_split + 63) / 64 * 64;
+    if (col_k < s64) { if (col_k >= A.c_split) return false; }
+    else col = col_k - s64 + A.c_split;
+  }
+  if (col >= A.cols) return false;
+  src = r * A.s_row + (long long)col * A.s_col + A.tap_off[tap];
+  return true;
+}
+__global__ void pack_weight_kernel(const float* w, bf16* out, PackArgs A, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long src;
+    out[i] = __float2bfloat16(pack_decode(A, i, src) ? w[src] : 0.0f);
+  }
+}
+// destination-major gather so the fp32 gradient writes are coalesced: one thread per (row, col, tap)
+__global__ void unpack_wgrad_kernel(const float* dwp, float* grad, PackArgs A, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % A.ntaps);
+    long long rc = i / A.ntaps;
+    long long row, col;
+    if (A.s_row >= A.s_col) { col = rc % A.cols; row = rc / A.cols; } else { row = rc % A.rows; col = rc / A.rows; }
+    int col_k = (int)col;
+    if (A.c_split > 0 && col >= A.c_split) col_k = (int)col - A.c_split + (A.c_split + 63) / 64 * 64;
+    const long long pk = A.tap_major_rows ? ((long long)tap * A.rows + row) * A.row_len + col_k
+                                          : row * A.row_len + (long long)tap * A.cols_k + col_k;
+    grad[row * A.s_row + col * A.s_col + A.tap_off[tap]] += dwp[pk];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ DDPM
+__global__ void q_sample_kernel(const float* x, const float* noise, const float* sqrtab, const float* sqrtmab,
+                                const long long* ts, bf16* xt, int ldo, int N, int C, int HW) {
+  const long long P = (long long)N * HW;
+  const int Cv = ldo / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P * Cv; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % P; const int cv = (int)(i / P);
+    const long long n = p / HW, hw = p % HW;
+    const long long t = ts[n];
+    const float a = sqrtab[t], b = sqrtmab[t];
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cv * 8 + j;
+      if (c < C) {
+        const long long k = (n * C + c) * HW + hw;
+        // separate roundings, as the reference's eager mul / mul / add (new_scripy.py:408-411)
+        v[j] = __fadd_rn(__fmul_rn(a, x[k]), __fmul_rn(b, noise[k]));
+      } else v[j] = 0.f;
+    }
+    dm::store8(xt + p * ldo + cv * 8, v);
+  }
+}
+
+struct LossCfg { float hi_t, mid_t, hi_w, mid_w, lo_w, fcw; };
+
+__global__ void __launch_bounds__(256) loss_fwd_kernel(const float* pred, int ldp, const float* noise, const float* mask,
+                                                        float* acc, int N, int C, int HW, LossCfg L) {
+  __shared__ float sm[32];
+  const long long P = (long long)N * HW;
+  float s0 = 0.f, s1 = 0.f;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const long long n = p / HW, hw = p % HW;
+    float w = 1.f, h = 0.f;
+    if (mask) {
+      const float m = mask[p];
+      w = (m > L.hi_t) ? L.hi_w : ((m > L.mid_t) ? L.mid_w : L.lo_w);     // exact fp32 compares (new_scripy.py:420-424)
+      h = (m > L.hi_t) ? 1.f : 0.f;
+    }
+    for (int c = 0; c < C; ++c) {
+      const float pr = pred[p * ldp + c], nz = noise[(n * C + c) * HW + hw];
+      const float d = nz - pr;
+      s0 += d * d * w;
+      s1 += fabsf(pr * h - nz * h);
+    }
+  }
+  s0 = dm::block_sum(s0, sm);
+  s1 = dm::block_sum(s1, sm);
+  if (threadIdx.x == 0) { atomicAdd(acc, s0); atomicAdd(acc + 1, s1); }
+}
+__global__ void loss_final_kernel(const float* acc, float* loss, double cnt, float fcw) {
+  loss[0] = (float)((double)acc[0] / cnt + (double)fcw * (double)acc[1] / cnt);
+}
+__global__ void loss_bwd_kernel(const float* pred, int ldp, const float* noise, const float* mask, const float* gout,
+                                float* dpred, int lddp, int N, int C, int HW, LossCfg L, float inv_cnt) {
+  const long long P = (long long)N * HW;
+  const float go = gout[0] * inv_cnt;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const long long n = p / HW, hw = p % HW;
+    float w = 1.f, h = 0.f;
+    if (mask) {
+      const float m = mask[p];
+      w = (m > L.hi_t) ? L.hi_w : ((m > L.mid_t) ? L.mid_w : L.lo_w);
+      h = (m > L.hi_t) ? 1.f : 0.f;
+    }
+    for (int c = 0; c < lddp; ++c) {
+      float v = 0.f;
+      if (c < C) {
+        const float pr = pred[p * ldp + c], nz = noise[(n * C + c) * HW + hw];
+        const float e = pr * h - nz * h;
+        const float sg = e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f);
+        v = go * (2.f * w * (pr - nz) + L.fcw * h * sg);
+      }
+      dpred[p * lddp + c] = v;
+    }
+  }
+}
+
+__global__ void cfg_reverse_kernel(const float* eps, int ldp, const float* x, const float* z, float* x_out, bf16* xt_next,
+                                   int ldo, float gw, float a, float b, float s, int n, int C, int HW) {
+  const long long P = (long long)n * HW;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const long long i = p / HW, hw = p % HW;
+    for (int c0 = 0; c0 < ldo; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        if (c < C) {
+          const long long k = (i * C + c) * HW + hw;
+          const float e1 = eps[p * ldp + c], e2 = eps[(p + P) * ldp + c];
+          // eps = (1+w)*eps1 - w*eps2 ; x' = a*(x - eps*b) + s*z, each op rounded separately like the
+          // reference's eager kernels (new_scripy.py:470-475)
+          const float e = __fsub_rn(__fmul_rn(1.0f + gw, e1), __fmul_rn(gw, e2));
+          float r = __fmul_rn(a, __fsub_rn(x[k], __fmul_rn(e, b)));
+          if (z) r = __fadd_rn(r, __fmul_rn(s, z[k]));
+          x_out[k] = r;
+          v[j] = r;
+        } else v[j] = 0.f;
+      }
+      if (xt_next) {
+        dm::store8(xt_next + p * ldo + c0, v);
+        dm::store8(xt_next + (p + P) * ldo + c0, v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ optimizer
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* g, long long n, float* out) {
+  __shared__ float sm[32];
+  float s = 0.f;
+  const long long n4 = n / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = g4[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += g[i] * g[i];
+  s = dm::block_sum(s, sm);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// torch.optim.AdamW semantics (decoupled decay, bias-corrected), gradient pre-scaled by the
+// clip_grad_norm_ coefficient min(1, max_norm / (norm + 1e-6)) (new_scripy.py:798-801).
+__global__ void __launch_bounds__(256) adamw_kernel(float* p, const float* g, float* m, float* v, long long n, float lr,
+                                                     float b1, float b2, float eps, float wd, float bc1, float bc2,
+                                                     const float* gnorm_sq, float max_norm) {
+  float clip = 1.f;
+  if (gnorm_sq != nullptr && max_norm > 0.f) {
+    const float c = max_norm / (sqrtf(gnorm_sq[0]) + 1e-6f);
+    clip = c < 1.f ? c : 1.f;
+  }
+  const float step = lr / bc1, rs2 = 1.0f / sqrtf(bc2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * clip;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = m[i] + (1.f - b1) * (gi - m[i]);
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    pi -= step * mi / (sqrtf(vi) * rs2 + eps);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
+}  // namespace
+
+static void fill_pack(PackArgs& A, int rows, int cols, int ntaps, const long long* tap_off, long long s_row, long long s_col,
+                      int c_split, int cols_k, long long row_len, int tap_major_rows) {
+  memset(&A, 0, sizeof A);
+  A.rows = rows; A.cols = cols; A.ntaps = ntaps; A.s_row = s_row; A.s_col = s_col; A.c_split = c_split;
+  A.cols_k = cols_k; A.row_len = row_len; A.tap_major_rows = tap_major_rows;
+  for (int i = 0; i < ntaps && i < 16; ++i) A.tap_off[i] = tap_off[i];
+}
+
+extern "C" int dm_pack_weight(const float* w, void* out, int rows, int cols, int ntaps, const long long* tap_off_host,
+                              long long s_row, long long s_col, int c_split, int cols_k, long long row_len,
+                              int tap_major_rows, void* stream) {
+  if (ntaps < 1 || ntaps > 16) { dm_set_error("dm_pack_weight: 1..16 taps"); return DM_ERR_ARG; }
+  PackArgs A; fill_pack(A, rows, cols, ntaps, tap_off_host, s_row, s_col, c_split, cols_k, row_len, tap_major_rows);
+  const long long total = (tap_major_rows ? (long long)ntaps * rows : (long long)rows) * row_len;
+  pack_weight_kernel<<<grid_for(total), 256, 0, ST>>>(w, (bf16*)out, A, total);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+extern "C" int dm_unpack_wgrad(const float* dwp, float* grad, int rows, int cols, int ntaps, const long long* tap_off_host,
+                               long long s_row, long long s_col, int c_split, int cols_k, long long row_len,
+                               int tap_major_rows, void* stream) {
+  if (ntaps < 1 || ntaps > 16) { dm_set_error("dm_unpack_wgrad: 1..16 taps"); return DM_ERR_ARG; }
+  PackArgs A; fill_pack(A, rows, cols, ntaps, tap_off_host, s_row, s_col, c_split, cols_k, row_len, tap_major_rows);
+  const long long total = (long long)rows * cols * ntaps;
+  unpack_wgrad_kernel<<<grid_for(total), 256, 0, ST>>>(dwp, grad, A, total);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
+extern "C" int dm_q_sample(const float* x, const float* noise, const float* sqrtab, const float* sqrtmab, const long long* ts,
+                           void* xt, int ldo, int N, int C, int H, int W, void* stream) {
+  if (ldo & 7) { dm_set_error("dm_q_sample: pitch must be a multiple of 8"); return DM_ERR_ARG; }
+  q_sample_kernel<<<grid_for((long long)N * H * W * (ldo / 8)), 256, 0, ST>>>(x, noise, sqrtab, sqrtmab, ts, (bf16*)xt, ldo, N, C, H * W);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+extern "C" int dm_ddpm_loss_fwd(const float* pred, int ldp, const float* noise, const float* mask, float* loss, float* scratch,
+                                int N, int C, int H, int W, float hi_t, float mid_t, float hi_w, float mid_w, float lo_w,
+                                float fcw, void* stream) {
+  cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * sizeof(float), ST);
+  if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
+  LossCfg L{hi_t, mid_t, hi_w, mid_w, lo_w, mask ? fcw : 0.f};
+  loss_fwd_kernel<<<grid_for((long long)N * H * W), 256, 0, ST>>>(pred, ldp, noise, mask, scratch, N, C, H * W, L);
+  DM_CHECK_LAUNCH();
+  loss_final_kernel<<<1, 1, 0, ST>>>(scratch, loss, (double)N * C * H * W, L.fcw);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+extern "C" int dm_ddpm_loss_bwd(const float* pred, int ldp, const float* noise, const float* mask, const float* gout,
+                                void* dpred, int lddp, int N, int C, int H, int W, float hi_t, float mid_t, float hi_w,
+                                float mid_w, float lo_w, float fcw, void* stream) {
+  LossCfg L{hi_t, mid_t, hi_w, mid_w, lo_w, mask ? fcw : 0.f};
+  loss_bwd_kernel<<<grid_for((long long)N * H * W), 256, 0, ST>>>(pred, ldp, noise, mask, gout, (float*)dpred, lddp, N, C, H * W, L,
+                                                                 (float)(1.0 / ((double)N * C * H * W)));
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+extern "C" int dm_cfg_reverse_step(const float* eps, int ldp, const float* x, const float* z, float* x_out, void* xt_next,
+                                   int ldo, float guide_w, float oneover_sqrta, float mab_over_sqrtmab, float sqrt_beta,
+                                   int n, int C, int H, int W, void* stream) {
+  if (ldo & 7) { dm_set_error("dm_cfg_reverse_step: pitch must be a multiple of 8"); return DM_ERR_ARG; }
+  cfg_reverse_kernel<<<grid_for((long long)n * H * W), 256, 0, ST>>>(eps, ldp, x, z, x_out, (bf16*)xt_next, ldo, guide_w,
+                                                                    oneover_sqrta, mab_over_sqrtmab, sqrt_beta, n, C, H * W);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
+extern "C" int dm_sumsq(const float* g, long long n, float* out, void* stream) {
+  sumsq_kernel<<<grid_for(n / 4 + 1), 256, 0, ST>>>(g, n, out);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+extern "C" int dm_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                        float eps, float wd, float bc1, float bc2, const float* gnorm_sq, float max_norm, void* stream) {
+  adamw_kernel<<<grid_for(n), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2, gnorm_sq, max_norm);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}

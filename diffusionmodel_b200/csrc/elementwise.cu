@@ -1,0 +1,879 @@
+// Bandwidth-bound kernels of the diffusion hot path: normalisation + activation, squeeze-excite and
+// coordinate-attention pooling/gating, FiLM, bilinear upsample + concat, pooling, LocalEnhancer mask
+// weighting, layout conversion.  All activations are bf16 NHWC with a channel pitch; every thread
+// moves 16-byte vectors (8 channels) and all reductions are fp32 (warp shuffles + shared memory).
+#include <stdio.h>
+
+#include "common.cuh"
+#include "dm_b200.h"
+
+using dm::bf16;
+using dm::load8;
+using dm::store8;
+
+namespace {
+
+constexpr int kEwThreads = 256;
+
+inline int ew_grid(long long total) {
+  long long b = (total + kEwThreads - 1) / kEwThreads;
+  long long cap = (long long)DM_NUM_SMS * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// Generic (pixel, 8-channel vector) elementwise driver.  F::operator()(p, c0) handles channels [c0, c0+8).
+template <class F>
+__global__ void __launch_bounds__(kEwThreads) ew_kernel(unsigned total, unsigned Cv, F f) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned p = i / Cv, cv = i - p * Cv;
+    f(p, (int)(cv * 8));
+  }
+}
+template <class F>
+int ew_launch(long long P, int C, F f, cudaStream_t st) {
+  long long Cv = (C + 7) / 8, total = P * Cv;
+  if (total <= 0) return DM_OK;
+  if (total >= (1ll << 32)) { dm_set_error("elementwise: tensor too large"); return DM_ERR_ARG; }
+  ew_kernel<F><<<ew_grid(total), kEwThreads, 0, st>>>((unsigned)total, (unsigned)Cv, f);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
+__device__ __forceinline__ void ldp8(const float* p, int c0, int C, float (&o)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = (c0 + j < C) ? __ldg(p + c0 + j) : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------- reductions
+// out1[g][c] (+ out2[g][c]) += scale * sum over the `count` pixels of group g.
+struct RedArgs {
+  const bf16* a; const bf16* b;
+  long long a_hi, a_lo, a_ps, b_hi, b_lo, b_ps;   // group base = (g/gdiv)*hi + (g%gdiv)*lo ; pixel stride ps
+  int gdiv, count, C, mode, act, G, stat_div;      // stat index for mode 4: (g / stat_div) * G + c / (C/G)
+  const float *mean, *invstd, *gamma, *beta;
+  float scale;
+  float *out1, *out2;
+};
+// mode 0: s1 = sum a            1: s1 = sum a, s2 = sum a^2        2: s1 = sum a*b, s2 = sum a
+// mode 3: BN bwd   g = a*act'(xhat*gamma+beta), xhat = (b-mean[c])*invstd[c];  s1 = sum g, s2 = sum g*xhat
+// mode 4: GN bwd   same with mean/invstd per (sample, group)
+__global__ void __launch_bounds__(256) nc_reduce_kernel(RedArgs A) {
+  __shared__ float sm[256 * 16];
+  const int Cv = (A.C + 7) / 8;
+  const int VPB = Cv < 256 ? Cv : 256;
+  const int R = 256 / VPB;
+  const int t = threadIdx.x, cvl = t % VPB, r = t / VPB;
+  const int cv = blockIdx.y * VPB + cvl;
+  const int g = blockIdx.z;
+  const int c0 = cv * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  const bool live = (r < R) && (cv < Cv);
+  if (live) {
+    const bf16* pa = A.a + (long long)(g / A.gdiv) * A.a_hi + (long long)(g % A.gdiv) * A.a_lo + c0;
+    const bf16* pb = A.b ? A.b + (long long)(g / A.gdiv) * A.b_hi + (long long)(g % A.gdiv) * A.b_lo + c0 : nullptr;
+    float mu[8], is[8], ga[8], be[8];
+    if (A.mode >= 3) {
+      ldp8(A.gamma, c0, A.C, ga); ldp8(A.beta, c0, A.C, be);
+      if (A.mode == 3) { ldp8(A.mean, c0, A.C, mu); ldp8(A.invstd, c0, A.C, is); }
+      else {
+        const int cg = A.C / A.G;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c0 + j < A.C ? c0 + j : A.C - 1;
+          const int si = (g / A.stat_div) * A.G + c / cg;
+          mu[j] = __ldg(A.mean + si); is[j] = __ldg(A.invstd + si);
+        }
+      }
+    }
+    const int chunk = (A.count + gridDim.x - 1) / gridDim.x;
+    const int i0 = blockIdx.x * chunk;
+    const int i1 = min(A.count, i0 + chunk);
+    for (int i = i0 + r; i < i1; i += R) {
+      float va[8], vb[8];
+      load8(pa + (long long)i * A.a_ps, va);
+      if (pb) load8(pb + (long long)i * A.b_ps, vb);
+      if (A.mode == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] += va[j];
+      } else if (A.mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] += va[j]; s2[j] += va[j] * va[j]; }
+      } else if (A.mode == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] += va[j] * vb[j]; s2[j] += va[j]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (vb[j] - mu[j]) * is[j];
+          const float gg = va[j] * dm::act_grad_f(xh * ga[j] + be[j], A.act);
+          s1[j] += gg; s2[j] += gg * xh;
+        }
+      }
+    }
+  }
+  // reduce over the R pixel rows of the block
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sm[t * 16 + j] = s1[j]; sm[t * 16 + 8 + j] = s2[j]; }
+  __syncthreads();
+  if (r == 0 && cv < Cv) {
+    for (int rr = 1; rr < R; ++rr) {
+      const float* o = sm + (rr * VPB + cvl) * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1[j] += o[j]; s2[j] += o[8 + j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (c0 + j < A.C) {
+        atomicAdd(A.out1 + (long long)g * A.C + c0 + j, s1[j] * A.scale);
+        if (A.out2) atomicAdd(A.out2 + (long long)g * A.C + c0 + j, s2[j] * A.scale);
+      }
+    }
+  }
+}
+
+int launch_reduce(RedArgs& A, int groups, cudaStream_t st) {
+  const int Cv = (A.C + 7) / 8;
+  const int VPB = Cv < 256 ? Cv : 256;
+  const int R = 256 / VPB;
+  const int cvt = (Cv + VPB - 1) / VPB;
+  long long want = (long long)DM_NUM_SMS * 6 / ((long long)groups * cvt);
+  int maxs = A.count / (R * 4); if (maxs < 1) maxs = 1;
+  int splits = (int)(want < 1 ? 1 : (want > maxs ? maxs : want));
+  if (groups > 65535) { dm_set_error("reduce: too many groups"); return DM_ERR_ARG; }
+  dim3 grid(splits, cvt, groups);
+  nc_reduce_kernel<<<grid, 256, 0, st>>>(A);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
+__global__ void zero_kernel(float* p, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = 0.f;
+}
+int zero_f32(float* p, long long n, cudaStream_t st) {
+  if (n <= 0) return DM_OK;
+  zero_kernel<<<ew_grid(n), kEwThreads, 0, st>>>(p, n);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
+// ---------------------------------------------------------------------------------- BatchNorm
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* partials, int m_tiles, int ld, int C, double count,
+                                                            float* mean, float* invstd, float* rmean, float* rvar,
+                                                            float momentum, float eps) {
+  __shared__ double s1[32][33], s2[32][33];
+  const int cl = threadIdx.x & 31, rr = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double a = 0.0, b = 0.0;
+  if (c < C)
+    for (int t = rr; t < m_tiles; t += 32) {
+      a += (double)partials[(long long)t * 2 * ld + c];
+      b += (double)partials[(long long)t * 2 * ld + ld + c];
+    }
+  s1[rr][cl] = a; s2[rr][cl] = b;
+  __syncthreads();
+  if (rr == 0 && c < C) {
+    if (m_tiles > 0) {
+      for (int k = 1; k < 32; ++k) { a += s1[k][cl]; b += s2[k][cl]; }
+      const double mu = a / count;
+      double var = b / count - mu * mu;
+      if (var < 0.0) var = 0.0;
+      mean[c] = (float)mu;
+      invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+      if (rmean) {
+        const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+        rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mu;
+        rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+      }
+    } else {
+      mean[c] = rmean[c];
+      invstd[c] = 1.0f / sqrtf(rvar[c] + eps);
+    }
+  }
+}
+
+struct BnFwd {
+  const bf16* y; int ldy; const float *mean, *invstd, *gamma, *beta; bf16* z; int ldz; int C, act;
+  __device__ void operator()(unsigned p, int c0) const {
+    float v[8], mu[8], is[8], ga[8], be[8];
+    load8(y + (long long)p * ldy + c0, v);
+    ldp8(mean, c0, C, mu); ldp8(invstd, c0, C, is); ldp8(gamma, c0, C, ga); ldp8(beta, c0, C, be);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? dm::act_f((v[j] - mu[j]) * is[j] * ga[j] + be[j], act) : 0.f;
+    store8(z + (long long)p * ldz + c0, v);
+  }
+};
+
+struct BnBwd {
+  const bf16* dz; int lddz; const bf16* y; int ldy; const float *mean, *invstd, *gamma, *beta;
+  const float* sums;   // [2][C]: sum g, sum g*xhat
+  bf16* dy; int lddy; int C, act, training; float invP;
+  __device__ void operator()(unsigned p, int c0) const {
+    float g[8], v[8], mu[8], is[8], ga[8], be[8], s1[8], s2[8];
+    load8(dz + (long long)p * lddz + c0, g);
+    load8(y + (long long)p * ldy + c0, v);
+    ldp8(mean, c0, C, mu); ldp8(invstd, c0, C, is); ldp8(gamma, c0, C, ga); ldp8(beta, c0, C, be);
+    ldp8(sums, c0, C, s1); ldp8(sums + C, c0, C, s2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (v[j] - mu[j]) * is[j];
+      const float gg = g[j] * dm::act_grad_f(xh * ga[j] + be[j], act);
+      const float t = training ? (gg - s1[j] * invP - xh * s2[j] * invP) : gg;
+      g[j] = (c0 + j < C) ? ga[j] * is[j] * t : 0.f;
+    }
+    store8(dy + (long long)p * lddy + c0, g);
+  }
+};
+
+__global__ void accum2_kernel(const float* s, float* dgamma, float* dbeta, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { dbeta[c] += s[c]; dgamma[c] += s[C + c]; }
+}
+
+// ---------------------------------------------------------------------------------- GroupNorm
+__global__ void gn_fold_fwd_kernel(const float* S, int N, int C, int G, double cnt, float eps, float* mean, float* rstd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * G) return;
+  const int n = i / G, g = i % G, cg = C / G;
+  double a = 0, b = 0;
+  for (int c = g * cg; c < (g + 1) * cg; ++c) { a += S[(long long)n * C + c]; b += S[(long long)(N + n) * C + c]; }
+  const double mu = a / cnt;
+  double var = b / cnt - mu * mu; if (var < 0) var = 0;
+  mean[i] = (float)mu; rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+struct GnFwd {
+  const bf16* x; int ldx; const float *mean, *rstd, *gamma, *beta; bf16* z; int ldz; int C, G, HW, act;
+  __device__ void operator()(unsigned p, int c0) const {
+    float v[8], ga[8], be[8];
+    load8(x + (long long)p * ldx + c0, v);
+    ldp8(gamma, c0, C, ga); ldp8(beta, c0, C, be);
+    const int n = p / HW, cg = C / G;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j < C ? c0 + j : C - 1;
+      const int si = n * G + c / cg;
+      v[j] = (c0 + j < C) ? dm::act_f((v[j] - __ldg(mean + si)) * __ldg(rstd + si) * ga[j] + be[j], act) : 0.f;
+    }
+    store8(z + (long long)p * ldz + c0, v);
+  }
+};
+// S = [2][N][C] sums (g, g*xhat) -> m[2][N*G] group means of (g*gamma), (g*gamma*xhat); dgamma/dbeta +=
+__global__ void gn_fold_bwd_kernel(const float* S, const float* gamma, int N, int C, int G, double cnt, float* m,
+                                   float* dgamma, float* dbeta) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N * G) {
+    const int n = i / G, g = i % G, cg = C / G;
+    double a = 0, b = 0;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) {
+      a += (double)gamma[c] * S[(long long)n * C + c];
+      b += (double)gamma[c] * S[(long long)(N + n) * C + c];
+    }
+    m[i] = (float)(a / cnt); m[N * G + i] = (float)(b / cnt);
+  }
+  if (i < C) {
+    float a = 0, b = 0;
+    for (int n = 0; n < N; ++n) { a += S[(long long)n * C + i]; b += S[(long long)(N + n) * C + i]; }
+    dbeta[i] += a; dgamma[i] += b;
+  }
+}
+struct GnBwd {
+  const bf16* dz; int lddz; const bf16* x; int ldx; const float *mean, *rstd, *gamma, *beta, *m;
+  bf16* dx; int lddx; int C, G, HW, N, act;
+  __device__ void operator()(unsigned p, int c0) const {
+    float g[8], v[8], ga[8], be[8];
+    load8(dz + (long long)p * lddz + c0, g);
+    load8(x + (long long)p * ldx + c0, v);
+    ldp8(gamma, c0, C, ga); ldp8(beta, c0, C, be);
+    const int n = p / HW, cg = C / G;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j < C ? c0 + j : C - 1;
+      const int si = n * G + c / cg;
+      const float rs = __ldg(rstd + si);
+      const float xh = (v[j] - __ldg(mean + si)) * rs;
+      const float gg = g[j] * dm::act_grad_f(xh * ga[j] + be[j], act);
+      g[j] = (c0 + j < C) ? rs * (gg * ga[j] - __ldg(m + si) - xh * __ldg(m + N * G + si)) : 0.f;
+    }
+    store8(dx + (long long)p * lddx + c0, g);
+  }
+};
+
+// ---------------------------------------------------------------------------------- SE / residual
+struct SeFwd {
+  const bf16* x2; int ld2; const float* gate; const bf16* res; int ldr; bf16* out; int ldo; int C, HW; float scale;
+  __device__ void operator()(unsigned p, int c0) const {
+    float a[8], r[8], gt[8];
+    load8(x2 + (long long)p * ld2 + c0, a);
+    load8(res + (long long)p * ldr + c0, r);
+    const int n = p / HW;
+    if (gate) ldp8(gate + (long long)n * C, c0, C, gt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = (c0 + j < C) ? (r[j] + a[j] * (gate ? gt[j] : 1.f)) * scale : 0.f;
+    store8(out + (long long)p * ldo + c0, a);
+  }
+};
+struct SeBwd {
+  const bf16* dout; int lddo; const float *gate, *dpool; bf16* dx2; int lddx2; bf16* dres; int lddr; int C, HW; float scale, invHW;
+  __device__ void operator()(unsigned p, int c0) const {
+    float g[8], gt[8], dp[8], o[8];
+    load8(dout + (long long)p * lddo + c0, g);
+    const int n = p / HW;
+    if (gate) ldp8(gate + (long long)n * C, c0, C, gt);
+    if (dpool) ldp8(dpool + (long long)n * C, c0, C, dp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gs = g[j] * scale;
+      o[j] = (c0 + j < C) ? gs * (gate ? gt[j] : 1.f) + (dpool ? dp[j] * invHW : 0.f) : 0.f;
+      g[j] = (c0 + j < C) ? gs : 0.f;
+    }
+    store8(dx2 + (long long)p * lddx2 + c0, o);
+    if (dres) store8(dres + (long long)p * lddr + c0, g);
+  }
+};
+
+// ---------------------------------------------------------------------------------- CoordAttn gates
+struct CaFwd {
+  const bf16* x; int ldx; const float *ah, *aw; bf16* out; int ldo; int C, H, W;
+  __device__ void operator()(unsigned p, int c0) const {
+    float v[8], a[8], b[8];
+    load8(x + (long long)p * ldx + c0, v);
+    const int w = p % W, nh = p / W;            // nh = n*H + h
+    const int n = nh / H;
+    ldp8(ah + (long long)nh * C, c0, C, a);
+    ldp8(aw + ((long long)n * W + w) * C, c0, C, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? v[j] * (a[j] + b[j]) : 0.f;
+    store8(out + (long long)p * ldo + c0, v);
+  }
+};
+struct CaBwd {
+  const bf16* dout; int lddo; const float *ah, *aw, *dxh, *dxw; bf16* dx; int lddx; int C, H, W; float invW, invH;
+  __device__ void operator()(unsigned p, int c0) const {
+    float g[8], a[8], b[8], e[8], f[8];
+    load8(dout + (long long)p * lddo + c0, g);
+    const int w = p % W, nh = p / W;
+    const int n = nh / H;
+    ldp8(ah + (long long)nh * C, c0, C, a);
+    ldp8(aw + ((long long)n * W + w) * C, c0, C, b);
+    ldp8(dxh + (long long)nh * C, c0, C, e);
+    ldp8(dxw + ((long long)n * W + w) * C, c0, C, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = (c0 + j < C) ? g[j] * (a[j] + b[j]) + e[j] * invW + f[j] * invH : 0.f;
+    store8(dx + (long long)p * lddx + c0, g);
+  }
+};
+
+// ---------------------------------------------------------------------------------- FiLM
+struct FilmFwd {
+  const bf16* x; int ldx; const float *ce, *te; bf16* out; int ldo; int C, HW;
+  __device__ void operator()(unsigned p, int c0) const {
+    float v[8], a[8], b[8];
+    load8(x + (long long)p * ldx + c0, v);
+    const int n = p / HW;
+    ldp8(ce + (long long)n * C, c0, C, a); ldp8(te + (long long)n * C, c0, C, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? a[j] * v[j] + b[j] : 0.f;
+    store8(out + (long long)p * ldo + c0, v);
+  }
+};
+struct ScaleNC {   // dx = dout * ce[n,c]
+  const bf16* dout; int lddo; const float* ce; bf16* dx; int lddx; int C, HW;
+  __device__ void operator()(unsigned p, int c0) const {
+    float v[8], a[8];
+    load8(dout + (long long)p * lddo + c0, v);
+    ldp8(ce + (long long)(p / HW) * C, c0, C, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? v[j] * a[j] : 0.f;
+    store8(dx + (long long)p * lddx + c0, v);
+  }
+};
+
+// ---------------------------------------------------------------------------------- upsample + cat
+struct Lerp { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Lerp lerp_src(int o, int in, float scale) {
+  // at::native upsample_bilinear2d, align_corners=True: src = scale*dst, scale = (in-1)/(out-1)
+  const float s = scale * (float)o;
+  Lerp L; L.i0 = (int)s; L.i1 = L.i0 + (L.i0 < in - 1 ? 1 : 0); L.l1 = s - (float)L.i0; L.l0 = 1.0f - L.l1;
+  return L;
+}
+struct UpcatFwd {
+  const bf16* a; int lda, Ca; const bf16* b; int ldb, Cb; bf16* out; int ldo; int h, w; float sy, sx;
+  __device__ void operator()(unsigned p, int c0) const {
+    const int W2 = 2 * w, H2 = 2 * h;
+    const int ox = p % W2, oy = (p / W2) % H2, n = p / (W2 * H2);
+    const Lerp Y = lerp_src(oy, h, sy), X = lerp_src(ox, w, sx);
+    const bf16* src; int ld, c, C;
+    if (c0 < Ca) { src = a; ld = lda; c = c0; C = Ca; } else { src = b; ld = ldb; c = c0 - Ca; C = Cb; }
+    const long long base = (long long)n * h * w;
+    float v00[8], v01[8], v10[8], v11[8], o[8];
+    load8(src + (base + (long long)Y.i0 * w + X.i0) * ld + c, v00);
+    load8(src + (base + (long long)Y.i0 * w + X.i1) * ld + c, v01);
+    load8(src + (base + (long long)Y.i1 * w + X.i0) * ld + c, v10);
+    load8(src + (base + (long long)Y.i1 * w + X.i1) * ld + c, v11);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = (c + j < C) ? Y.l0 * (X.l0 * v00[j] + X.l1 * v01[j]) + Y.l1 * (X.l0 * v10[j] + X.l1 * v11[j]) : 0.f;
+    store8(out + (long long)p * ldo + c0, o);
+  }
+};
+// gather-form backward: every input pixel sums the output pixels that sampled it (deterministic)
+struct UpcatBwd {
+  const bf16* dout; int lddo; bf16* da; int ldda, Ca; bf16* db; int lddb, Cb; int h, w; float sy, sx;
+  __device__ void operator()(unsigned p, int c0) const {
+    const int ix = p % w, iy = (p / w) % h, n = p / (w * h);
+    const int W2 = 2 * w, H2 = 2 * h;
+    int oy0 = sy > 0.f ? (int)floorf((float)(iy - 1) / sy) : 0; if (oy0 < 0) oy0 = 0;
+    int oy1 = sy > 0.f ? (int)ceilf((float)(iy + 1) / sy) : H2 - 1; if (oy1 > H2 - 1) oy1 = H2 - 1;
+    int ox0 = sx > 0.f ? (int)floorf((float)(ix - 1) / sx) : 0; if (ox0 < 0) ox0 = 0;
+    int ox1 = sx > 0.f ? (int)ceilf((float)(ix + 1) / sx) : W2 - 1; if (ox1 > W2 - 1) ox1 = W2 - 1;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int oy = oy0; oy <= oy1; ++oy) {
+      const Lerp Y = lerp_src(oy, h, sy);
+      const float wy = (Y.i0 == iy ? Y.l0 : 0.f) + (Y.i1 == iy ? Y.l1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        const Lerp X = lerp_src(ox, w, sx);
+        const float wx = (X.i0 == ix ? X.l0 : 0.f) + (X.i1 == ix ? X.l1 : 0.f);
+        if (wx == 0.f) continue;
+        float g[8];
+        load8(dout + (((long long)n * H2 + oy) * W2 + ox) * lddo + c0, g);
+        const float wt = wy * wx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += wt * g[j];
+      }
+    }
+    if (c0 < Ca) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (c0 + j >= Ca) acc[j] = 0.f;
+      store8(da + (long long)p * ldda + c0, acc);
+    } else {
+      const int c = c0 - Ca;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (c + j >= Cb) acc[j] = 0.f;
+      store8(db + (long long)p * lddb + c, acc);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------- pooling
+struct AvgPoolFwd {
+  const bf16* x; int ldx; bf16* out; int ldo; int H, W, C, k, act;
+  __device__ void operator()(unsigned p, int c0) const {
+    const int Wo = W / k, Ho = H / k;
+    const int ox = p % Wo, oy = (p / Wo) % Ho, n = p / (Wo * Ho);
+    float acc[8], v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx) {
+        load8(x + (((long long)n * H + oy * k + dy) * W + ox * k + dx) * ldx + c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    const float inv = 1.0f / (float)(k * k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = (c0 + j < C) ? dm::act_f(acc[j] * inv, act) : 0.f;
+    store8(out + (long long)p * ldo + c0, acc);
+  }
+};
+struct AvgPoolBwd {
+  const bf16* dout; int lddo; const bf16* x; int ldx; bf16* dx; int lddx; int H, W, C, k, act;
+  __device__ void operator()(unsigned p, int c0) const {
+    const int Wo = W / k, Ho = H / k;
+    const int ox = p % Wo, oy = (p / Wo) % Ho, n = p / (Wo * Ho);
+    float acc[8], v[8], g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx_ = 0; dx_ < k; ++dx_) {
+        load8(x + (((long long)n * H + oy * k + dy) * W + ox * k + dx_) * ldx + c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    const float inv = 1.0f / (float)(k * k);
+    load8(dout + (long long)p * lddo + c0, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = (c0 + j < C) ? g[j] * dm::act_grad_f(acc[j] * inv, act) * inv : 0.f;
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx_ = 0; dx_ < k; ++dx_)
+        store8(dx + (((long long)n * H + oy * k + dy) * W + ox * k + dx_) * lddx + c0, g);
+  }
+};
+struct MaxPoolFwd {
+  const bf16* x; int ldx; bf16* out; int ldo; int H, W, C;
+  __device__ void operator()(unsigned p, int c0) const {
+    const int Wo = W / 2, Ho = H / 2;
+    const int ox = p % Wo, oy = (p / Wo) % Ho, n = p / (Wo * Ho);
+    float m[8], v[8];
+    const long long b = (((long long)n * H + oy * 2) * W + ox * 2);
+    load8(x + b * ldx + c0, m);
+    const long long offs[3] = {1, (long long)W, (long long)W + 1};
+    for (int t = 0; t < 3; ++t) {
+      load8(x + (b + offs[t]) * ldx + c0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = (v[j] > m[j] || v[j] != v[j]) ? v[j] : m[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (c0 + j >= C) m[j] = 0.f;
+    store8(out + (long long)p * ldo + c0, m);
+  }
+};
+struct MaxPoolBwd {
+  const bf16* dout; int lddo; const bf16* x; int ldx; bf16* dx; int lddx; int H, W, C;
+  __device__ void operator()(unsigned p, int c0) const {
+    const int Wo = W / 2, Ho = H / 2;
+    const int ox = p % Wo, oy = (p / Wo) % Ho, n = p / (Wo * Ho);
+    float m[8], v[4][8], g[8];
+    int am[8];
+    const long long b = (((long long)n * H + oy * 2) * W + ox * 2);
+    const long long offs[4] = {0, 1, (long long)W, (long long)W + 1};
+    for (int t = 0; t < 4; ++t) load8(x + (b + offs[t]) * ldx + c0, v[t]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { m[j] = v[0][j]; am[j] = 0; }
+    for (int t = 1; t < 4; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (v[t][j] > m[j] || v[t][j] != v[t][j]) { m[j] = v[t][j]; am[j] = t; }
+    load8(dout + (long long)p * lddo + c0, g);
+    for (int t = 0; t < 4; ++t) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (am[j] == t && c0 + j < C) ? g[j] : 0.f;
+      store8(dx + (b + offs[t]) * lddx + c0, o);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------- misc elementwise
+struct MaskFma {
+  const bf16* x; int ldx; const bf16* y; int ldy; const float* mask; float thresh; bf16* out; int ldo; int C;
+  __device__ void operator()(unsigned p, int c0) const {
+    float a[8], b[8];
+    load8(y + (long long)p * ldy + c0, b);
+    if (x) load8(x + (long long)p * ldx + c0, a);
+    const float hi = (__ldg(mask + p) > thresh) ? 1.f : 0.f;     // exact fp32 compare, NaN -> 0 (new_scripy.py:173)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = (c0 + j < C) ? (x ? a[j] : 0.f) + b[j] * hi : 0.f;
+    store8(out + (long long)p * ldo + c0, a);
+  }
+};
+struct Axpby {
+  const bf16* a; int lda; const bf16* b; int ldb; bf16* out; int ldo; int C; float sa, sb;
+  __device__ void operator()(unsigned p, int c0) const {
+    float u[8], v[8];
+    load8(a + (long long)p * lda + c0, u);
+    if (b) load8(b + (long long)p * ldb + c0, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = (c0 + j < C) ? sa * u[j] + (b ? sb * v[j] : 0.f) : 0.f;
+    store8(out + (long long)p * ldo + c0, u);
+  }
+};
+struct S2D {
+  const bf16* x; int ldx; bf16* y; int ldy; int H, W, C, k;    // x [N,H*k,W*k,C] -> y [N,H,W,k*k*C]
+  __device__ void operator()(unsigned p, int c0) const {
+    // p indexes INPUT pixels of x
+    const int Wi = W * k, Hi = H * k;
+    const int xx = p % Wi, yy = (p / Wi) % Hi, n = p / (Wi * Hi);
+    const int ow = xx / k, kx = xx % k, oh = yy / k, ky = yy % k;
+    uint4 v = *reinterpret_cast<const uint4*>(x + (long long)p * ldx + c0);
+    *reinterpret_cast<uint4*>(y + (((long long)n * H + oh) * W + ow) * ldy + (ky * k + kx) * C + c0) = v;
+  }
+};
+
+__global__ void nchw_to_nhwc_kernel(const float* x, bf16* y, int ldy, int N, int C, int HW) {
+  const long long P = (long long)N * HW;
+  const int Cv = ldy / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P * Cv; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % P; const int cv = (int)(i / P);
+    const long long n = p / HW, hw = p % HW;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int c = cv * 8 + j; v[j] = c < C ? x[(n * C + c) * HW + hw] : 0.f; }
+    store8(y + p * ldy + cv * 8, v);
+  }
+}
+__global__ void nchw_to_nhwc_f32_kernel(const float* x, float* y, int ldy, int N, int C, int HW) {
+  const long long P = (long long)N * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P * ldy; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % P; const int c = (int)(i / P);
+    const long long n = p / HW, hw = p % HW;
+    y[p * ldy + c] = c < C ? x[(n * C + c) * HW + hw] : 0.f;
+  }
+}
+// fp32 NHWC (pitch ldx) -> bf16 NHWC (pitch ldy), pad lanes zero
+__global__ void cast_nhwc_kernel(const float* x, int ldx, bf16* y, int ldy, long long P, int C) {
+  const int Cv = ldy / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P * Cv; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / Cv; const int cv = (int)(i % Cv);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int c = cv * 8 + j; v[j] = c < C ? x[p * ldx + c] : 0.f; }
+    store8(y + p * ldy + cv * 8, v);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const void* x, int x_f32, int ldx, float* y, int N, int C, int HW) {
+  const long long P = (long long)N * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P * C; i += (long long)gridDim.x * blockDim.x) {
+    const long long hw = i % HW; const int c = (int)((i / HW) % C); const long long n = i / ((long long)HW * C);
+    const long long p = n * HW + hw;
+    y[i] = x_f32 ? reinterpret_cast<const float*>(x)[p * ldx + c] : __bfloat162float(reinterpret_cast<const bf16*>(x)[p * ldx + c]);
+  }
+}
+
+}  // namespace
+
+// =========================================================================================== C ABI
+#define ST ((cudaStream_t)stream)
+#define REQ8(v, name) if ((v) & 7) { dm_set_error(name ": channel pitch must be a multiple of 8"); return DM_ERR_ARG; }
+
+extern "C" int dm_nchw_to_nhwc(const float* x, void* y, int ldy, int y_f32, int N, int C, int H, int W, void* stream) {
+  if (y_f32) {
+    long long tot = (long long)N * H * W * ldy;
+    nchw_to_nhwc_f32_kernel<<<ew_grid(tot), kEwThreads, 0, ST>>>(x, (float*)y, ldy, N, C, H * W);
+  } else {
+    REQ8(ldy, "dm_nchw_to_nhwc");
+    long long tot = (long long)N * H * W * (ldy / 8);
+    nchw_to_nhwc_kernel<<<ew_grid(tot), kEwThreads, 0, ST>>>(x, (bf16*)y, ldy, N, C, H * W);
+  }
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+extern "C" int dm_cast_nhwc(const float* x, int ldx, void* y, int ldy, long long P, int C, void* stream) {
+  REQ8(ldy, "dm_cast_nhwc");
+  cast_nhwc_kernel<<<ew_grid(P * (ldy / 8)), kEwThreads, 0, ST>>>(x, ldx, (bf16*)y, ldy, P, C);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+extern "C" int dm_nhwc_to_nchw(const void* x, int x_f32, int ldx, float* y, int N, int C, int H, int W, void* stream) {
+  long long tot = (long long)N * H * W * C;
+  nhwc_to_nchw_kernel<<<ew_grid(tot), kEwThreads, 0, ST>>>(x, x_f32, ldx, y, N, C, H * W);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+extern "C" int dm_space_to_depth(const void* x, int ldx, void* y, int ldy, int N, int H, int W, int C, int k, void* stream) {
+  REQ8(ldx, "dm_space_to_depth"); REQ8(ldy, "dm_space_to_depth"); REQ8(C, "dm_space_to_depth");
+  S2D f{(const bf16*)x, ldx, (bf16*)y, ldy, H, W, C, k};
+  return ew_launch((long long)N * H * k * W * k, C, f, ST);
+}
+
+extern "C" int dm_bn_finalize(const float* partials, int m_tiles, int ld, int C, double count, float* mean, float* invstd,
+                              float* running_mean, float* running_var, float momentum, float eps, void* stream) {
+  bn_finalize_kernel<<<dm::cdiv(C, 32), 1024, 0, ST>>>(partials, m_tiles, ld, C, count, mean, invstd, running_mean,
+                                                       running_var, momentum, eps);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+extern "C" int dm_bn_act_fwd(const void* y, int ldy, const float* mean, const float* invstd, const float* gamma,
+                             const float* beta, void* z, int ldz, long long P, int C, int act, void* stream) {
+  REQ8(ldy, "dm_bn_act_fwd"); REQ8(ldz, "dm_bn_act_fwd");
+  BnFwd f{(const bf16*)y, ldy, mean, invstd, gamma, beta, (bf16*)z, ldz, C, act};
+  return ew_launch(P, C, f, ST);
+}
+extern "C" int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, const float* mean, const float* invstd,
+                             const float* gamma, const float* beta, void* dy, int lddy, float* dgamma, float* dbeta,
+                             float* scratch, long long P, int C, int act, int training, void* stream) {
+  REQ8(lddz, "dm_bn_act_bwd"); REQ8(ldy, "dm_bn_act_bwd"); REQ8(lddy, "dm_bn_act_bwd");
+  if (P >= (1ll << 31)) { dm_set_error("dm_bn_act_bwd: too many pixels"); return DM_ERR_ARG; }
+  int rc = zero_f32(scratch, 2 * C, ST);
+  if (rc) return rc;
+  RedArgs A{};
+  A.a = (const bf16*)dz; A.b = (const bf16*)y;
+  A.a_hi = 0; A.a_lo = 0; A.a_ps = lddz; A.b_hi = 0; A.b_lo = 0; A.b_ps = ldy;
+  A.gdiv = 1; A.count = (int)P; A.C = C; A.mode = 3; A.act = act; A.G = 1; A.stat_div = 1;
+  A.mean = mean; A.invstd = invstd; A.gamma = gamma; A.beta = beta; A.scale = 1.f;
+  A.out1 = scratch; A.out2 = scratch + C;
+  rc = launch_reduce(A, 1, ST);
+  if (rc) return rc;
+  BnBwd f{(const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, scratch, (bf16*)dy, lddy, C, act,
+          training, (float)(1.0 / (double)P)};
+  rc = ew_launch(P, C, f, ST);
+  if (rc) return rc;
+  accum2_kernel<<<dm::cdiv(C, 256), 256, 0, ST>>>(scratch, dgamma, dbeta, C);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
+extern "C" int dm_gn_act_fwd(const void* x, int ldx, const float* gamma, const float* beta, void* z, int ldz, float* mean,
+                             float* rstd, float* scratch, int N, int HW, int C, int G, float eps, int act, void* stream) {
+  REQ8(ldx, "dm_gn_act_fwd"); REQ8(ldz, "dm_gn_act_fwd");
+  if (C % G) { dm_set_error("dm_gn_act_fwd: C must be divisible by G"); return DM_ERR_ARG; }
+  int rc = zero_f32(scratch, 2LL * N * C, ST);
+  if (rc) return rc;
+  RedArgs A{};
+  A.a = (const bf16*)x; A.b = nullptr; A.a_hi = (long long)HW * ldx; A.a_lo = 0; A.a_ps = ldx;
+  A.gdiv = 1; A.count = HW; A.C = C; A.mode = 1; A.scale = 1.f; A.G = G; A.stat_div = 1;
+  A.out1 = scratch; A.out2 = scratch + (long long)N * C;
+  rc = launch_reduce(A, N, ST);
+  if (rc) return rc;
+  gn_fold_fwd_kernel<<<dm::cdiv(N * G, 128), 128, 0, ST>>>(scratch, N, C, G, (double)HW * (C / G), eps, mean, rstd);
+  DM_CHECK_LAUNCH();
+  GnFwd f{(const bf16*)x, ldx, mean, rstd, gamma, beta, (bf16*)z, ldz, C, G, HW, act};
+  return ew_launch((long long)N * HW, C, f, ST);
+}
+extern "C" int dm_gn_act_bwd(const void* dz, int lddz, const void* x, int ldx, const float* mean, const float* rstd,
+                             const float* gamma, const float* beta, void* dx, int lddx, float* dgamma, float* dbeta,
+                             float* scratch, int N, int HW, int C, int G, int act, void* stream) {
+  REQ8(lddz, "dm_gn_act_bwd"); REQ8(ldx, "dm_gn_act_bwd"); REQ8(lddx, "dm_gn_act_bwd");
+  int rc = zero_f32(scratch, 2LL * N * C, ST);
+  if (rc) return rc;
+  RedArgs A{};
+  A.a = (const bf16*)dz; A.b = (const bf16*)x;
+  A.a_hi = (long long)HW * lddz; A.a_lo = 0; A.a_ps = lddz; A.b_hi = (long long)HW * ldx; A.b_lo = 0; A.b_ps = ldx;
+  A.gdiv = 1; A.count = HW; A.C = C; A.mode = 4; A.act = act; A.G = G; A.stat_div = 1;
+  A.mean = mean; A.invstd = rstd; A.gamma = gamma; A.beta = beta; A.scale = 1.f;
+  A.out1 = scratch; A.out2 = scratch + (long long)N * C;
+  rc = launch_reduce(A, N, ST);
+  if (rc) return rc;
+  float* m = scratch + 2LL * N * C;
+  int nt = N * G > C ? N * G : C;
+  gn_fold_bwd_kernel<<<dm::cdiv(nt, 128), 128, 0, ST>>>(scratch, gamma, N, C, G, (double)HW * (C / G), m, dgamma, dbeta);
+  DM_CHECK_LAUNCH();
+  GnBwd f{(const bf16*)dz, lddz, (const bf16*)x, ldx, mean, rstd, gamma, beta, m, (bf16*)dx, lddx, C, G, HW, N, act};
+  return ew_launch((long long)N * HW, C, f, ST);
+}
+
+extern "C" int dm_pool_nhw(const void* x, int ldx, float* out, int N, int HW, int C, float scale, void* stream) {
+  REQ8(ldx, "dm_pool_nhw");
+  int rc = zero_f32(out, (long long)N * C, ST);
+  if (rc) return rc;
+  RedArgs A{};
+  A.a = (const bf16*)x; A.a_hi = (long long)HW * ldx; A.a_ps = ldx; A.gdiv = 1; A.count = HW; A.C = C; A.mode = 0;
+  A.scale = scale; A.out1 = out; A.G = 1; A.stat_div = 1;
+  return launch_reduce(A, N, ST);
+}
+extern "C" int dm_pool_prod_nhw(const void* a, int lda, const void* b, int ldb, float* out, int N, int HW, int C,
+                                float scale, void* stream) {
+  REQ8(lda, "dm_pool_prod_nhw"); REQ8(ldb, "dm_pool_prod_nhw");
+  int rc = zero_f32(out, (long long)N * C, ST);
+  if (rc) return rc;
+  RedArgs A{};
+  A.a = (const bf16*)a; A.b = (const bf16*)b;
+  A.a_hi = (long long)HW * lda; A.a_ps = lda; A.b_hi = (long long)HW * ldb; A.b_ps = ldb;
+  A.gdiv = 1; A.count = HW; A.C = C; A.mode = 2; A.scale = scale; A.out1 = out; A.out2 = nullptr; A.G = 1; A.stat_div = 1;
+  return launch_reduce(A, N, ST);
+}
+extern "C" int dm_colsum(const void* dy, int lddy, float* db, long long P, int C, void* stream) {
+  REQ8(lddy, "dm_colsum");
+  if (P >= (1ll << 31)) { dm_set_error("dm_colsum: too many pixels"); return DM_ERR_ARG; }
+  RedArgs A{};
+  A.a = (const bf16*)dy; A.a_ps = lddy; A.gdiv = 1; A.count = (int)P; A.C = C; A.mode = 0; A.scale = 1.f; A.out1 = db;
+  A.G = 1; A.stat_div = 1;
+  return launch_reduce(A, 1, ST);
+}
+extern "C" int dm_se_apply_fwd(const void* x2, int ld2, const float* gate, const void* res, int ldr, void* out, int ldo,
+                               int N, int HW, int C, float scale, void* stream) {
+  REQ8(ld2, "dm_se_apply_fwd"); REQ8(ldr, "dm_se_apply_fwd"); REQ8(ldo, "dm_se_apply_fwd");
+  SeFwd f{(const bf16*)x2, ld2, gate, (const bf16*)res, ldr, (bf16*)out, ldo, C, HW, scale};
+  return ew_launch((long long)N * HW, C, f, ST);
+}
+extern "C" int dm_se_apply_bwd(const void* dout, int lddo, const float* gate, const float* dpool, void* dx2, int lddx2,
+                               void* dres, int lddr, int N, int HW, int C, float scale, void* stream) {
+  REQ8(lddo, "dm_se_apply_bwd"); REQ8(lddx2, "dm_se_apply_bwd"); REQ8(lddr, "dm_se_apply_bwd");
+  SeBwd f{(const bf16*)dout, lddo, gate, dpool, (bf16*)dx2, lddx2, (bf16*)dres, lddr, C, HW, scale, 1.0f / (float)HW};
+  return ew_launch((long long)N * HW, C, f, ST);
+}
+
+extern "C" int dm_ca_pool(const void* a, int lda, const void* b, int ldb, float* oh, float* ow, int N, int H, int W, int C,
+                          float scale_h, float scale_w, void* stream) {
+  REQ8(lda, "dm_ca_pool"); if (b) REQ8(ldb, "dm_ca_pool");
+  int rc = zero_f32(oh, (long long)N * H * C, ST); if (rc) return rc;
+  rc = zero_f32(ow, (long long)N * W * C, ST); if (rc) return rc;
+  RedArgs A{};
+  A.a = (const bf16*)a; A.b = (const bf16*)b; A.C = C; A.mode = b ? 2 : 0; A.G = 1; A.stat_div = 1;
+  // rows: group g = n*H + h, pixels along w
+  A.gdiv = 1; A.a_hi = (long long)W * lda; A.a_lo = 0; A.a_ps = lda; A.b_hi = (long long)W * ldb; A.b_lo = 0; A.b_ps = ldb;
+  A.count = W; A.scale = scale_h; A.out1 = oh; A.out2 = nullptr;
+  rc = launch_reduce(A, N * H, ST); if (rc) return rc;
+  // columns: group g = n*W + w, pixels along h (stride W)
+  A.gdiv = W; A.a_hi = (long long)H * W * lda; A.a_lo = lda; A.a_ps = (long long)W * lda;
+  A.b_hi = (long long)H * W * ldb; A.b_lo = ldb; A.b_ps = (long long)W * ldb;
+  A.count = H; A.scale = scale_w; A.out1 = ow;
+  return launch_reduce(A, N * W, ST);
+}
+extern "C" int dm_ca_gate_fwd(const void* x, int ldx, const float* ah, const float* aw, void* out, int ldo, int N, int H,
+                              int W, int C, void* stream) {
+  REQ8(ldx, "dm_ca_gate_fwd"); REQ8(ldo, "dm_ca_gate_fwd");
+  CaFwd f{(const bf16*)x, ldx, ah, aw, (bf16*)out, ldo, C, H, W};
+  return ew_launch((long long)N * H * W, C, f, ST);
+}
+extern "C" int dm_ca_gate_bwd(const void* dout, int lddo, const float* ah, const float* aw, const float* dxh,
+                              const float* dxw, void* dx, int lddx, int N, int H, int W, int C, void* stream) {
+  REQ8(lddo, "dm_ca_gate_bwd"); REQ8(lddx, "dm_ca_gate_bwd");
+  CaBwd f{(const bf16*)dout, lddo, ah, aw, dxh, dxw, (bf16*)dx, lddx, C, H, W, 1.0f / (float)W, 1.0f / (float)H};
+  return ew_launch((long long)N * H * W, C, f, ST);
+}
+
+extern "C" int dm_upcat_fwd(const void* a, int lda, int Ca, const void* b, int ldb, int Cb, void* out, int ldo, int N,
+                            int h, int w, void* stream) {
+  REQ8(lda, "dm_upcat_fwd"); REQ8(ldb, "dm_upcat_fwd"); REQ8(ldo, "dm_upcat_fwd"); REQ8(Ca, "dm_upcat_fwd(Ca)");
+  UpcatFwd f{(const bf16*)a, lda, Ca, (const bf16*)b, ldb, Cb, (bf16*)out, ldo, h, w,
+             h > 1 ? (float)(h - 1) / (float)(2 * h - 1) : 0.f, w > 1 ? (float)(w - 1) / (float)(2 * w - 1) : 0.f};
+  return ew_launch((long long)N * 4 * h * w, Ca + Cb, f, ST);
+}
+extern "C" int dm_upcat_bwd(const void* dout, int lddo, void* da, int ldda, int Ca, void* db, int lddb, int Cb, int N,
+                            int h, int w, void* stream) {
+  REQ8(lddo, "dm_upcat_bwd"); REQ8(ldda, "dm_upcat_bwd"); REQ8(lddb, "dm_upcat_bwd"); REQ8(Ca, "dm_upcat_bwd(Ca)");
+  UpcatBwd f{(const bf16*)dout, lddo, (bf16*)da, ldda, Ca, (bf16*)db, lddb, Cb, h, w,
+             h > 1 ? (float)(h - 1) / (float)(2 * h - 1) : 0.f, w > 1 ? (float)(w - 1) / (float)(2 * w - 1) : 0.f};
+  return ew_launch((long long)N * h * w, Ca + Cb, f, ST);
+}
+extern "C" int dm_film_fwd(const void* x, int ldx, const float* ce, const float* te, void* out, int ldo, int N, int HW,
+                           int C, void* stream) {
+  REQ8(ldx, "dm_film_fwd"); REQ8(ldo, "dm_film_fwd");
+  FilmFwd f{(const bf16*)x, ldx, ce, te, (bf16*)out, ldo, C, HW};
+  return ew_launch((long long)N * HW, C, f, ST);
+}
+extern "C" int dm_film_bwd(const void* dout, int lddo, const void* x, int ldx, const float* ce, void* dx, int lddx,
+                           float* dce, float* dte, int N, int HW, int C, void* stream) {
+  REQ8(lddo, "dm_film_bwd"); REQ8(ldx, "dm_film_bwd"); REQ8(lddx, "dm_film_bwd");
+  int rc = zero_f32(dce, (long long)N * C, ST); if (rc) return rc;
+  rc = zero_f32(dte, (long long)N * C, ST); if (rc) return rc;
+  RedArgs A{};
+  A.a = (const bf16*)dout; A.b = (const bf16*)x;
+  A.a_hi = (long long)HW * lddo; A.a_ps = lddo; A.b_hi = (long long)HW * ldx; A.b_ps = ldx;
+  A.gdiv = 1; A.count = HW; A.C = C; A.mode = 2; A.scale = 1.f; A.out1 = dce; A.out2 = dte; A.G = 1; A.stat_div = 1;
+  rc = launch_reduce(A, N, ST); if (rc) return rc;
+  ScaleNC f{(const bf16*)dout, lddo, ce, (bf16*)dx, lddx, C, HW};
+  return ew_launch((long long)N * HW, C, f, ST);
+}
+
+extern "C" int dm_avgpool_act_fwd(const void* x, int ldx, void* out, int ldo, int N, int H, int W, int C, int k, int act,
+                                  void* stream) {
+  REQ8(ldx, "dm_avgpool_act_fwd"); REQ8(ldo, "dm_avgpool_act_fwd");
+  AvgPoolFwd f{(const bf16*)x, ldx, (bf16*)out, ldo, H, W, C, k, act};
+  return ew_launch((long long)N * (H / k) * (W / k), C, f, ST);
+}
+extern "C" int dm_avgpool_act_bwd(const void* dout, int lddo, const void* x, int ldx, void* dx, int lddx, int N, int H,
+                                  int W, int C, int k, int act, void* stream) {
+  REQ8(lddo, "dm_avgpool_act_bwd"); REQ8(ldx, "dm_avgpool_act_bwd"); REQ8(lddx, "dm_avgpool_act_bwd");
+  AvgPoolBwd f{(const bf16*)dout, lddo, (const bf16*)x, ldx, (bf16*)dx, lddx, H, W, C, k, act};
+  return ew_launch((long long)N * (H / k) * (W / k), C, f, ST);
+}
+extern "C" int dm_maxpool2_fwd(const void* x, int ldx, void* out, int ldo, int N, int H, int W, int C, void* stream) {
+  REQ8(ldx, "dm_maxpool2_fwd"); REQ8(ldo, "dm_maxpool2_fwd");
+  MaxPoolFwd f{(const bf16*)x, ldx, (bf16*)out, ldo, H, W, C};
+  return ew_launch((long long)N * (H / 2) * (W / 2), C, f, ST);
+}
+extern "C" int dm_maxpool2_bwd(const void* dout, int lddo, const void* x, int ldx, void* dx, int lddx, int N, int H, int W,
+                               int C, void* stream) {
+  REQ8(lddo, "dm_maxpool2_bwd"); REQ8(ldx, "dm_maxpool2_bwd"); REQ8(lddx, "dm_maxpool2_bwd");
+  MaxPoolBwd f{(const bf16*)dout, lddo, (const bf16*)x, ldx, (bf16*)dx, lddx, H, W, C};
+  return ew_launch((long long)N * (H / 2) * (W / 2), C, f, ST);
+}
+
+extern "C" int dm_mask_fma(const void* x, int ldx, const void* y, int ldy, const float* mask, float thresh, void* out,
+                           int ldo, long long P, int C, void* stream) {
+  if (x) REQ8(ldx, "dm_mask_fma"); REQ8(ldy, "dm_mask_fma"); REQ8(ldo, "dm_mask_fma");
+  MaskFma f{(const bf16*)x, ldx, (const bf16*)y, ldy, mask, thresh, (bf16*)out, ldo, C};
+  return ew_launch(P, C, f, ST);
+}
+extern "C" int dm_axpby(const void* a, int lda, const void* b, int ldb, void* out, int ldo, long long P, int C, float sa,
+                        float sb, void* stream) {
+  REQ8(lda, "dm_axpby"); if (b) REQ8(ldb, "dm_axpby"); REQ8(ldo, "dm_axpby");
+  Axpby f{(const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)out, ldo, C, sa, sb};
+  return ew_launch(P, C, f, ST);
+}

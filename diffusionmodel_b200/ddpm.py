@@ -1,0 +1,136 @@
+"""DDPM process on the sm_100a kernels: drop-in mirror of the reference ``DDPM`` module.
+
+Mirrors new_scripy.py:358-477 (schedules, weighted-loss training forward, CFG reverse sampling) and
+MNIST_script.py:190-300 (MSE loss, ``sample`` also returning the stored trajectory).  The seven
+schedule tables are registered as buffers under the reference's names, so reference checkpoints
+(``{'model_state_dict': ddpm.state_dict()}``) load unchanged.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def ddpm_schedules(beta1, beta2, T):
+    """Seven fp32 tables with T+1 entries, indexed 1..T (new_scripy.py:358-384).  Kept as the same torch
+    expressions as the reference so the tables are bit-identical."""
+    assert beta1 < beta2 < 1.0, "beta1 and beta2 must be in (0, 1)"
+    beta_t = (beta2 - beta1) * torch.arange(0, T + 1, dtype=torch.float32) / T + beta1
+    alpha_t = 1 - beta_t
+    alphabar_t = torch.cumsum(torch.log(alpha_t), dim=0).exp()
+    sqrtmab = torch.sqrt(1 - alphabar_t)
+    return {
+        "alpha_t": alpha_t,
+        "oneover_sqrta": 1 / torch.sqrt(alpha_t),
+        "sqrt_beta_t": torch.sqrt(beta_t),
+        "alphabar_t": alphabar_t,
+        "sqrtab": torch.sqrt(alphabar_t),
+        "sqrtmab": sqrtmab,
+        "mab_over_sqrtmab": (1 - alpha_t) / sqrtmab,
+    }
+
+
+class DDPM(nn.Module):
+    """``DDPM(nn_model, betas, n_T, device, drop_prob=0.1)`` (new_scripy.py:386-399).
+
+    ``forward(x, c, attn_mask)`` -> scalar loss; ``forward(x, c)`` for the MNIST denoiser.
+    ``sample(n_sample, size, device, guide_w)`` -> images (MNIST variant: ``(images, stored)``).
+
+    Extensions that default to the shipped behaviour:
+      * ``enhance_with_attn_map``: feed ``attn_mask`` to LocalEnhancer as the attention map the
+        reference call site meant (new_scripy.py:353).  Default False = shipped (+0) semantics.
+      * ``sample_noise``: "reference" draws x_T and every step's z from the CPU generator exactly like
+        new_scripy.py:445,465 (same stream for a given seed); "device" draws on the GPU.
+    """
+
+    def __init__(self, nn_model, betas, n_T, device, drop_prob=0.1, enhance_with_attn_map=False,
+                 sample_noise="reference"):
+        super().__init__()
+        self.nn_model = nn_model.to(device)
+        # reference training code drives ddpm.scaler (fp16 AMP); bf16 needs no loss scaling
+        self.scaler = torch.amp.GradScaler("cuda", enabled=False)
+        for k, v in ddpm_schedules(betas[0], betas[1], n_T).items():
+            self.register_buffer(k, v)
+        self.n_T = n_T
+        self.device = device
+        self.drop_prob = drop_prob
+        self.loss_mse = nn.MSELoss()
+        self.n_classes = self.nn_model.n_classes
+        self.variant = getattr(nn_model, "variant", "rdd")
+        self.enhance_with_attn_map = enhance_with_attn_map
+        self.sample_noise = sample_noise
+        self._host_sched = None
+
+    # ------------------------------------------------------------------ training
+    def draw_randoms(self, x, c):
+        """RNG draw order of the reference (new_scripy.py:405-413; MNIST_script.py:239-249)."""
+        ts = torch.randint(1, self.n_T + 1, (x.shape[0],)).to(self.device)
+        noise = torch.randn_like(x)
+        if self.variant == "rdd":
+            ctx_mask = torch.bernoulli(torch.ones_like(c, dtype=torch.float) * (1 - self.drop_prob)).to(self.device)
+        else:
+            ctx_mask = torch.bernoulli(torch.zeros_like(c) + self.drop_prob).to(self.device)
+        return ts, noise, ctx_mask
+
+    def forward(self, x, c, attn_mask=None, randoms=None):
+        ts, noise, ctx_mask = randoms if randoms is not None else self.draw_randoms(x, c)
+        x = x.contiguous().float()
+        noise = noise.contiguous().float()
+        xt = ops.q_sample(x, noise, self.sqrtab, self.sqrtmab, ts.long())
+        kw = {}
+        if self.variant == "rdd":
+            if attn_mask is None:
+                raise RuntimeError("DDPM.forward: attn_mask is required (new_scripy.py:401)")
+            attn_mask = attn_mask.to(self.device)
+            if self.enhance_with_attn_map:
+                kw["attn_map"] = attn_mask
+        pred = self.nn_model.forward_nhwc(xt, c, ts / self.n_T, ctx_mask, **kw)
+        return ops.ddpm_loss(pred, noise, attn_mask if self.variant == "rdd" else None)
+
+    # ------------------------------------------------------------------ sampling
+    def _sched(self):
+        if self._host_sched is None:
+            self._host_sched = {k: getattr(self, k).detach().cpu().tolist()
+                                for k in ("oneover_sqrta", "mab_over_sqrtmab", "sqrt_beta_t")}
+        return self._host_sched
+
+    def _randn(self, shape, device):
+        if self.sample_noise == "reference":
+            return torch.randn(*shape).to(device)
+        return torch.randn(*shape, device=device)
+
+    @torch.no_grad()
+    def sample(self, n_sample, size, device, guide_w=0.0, refine_steps=2, steps=None, noise=None):
+        """Classifier-free-guided reverse loop (new_scripy.py:441-477; MNIST_script.py:254-300).
+        ``steps`` truncates the loop and ``noise=(x_T, {i: z_i})`` injects the noise (tests)."""
+        sched = self._sched()
+        n_T = self.n_T
+        x_i = (noise[0].to(device) if noise is not None else self._randn((n_sample, *size), device)).float().contiguous()
+        ncls = 10 if self.variant == "mnist" else self.n_classes        # MNIST_script.py:262 hard-codes 10
+        c_i = torch.arange(0, ncls, device=device).repeat(int(n_sample / ncls)).repeat(2)
+        ctx_mask = torch.zeros_like(c_i)
+        ctx_mask[n_sample:] = 1.0
+        xt = ops.to_nhwc(torch.cat([x_i, x_i], 0))
+        store = []
+        done = 0
+        for i in range(n_T, 0, -1):
+            t_is = torch.full((2 * n_sample,), i / n_T, device=device, dtype=torch.float32)
+            if i > 1:
+                z = (noise[1][i].to(device) if noise is not None else self._randn((n_sample, *size), device))
+                z = z.float().contiguous()
+            else:
+                z = None
+            eps = self.nn_model.forward_nhwc(xt, c_i, t_is, ctx_mask)
+            x_i, xt = ops.cfg_reverse_step(eps, x_i, z, guide_w, sched["oneover_sqrta"][i],
+                                           sched["mab_over_sqrtmab"][i], sched["sqrt_beta_t"][i])
+            if self.variant == "mnist" and (i % 20 == 0 or i == n_T or i < 8):
+                store.append(x_i.detach().cpu().numpy())
+            done += 1
+            if steps is not None and done >= steps:
+                break
+        if self.variant == "mnist":
+            return x_i, np.array(store)
+        return x_i

@@ -1,0 +1,757 @@
+"""Autograd operators over the sm_100a kernels.
+
+Activations travel as bf16 NHWC tensors ``[N, H, W, ld]`` (``ld`` = channel pitch, a multiple of 8,
+pad lanes zero; channel slices of such tensors are valid operands).  Parameters stay fp32 in the
+reference's layouts; their gradients are accumulated by the kernels directly into ``param.grad``
+(the Functions return ``None`` for parameter inputs), which avoids ~400 tiny accumulation kernels
+per backward pass.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import call
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+_weights_epoch = 0            # bumped by the fused optimizer (it writes parameters behind torch's back)
+
+
+def bump_weights_epoch():
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def r8(c):
+    return (c + 7) // 8 * 8
+
+
+def r64(c):
+    return (c + 63) // 64 * 64
+
+
+def _chk(t, name="tensor"):
+    if t.device.type != "cuda":
+        raise _lib.DmB200Error(f"{name}: the hot path runs on CUDA only (got {t.device}); there is no CPU fallback")
+    if t.dtype != torch.bfloat16 or t.dim() != 4 or t.stride(3) != 1:
+        raise _lib.DmB200Error(f"{name}: expected a bf16 NHWC activation, got {t.dtype} {tuple(t.shape)} {t.stride()}")
+    n, h, w, _ = t.shape
+    ld = t.stride(2)
+    if t.stride(1) != w * ld or t.stride(0) != h * w * ld or ld % 8 or t.data_ptr() % 16:
+        raise _lib.DmB200Error(f"{name}: unsupported strides {t.stride()} for shape {tuple(t.shape)}")
+    return ld
+
+
+def new_act(n, h, w, c, device, dtype=torch.bfloat16):
+    return torch.empty((n, h, w, r8(c)), device=device, dtype=dtype)
+
+
+def grad_buf(p):
+    """fp32 accumulation target for a parameter's gradient."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
+
+# --------------------------------------------------------------------------------------- weight packs
+class WeightPack:
+    """bf16 K-major packs of one conv weight for the implicit-GEMM kernels, rebuilt when the fp32
+    master parameter changes (torch-side in-place update or the fused optimizer epoch)."""
+
+    def __init__(self):
+        self.cache = {}
+
+    def get(self, w, kind, **kw):
+        key = (kind, tuple(sorted(kw.items())))
+        stamp = (w._version, _weights_epoch, w.data_ptr())
+        hit = self.cache.get(key)
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        out = _PACKERS[kind](w.detach(), **kw)
+        self.cache[key] = (stamp, out)
+        return out
+
+
+def _taps(offs):
+    arr = (ctypes.c_longlong * 16)(*offs, *([0] * (16 - len(offs))))
+    return arr
+
+
+def _pack(w, rows, cols, tap_offs, s_row, s_col, c_split, cols_k, row_len, tap_major):
+    total_rows = rows * (len(tap_offs) if tap_major else 1)
+    out = torch.empty((total_rows, row_len), device=w.device, dtype=torch.bfloat16)
+    call("dm_pack_weight", _p(w), _p(out), rows, cols, len(tap_offs), _taps(tap_offs), s_row, s_col, c_split,
+         cols_k, row_len, 1 if tap_major else 0, _stream())
+    return out
+
+
+def _cols_k(cin, c_split):
+    return r64(cin) if not c_split else r64(c_split) + r64(cin - c_split)
+
+
+def conv_geom(w, c_split=0):
+    cout, cin, kh, kw = w.shape
+    ck = _cols_k(cin, c_split)
+    return cout, cin, kh, kw, ck
+
+
+def _pack_fwd(w, c_split=0):
+    cout, cin, kh, kw, ck = conv_geom(w, c_split)
+    offs = [r * kw + s for r in range(kh) for s in range(kw)]
+    return _pack(w, cout, cin, offs, cin * kh * kw, kh * kw, c_split, ck, kh * kw * ck, False)
+
+
+def _pack_dgrad(w):
+    """stride-1 data gradient = conv with the 180-degree rotated kernel and Cin/Cout swapped."""
+    cout, cin, kh, kw = w.shape
+    ck = r64(cout)
+    offs = [(kh - 1 - r) * kw + (kw - 1 - s) for r in range(kh) for s in range(kw)]
+    return _pack(w, cin, cout, offs, kh * kw, cin * kh * kw, 0, ck, kh * kw * ck, False)
+
+
+def _pack_s2dgrad(w):
+    """k=4, s=2, p=1 data gradient: four output-parity phases of 2x2 taps (see dm_conv2d_s2_dgrad)."""
+    cout, cin, kh, kw = w.shape
+    assert kh == 4 and kw == 4
+    ck = r64(cout)
+    rsel = {0: (1, 3), 1: (0, 2)}
+    packs = []
+    for ph in range(2):
+        for pw in range(2):
+            offs = [r * kw + s for r in rsel[ph] for s in rsel[pw]]
+            packs.append(_pack(w, cin, cout, offs, kh * kw, cin * kh * kw, 0, ck, 4 * ck, False))
+    return torch.cat(packs, 0)
+
+
+def _pack_convt_fwd(w):
+    """ConvTranspose2d weight [Cin, Cout, k, k] -> rows (tap, co), K = ci."""
+    cin, cout, k, _ = w.shape
+    offs = [t for t in range(k * k)]
+    return _pack(w, cout, cin, offs, k * k, cout * k * k, 0, r64(cin), r64(cin), True)
+
+
+def _pack_convt_dgrad(w):
+    """rows ci, K = (tap, co): a 1x1 conv over the space-to-depth'd output gradient."""
+    cin, cout, k, _ = w.shape
+    offs = [t for t in range(k * k)]
+    return _pack(w, cin, cout, offs, cout * k * k, k * k, 0, cout, r64(k * k * cout), False)
+
+
+_PACKERS = {"fwd": _pack_fwd, "dgrad": _pack_dgrad, "s2dgrad": _pack_s2dgrad,
+            "convt_fwd": _pack_convt_fwd, "convt_dgrad": _pack_convt_dgrad}
+
+
+# --------------------------------------------------------------------------------------- convolution
+def conv_mtiles(n, ho, wo):
+    return _lib.fn("dm_conv2d_fwd_mtiles")(n, ho, wo)
+
+
+class _Conv2d(torch.autograd.Function):
+    """nn.Conv2d (new_scripy.py:184 etc.) on one or two channel-concatenated NHWC sources."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, weight, bias, pack, c0, c1, stride, pad, want_stats, out_f32):
+        ld0 = _chk(x0, "conv input")
+        ld1 = _chk(x1, "conv input 2") if x1 is not None else 0
+        n, hin, win, _ = x0.shape
+        cout, cin, kh, kw = weight.shape
+        assert cin == c0 + c1, (cin, c0, c1)
+        ho = (hin + 2 * pad - kh) // stride + 1
+        wo = (win + 2 * pad - kw) // stride + 1
+        wpk = pack.get(weight, "fwd", c_split=c0 if x1 is not None else 0)
+        if out_f32:
+            y = torch.empty((n, ho, wo, (cout + 3) // 4 * 4), device=x0.device, dtype=torch.float32)
+        else:
+            y = new_act(n, ho, wo, cout, x0.device)
+        stats = None
+        if want_stats:
+            mt = conv_mtiles(n, ho, wo)
+            stats = torch.empty((mt, 2, cout), device=x0.device, dtype=torch.float32)
+        call("dm_conv2d_fwd", _p(x0), c0, ld0, _p(x1), c1, ld1, _p(wpk), _p(bias), _p(y), y.stride(2), int(out_f32),
+             _p(stats), cout, n, hin, win, cout, kh, kw, stride, pad, _stream())
+        ctx.save_for_backward(x0, x1, weight, bias)
+        ctx.pack, ctx.geom = pack, (c0, c1, stride, pad, out_f32)
+        ctx.mark_non_differentiable(*([stats] if stats is not None else []))
+        return (y, stats) if want_stats else (y, None)
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        x0, x1, weight, bias = ctx.saved_tensors
+        c0, c1, stride, pad, out_f32 = ctx.geom
+        cout, cin, kh, kw = weight.shape
+        n, hin, win, _ = x0.shape
+        ho, wo = dy.shape[1], dy.shape[2]
+        st = _stream()
+        if out_f32:      # fp32 head output: its gradient arrives as fp32 NHWC; the GEMMs take bf16
+            dyb = new_act(n, ho, wo, cout, dy.device)
+            dy = dy.contiguous()
+            call("dm_cast_nhwc", _p(dy), dy.stride(2), _p(dyb), dyb.stride(2), n * ho * wo, cout, st)
+            dy = dyb
+        lddy = _chk(dy, "conv grad")
+        # bias gradient: column sums of dy
+        if bias is not None:
+            call("dm_colsum", _p(dy), lddy, _p(grad_buf(bias)), n * ho * wo, cout, st)
+        # weight gradient: packed fp32 [Cout][taps][Cin_k] then scattered (+=) into the NCHW parameter grad
+        ck = _cols_k(cin, c0 if x1 is not None else 0)
+        dwp = torch.zeros((cout, kh * kw * ck), device=dy.device, dtype=torch.float32)
+        call("dm_conv2d_wgrad", _p(x0), c0, x0.stride(2), _p(x1), c1, x1.stride(2) if x1 is not None else 0, _p(dy),
+             lddy, _p(dwp), n, hin, win, cout, kh, kw, stride, pad, st)
+        offs = [r * kw + s for r in range(kh) for s in range(kw)]
+        call("dm_unpack_wgrad", _p(dwp), _p(grad_buf(weight)), cout, cin, kh * kw, _taps(offs), cin * kh * kw, kh * kw,
+             c0 if x1 is not None else 0, ck, kh * kw * ck, 0, st)
+        # data gradient
+        dx0 = dx1 = None
+        need0 = ctx.needs_input_grad[0]
+        need1 = x1 is not None and ctx.needs_input_grad[1]
+        if need0 or need1:
+            # one gradient tensor for both sources; the halves are channel slices of it
+            width = x0.shape[3] + (x1.shape[3] if x1 is not None else 0)
+            dx = torch.empty((n, hin, win, width), device=dy.device, dtype=torch.bfloat16)
+            if stride == 1:
+                wd = ctx.pack.get(weight, "dgrad")
+                call("dm_conv2d_fwd", _p(dy), cout, lddy, None, 0, 0, _p(wd), None, _p(dx), dx.stride(2), 0, None, 0,
+                     n, ho, wo, cin, kh, kw, 1, kh - 1 - pad, st)
+            else:
+                wd = ctx.pack.get(weight, "s2dgrad")
+                call("dm_conv2d_s2_dgrad", _p(dy), cout, lddy, _p(wd), _p(dx), cin, dx.stride(2), n, ho, wo, st)
+            if x1 is None:
+                dx0 = dx
+            else:
+                dx0, dx1 = dx[..., :c0], dx[..., c0:]
+        return dx0, dx1, None, None, None, None, None, None, None, None, None
+
+
+def conv2d(x0, weight, bias, pack, *, x1=None, c0=None, c1=0, stride=1, pad=0, want_stats=False, out_f32=False):
+    c0 = weight.shape[1] - c1 if c0 is None else c0
+    if x1 is not None and (c0 % 8 or x0.shape[3] != c0):
+        raise _lib.DmB200Error("dual-source conv needs a tight first source with a multiple-of-8 channel count")
+    return _Conv2d.apply(x0, x1, weight, bias, pack, c0, c1, stride, pad, want_stats, out_f32)
+
+
+class _ConvT(torch.autograd.Function):
+    """nn.ConvTranspose2d(k, stride=k) (new_scripy.py:298; MNIST_script.py:88,141)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pack, k):
+        ldx = _chk(x, "convT input")
+        n, hin, win, _ = x.shape
+        cin, cout = weight.shape[0], weight.shape[1]
+        wpk = pack.get(weight, "convt_fwd")
+        y = new_act(n, hin * k, win * k, cout, x.device)
+        call("dm_convt_fwd", _p(x), cin, ldx, _p(wpk), _p(bias), _p(y), y.stride(2), n, hin, win, cout, k, _stream())
+        ctx.save_for_backward(x, weight, bias)
+        ctx.pack, ctx.k = pack, k
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias = ctx.saved_tensors
+        k = ctx.k
+        cin, cout = weight.shape[0], weight.shape[1]
+        n, hin, win, _ = x.shape
+        lddy = _chk(dy, "convT grad")
+        st = _stream()
+        if bias is not None:
+            call("dm_colsum", _p(dy), lddy, _p(grad_buf(bias)), n * hin * k * win * k, cout, st)
+        # gather the k x k output blocks onto channels: [N, hin, win, k*k*cout]
+        kc = k * k * cout
+        s2d = new_act(n, hin, win, kc, dy.device)
+        call("dm_space_to_depth", _p(dy), lddy, _p(s2d), s2d.stride(2), n, hin, win, cout, k, st)
+        # weight gradient: rows (tap, co), K columns ci
+        ck = r64(cin)
+        dwp = torch.zeros((kc, ck), device=dy.device, dtype=torch.float32)
+        call("dm_conv2d_wgrad", _p(x), cin, x.stride(2), None, 0, 0, _p(s2d), s2d.stride(2), _p(dwp), n, hin, win, kc,
+             1, 1, 1, 0, st)
+        offs = [t for t in range(k * k)]
+        call("dm_unpack_wgrad", _p(dwp), _p(grad_buf(weight)), cout, cin, k * k, _taps(offs), k * k, cout * k * k, 0,
+             ck, ck, 1, st)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wd = ctx.pack.get(weight, "convt_dgrad")
+            dx = new_act(n, hin, win, cin, dy.device)
+            call("dm_conv2d_fwd", _p(s2d), kc, s2d.stride(2), None, 0, 0, _p(wd), None, _p(dx), dx.stride(2), 0, None, 0,
+                 n, hin, win, cin, 1, 1, 1, 0, st)
+        return dx, None, None, None, None
+
+
+def conv_transpose(x, weight, bias, pack, k):
+    return _ConvT.apply(x, weight, bias, pack, k)
+
+
+# --------------------------------------------------------------------------------------- normalisation
+class _BnAct(torch.autograd.Function):
+    """BatchNorm2d (eps 1e-5, momentum 0.1) + activation (new_scripy.py:185-186)."""
+
+    @staticmethod
+    def forward(ctx, y, stats, gamma, beta, rmean, rvar, c, training, act, momentum, eps):
+        ldy = _chk(y, "bn input")
+        n, h, w, _ = y.shape
+        mean = torch.empty(c, device=y.device, dtype=torch.float32)
+        invstd = torch.empty(c, device=y.device, dtype=torch.float32)
+        st = _stream()
+        if training:
+            call("dm_bn_finalize", _p(stats), stats.shape[0], stats.shape[2], c, float(n * h * w), _p(mean), _p(invstd),
+                 _p(rmean), _p(rvar), momentum, eps, st)
+        else:
+            call("dm_bn_finalize", None, 0, 0, c, 1.0, _p(mean), _p(invstd), _p(rmean), _p(rvar), momentum, eps, st)
+        z = torch.empty_like(y)
+        call("dm_bn_act_fwd", _p(y), ldy, _p(mean), _p(invstd), _p(gamma), _p(beta), _p(z), z.stride(2), n * h * w, c,
+             act, st)
+        ctx.save_for_backward(y, mean, invstd, gamma, beta)
+        ctx.cfg = (c, training, act)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        y, mean, invstd, gamma, beta = ctx.saved_tensors
+        c, training, act = ctx.cfg
+        lddz = _chk(dz, "bn grad")
+        n, h, w, _ = y.shape
+        dy = torch.empty_like(y)
+        scratch = torch.empty(2 * c, device=y.device, dtype=torch.float32)
+        call("dm_bn_act_bwd", _p(dz), lddz, _p(y), y.stride(2), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(dy),
+             dy.stride(2), _p(grad_buf(gamma)), _p(grad_buf(beta)), _p(scratch), n * h * w, c, act, int(training),
+             _stream())
+        return dy, None, None, None, None, None, None, None, None, None, None
+
+
+def bn_act(y, stats, bn, act):
+    training = bn.training
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return _BnAct.apply(y, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_features, training, act,
+                        float(bn.momentum), float(bn.eps))
+
+
+class _GnAct(torch.autograd.Function):
+    """GroupNorm(G, C) + activation (new_scripy.py:167-168,299-300,312-313)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, c, groups, eps, act):
+        ldx = _chk(x, "gn input")
+        n, h, w, _ = x.shape
+        mean = torch.empty(n * groups, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(n * groups, device=x.device, dtype=torch.float32)
+        scratch = torch.empty(2 * n * c, device=x.device, dtype=torch.float32)
+        z = torch.empty_like(x)
+        call("dm_gn_act_fwd", _p(x), ldx, _p(gamma), _p(beta), _p(z), z.stride(2), _p(mean), _p(rstd), _p(scratch), n,
+             h * w, c, groups, eps, act, _stream())
+        ctx.save_for_backward(x, mean, rstd, gamma, beta)
+        ctx.cfg = (c, groups, act)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, mean, rstd, gamma, beta = ctx.saved_tensors
+        c, groups, act = ctx.cfg
+        lddz = _chk(dz, "gn grad")
+        n, h, w, _ = x.shape
+        dx = torch.empty_like(x)
+        scratch = torch.empty(2 * n * c + 2 * n * groups, device=x.device, dtype=torch.float32)
+        call("dm_gn_act_bwd", _p(dz), lddz, _p(x), x.stride(2), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dx),
+             dx.stride(2), _p(grad_buf(gamma)), _p(grad_buf(beta)), _p(scratch), n, h * w, c, groups, act, _stream())
+        return dx, None, None, None, None, None, None
+
+
+def gn_act(x, gn, act):
+    return _GnAct.apply(x, gn.weight, gn.bias, gn.num_channels, gn.num_groups, float(gn.eps), act)
+
+
+# --------------------------------------------------------------------------------------- tiny sub-graphs
+def _run_small(fn_small, inputs, params):
+    """Run a tiny fp32 torch sub-graph (a few [N,C]-sized linears) under its own autograd tape so the
+    enclosing Function can back-propagate through it with torch.autograd.grad."""
+    with torch.enable_grad():
+        ins = [t.detach().requires_grad_(True) for t in inputs]
+        outs = fn_small(*ins)
+    return ins, outs
+
+
+def _small_backward(ins, outs, grads, params):
+    live = [p for p in params if p.requires_grad]
+    res = torch.autograd.grad(outs, ins + live, grads, allow_unused=True)
+    for p, g in zip(live, res[len(ins):]):
+        if g is not None:
+            grad_buf(p).add_(g)
+    return res[:len(ins)]
+
+
+class _SeResidual(torch.autograd.Function):
+    """out = (res + x2 * gate(x2)) * scale, gate = SEBlock MLP on the global average pool
+    (new_scripy.py:154-158,196-205).  mlp=None: plain (res + x2) * scale (MNIST_script.py:57-61)."""
+
+    @staticmethod
+    def forward(ctx, x2, res, c, scale, mlp, *params):
+        ld2, ldr = _chk(x2, "se x2"), _chk(res, "se residual")
+        n, h, w, _ = x2.shape
+        st = _stream()
+        gate = None
+        ctx.small = None
+        if mlp is not None:
+            pooled = torch.empty((n, c), device=x2.device, dtype=torch.float32)
+            call("dm_pool_nhw", _p(x2), ld2, _p(pooled), n, h * w, c, 1.0 / (h * w), st)
+            ins, gate_g = _run_small(mlp, [pooled], params)
+            gate = gate_g.detach().contiguous()
+            ctx.small = (ins, gate_g)
+        out = torch.empty_like(x2)
+        call("dm_se_apply_fwd", _p(x2), ld2, _p(gate), _p(res), ldr, _p(out), out.stride(2), n, h * w, c, scale, st)
+        ctx.save_for_backward(x2, gate)
+        ctx.cfg = (c, scale, params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, gate = ctx.saved_tensors
+        c, scale, params = ctx.cfg
+        lddo = _chk(dout, "se grad")
+        n, h, w, _ = x2.shape
+        st = _stream()
+        dpool = None
+        if ctx.small is not None:
+            dgate = torch.empty((n, c), device=x2.device, dtype=torch.float32)
+            call("dm_pool_prod_nhw", _p(dout), lddo, _p(x2), x2.stride(2), _p(dgate), n, h * w, c, scale, st)
+            ins, gate_g = ctx.small
+            (dpool,) = _small_backward(ins, [gate_g], [dgate], list(params))
+            dpool = dpool.contiguous()
+        dx2 = torch.empty_like(x2)
+        dres = torch.empty_like(x2)
+        call("dm_se_apply_bwd", _p(dout), lddo, _p(gate), _p(dpool), _p(dx2), dx2.stride(2), _p(dres), dres.stride(2), n,
+             h * w, c, scale, st)
+        return (dx2, dres, None, None, None) + (None,) * len(params)
+
+
+def se_residual(x2, res, c, scale, se_fc=None):
+    if se_fc is None:
+        return _SeResidual.apply(x2, res, c, scale, None)
+    w1, w2 = se_fc[0].weight, se_fc[2].weight
+
+    def mlp(y):
+        return torch.sigmoid(torch.nn.functional.linear(
+            torch.nn.functional.gelu(torch.nn.functional.linear(y, w1)), w2))
+    return _SeResidual.apply(x2, res, c, scale, mlp, w1, w2)
+
+
+class _CoordAttn(torch.autograd.Function):
+    """x * (alpha' * a_h + beta' * a_w) with the directional pooling and the gating pass as kernels and
+    the C/16-wide gate MLP as a tiny fp32 sub-graph (new_scripy.py:97-140)."""
+
+    @staticmethod
+    def forward(ctx, x, c, gates, *params):
+        ldx = _chk(x, "coordattn input")
+        n, h, w, _ = x.shape
+        st = _stream()
+        xh = torch.empty((n, h, c), device=x.device, dtype=torch.float32)
+        xw = torch.empty((n, w, c), device=x.device, dtype=torch.float32)
+        call("dm_ca_pool", _p(x), ldx, None, 0, _p(xh), _p(xw), n, h, w, c, 1.0 / w, 1.0 / h, st)
+        ins, (ah_g, aw_g) = _run_small(gates, [xh, xw], params)
+        ah, aw = ah_g.detach().contiguous(), aw_g.detach().contiguous()
+        out = torch.empty_like(x)
+        call("dm_ca_gate_fwd", _p(x), ldx, _p(ah), _p(aw), _p(out), out.stride(2), n, h, w, c, st)
+        ctx.save_for_backward(x, ah, aw)
+        ctx.small = (ins, (ah_g, aw_g))
+        ctx.cfg = (c, params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, ah, aw = ctx.saved_tensors
+        c, params = ctx.cfg
+        lddo = _chk(dout, "coordattn grad")
+        n, h, w, _ = x.shape
+        st = _stream()
+        dah = torch.empty((n, h, c), device=x.device, dtype=torch.float32)
+        daw = torch.empty((n, w, c), device=x.device, dtype=torch.float32)
+        call("dm_ca_pool", _p(dout), lddo, _p(x), x.stride(2), _p(dah), _p(daw), n, h, w, c, 1.0, 1.0, st)
+        ins, outs = ctx.small
+        dxh, dxw = _small_backward(ins, list(outs), [dah, daw], list(params))
+        dx = torch.empty_like(x)
+        call("dm_ca_gate_bwd", _p(dout), lddo, _p(ah), _p(aw), _p(dxh.contiguous()), _p(dxw.contiguous()), _p(dx),
+             dx.stride(2), n, h, w, c, st)
+        return (dx, None, None) + (None,) * len(params)
+
+
+def coord_attn(x, c, gates, params):
+    return _CoordAttn.apply(x, c, gates, *params)
+
+
+# --------------------------------------------------------------------------------------- resampling / glue
+class _Upcat(torch.autograd.Function):
+    """cat((a, b), 1) -> Upsample(x2, bilinear, align_corners=True) (new_scripy.py:242,251)."""
+
+    @staticmethod
+    def forward(ctx, a, b, ca, cb):
+        lda, ldb = _chk(a, "upcat a"), _chk(b, "upcat b")
+        n, h, w, _ = a.shape
+        out = new_act(n, 2 * h, 2 * w, ca + cb, a.device)
+        call("dm_upcat_fwd", _p(a), lda, ca, _p(b), ldb, cb, _p(out), out.stride(2), n, h, w, _stream())
+        ctx.cfg = (ca, cb, n, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ca, cb, n, h, w = ctx.cfg
+        lddo = _chk(dout, "upcat grad")
+        da = new_act(n, h, w, ca, dout.device)
+        db = new_act(n, h, w, cb, dout.device)
+        call("dm_upcat_bwd", _p(dout), lddo, _p(da), da.stride(2), ca, _p(db), db.stride(2), cb, n, h, w, _stream())
+        return da, db, None, None
+
+
+def upcat(a, b, ca, cb):
+    return _Upcat.apply(a, b, ca, cb)
+
+
+class _Film(torch.autograd.Function):
+    """cemb * x + temb broadcast over pixels (new_scripy.py:348-349)."""
+
+    @staticmethod
+    def forward(ctx, x, ce, te, c):
+        ldx = _chk(x, "film input")
+        n, h, w, _ = x.shape
+        ce, te = ce.contiguous().float(), te.contiguous().float()
+        out = torch.empty_like(x)
+        call("dm_film_fwd", _p(x), ldx, _p(ce), _p(te), _p(out), out.stride(2), n, h * w, c, _stream())
+        ctx.save_for_backward(x, ce)
+        ctx.c = c
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, ce = ctx.saved_tensors
+        c = ctx.c
+        lddo = _chk(dout, "film grad")
+        n, h, w, _ = x.shape
+        dx = torch.empty_like(x)
+        dce = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        dte = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        call("dm_film_bwd", _p(dout), lddo, _p(x), x.stride(2), _p(ce), _p(dx), dx.stride(2), _p(dce), _p(dte), n, h * w,
+             c, _stream())
+        return dx, dce, dte, None
+
+
+def film(x, ce, te, c):
+    return _Film.apply(x, ce, te, c)
+
+
+class _AvgPoolAct(torch.autograd.Function):
+    """AvgPool2d(k) + GELU (new_scripy.py:290; MNIST_script.py:132)."""
+
+    @staticmethod
+    def forward(ctx, x, c, k, act):
+        ldx = _chk(x, "avgpool input")
+        n, h, w, _ = x.shape
+        out = new_act(n, h // k, w // k, c, x.device)
+        call("dm_avgpool_act_fwd", _p(x), ldx, _p(out), out.stride(2), n, h, w, c, k, act, _stream())
+        ctx.save_for_backward(x)
+        ctx.cfg = (c, k, act)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        c, k, act = ctx.cfg
+        lddo = _chk(dout, "avgpool grad")
+        n, h, w, _ = x.shape
+        dx = torch.zeros_like(x) if (h % k or w % k) else torch.empty_like(x)
+        call("dm_avgpool_act_bwd", _p(dout), lddo, _p(x), x.stride(2), _p(dx), dx.stride(2), n, h, w, c, k, act, _stream())
+        return dx, None, None, None
+
+
+def avgpool_act(x, c, k, act):
+    return _AvgPoolAct.apply(x, c, k, act)
+
+
+class _MaxPool2(torch.autograd.Function):
+    """MaxPool2d(2) (MNIST_script.py:74)."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        ldx = _chk(x, "maxpool input")
+        n, h, w, _ = x.shape
+        out = new_act(n, h // 2, w // 2, c, x.device)
+        call("dm_maxpool2_fwd", _p(x), ldx, _p(out), out.stride(2), n, h, w, c, _stream())
+        ctx.save_for_backward(x)
+        ctx.c = c
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        lddo = _chk(dout, "maxpool grad")
+        n, h, w, _ = x.shape
+        dx = torch.zeros_like(x) if (h % 2 or w % 2) else torch.empty_like(x)
+        call("dm_maxpool2_bwd", _p(dout), lddo, _p(x), x.stride(2), _p(dx), dx.stride(2), n, h, w, ctx.c, _stream())
+        return dx, None
+
+
+def maxpool2(x, c):
+    return _MaxPool2.apply(x, c)
+
+
+class _MaskFma(torch.autograd.Function):
+    """x + y * (mask > thresh): the LocalEnhancer attention-mask weighting (new_scripy.py:173-174)."""
+
+    @staticmethod
+    def forward(ctx, x, y, mask, thresh, c):
+        ldx, ldy = _chk(x, "mask_fma x"), _chk(y, "mask_fma y")
+        n, h, w, _ = x.shape
+        mask = mask.contiguous().float()
+        out = torch.empty_like(x)
+        call("dm_mask_fma", _p(x), ldx, _p(y), ldy, _p(mask), thresh, _p(out), out.stride(2), n * h * w, c, _stream())
+        ctx.save_for_backward(mask)
+        ctx.cfg = (thresh, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (mask,) = ctx.saved_tensors
+        thresh, c = ctx.cfg
+        lddo = _chk(dout, "mask_fma grad")
+        n, h, w, _ = dout.shape
+        dy = torch.empty_like(dout)
+        call("dm_mask_fma", None, 0, _p(dout), lddo, _p(mask), thresh, _p(dy), dy.stride(2), n * h * w, c, _stream())
+        return dout, dy, None, None, None
+
+
+def mask_fma(x, y, mask, thresh, c):
+    return _MaskFma.apply(x, y, mask, thresh, c)
+
+
+class _Fork(torch.autograd.Function):
+    """Use one activation twice; the two incoming gradients are summed by one fused kernel."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.c = c
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        if g1 is None or g2 is None:
+            return (g1 if g2 is None else g2), None
+        ld1, ld2 = _chk(g1, "fork grad"), _chk(g2, "fork grad")
+        n, h, w, _ = g1.shape
+        out = new_act(n, h, w, ctx.c, g1.device)
+        call("dm_axpby", _p(g1), ld1, _p(g2), ld2, _p(out), out.stride(2), n * h * w, ctx.c, 1.0, 1.0, _stream())
+        return out, None
+
+
+def fork(x, c):
+    return _Fork.apply(x, c)
+
+
+# --------------------------------------------------------------------------------------- layout boundary
+class _ToNhwc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        if x.device.type != "cuda":
+            raise _lib.DmB200Error("the hot path runs on CUDA only; there is no CPU fallback")
+        x = x.contiguous().float()
+        n, c, h, w = x.shape
+        y = new_act(n, h, w, c, x.device)
+        call("dm_nchw_to_nhwc", _p(x), _p(y), y.stride(2), 0, n, c, h, w, _stream())
+        ctx.c = c
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ld = _chk(dy, "input grad")
+        n, h, w, _ = dy.shape
+        dx = torch.empty((n, ctx.c, h, w), device=dy.device, dtype=torch.float32)
+        call("dm_nhwc_to_nchw", _p(dy), 0, ld, _p(dx), n, ctx.c, h, w, _stream())
+        return dx
+
+
+def to_nhwc(x):
+    return _ToNhwc.apply(x)
+
+
+class _ToNchwF32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, c):
+        n, h, w, ld = y.shape
+        out = torch.empty((n, c, h, w), device=y.device, dtype=torch.float32)
+        call("dm_nhwc_to_nchw", _p(y), int(y.dtype == torch.float32), y.stride(2), _p(out), n, c, h, w, _stream())
+        ctx.cfg = (c, ld, y.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        c, ld, dtype = ctx.cfg
+        dout = dout.contiguous().float()
+        n, _, h, w = dout.shape
+        dy = torch.empty((n, h, w, ld), device=dout.device, dtype=dtype)
+        call("dm_nchw_to_nhwc", _p(dout), _p(dy), ld, int(dtype == torch.float32), n, c, h, w, _stream())
+        return dy, None
+
+
+def to_nchw_f32(y, c):
+    return _ToNchwF32.apply(y, c)
+
+
+# --------------------------------------------------------------------------------------- DDPM kernels
+LOSS_CFG = dict(hi_t=1.2, mid_t=0.8, hi_w=3.0, mid_w=1.0, lo_w=0.5, fcw=2.0)   # new_scripy.py:31-36
+
+
+def q_sample(x, noise, sqrtab, sqrtmab, ts):
+    """x_t as the bf16 NHWC tensor the first conv consumes (new_scripy.py:408-411)."""
+    n, c, h, w = x.shape
+    xt = new_act(n, h, w, c, x.device)
+    call("dm_q_sample", _p(x.contiguous()), _p(noise.contiguous()), _p(sqrtab), _p(sqrtmab), _p(ts.contiguous()), _p(xt),
+         xt.stride(2), n, c, h, w, _stream())
+    return xt
+
+
+class _DdpmLoss(torch.autograd.Function):
+    """Attention-weighted noise-prediction loss (new_scripy.py:417-437); mask=None: MSE (MNIST_script.py:252)."""
+
+    @staticmethod
+    def forward(ctx, pred, noise, mask, cfg):
+        n, h, w, ldp = pred.shape
+        c = noise.shape[1]
+        loss = torch.empty((), device=pred.device, dtype=torch.float32)
+        scratch = torch.empty(8, device=pred.device, dtype=torch.float32)
+        vals = [cfg[k] for k in ("hi_t", "mid_t", "hi_w", "mid_w", "lo_w", "fcw")]
+        call("dm_ddpm_loss_fwd", _p(pred), pred.stride(2), _p(noise), _p(mask), _p(loss), _p(scratch), n, c, h, w, *vals,
+             _stream())
+        ctx.save_for_backward(pred, noise, mask)
+        ctx.vals = vals
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        pred, noise, mask = ctx.saved_tensors
+        n, h, w, _ = pred.shape
+        c = noise.shape[1]
+        dpred = torch.empty_like(pred)
+        gout = gout.contiguous().float()
+        call("dm_ddpm_loss_bwd", _p(pred), pred.stride(2), _p(noise), _p(mask), _p(gout), _p(dpred), dpred.stride(2), n, c,
+             h, w, *ctx.vals, _stream())
+        return dpred, None, None, None
+
+
+def ddpm_loss(pred_nhwc_f32, noise, mask):
+    noise = noise.contiguous().float()
+    mask = mask.contiguous().float() if mask is not None else None
+    return _DdpmLoss.apply(pred_nhwc_f32, noise, mask, LOSS_CFG)
+
+
+def cfg_reverse_step(eps_nhwc_f32, x, z, guide_w, a, b, s, want_next=True):
+    """One classifier-free-guided reverse step (new_scripy.py:468-475).  Returns (x_next fp32 NCHW,
+    doubled bf16 NHWC batch for the next denoiser call)."""
+    n, c, h, w = x.shape
+    x_out = torch.empty_like(x)
+    xt = new_act(2 * n, h, w, c, x.device) if want_next else None
+    call("dm_cfg_reverse_step", _p(eps_nhwc_f32), eps_nhwc_f32.stride(2), _p(x), _p(z), _p(x_out), _p(xt),
+         xt.stride(2) if xt is not None else 8, float(guide_w), float(a), float(b), float(s), n, c, h, w, _stream())
+    return x_out, xt

@@ -1,0 +1,88 @@
+"""Optimizer side of the train step: global grad-norm clip + AdamW as two kernels over flat buffers.
+
+Replaces ``scaler.unscale_ / clip_grad_norm_(params, 1.0) / AdamW.step`` (new_scripy.py:797-803):
+all parameters are re-homed as views of one flat fp32 buffer (names, shapes and state_dict unchanged),
+their gradients as views of a second one, so the clip and the update are one ``dm_sumsq`` and one
+``dm_adamw`` launch and a data-parallel gradient all-reduce is one NCCL call on one tensor.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import ops
+from ._lib import call
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """AdamW (decoupled weight decay, bias correction: torch.optim.AdamW semantics) with optional
+    global-norm clipping folded into the update.  ``param_groups[0]['lr']`` stays schedulable."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=0.0):
+        params = [p for p in params if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.max_grad_norm = float(max_grad_norm)
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdamW runs on CUDA only; there is no CPU fallback")
+        self._params = params
+        self._offsets = []
+        off = 0
+        for p in params:
+            self._offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self._n = off
+        self.flat_param = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(off, device=dev, dtype=torch.float32)
+        self._gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self._step = 0
+        with torch.no_grad():
+            for p, o in zip(params, self._offsets):
+                view = self.flat_param[o:o + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+        self._attach_grads()
+
+    def _attach_grads(self):
+        for p, o in zip(self._params, self._offsets):
+            gv = self.flat_grad[o:o + p.numel()].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != gv.data_ptr():
+                if p.grad is not None:
+                    gv.copy_(p.grad)
+                p.grad = gv
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.flat_grad.zero_()
+        self._attach_grads()
+
+    @torch.no_grad()
+    def grad_norm(self):
+        """Global L2 norm of the (flat) gradient as a device scalar."""
+        self._attach_grads()
+        self._gnorm_sq.zero_()
+        call("dm_sumsq", _p(self.flat_grad), self._n, _p(self._gnorm_sq), ops._stream())
+        return self._gnorm_sq.sqrt()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        self._attach_grads()
+        g = self.param_groups[0]
+        self._step += 1
+        b1, b2 = g["betas"]
+        st = ops._stream()
+        gn = None
+        if self.max_grad_norm > 0:
+            self._gnorm_sq.zero_()
+            call("dm_sumsq", _p(self.flat_grad), self._n, _p(self._gnorm_sq), st)
+            gn = _p(self._gnorm_sq)
+        call("dm_adamw", _p(self.flat_param), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq), self._n,
+             float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
+             1.0 - b1 ** self._step, 1.0 - b2 ** self._step, gn, self.max_grad_norm, st)
+        ops.bump_weights_epoch()

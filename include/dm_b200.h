@@ -1,0 +1,158 @@
+/* dm_b200.h -- C-ABI of libdm_b200.so: the B200 (sm_100a) kernels behind the DiffusionModel hot path.
+ *
+ * The reference (Shen-Yuuu/DiffusionModel) has no FFI layer: its hot path is torch.nn modules calling
+ * aten -> cuDNN/cuBLAS.  The boundary this library replaces is therefore the set of aten/cuDNN calls
+ * made by ContextUnet / DDPM (file:line under /root/reference cited per entry point); the Python host
+ * mirror (diffusionmodel_b200/unet.py, ddpm.py) keeps the reference's module names, signatures and
+ * state_dict layout and binds these symbols through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; `stream` is a cudaStream_t passed as void*;
+ *   - activations are bf16, NHWC, with a channel pitch `ld*` (elements, multiple of 8; pad lanes are
+ *     written as zero); "P" is a pixel count (N*H*W); small per-(sample,channel) tensors are fp32;
+ *   - parameter-gradient outputs are ACCUMULATED (+=) into fp32 buffers in the reference's layouts;
+ *   - every function returns 0 on success, <0 on error (dm_last_error() has the message); nothing
+ *     falls back to the CPU and nothing synchronises the stream.
+ */
+#ifndef DM_B200_H_
+#define DM_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* dm_last_error(void);
+int dm_version(void);
+void dm_debug_set(int key, long long value);
+
+/* ---- tcgen05 implicit-GEMM convolutions (conv_gemm.cu) ------------------------------------------
+ * nn.Conv2d forward: new_scripy.py:166,169,184,188,217,222,225,229,243,311,314; MNIST_script.py:42,46,149,152.
+ * x0 (++ x1 concatenated on channels: replaces torch.cat new_scripy.py:355 / MNIST_script.py:186),
+ * wpk = dm_pack_weight() output [Cout][kh*kw][Cin_k]; y bf16 (y_f32=0) or fp32 (y_f32=1, ldy%4==0);
+ * stats (nullable): [dm_conv2d_fwd_mtiles()][2][stats_ld] per-tile sum / sum-of-squares of y for the
+ * train-mode BatchNorm that follows.  The data gradient of a stride-1 conv is the same call with the
+ * flipped/transposed weight pack and pad' = k-1-pad. */
+int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, int C1, int ld1, const void* wpk,
+                  const float* bias, void* y, int ldy, int y_f32, float* stats, int stats_ld, int N, int Hin,
+                  int Win, int Cout, int kh, int kw, int stride, int pad, void* stream);
+int dm_conv2d_fwd_mtiles(int N, int Ho, int Wo);
+/* data gradient of Conv2d(k=4, s=2, p=1) (new_scripy.py:229); wpk = 4 phase packs, see weights.py */
+int dm_conv2d_s2_dgrad(const void* dy, int Cout, int lddy, const void* wpk, void* dx, int Cin, int lddx,
+                       int N, int Ho, int Wo, void* stream);
+/* nn.ConvTranspose2d with kernel == stride (new_scripy.py:298; MNIST_script.py:88,141) */
+int dm_convt_fwd(const void* x, int Cin, int ldx, const void* wpk, const float* bias, void* y, int ldy, int N,
+                 int Hin, int Win, int Cout, int k, void* stream);
+/* weight gradient: dwp[Cout][kh*kw][Cin_k] fp32 += dy^T * im2col(x) (cuDNN wgrad of the sites above) */
+int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, int C1, int ld1, const void* dy, int lddy,
+                    float* dwp, int N, int Hin, int Win, int Cout, int kh, int kw, int stride, int pad,
+                    void* stream);
+
+/* ---- weight packing (pack.cu) --------------------------------------------------------------------
+ * out[row][tap][col] (tap_major_rows=0) or out[tap][row][col] (=1) in bf16, col padded with zeros to
+ * cols_k, row padded to row_len; source element = w[row*s_row + col*s_col + tap_off[tap]].
+ * c_split>0: columns >= c_split start at round_up(c_split,64) (dual-source convs). */
+int dm_pack_weight(const float* w, void* out, int rows, int cols, int ntaps, const long long* tap_off_host,
+                   long long s_row, long long s_col, int c_split, int cols_k, long long row_len,
+                   int tap_major_rows, void* stream);
+/* inverse gather: grad[...] += dwp[...] with the same addressing (fp32 -> fp32) */
+int dm_unpack_wgrad(const float* dwp, float* grad, int rows, int cols, int ntaps, const long long* tap_off_host,
+                    long long s_row, long long s_col, int c_split, int cols_k, long long row_len,
+                    int tap_major_rows, void* stream);
+
+/* ---- layout conversion --------------------------------------------------------------------------- */
+int dm_nchw_to_nhwc(const float* x, void* y, int ldy, int y_f32, int N, int C, int H, int W, void* stream);
+int dm_cast_nhwc(const float* x, int ldx, void* y, int ldy, long long P, int C, void* stream);  /* fp32 -> bf16 NHWC */
+int dm_nhwc_to_nchw(const void* x, int x_f32, int ldx, float* y, int N, int C, int H, int W, void* stream);
+int dm_space_to_depth(const void* x, int ldx, void* y, int ldy, int N, int H, int W, int C, int k, void* stream);
+
+/* ---- BatchNorm2d + GELU (new_scripy.py:185-186,189-190,218-219,226-227) ---------------------------
+ * finalize: partial sums -> batch mean / invstd (+ running-stat update, momentum 0.1, unbiased var);
+ * m_tiles == 0: eval mode, mean/invstd from the running buffers. */
+int dm_bn_finalize(const float* partials, int m_tiles, int ld, int C, double count, float* mean, float* invstd,
+                   float* running_mean, float* running_var, float momentum, float eps, void* stream);
+int dm_bn_act_fwd(const void* y, int ldy, const float* mean, const float* invstd, const float* gamma,
+                  const float* beta, void* z, int ldz, long long P, int C, int act, void* stream);
+/* dy = BN/act backward; dgamma/dbeta += ; scratch >= 2*C floats; training=0 drops the batch-stat terms */
+int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, const float* mean, const float* invstd,
+                  const float* gamma, const float* beta, void* dy, int lddy, float* dgamma, float* dbeta,
+                  float* scratch, long long P, int C, int act, int training, void* stream);
+
+/* ---- GroupNorm(8,C) + ReLU/GELU (new_scripy.py:167-168,299-300,312-313) --------------------------- */
+int dm_gn_act_fwd(const void* x, int ldx, const float* gamma, const float* beta, void* z, int ldz, float* mean,
+                  float* rstd, float* scratch, int N, int HW, int C, int G, float eps, int act, void* stream);
+int dm_gn_act_bwd(const void* dz, int lddz, const void* x, int ldx, const float* mean, const float* rstd,
+                  const float* gamma, const float* beta, void* dx, int lddx, float* dgamma, float* dbeta,
+                  float* scratch, int N, int HW, int C, int G, int act, void* stream);
+
+/* ---- per-(sample,channel) reductions and the SEBlock gate (new_scripy.py:154-158,196-205) ---------- */
+int dm_pool_nhw(const void* x, int ldx, float* out, int N, int HW, int C, float scale, void* stream);
+int dm_pool_prod_nhw(const void* a, int lda, const void* b, int ldb, float* out, int N, int HW, int C, float scale,
+                     void* stream);
+/* out = (res + x2*gate[n,c]) * scale   (gate NULL -> 1) */
+int dm_se_apply_fwd(const void* x2, int ld2, const float* gate, const void* res, int ldr, void* out, int ldo,
+                    int N, int HW, int C, float scale, void* stream);
+/* dx2 = dout*scale*gate + dpool[n,c]/HW ; dres = dout*scale  (gate/dpool nullable) */
+int dm_se_apply_bwd(const void* dout, int lddo, const float* gate, const float* dpool, void* dx2, int lddx2,
+                    void* dres, int lddr, int N, int HW, int C, float scale, void* stream);
+
+/* ---- CoordAttn directional pooling and gating (new_scripy.py:97-140) ------------------------------- */
+int dm_ca_pool(const void* a, int lda, const void* b, int ldb, float* oh, float* ow, int N, int H, int W, int C,
+               float scale_h, float scale_w, void* stream);   /* oh[n,h,c]=scale_h*sum_w a*b ; b NULL -> a */
+int dm_ca_gate_fwd(const void* x, int ldx, const float* ah, const float* aw, void* out, int ldo, int N, int H,
+                   int W, int C, void* stream);
+int dm_ca_gate_bwd(const void* dout, int lddo, const float* ah, const float* aw, const float* dxh,
+                   const float* dxw, void* dx, int lddx, int N, int H, int W, int C, void* stream);
+
+/* ---- cat + bilinear x2 (align_corners=True) + FiLM (new_scripy.py:242,251,348-349) ----------------- */
+int dm_upcat_fwd(const void* a, int lda, int Ca, const void* b, int ldb, int Cb, void* out, int ldo, int N, int h,
+                 int w, void* stream);
+int dm_upcat_bwd(const void* dout, int lddo, void* da, int ldda, int Ca, void* db, int lddb, int Cb, int N, int h,
+                 int w, void* stream);
+int dm_film_fwd(const void* x, int ldx, const float* ce, const float* te, void* out, int ldo, int N, int HW, int C,
+                void* stream);
+int dm_film_bwd(const void* dout, int lddo, const void* x, int ldx, const float* ce, void* dx, int lddx, float* dce,
+                float* dte, int N, int HW, int C, void* stream);
+
+/* ---- pooling (new_scripy.py:290; MNIST_script.py:74,132) ------------------------------------------ */
+int dm_avgpool_act_fwd(const void* x, int ldx, void* out, int ldo, int N, int H, int W, int C, int k, int act,
+                       void* stream);
+int dm_avgpool_act_bwd(const void* dout, int lddo, const void* x, int ldx, void* dx, int lddx, int N, int H, int W,
+                       int C, int k, int act, void* stream);
+int dm_maxpool2_fwd(const void* x, int ldx, void* out, int ldo, int N, int H, int W, int C, void* stream);
+int dm_maxpool2_bwd(const void* dout, int lddo, const void* x, int ldx, void* dx, int lddx, int N, int H, int W,
+                    int C, void* stream);
+
+/* ---- LocalEnhancer mask weighting (new_scripy.py:172-174) and generic glue -------------------------- */
+int dm_mask_fma(const void* x, int ldx, const void* y, int ldy, const float* mask, float thresh, void* out,
+                int ldo, long long P, int C, void* stream);   /* out = (x?x:0) + y*(mask>thresh) */
+int dm_axpby(const void* a, int lda, const void* b, int ldb, void* out, int ldo, long long P, int C, float sa,
+             float sb, void* stream);                         /* out = sa*a + sb*b (b nullable) */
+int dm_colsum(const void* dy, int lddy, float* db, long long P, int C, void* stream);   /* db[c] += sum_p dy */
+
+/* ---- DDPM q-sample, losses, CFG reverse step (new_scripy.py:405-437,467-475; MNIST_script.py:239-252,287-295) */
+int dm_q_sample(const float* x, const float* noise, const float* sqrtab, const float* sqrtmab, const long long* ts,
+                void* xt, int ldo, int N, int C, int H, int W, void* stream);
+/* loss = mean((noise-pred)^2 * w(mask)) + fcw*mean(|pred*h - noise*h|); mask NULL -> plain MSE.
+ * pred: fp32 NHWC pitch ldp; noise fp32 NCHW; loss: one float (overwritten); scratch >= 1024 floats. */
+int dm_ddpm_loss_fwd(const float* pred, int ldp, const float* noise, const float* mask, float* loss, float* scratch,
+                     int N, int C, int H, int W, float hi_t, float mid_t, float hi_w, float mid_w, float lo_w,
+                     float fcw, void* stream);
+/* dpred: fp32 NHWC, pitch lddp (the gradient of the fp32 prediction) */
+int dm_ddpm_loss_bwd(const float* pred, int ldp, const float* noise, const float* mask, const float* gout, void* dpred,
+                     int lddp, int N, int C, int H, int W, float hi_t, float mid_t, float hi_w, float mid_w,
+                     float lo_w, float fcw, void* stream);
+/* eps = (1+w)*eps[:n] - w*eps[n:];  x' = a*(x - eps*b) + s*z;  writes x' (fp32 NCHW) and the doubled
+ * bf16 NHWC batch the next U-Net call consumes.  eps: fp32 NHWC [2n,H,W,ldp]; z nullable (i == 1). */
+int dm_cfg_reverse_step(const float* eps, int ldp, const float* x, const float* z, float* x_out, void* xt_next,
+                        int ldo, float guide_w, float oneover_sqrta, float mab_over_sqrtmab, float sqrt_beta, int n,
+                        int C, int H, int W, void* stream);
+
+/* ---- optimizer side (new_scripy.py:797-803) --------------------------------------------------------- */
+int dm_sumsq(const float* g, long long n, float* out, void* stream);          /* *out += sum g^2 */
+int dm_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+             float eps, float wd, float bc1, float bc2, const float* gnorm_sq, float max_norm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DM_B200_H_ */

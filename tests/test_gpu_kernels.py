@@ -1,0 +1,343 @@
+"""Kernel-level parity (GPU): every C-ABI entry point against a CPU restatement of the aten op it
+replaces, on seeded inputs.  Convolutions are checked against fp32 CPU convolutions of the
+bf16-rounded operands (precision-matched: the kernels round operands to bf16 and accumulate in fp32).
+Tolerances (rel-L2): bf16-stored outputs 4e-3 (one bf16 rounding), fp32 outputs 2e-4.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_port as P
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 4e-3
+F32_TOL = 2e-4
+
+
+def bf(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def nhwc(x, dev, ld=None):
+    """fp32 NCHW (CPU) -> bf16 NHWC on the device with zero pad lanes."""
+    n, c, h, w = x.shape
+    ld = ld or (c + 7) // 8 * 8
+    out = torch.zeros((n, h, w, ld), dtype=torch.bfloat16)
+    out[..., :c] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out.to(dev)
+
+
+def nchw(y, c):
+    return y[..., :c].float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def rel(a, b):
+    return P.rel_l2(a, b)
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad
+    (2, 16, 16, 64, 64, 3, 1, 1),
+    (1, 32, 32, 3, 16, 3, 1, 1),
+    (2, 16, 16, 16, 3, 3, 1, 1),
+    (2, 16, 16, 48, 80, 1, 1, 0),
+    (2, 16, 16, 32, 32, 4, 2, 1),
+    (3, 28, 28, 16, 16, 3, 1, 1),
+    (2, 14, 14, 32, 16, 3, 1, 1),
+    (5, 7, 7, 32, 32, 3, 1, 1),
+    (1, 32, 32, 320, 272, 3, 1, 1),
+    (1, 128, 128, 192, 192, 3, 1, 1),
+    (1, 64, 64, 128, 128, 4, 2, 1),
+    (1, 256, 256, 64, 64, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv2d_fwd_bwd(dev, case):
+    from diffusionmodel_b200 import ops
+    n, h, w, cin, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(hash(case) % 10000)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g) * 0.1
+    xr = x.clone().requires_grad_(True)
+    wr = bf(wt).requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    y_ref = F.conv2d(xr, wr, br, stride, pad)
+    ho, wo = y_ref.shape[2:]
+    dy = bf(torch.randn(n, cout, ho, wo, generator=g))
+    y_ref.backward(dy)
+
+    xd = nhwc(x, dev).requires_grad_(True)
+    wd = torch.nn.Parameter(wt.to(dev))
+    bd = torch.nn.Parameter(b.to(dev))
+    y, stats = ops.conv2d(xd, wd, bd, ops.WeightPack(), stride=stride, pad=pad, want_stats=True)
+    assert rel(nchw(y, cout), y_ref) < BF16_TOL
+    if y.shape[3] > cout:
+        assert float(y[..., cout:].float().abs().max()) == 0.0          # pad lanes are zero
+    # fused BatchNorm statistics: per-channel sum / sum of squares of the fp32 accumulators
+    s = stats.sum(0).cpu()
+    yr = y_ref.detach()
+    assert rel(s[0], yr.sum((0, 2, 3))) < 1e-3 or float((s[0] - yr.sum((0, 2, 3))).abs().max()) < 1e-2
+    assert rel(s[1], (yr * yr).sum((0, 2, 3))) < 1e-3
+    y.backward(nhwc(dy, dev))
+    torch.cuda.synchronize()
+    assert rel(nchw(xd.grad, cin), xr.grad) < BF16_TOL
+    assert rel(wd.grad.cpu(), wr.grad) < F32_TOL
+    assert rel(bd.grad.cpu(), br.grad) < F32_TOL
+
+
+def test_conv2d_f32_head_and_dual_source(dev):
+    """cat(x0, x1) -> conv without materialising the concat; fp32 output for the prediction head."""
+    from diffusionmodel_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n, h, w, c0, c1, cout = 2, 16, 16, 16, 16, 3
+    x0 = bf(torch.randn(n, c0, h, w, generator=g))
+    x1 = bf(torch.randn(n, c1, h, w, generator=g))
+    wt = torch.randn(cout, c0 + c1, 3, 3, generator=g) / math.sqrt((c0 + c1) * 9)
+    b = torch.randn(cout, generator=g) * 0.1
+    x0r, x1r = x0.clone().requires_grad_(True), x1.clone().requires_grad_(True)
+    wr = bf(wt).requires_grad_(True)
+    y_ref = F.conv2d(torch.cat((x0r, x1r), 1), wr, b, 1, 1)
+    dy = torch.randn(n, cout, h, w, generator=g)
+    y_ref.backward(bf(dy))
+    x0d, x1d = nhwc(x0, dev).requires_grad_(True), nhwc(x1, dev).requires_grad_(True)
+    wd = torch.nn.Parameter(wt.to(dev))
+    bd = torch.nn.Parameter(b.to(dev))
+    y, _ = ops.conv2d(x0d, wd, bd, ops.WeightPack(), x1=x1d, c1=c1, stride=1, pad=1, out_f32=True)
+    assert y.dtype == torch.float32 and y.shape[3] == 4
+    assert rel(nchw(y, cout), y_ref) < F32_TOL
+    gy = torch.zeros_like(y)
+    gy[..., :cout] = bf(dy).permute(0, 2, 3, 1).to(dev)
+    y.backward(gy)
+    assert rel(nchw(x0d.grad, c0), x0r.grad) < BF16_TOL
+    assert rel(nchw(x1d.grad, c1), x1r.grad) < BF16_TOL
+    assert rel(wd.grad.cpu(), wr.grad) < F32_TOL
+
+
+@pytest.mark.parametrize("case", [(4, 2, 2, 128, 128, 8), (3, 1, 1, 32, 32, 7), (2, 7, 7, 64, 16, 2)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv_transpose(dev, case):
+    from diffusionmodel_b200 import ops
+    n, h, w, cin, cout, k = case
+    g = torch.Generator().manual_seed(7)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = torch.randn(cin, cout, k, k, generator=g) / math.sqrt(cin)
+    b = torch.randn(cout, generator=g) * 0.1
+    xr = x.clone().requires_grad_(True)
+    wr = bf(wt).requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    y_ref = F.conv_transpose2d(xr, wr, br, k)
+    dy = bf(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    xd = nhwc(x, dev).requires_grad_(True)
+    wd, bd = torch.nn.Parameter(wt.to(dev)), torch.nn.Parameter(b.to(dev))
+    y = ops.conv_transpose(xd, wd, bd, ops.WeightPack(), k)
+    assert rel(nchw(y, cout), y_ref) < BF16_TOL
+    y.backward(nhwc(dy, dev))
+    assert rel(nchw(xd.grad, cin), xr.grad) < BF16_TOL
+    assert rel(wd.grad.cpu(), wr.grad) < F32_TOL
+    assert rel(bd.grad.cpu(), br.grad) < F32_TOL
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("shape", [(4, 24, 16, 16), (2, 192, 32, 32), (3, 20, 7, 7)])
+def test_bn_gelu(dev, shape, training):
+    """Sequential(Conv2d, BatchNorm2d, GELU) against the reference ops incl. running-stat update."""
+    from diffusionmodel_b200 import ops, unet
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(11)
+    seq = torch.nn.Sequential(torch.nn.Conv2d(c, c, 3, 1, 1), torch.nn.BatchNorm2d(c), torch.nn.GELU())
+    with torch.no_grad():
+        seq[1].weight.copy_(0.5 + torch.rand(c, generator=g)); seq[1].bias.copy_(torch.randn(c, generator=g) * 0.2)
+        seq[1].running_mean.copy_(torch.randn(c, generator=g) * 0.1); seq[1].running_var.copy_(0.5 + torch.rand(c, generator=g))
+        seq[0].weight.copy_(bf(seq[0].weight))
+    import copy
+    ref = copy.deepcopy(seq).train(training)
+    x = bf(torch.randn(n, c, h, w, generator=g))
+    xr = x.clone().requires_grad_(True)
+    z_ref = ref(xr)
+    dz = bf(torch.randn(z_ref.shape, generator=g))
+    z_ref.backward(dz)
+    mod = seq.to(dev).train(training)
+    xd = nhwc(x, dev).requires_grad_(True)
+    z = unet.conv_bn_act(xd, mod)
+    assert rel(nchw(z, c), z_ref) < 6e-3
+    z.backward(nhwc(dz, dev))
+    assert rel(nchw(xd.grad, c), xr.grad) < 1.2e-2
+    assert rel(mod[1].weight.grad.cpu(), ref[1].weight.grad) < 8e-3
+    assert rel(mod[1].bias.grad.cpu(), ref[1].bias.grad) < 8e-3
+    assert rel(mod[0].weight.grad.cpu(), ref[0].weight.grad) < 1.2e-2
+    if training:
+        assert rel(mod[1].running_mean.cpu(), ref[1].running_mean) < 2e-3
+        assert rel(mod[1].running_var.cpu(), ref[1].running_var) < 2e-3
+        assert int(mod[1].num_batches_tracked) == int(ref[1].num_batches_tracked)
+
+
+@pytest.mark.parametrize("act", ["relu", "gelu"])
+@pytest.mark.parametrize("shape", [(2, 64, 16, 16), (3, 16, 7, 7), (2, 192, 32, 32)])
+def test_group_norm_act(dev, shape, act):
+    from diffusionmodel_b200 import ops
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(13)
+    gn = torch.nn.GroupNorm(8, c)
+    with torch.no_grad():
+        gn.weight.copy_(0.5 + torch.rand(c, generator=g)); gn.bias.copy_(torch.randn(c, generator=g) * 0.2)
+    import copy
+    ref = copy.deepcopy(gn)
+    x = bf(torch.randn(n, c, h, w, generator=g) * 1.5 + 0.3)
+    xr = x.clone().requires_grad_(True)
+    z_ref = (F.relu if act == "relu" else F.gelu)(ref(xr))
+    dz = bf(torch.randn(z_ref.shape, generator=g))
+    z_ref.backward(dz)
+    gn = gn.to(dev)
+    xd = nhwc(x, dev).requires_grad_(True)
+    z = ops.gn_act(xd, gn, ops.ACT_RELU if act == "relu" else ops.ACT_GELU)
+    assert rel(nchw(z, c), z_ref) < BF16_TOL
+    z.backward(nhwc(dz, dev))
+    assert rel(nchw(xd.grad, c), xr.grad) < BF16_TOL
+    assert rel(gn.weight.grad.cpu(), ref.weight.grad) < 1e-3
+    assert rel(gn.bias.grad.cpu(), ref.bias.grad) < 1e-3
+
+
+def test_upcat_film_pool(dev):
+    from diffusionmodel_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    n, ca, cb, h, w = 2, 16, 24, 8, 8
+    a = bf(torch.randn(n, ca, h, w, generator=g)); b = bf(torch.randn(n, cb, h, w, generator=g))
+    ce = torch.randn(n, ca, generator=g); te = torch.randn(n, ca, generator=g)
+    ar, br_, cer, ter = (t.clone().requires_grad_(True) for t in (a, b, ce, te))
+    fa = cer[:, :, None, None] * ar + ter[:, :, None, None]
+    up_ref = F.interpolate(torch.cat((fa, br_), 1), scale_factor=2, mode="bilinear", align_corners=True)
+    dy = bf(torch.randn(up_ref.shape, generator=g))
+    up_ref.backward(dy)
+    ad, bd = nhwc(a, dev).requires_grad_(True), nhwc(b, dev).requires_grad_(True)
+    ced, ted = ce.to(dev).requires_grad_(True), te.to(dev).requires_grad_(True)
+    up = ops.upcat(ops.film(ad, ced, ted, ca), bd, ca, cb)
+    assert rel(nchw(up, ca + cb), up_ref) < 6e-3
+    up.backward(nhwc(dy, dev))
+    assert rel(nchw(ad.grad, ca), ar.grad) < 8e-3
+    assert rel(nchw(bd.grad, cb), br_.grad) < BF16_TOL
+    assert rel(ced.grad.cpu(), cer.grad) < 8e-3
+    assert rel(ted.grad.cpu(), ter.grad) < 8e-3
+    # AvgPool2d(k)+GELU and MaxPool2d(2)
+    x = bf(torch.randn(2, 16, 16, 16, generator=g))
+    for k in (8, 2):
+        xr = x.clone().requires_grad_(True)
+        ref = F.gelu(F.avg_pool2d(xr, k))
+        d = bf(torch.randn(ref.shape, generator=g))
+        ref.backward(d)
+        xd = nhwc(x, dev).requires_grad_(True)
+        out = ops.avgpool_act(xd, 16, k, ops.ACT_GELU)
+        assert rel(nchw(out, 16), ref) < BF16_TOL
+        out.backward(nhwc(d, dev))
+        assert rel(nchw(xd.grad, 16), xr.grad) < BF16_TOL
+    xr = x.clone().requires_grad_(True)
+    ref = F.max_pool2d(xr, 2)
+    d = bf(torch.randn(ref.shape, generator=g))
+    ref.backward(d)
+    xd = nhwc(x, dev).requires_grad_(True)
+    out = ops.maxpool2(xd, 16)
+    assert torch.equal(nchw(out, 16), ref.detach())
+    out.backward(nhwc(d, dev))
+    assert torch.equal(nchw(xd.grad, 16), xr.grad)
+
+
+def test_local_enhancer_mask_bit_exact(dev):
+    """(mask > 1.2) index set must be bit-exact incl. the threshold itself, its neighbours and NaN."""
+    from diffusionmodel_b200 import ops
+    g = torch.Generator().manual_seed(19)
+    n, c, h, w = 2, 16, 8, 8
+    x = bf(torch.randn(n, c, h, w, generator=g)); y = bf(torch.randn(n, c, h, w, generator=g))
+    mask = torch.rand(n, h, w, generator=g) * 3
+    mask[0, 0, 0] = 1.2
+    mask[0, 0, 1] = torch.nextafter(torch.tensor(1.2), torch.tensor(2.0))
+    mask[0, 0, 2] = torch.nextafter(torch.tensor(1.2), torch.tensor(0.0))
+    mask[0, 0, 3] = float("nan")
+    mask[0, 0, 4] = float("inf")
+    high = (mask > 1.2).float().unsqueeze(1)
+    ref = x + y * high
+    xd, yd = nhwc(x, dev).requires_grad_(True), nhwc(y, dev).requires_grad_(True)
+    out = ops.mask_fma(xd, yd, mask.to(dev), 1.2, c)
+    got = nchw(out, c)
+    assert torch.equal(got, bf(ref))
+    # the index set itself: where y != 0 the output differs from x exactly on the high pixels
+    sel = (got != x).any(1)
+    assert torch.equal(sel, (high[:, 0] > 0) & (y != 0).any(1))
+    d = bf(torch.randn(n, c, h, w, generator=g))
+    out.backward(nhwc(d, dev))
+    assert torch.equal(nchw(yd.grad, c), bf(d * high))
+    assert torch.equal(nchw(xd.grad, c), d)
+
+
+def test_q_sample_loss_reverse_step(dev):
+    from diffusionmodel_b200 import ops
+    g = torch.Generator().manual_seed(23)
+    n, c, h, w, n_T = 4, 3, 16, 16, 700
+    sched = P.ddpm_schedules(1e-4, 0.02, n_T)
+    x = torch.rand(n, c, h, w, generator=g) * 2 - 1
+    noise = torch.randn(n, c, h, w, generator=g)
+    ts = torch.randint(1, n_T + 1, (n,), generator=g)
+    xt_ref = P.q_sample(sched, x, ts, noise)
+    xt = ops.q_sample(x.to(dev), noise.to(dev), sched["sqrtab"].to(dev), sched["sqrtmab"].to(dev), ts.to(dev))
+    assert torch.equal(nchw(xt, c), bf(xt_ref))                     # bit-exact up to the bf16 store
+    # weighted loss fwd/bwd, incl. exact-threshold mask values
+    mask = P.synth_attn_mask(n, h, g)
+    mask[0, 0, 0], mask[0, 0, 1] = 1.2, 0.8
+    pred = torch.randn(n, c, h, w, generator=g)
+    pr = pred.clone().requires_grad_(True)
+    loss_ref = P.weighted_loss(noise, pr, mask)
+    loss_ref.backward()
+    pd = torch.zeros(n, h, w, 4)
+    pd[..., :c] = pred.permute(0, 2, 3, 1)
+    pd = pd.to(dev).requires_grad_(True)
+    loss = ops.ddpm_loss(pd, noise.to(dev), mask.to(dev))
+    assert abs(float(loss) - float(loss_ref)) < 2e-6 * abs(float(loss_ref)) + 1e-7
+    loss.backward()
+    assert rel(pd.grad[..., :c].cpu().permute(0, 3, 1, 2), pr.grad) < 1e-6
+    # plain MSE (MNIST)
+    pr2 = pred.clone().requires_grad_(True)
+    l2 = F.mse_loss(noise, pr2); l2.backward()
+    pd2 = pd.detach().clone().requires_grad_(True)
+    l2d = ops.ddpm_loss(pd2, noise.to(dev), None)
+    assert abs(float(l2d) - float(l2)) < 2e-6 * float(l2)
+    l2d.backward()
+    assert rel(pd2.grad[..., :c].cpu().permute(0, 3, 1, 2), pr2.grad) < 1e-6
+    # CFG combine + reverse step: bit-exact in fp32 given the same eps
+    ns = 2
+    eps = torch.randn(2 * ns, c, h, w, generator=g)
+    xi = torch.randn(ns, c, h, w, generator=g)
+    z = torch.randn(ns, c, h, w, generator=g)
+    for i, zz in ((350, z), (1, 0)):
+        ref = P.reverse_step(sched, xi, eps[:ns], eps[ns:], zz, i, 2.0)
+        ed = torch.zeros(2 * ns, h, w, 4)
+        ed[..., :c] = eps.permute(0, 2, 3, 1)
+        x_out, xt_next = ops.cfg_reverse_step(ed.to(dev), xi.to(dev), zz.to(dev) if i > 1 else None, 2.0,
+                                              float(sched["oneover_sqrta"][i]), float(sched["mab_over_sqrtmab"][i]),
+                                              float(sched["sqrt_beta_t"][i]))
+        assert torch.equal(x_out.cpu(), ref)
+        assert torch.equal(nchw(xt_next, c), bf(torch.cat([ref, ref], 0)))
+
+
+def test_fused_adamw_matches_torch(dev):
+    from diffusionmodel_b200 import FusedAdamW
+    g = torch.Generator().manual_seed(29)
+    shapes = [(33, 7), (5,), (16, 3, 3, 3), (1,)]
+    ps = [torch.randn(s, generator=g) for s in shapes]
+    ref = [torch.nn.Parameter(p.clone()) for p in ps]
+    mine = [torch.nn.Parameter(p.clone().to(dev)) for p in ps]
+    o_ref = torch.optim.AdamW(ref, lr=1e-2, weight_decay=1e-2)
+    o = FusedAdamW(mine, lr=1e-2, weight_decay=1e-2, max_grad_norm=1.0)
+    for _ in range(3):
+        grads = [torch.randn(s, generator=g) for s in shapes]
+        for p, gr in zip(ref, grads):
+            p.grad = gr.clone()
+        for p, gr in zip(mine, grads):
+            p.grad.copy_(gr.to(dev))
+        torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        o_ref.step(); o.step(); o.zero_grad()
+    for a, b in zip(mine, ref):
+        assert rel(a.detach().cpu(), b.detach()) < 1e-5
