@@ -1,0 +1,296 @@
+"""Headline benchmark: DDPM train step of the enhanced ContextUnet (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode train|sample]
+
+One "step" = one optimizer step of the reference training loop at Cfg defaults
+(new_scripy.py:22-67,777-803): ACCUM_STEPS=4 micro-batches of BATCH_SIZE=4 synthetic 3x256x256 images
+(fwd + bwd each), then global-norm clip (1.0) + AdamW(lr 1e-4, wd 1e-5) -- 16 images per step per GPU,
+n_feat=192, n_classes=5, n_T=700, bf16 operands / fp32 accumulate, LocalEnhancer executed with the
+attention map (so the reference's full 1346 GFLOP/img forward is computed, none of it skipped).
+
+value : img/s with the step's inputs already resident in HBM (CUDA events, max over ranks).
+e2e   : the same through the public module API with HOST (pinned) buffers: every micro-batch is
+        copied host->device and its loss read back device->host inside the timed region.
+N > 1 : data parallel, one process per GPU (torchrun), fixed per-GPU batch (weak scaling), one NCCL
+        all-reduce of the flat gradient per optimizer step.
+--impl reference : the CPU oracle port of the reference (oracle/ref_port.py; the Python reference
+        itself cannot travel to the GPU box) on the host cores, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(n_feat=192, in_ch=3, n_T=700, betas=(1e-4, 0.02), drop_prob=0.1, batch=4, accum=4, lr=1e-4, wd=1e-5,
+           img=256, n_classes=5)
+GFLOP_PER_IMG_FWD = 1346.17          # SURVEY.md 8(d), hooks on the imported reference
+GFLOP_PER_IMG_TRAIN = 4038.5
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_batch(gen, batch, img, n_classes):
+    """Synthetic road-damage-shaped batch: images in [-1,1], labels, attention map built like
+    CrackDataset.__getitem__ (new_scripy.py:535-546): 0.5, lower half 1.0, one random bbox 3.0."""
+    x = torch.rand(batch, 3, img, img, generator=gen) * 2 - 1
+    c = torch.randint(0, n_classes, (batch,), generator=gen)
+    m = torch.full((batch, img, img), 0.5)
+    m[:, img // 2:, :] = 1.0
+    for b in range(batch):
+        xs = torch.randint(0, img, (2,), generator=gen).sort().values
+        ys = torch.randint(0, img, (2,), generator=gen).sort().values
+        m[b, int(ys[0]):int(ys[1]) + 1, int(xs[0]):int(xs[1]) + 1] = 3.0
+    return x, c, m
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """CPU oracle port of the reference train micro-step, bounded sample: ONE image fwd+bwd per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_port as P
+    import diffusionmodel_b200 as D
+    torch.manual_seed(0)
+    cores = torch.get_num_threads()
+    net = D.ContextUnet(CFG["in_ch"], CFG["n_feat"], CFG["n_classes"])          # parameter container only (CPU)
+    sd = {"nn_model." + k: v.detach().clone() for k, v in net.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    sched = P.ddpm_schedules(*CFG["betas"], CFG["n_T"])
+    gen = torch.Generator().manual_seed(0)
+    x, c, m = synth_batch(gen, 1, CFG["img"], CFG["n_classes"])
+
+    def step():
+        ts, noise, ctx = P.draw_train_randoms(x, c, CFG["n_T"], CFG["drop_prob"], "rdd")
+        for v in sd.values():
+            v.grad = None
+        loss = P.ddpm_loss(sd, sched, x, c, m, ts, noise, ctx, variant="rdd", n_T=CFG["n_T"], training=True, attn_map=m)
+        loss.backward()
+        return float(loss)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = 1.0 / dt
+    sample = "1 image fwd+bwd per step (F=192, 3x256x256, fp32, CPU oracle port of new_scripy.DDPM.forward), no optimizer"
+    line = {"impl": "reference", "metric": "ddpm_train_imgs_per_s", "value": val, "unit": "img/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": "new_scripy.ContextUnet DDPM train step, Cfg defaults (n_feat=192, 3x256x256, n_T=700, "
+                        "5 classes), batch 4 x accum 4 per GPU, clip 1.0 + AdamW; LocalEnhancer fed the attention map",
+            "global_batch": CFG["batch"] * CFG["accum"] * n, "micro_batch": CFG["batch"], "accum_steps": CFG["accum"],
+            "parallelism": f"dp{n}", "l2": "per-step working set (>5 GB of activations) is far larger than the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def cpu_baseline_sample():
+    """Oracle port timed on this box's host cores: one image, fwd+bwd (about 15-30 s)."""
+    from oracle import ref_port as P
+    import diffusionmodel_b200 as D
+    cores = torch.get_num_threads()
+    net = D.ContextUnet(CFG["in_ch"], CFG["n_feat"], CFG["n_classes"])
+    sd = {"nn_model." + k: v.detach().clone() for k, v in net.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    sched = P.ddpm_schedules(*CFG["betas"], CFG["n_T"])
+    gen = torch.Generator().manual_seed(0)
+    x, c, m = synth_batch(gen, 1, CFG["img"], CFG["n_classes"])
+    ts, noise, ctx = P.draw_train_randoms(x, c, CFG["n_T"], CFG["drop_prob"], "rdd")
+    t0 = time.perf_counter()
+    loss = P.ddpm_loss(sd, sched, x, c, m, ts, noise, ctx, variant="rdd", n_T=CFG["n_T"], training=True, attn_map=m)
+    loss.backward()
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": "1 image fwd+bwd (F=192, 3x256x256, fp32) through oracle/ref_port.py, single cold run"}
+
+
+def run_ours(args):
+    import diffusionmodel_b200 as D
+    from diffusionmodel_b200 import _lib, ops, parallel
+    rank, local, world = parallel.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)                                  # identical initial weights on every rank
+    net = D.ContextUnet(CFG["in_ch"], CFG["n_feat"], CFG["n_classes"])
+    ddpm = D.DDPM(net, CFG["betas"], CFG["n_T"], dev, CFG["drop_prob"], enhance_with_attn_map=True)
+    ddpm.to(dev).train()
+    opt = D.FusedAdamW(ddpm.parameters(), lr=CFG["lr"], weight_decay=CFG["wd"], max_grad_norm=1.0)
+    parallel.broadcast_parameters(opt.flat_param, [b for b in ddpm.buffers()])
+    torch.manual_seed(1234 + rank)                        # per-rank data / noise streams
+    gen = torch.Generator().manual_seed(100 + rank)
+    accum, batch = CFG["accum"], CFG["batch"]
+    host = [tuple(t.pin_memory() for t in synth_batch(gen, batch, CFG["img"], CFG["n_classes"])) for _ in range(accum)]
+    resident = [tuple(t.to(dev) for t in hb) for hb in host]
+    h2d = sum(t.numel() * t.element_size() for hb in host for t in hb)
+
+    def micro(x, c, m):
+        loss = ddpm(x, c, m) / accum
+        loss.backward()
+        return loss
+
+    def step_resident():
+        for x, c, m in resident:
+            micro(x, c, m)
+        parallel.allreduce_mean_(opt.flat_grad)
+        opt.step()
+        opt.zero_grad()
+
+    def step_e2e():
+        tot = 0.0
+        for hx, hc, hm in host:
+            x, c, m = hx.to(dev, non_blocking=True), hc.to(dev, non_blocking=True), hm.to(dev, non_blocking=True)
+            tot += micro(x, c, m).item()                  # device->host read of the loss, as new_scripy.py:789
+        parallel.allreduce_mean_(opt.flat_grad)
+        opt.step()
+        opt.zero_grad()
+        return tot
+
+    def timed(fn, steps):
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        return parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    imgs = accum * batch * world * args.steps
+    value = imgs / (ms * 1e-3)
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e = imgs / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel class (conv_gemm_kernel: fwd + dgrad implicit GEMMs), CUDA events
+    # around every launch of one extra instrumented step on the launching stream
+    prof = ops.enable_profile()
+    step_resident()
+    torch.cuda.synchronize()
+    ops.disable_profile()
+    agg = prof.summary()
+    pk, src = peaks()
+    line = None
+    if rank == 0:
+        conv = agg.get("conv_gemm", {"ms": 0.0, "flops": 0.0, "n": 0})
+        wg = agg.get("wgrad_gemm", {"ms": 0.0, "flops": 0.0, "n": 0})
+        ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+        peak = pk["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (fwd+dgrad implicit GEMM, all layers of one step)",
+                "achieved": ach, "peak": peak, "peak_source": f"{src} bf16_tflops_sustained", "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "launches": conv["n"], "ms_per_step": conv["ms"],
+                "wgrad": {"achieved": wg["flops"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] > 0 else 0.0,
+                          "ms_per_step": wg["ms"], "launches": wg["n"]},
+                "other_kernels_ms_per_step": sum(v["ms"] for k, v in agg.items() if k not in ("conv_gemm", "wgrad_gemm")),
+                "step_tflops": GFLOP_PER_IMG_TRAIN * accum * batch / 1e3 / (ms / args.steps * 1e-3) / 1e0 / 1e0}
+        roof["step_frac_of_peak"] = roof["step_tflops"] / peak
+        cpu = cpu_baseline_sample() if world == 1 else None
+        line = {"metric": "ddpm_train_imgs_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+                "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * accum,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

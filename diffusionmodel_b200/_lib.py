@@ -40,6 +40,7 @@ def lib() -> ctypes.CDLL:
         _lib.dm_last_error.restype = ctypes.c_char_p
         _lib.dm_debug_set.argtypes = [ctypes.c_int, ctypes.c_longlong]
         _lib.dm_debug_set.restype = None
+        _lib.dm_launch_count.restype = ctypes.c_longlong
     return _lib
 
 
@@ -112,6 +113,10 @@ def call(name, *args):
         msg = lib().dm_last_error().decode(errors="replace")
         raise DmB200Error(f"{name} failed (rc={rc}): {msg}")
     return rc
+
+
+def launch_count() -> int:
+    return int(lib().dm_launch_count())
 
 
 def debug_set(key: int, value: int) -> None:

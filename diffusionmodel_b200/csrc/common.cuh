@@ -11,11 +11,13 @@
 
 #define DM_CHECK_LAUNCH()                                      \
   do {                                                         \
+    dm_count_launch();                                         \
     cudaError_t e__ = cudaGetLastError();                      \
     if (e__ != cudaSuccess) { dm_set_error(cudaGetErrorString(e__)); return DM_ERR_CUDA; } \
   } while (0)
 
 void dm_set_error(const char* msg);
+void dm_count_launch();
 
 #define DM_NUM_SMS 148
 

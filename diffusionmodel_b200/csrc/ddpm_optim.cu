@@ -13,6 +13,9 @@ static thread_local char g_err[512] = "";
 void dm_set_error(const char* msg) { strncpy(g_err, msg, sizeof(g_err) - 1); g_err[sizeof(g_err) - 1] = 0; }
 extern "C" const char* dm_last_error(void) { return g_err; }
 extern "C" int dm_version(void) { return 100; }
+static long long g_launches = 0;
+void dm_count_launch() { ++g_launches; }
+extern "C" long long dm_launch_count(void) { return g_launches; }
 
 #define ST ((cudaStream_t)stream)
 
@@ -26,7 +29,7 @@ inline int grid_for(long long total, int threads = 256) {
 
 // ------------------------------------------------------------------------------------------ packing
 struct PackArgs {
-  long long tap_off[16];
+  long long tap_off[64];
   int rows, cols, ntaps, c_split, cols_k, tap_major_rows;
   long long s_row, s_col, row_len;
 };
@@ -220,13 +223,13 @@ static void fill_pack(PackArgs& A, int rows, int cols, int ntaps, const long lon
   memset(&A, 0, sizeof A);
   A.rows = rows; A.cols = cols; A.ntaps = ntaps; A.s_row = s_row; A.s_col = s_col; A.c_split = c_split;
   A.cols_k = cols_k; A.row_len = row_len; A.tap_major_rows = tap_major_rows;
-  for (int i = 0; i < ntaps && i < 16; ++i) A.tap_off[i] = tap_off[i];
+  for (int i = 0; i < ntaps && i < 64; ++i) A.tap_off[i] = tap_off[i];
 }
 
 extern "C" int dm_pack_weight(const float* w, void* out, int rows, int cols, int ntaps, const long long* tap_off_host,
                               long long s_row, long long s_col, int c_split, int cols_k, long long row_len,
                               int tap_major_rows, void* stream) {
-  if (ntaps < 1 || ntaps > 16) { dm_set_error("dm_pack_weight: 1..16 taps"); return DM_ERR_ARG; }
+  if (ntaps < 1 || ntaps > 64) { dm_set_error("dm_pack_weight: 1..64 taps"); return DM_ERR_ARG; }
   PackArgs A; fill_pack(A, rows, cols, ntaps, tap_off_host, s_row, s_col, c_split, cols_k, row_len, tap_major_rows);
   const long long total = (tap_major_rows ? (long long)ntaps * rows : (long long)rows) * row_len;
   pack_weight_kernel<<<grid_for(total), 256, 0, ST>>>(w, (bf16*)out, A, total);
@@ -236,7 +239,7 @@ extern "C" int dm_pack_weight(const float* w, void* out, int rows, int cols, int
 extern "C" int dm_unpack_wgrad(const float* dwp, float* grad, int rows, int cols, int ntaps, const long long* tap_off_host,
                                long long s_row, long long s_col, int c_split, int cols_k, long long row_len,
                                int tap_major_rows, void* stream) {
-  if (ntaps < 1 || ntaps > 16) { dm_set_error("dm_unpack_wgrad: 1..16 taps"); return DM_ERR_ARG; }
+  if (ntaps < 1 || ntaps > 64) { dm_set_error("dm_unpack_wgrad: 1..64 taps"); return DM_ERR_ARG; }
   PackArgs A; fill_pack(A, rows, cols, ntaps, tap_off_host, s_row, s_col, c_split, cols_k, row_len, tap_major_rows);
   const long long total = (long long)rows * cols * ntaps;
   unpack_wgrad_kernel<<<grid_for(total), 256, 0, ST>>>(dwp, grad, A, total);

@@ -83,7 +83,7 @@ class WeightPack:
 
 
 def _taps(offs):
-    arr = (ctypes.c_longlong * 16)(*offs, *([0] * (16 - len(offs))))
+    arr = (ctypes.c_longlong * 64)(*offs, *([0] * (64 - len(offs))))
     return arr
 
 
@@ -755,3 +755,58 @@ def cfg_reverse_step(eps_nhwc_f32, x, z, guide_w, a, b, s, want_next=True):
     call("dm_cfg_reverse_step", _p(eps_nhwc_f32), eps_nhwc_f32.stride(2), _p(x), _p(z), _p(x_out), _p(xt),
          xt.stride(2) if xt is not None else 8, float(guide_w), float(a), float(b), float(s), n, c, h, w, _stream())
     return x_out, xt
+
+
+# --------------------------------------------------------------------------------------- profiling hook
+class _Profile:
+    """CUDA-event timing of every C-ABI call on the launching stream (bench.py's roofline numbers)."""
+
+    def __init__(self):
+        self.records = []
+
+    @staticmethod
+    def _flops(name, a):
+        if name in ("dm_conv2d_fwd", "dm_conv2d_wgrad"):
+            if name == "dm_conv2d_fwd":
+                c0, c1, n, hin, win, cout, kh, kw, stride, pad = a[1], a[4], a[13], a[14], a[15], a[16], a[17], a[18], a[19], a[20]
+            else:
+                c0, c1, n, hin, win, cout, kh, kw, stride, pad = a[1], a[4], a[9], a[10], a[11], a[12], a[13], a[14], a[15], a[16]
+            ho, wo = (hin + 2 * pad - kh) // stride + 1, (win + 2 * pad - kw) // stride + 1
+            return 2.0 * n * ho * wo * cout * (c0 + c1) * kh * kw
+        if name == "dm_conv2d_s2_dgrad":
+            return 2.0 * a[7] * a[8] * a[9] * a[1] * a[5] * 16
+        if name == "dm_convt_fwd":
+            return 2.0 * a[7] * a[8] * a[9] * a[1] * a[10] * a[11] * a[11]
+        return 0.0
+
+    def call(self, name, *args):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = _lib.call(name, *args)
+        e1.record()
+        self.records.append((name, self._flops(name, args), e0, e1))
+        return rc
+
+    def summary(self):
+        groups = {"dm_conv2d_fwd": "conv_gemm", "dm_conv2d_s2_dgrad": "conv_gemm", "dm_convt_fwd": "conv_gemm",
+                  "dm_conv2d_wgrad": "wgrad_gemm"}
+        out = {}
+        for name, fl, e0, e1 in self.records:
+            g = groups.get(name, name)
+            d = out.setdefault(g, {"ms": 0.0, "flops": 0.0, "n": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["n"] += 1
+        return out
+
+
+def enable_profile():
+    global call
+    prof = _Profile()
+    call = prof.call
+    return prof
+
+
+def disable_profile():
+    global call
+    call = _lib.call

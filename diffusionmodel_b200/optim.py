@@ -12,7 +12,6 @@ import ctypes
 import torch
 
 from . import ops
-from ._lib import call
 
 
 def _p(t):
@@ -67,7 +66,7 @@ class FusedAdamW(torch.optim.Optimizer):
         """Global L2 norm of the (flat) gradient as a device scalar."""
         self._attach_grads()
         self._gnorm_sq.zero_()
-        call("dm_sumsq", _p(self.flat_grad), self._n, _p(self._gnorm_sq), ops._stream())
+        ops.call("dm_sumsq", _p(self.flat_grad), self._n, _p(self._gnorm_sq), ops._stream())
         return self._gnorm_sq.sqrt()
 
     @torch.no_grad()
@@ -80,9 +79,9 @@ class FusedAdamW(torch.optim.Optimizer):
         gn = None
         if self.max_grad_norm > 0:
             self._gnorm_sq.zero_()
-            call("dm_sumsq", _p(self.flat_grad), self._n, _p(self._gnorm_sq), st)
+            ops.call("dm_sumsq", _p(self.flat_grad), self._n, _p(self._gnorm_sq), st)
             gn = _p(self._gnorm_sq)
-        call("dm_adamw", _p(self.flat_param), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq), self._n,
+        ops.call("dm_adamw", _p(self.flat_param), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq), self._n,
              float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
              1.0 - b1 ** self._step, 1.0 - b2 ** self._step, gn, self.max_grad_norm, st)
         ops.bump_weights_epoch()
