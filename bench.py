@@ -249,6 +249,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     ops.disable_profile()
     agg = prof.summary()
+    if rank == 0 and os.environ.get("DM_BENCH_BREAKDOWN"):
+        with open(os.environ["DM_BENCH_BREAKDOWN"], "w") as f:
+            json.dump({k: v for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}, f, indent=1)
     pk, src = peaks()
     line = None
     if rank == 0:

@@ -57,36 +57,61 @@ def test_against_golden(dev, tag):
     loss = ddpm(x, c, attn if variant == "rdd" else None, randoms=(ts, noise, ctx))
     assert abs(float(loss) - float(g["loss_eval"])) < BAR * abs(float(g["loss_eval"]))
 
-    # ---- train mode vs the precision-matched oracle (bf16 conv/linear operands, fp32 elsewhere)
+    # ---- eval-mode gradients (no batch-statistic amplification) vs the fp32 oracle: every parameter
+    ddpm.zero_grad()
+    loss.backward()
+    torch.cuda.synchronize()
+
+    def oracle_grads(training, **kw):
+        sd_o = {k: v.clone() for k, v in sd.items()}
+        for k, v in sd_o.items():
+            if v.is_floating_point() and k.startswith("nn_model.") and "running" not in k:
+                v.requires_grad_(True)
+        lo = P.ddpm_loss(sd_o, sched, inp["x"], inp["c"], inp["attn_mask"], inp["ts"], inp["noise"], inp["ctx_mask"],
+                         variant=variant, n_T=n_T, training=training,
+                         attn_map=inp["attn_mask"] if (variant == "rdd" and use_map) else None, **kw)
+        lo.backward()
+        return float(lo), {k: v.grad for k, v in sd_o.items() if v.requires_grad and v.grad is not None}
+
+    def agg_err(mine, ref):
+        num = den = 0.0
+        worst = (0.0, "")
+        for k, gr in mine.items():
+            go = ref.get(k)
+            if go is None:
+                continue
+            num += float((gr.double() - go.double()).pow(2).sum()); den += float(go.double().pow(2).sum())
+        for k, gr in mine.items():
+            go = ref.get(k)
+            if go is not None and float(go.double().pow(2).sum()) > 1e-4 * den:      # tensors that carry real signal
+                r = P.rel_l2(gr, go)
+                if r > worst[0]:
+                    worst = (r, k)
+        return (num / den) ** 0.5, worst
+
+    _, g_eval = oracle_grads(False)
+    e_g, worst = agg_err(grads_of(ddpm), g_eval)
+    print(f"{tag}: eval-mode grad rel-L2 vs fp32 oracle = {e_g:.3e}; worst significant tensor {worst[1]} {worst[0]:.3e}")
+    assert e_g < BAR and worst[0] < 3e-2
+
+    # ---- train mode.  Batch-statistic BatchNorm amplifies bf16 rounding chaotically (SURVEY.md App. D:
+    # PyTorch's own autocast(bf16) run of the reference is ~1e-1 from fp32), so the end-to-end train-mode
+    # criterion is: loss within 2% of the fp32 reference, and our gradient no farther from the fp32
+    # reference than 1.5x the distance of the reference under torch.autocast(bfloat16).
     ddpm.train()
     ddpm.zero_grad()
     loss = ddpm(x, c, attn if variant == "rdd" else None, randoms=(ts, noise, ctx))
     loss.backward()
     torch.cuda.synchronize()
-    sd_o = {k: v.clone() for k, v in sd.items()}
-    for k, v in sd_o.items():
-        if v.is_floating_point() and k.startswith("nn_model.") and "running" not in k:
-            v.requires_grad_(True)
-    loss_o = P.ddpm_loss(sd_o, sched, inp["x"], inp["c"], inp["attn_mask"], inp["ts"], inp["noise"], inp["ctx_mask"],
-                         variant=variant, n_T=n_T, training=True, operand_dtype=torch.bfloat16,
-                         attn_map=inp["attn_mask"] if (variant == "rdd" and use_map) else None)
-    loss_o.backward()
-    print(f"{tag}: train loss ours {float(loss):.6f} matched-oracle {float(loss_o):.6f} fp32-ref {float(g['loss_train']):.6f}")
-    assert abs(float(loss) - float(loss_o)) < 2e-2 * abs(float(loss_o))
-    mine = grads_of(ddpm)
-    num = den = 0.0
-    worst = (0.0, "")
-    for k, gr in mine.items():
-        go = sd_o[k].grad
-        if go is None:
-            continue
-        num += float((gr.double() - go.double()).pow(2).sum()); den += float(go.double().pow(2).sum())
-        r = P.rel_l2(gr, go) if float(go.norm()) > 1e-6 else 0.0
-        if r > worst[0]:
-            worst = (r, k)
-    e_g = (num / den) ** 0.5
-    print(f"{tag}: train grad rel-L2 vs matched oracle = {e_g:.3e}; worst tensor {worst[1]} {worst[0]:.3e}")
-    assert e_g < 5e-2
+    l_ref, g_ref = oracle_grads(True)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        l_ac, g_ac = oracle_grads(True)
+    e_ours, _ = agg_err(grads_of(ddpm), g_ref)
+    e_ac, _ = agg_err({k: v.float() for k, v in g_ac.items()}, g_ref)
+    print(f"{tag}: train loss ours {float(loss):.6f} fp32-ref {l_ref:.6f} autocast-bf16 {l_ac:.6f}")
+    print(f"{tag}: train grad rel-L2 vs fp32 reference: ours {e_ours:.3e}, torch autocast(bf16) {e_ac:.3e}")
+    assert abs(float(loss) - l_ref) < 2e-2 * abs(l_ref)
+    assert e_ours < 1.5 * e_ac + 1e-2
     # BatchNorm running buffers after one train step
     bn_names = [str(s) for s in g["bn_names"]]
     got = torch.cat([ddpm.state_dict()[k].flatten().cpu() for k in bn_names])
