@@ -199,6 +199,7 @@ def run_ours(args):
     def step_resident():
         for x, c, m in resident:
             micro(x, c, m)
+        opt.flush()
         parallel.allreduce_mean_(opt.flat_grad)
         opt.step()
         opt.zero_grad()
@@ -208,6 +209,7 @@ def run_ours(args):
         for hx, hc, hm in host:
             x, c, m = hx.to(dev, non_blocking=True), hc.to(dev, non_blocking=True), hm.to(dev, non_blocking=True)
             tot += micro(x, c, m).item()                  # device->host read of the loss, as new_scripy.py:789
+        opt.flush()
         parallel.allreduce_mean_(opt.flat_grad)
         opt.step()
         opt.zero_grad()
@@ -252,6 +254,15 @@ def run_ours(args):
     if rank == 0 and os.environ.get("DM_BENCH_BREAKDOWN"):
         with open(os.environ["DM_BENCH_BREAKDOWN"], "w") as f:
             json.dump({k: v for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}, f, indent=1)
+    # host-side enqueue cost of one step (Python + autograd + ctypes), kernels stubbed out
+    real_call = ops.call
+    ops.call = lambda *a, **k: 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step_resident()
+    host_ms = (time.perf_counter() - t0) * 1e3
+    ops.call = real_call
+    torch.cuda.synchronize()
     pk, src = peaks()
     line = None
     if rank == 0:
@@ -273,7 +284,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * accum,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -53,19 +53,20 @@ _D = ctypes.c_double
 # argument signatures, in header order (p = pointer, i = int, l = long long, f = float, d = double)
 _SIGS = {
     "dm_conv2d_fwd": "pii pii p p pii pi iiiiiiii p",
-    "dm_conv2d_fwd_mtiles": "iii",
+    "dm_conv2d_fwd_stat_rows": "iiii",
     "dm_conv2d_s2_dgrad": "pii p pii iii p",
     "dm_convt_fwd": "pii p p pi iiiii p",
     "dm_conv2d_wgrad": "pii pii pi p iiiiiiii p",
     "dm_pack_weight": "p p iii p ll iil i p",
-    "dm_unpack_wgrad": "p p iii p ll iil i p",
+    "dm_unpack_wgrad": "p p iii p ll iil i i p",
     "dm_nchw_to_nhwc": "p pi i iiii p",
     "dm_cast_nhwc": "pi pi l i p",
     "dm_nhwc_to_nchw": "pii p iiii p",
     "dm_space_to_depth": "pi pi iiiii p",
     "dm_bn_finalize": "p iii d pp pp ff p",
     "dm_bn_act_fwd": "pi pppp pi l ii p",
-    "dm_bn_act_bwd": "pi pi pppp pi pp p l iii p",
+    "dm_bn_act_bwd": "pi pi pppp pi pp p p l iii p",
+    "dm_bn_act_bwd_scratch": "li",
     "dm_gn_act_fwd": "pi pp pi pp p iiii f i p",
     "dm_gn_act_bwd": "pi pi pppp pi pp p iiii i p",
     "dm_pool_nhw": "pi p iii f p",
@@ -93,6 +94,7 @@ _SIGS = {
     "dm_sumsq": "p l p p",
     "dm_adamw": "pppp l fffffff p f p",
 }
+_RET_LL = {"dm_bn_act_bwd_scratch"}          # size queries return long long, not a status
 _CT = {"p": _P, "i": _I, "l": _L, "f": _F, "d": _D}
 _bound = {}
 
@@ -102,7 +104,7 @@ def fn(name):
     if f is None:
         f = getattr(lib(), name)
         f.argtypes = [_CT[ch] for ch in _SIGS[name].replace(" ", "")]
-        f.restype = _I
+        f.restype = _L if name in _RET_LL else _I
         _bound[name] = f
     return f
 

@@ -34,7 +34,8 @@ constexpr int kUmmaK = 16;
 constexpr int kAStage = kBlockM * kBlockK * 2;       // 16 KB
 constexpr int kThreads = 192;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kAuxBytes = 4096 + 512;                // stats staging + barriers
+constexpr int kAuxBytes = 512;                       // barriers + TMEM slot (the BN-statistics slab follows, sized per launch)
+constexpr int kMaxStatBytes = 48 * 1024;
 constexpr int kMaxStages = 8;
 
 struct TapInfo { int8_t dy, dx, map, pad_; };
@@ -48,6 +49,7 @@ struct ConvParams {
   int tiles_w, tiles_h, tiles_b, m_tiles, n_tiles, block_n;
   int N, H, W;
   int stages, b_stage_bytes;
+  int stat_c;                   // channels covered by the statistics slab (n_tiles * block_n), 0 = no statistics
   void* out;
   int out_f32;
   long long sN, sH, sW;
@@ -75,6 +77,26 @@ struct WgradParams {
   unsigned idesc;
   unsigned long long desc_hi_a, desc_hi_b;
   unsigned lbo_a, lbo_b;
+};
+
+// kernel C (wgrad2): the transposed product.  M side = im2col(X): four [64 px][64 ch] boxes, each its own
+// (filter tap, 64-channel chunk) -> two M=128 accumulators per CTA that share every dY (N side) tile, so
+// a K-step moves (4 + nb) x 8 KB for 2 x 128 x N x 64 MACs.  Layers whose Cout is not a multiple of 128
+// (192, 48, 3) waste no MMA rows this way.
+struct Wgrad2Params {
+  CUtensorMap tmX[4];
+  CUtensorMap tmDY;
+  TapInfo taps[16];
+  int num_taps, chunks0, chunks1, dual;
+  int log_bw, log_bh, log_bn;       // 64-pixel patch
+  int tiles_w, tiles_h, tiles_b, patches;
+  int m_tiles, n_tiles, block_n, nb, splits, patches_per_split, total_boxes;
+  int Cout, cin_k, C0, C1;
+  int stages;
+  float* dwp;
+  unsigned idesc;
+  unsigned long long desc_hi;
+  unsigned lbo;
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -183,12 +205,12 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, int stages, int stage_
   uint32_t b = (smem_u32(raw) + 1023u) & ~1023u;
   L.base = b;
   uint32_t aux = b + (uint32_t)stages * (uint32_t)stage_bytes;
-  L.stat = aux;                       // 4096 B: [2 accum stages][4 warps][2][64]... see epilogue
-  L.full = aux + 4096;
+  L.full = aux;
   L.empty = L.full + 8 * kMaxStages;
   L.tfull = L.empty + 8 * kMaxStages;
   L.tempty = L.tfull + 16;
   L.tmem_slot = L.tempty + 16;
+  L.stat = aux + kAuxBytes;           // [2][stat_c] floats: per-CTA sum / sum of squares of the outputs
   return L;
 }
 
@@ -210,10 +232,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB);
   }
-  {
-    float* slab0 = reinterpret_cast<float*>(smem_raw + (L.stat - smem_u32(smem_raw)));
-    for (int i = threadIdx.x; i < 1024; i += kThreads) slab0[i] = 0.0f;
-  }
+  float* const slab = reinterpret_cast<float*>(smem_raw + (L.stat - smem_u32(smem_raw)));
+  for (int i = threadIdx.x; i < 2 * p.stat_c; i += kThreads) slab[i] = 0.0f;
   if (warp == 1) tc_alloc(L.tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -331,28 +351,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) { const float x = valid ? v[j] : 0.0f; s1[j] = x; s2[j] = x * x; }
           const float a = warp_colsum32(s1, lane), b2 = warp_colsum32(s2, lane);
-          // the four warps accumulate through shared-memory atomics into a [2][block_n] slab
-          float* slab = reinterpret_cast<float*>(smem_raw + (L.stat - smem_u32(smem_raw))) + as * 512;
-          atomicAdd(slab + cc + lane, a);
-          atomicAdd(slab + 256 + cc + lane, b2);
+          // accumulated over all of this CTA's tiles in shared memory (atomics: four warps share a column)
+          atomicAdd(slab + n_base + cc + lane, a);
+          atomicAdd(slab + p.stat_c + n_base + cc + lane, b2);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(L.tempty + 8 * as);
-      if (p.stats != nullptr) {
-        // all four epilogue warps have added their partials: flush the slab and re-zero it
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        float* slab = reinterpret_cast<float*>(smem_raw + (L.stat - smem_u32(smem_raw))) + as * 512;
-        const int e = threadIdx.x - 64;     // 0..127
-        float* g = p.stats + (long long)mt * 2 * p.stats_ld;
-        for (int c = e; c < p.block_n; c += 128) {
-          if (co0 + c < p.Cout) {
-            g[co0 + c] = slab[c];
-            g[p.stats_ld + co0 + c] = slab[256 + c];
-          }
-          slab[c] = 0.0f; slab[256 + c] = 0.0f;   // re-armed for tile it+2; ordered by the next tile's bar.sync
-        }
+    }
+    if (p.stats != nullptr) {
+      // one partial row per CTA: [blockIdx.x][2][stats_ld]
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = threadIdx.x - 64;     // 0..127
+      float* g = p.stats + (long long)blockIdx.x * 2 * p.stats_ld;
+      for (int c = e; c < p.Cout; c += 128) {
+        g[c] = slab[c];
+        g[p.stats_ld + c] = slab[p.stat_c + c];
       }
     }
   }
@@ -480,6 +495,143 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
   if (warp == 1) { __syncwarp(); tc_fence_after(); tc_dealloc(tmem_base, 512); }
 }
 
+// ------------------------------------------------------------------------------------------ kernel C
+__global__ void __launch_bounds__(kThreads, 1) wgrad2_gemm_kernel(const __grid_constant__ Wgrad2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_bytes = 4 * 8192, b_bytes = p.nb * 8192;
+  const int stage_bytes = a_bytes + b_bytes;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + (uint32_t)p.stages * (uint32_t)stage_bytes;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages, bar_tfull = bar_empty + 8 * kMaxStages,
+                 bar_tempty = bar_tfull + 8, tmem_slot = bar_tempty + 8;
+  const int chunks = p.chunks0 + p.chunks1;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_tfull, 1); mbar_init(bar_tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmX[0]); tma_prefetch_desc(&p.tmDY); }
+  if (warp == 1) tc_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // tile -> (split, n tile, m tile); m fastest: CTAs running together sweep the same pixel range, so
+  // the dY tile and the (overlapping) shifted X boxes are shared through L2
+  auto decode = [&](int tile, int& mt, int& nt, int& sp) {
+    mt = tile % p.m_tiles; tile /= p.m_tiles;
+    nt = tile % p.n_tiles; sp = tile / p.n_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt, nt, sp; decode(tile, mt, nt, sp);
+        const int nA = min(4, p.total_boxes - mt * 4);
+        const int p0 = sp * p.patches_per_split;
+        const int p1 = min(p.patches, p0 + p.patches_per_split);
+        int bmap[4], bc0[4], bdx[4], bdy[4];
+        for (int j = 0; j < 4; ++j) {
+          const int box = min(mt * 4 + j, p.total_boxes - 1);
+          const int tap = box / chunks, ch = box - tap * chunks;
+          const TapInfo t = p.taps[tap];
+          bmap[j] = t.map; bc0[j] = ch * 64; bdx[j] = t.dx; bdy[j] = t.dy;
+          if (p.dual && ch >= p.chunks0) { bmap[j] = 1; bc0[j] = (ch - p.chunks0) * 64; }
+        }
+        for (int pp = p0; pp < p1; ++pp) {
+          const int tw = pp % p.tiles_w, th = (pp / p.tiles_w) % p.tiles_h, tb = pp / (p.tiles_w * p.tiles_h);
+          const int w0 = tw << p.log_bw, h0 = th << p.log_bh, n0 = tb << p.log_bn;
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
+          const uint32_t fb = bar_full + 8 * stage;
+          mbar_expect_tx(fb, (nA + p.nb) * 8192);
+          for (int j = 0; j < p.nb; ++j) tma_load_4d(sb + j * 8192, &p.tmDY, nt * p.block_n + j * 64, w0, h0, n0, fb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nA) tma_load_4d(sa + j * 8192, &p.tmX[bmap[j]], bc0[j], w0 + bdx[j], h0 + bdy[j], n0, fb);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        int mt, nt, sp; decode(tile, mt, nt, sp);
+        const int nA = min(4, p.total_boxes - mt * 4);
+        const int nh = nA > 2 ? 2 : 1;
+        const int p0 = sp * p.patches_per_split;
+        const int p1 = min(p.patches, p0 + p.patches_per_split);
+        mbar_wait(bar_tempty, (uint32_t)((it & 1) ^ 1));
+        tc_fence_after();
+        for (int pp = p0; pp < p1; ++pp) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
+          const uint64_t bdesc = p.desc_hi | ((uint64_t)p.lbo << 16) | (uint64_t)((sb & 0x3FFFFu) >> 4);
+          for (int h = 0; h < nh; ++h) {
+            const uint32_t sah = sa + h * 16384;
+            const uint64_t adesc = p.desc_hi | ((uint64_t)p.lbo << 16) | (uint64_t)((sah & 0x3FFFFu) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)      // 16 pixels per MMA = two 8-row swizzle groups = 2048 B
+              tc_mma_bf16(tmem_base + (uint32_t)(h * 256), adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc,
+                          (pp != p0) | (k != 0));
+          }
+          tc_commit(bar_empty + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_tfull);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int mt, nt, sp; decode(tile, mt, nt, sp);
+      const int nA = min(4, p.total_boxes - mt * 4);
+      const int nh = nA > 2 ? 2 : 1;
+      mbar_wait(bar_tfull, (uint32_t)(it & 1));
+      tc_fence_after();
+      for (int h = 0; h < nh; ++h) {
+        const int box = mt * 4 + 2 * h + (r >> 6);
+        const int tap = box / chunks, ch = box - tap * chunks;
+        const int cil = r & 63;
+        const bool first = !(p.dual && ch >= p.chunks0);
+        const int creal = first ? ch * 64 + cil : (ch - p.chunks0) * 64 + cil;
+        const bool live = box < p.total_boxes && creal < (first ? p.C0 : p.C1);
+        float* dst = p.dwp + (long long)tap * p.cin_k + ch * 64 + cil;
+        const long long co_stride = (long long)p.num_taps * p.cin_k;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256);
+        for (int cc = 0; cc < p.block_n; cc += 32) {
+          float v[32];
+          tc_ld32(t_row + (uint32_t)cc, v);
+          if (live) {
+            const int co0 = nt * p.block_n + cc;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (co0 + j < p.Cout)
+                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)(co0 + j) * co_stride), "f"(v[j]) : "memory");
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tc_dealloc(tmem_base, 512); }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 long long g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -572,22 +724,26 @@ struct ConvGeom {
 extern "C" void dm_debug_set(int key, long long value) { if (key >= 0 && key < 8) g_debug[key] = value; }
 
 // Generic launcher for kernel A.  All geometry is resolved by the typed entry points below.
+static int conv_grid(int tiles) { return tiles < DM_NUM_SMS ? tiles : DM_NUM_SMS; }
+
 static int launch_conv(ConvParams& P, cudaStream_t st) {
   int stage_bytes = kAStage + P.b_stage_bytes;
-  int stages = (kSmemBudget - 1024 - kAuxBytes) / stage_bytes;
+  P.stat_c = P.stats ? (P.n_tiles * P.block_n + 31) / 32 * 32 : 0;   // whole 32-lane chunks
+  const int stat_bytes = 8 * P.stat_c;
+  if (stat_bytes > kMaxStatBytes) { dm_set_error("conv_gemm: too many output channels for fused BatchNorm statistics"); return DM_ERR_ARG; }
+  int stages = (kSmemBudget - 1024 - kAuxBytes - stat_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (g_debug[0] > 0 && g_debug[0] < stages) stages = (int)g_debug[0];
   if (stages < 2) { dm_set_error("conv_gemm: not enough shared memory for 2 stages"); return DM_ERR_ARG; }
   P.stages = stages;
-  size_t smem = 1024 + (size_t)stages * stage_bytes + kAuxBytes;
+  size_t smem = 1024 + (size_t)stages * stage_bytes + kAuxBytes + stat_bytes;
   if (!g_attr_a) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
     g_attr_a = true;
   }
-  int tiles = P.m_tiles * P.n_tiles;
-  int grid = tiles < DM_NUM_SMS ? tiles : DM_NUM_SMS;
-  if (g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
+  int grid = conv_grid(P.m_tiles * P.n_tiles);
+  if (!P.stats && g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
   conv_gemm_kernel<<<grid, kThreads, smem, st>>>(P);
   DM_CHECK_LAUNCH();
   return DM_OK;
@@ -610,7 +766,7 @@ static void fill_common(ConvParams& P, int N, int H, int W, int Cout_rows, int b
 // ---------------------------------------------------------------------------------------------------
 // dm_conv2d_fwd: y[N,Ho,Wo,Cout] = conv(x0 (++ x1 on channels), Wp) + bias    (bf16 NHWC in, bf16/fp32 out)
 // stride 1: any kh,kw,pad.  stride 2: even Hin,Win (parity views), single source.
-// stats (optional): per-M-tile partial sums [m_tiles][2][stats_ld] of y and y^2 for train-mode BatchNorm.
+// stats (optional): per-CTA partial sums [dm_conv2d_fwd_stat_rows()][2][stats_ld] of y and y^2 for train-mode BatchNorm.
 extern "C" int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, int C1, int ld1, const void* wpk,
                              const float* bias, void* y, int ldy, int y_f32, float* stats, int stats_ld, int N, int Hin,
                              int Win, int Cout, int kh, int kw, int stride, int pad, void* stream) {
@@ -665,9 +821,11 @@ extern "C" int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, in
   return launch_conv(P, (cudaStream_t)stream);
 }
 
-extern "C" int dm_conv2d_fwd_mtiles(int N, int Ho, int Wo) {
+// rows of the statistics buffer dm_conv2d_fwd writes: one per CTA of the persistent grid
+extern "C" int dm_conv2d_fwd_stat_rows(int N, int Ho, int Wo, int Cout) {
   int a, b, c; pick_patch(Wo, Ho, kBlockM, a, b, c);
-  return dm::cdiv(Wo, 1 << a) * dm::cdiv(Ho, 1 << b) * dm::cdiv(N, 1 << c);
+  const int m_tiles = dm::cdiv(Wo, 1 << a) * dm::cdiv(Ho, 1 << b) * dm::cdiv(N, 1 << c);
+  return conv_grid(m_tiles * dm::cdiv(Cout, pick_block_n(Cout)));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -737,8 +895,31 @@ extern "C" int dm_convt_fwd(const void* x, int Cin, int ldx, const void* wpk, co
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Split-K choice for the weight-gradient GEMMs: `base` output tiles, `patches` 64-pixel K-steps.
+// Static round-robin tile schedule => time ~ waves * (K-steps per split + per-tile overhead); pick the
+// split count that minimises it (i.e. fills the last wave) instead of a fixed "two waves" rule.
+static int pick_splits(int base, int patches, int tile_overhead_steps) {
+  int max_splits = patches / 8; if (max_splits < 1) max_splits = 1;
+  if (max_splits > 1024) max_splits = 1024;
+  int best = 1; double best_cost = 1e30;
+  for (int s = 1; s <= max_splits; ++s) {
+    const int pps = dm::cdiv(patches, s);
+    const int se = dm::cdiv(patches, pps);
+    if (se != s) continue;
+    const long long tiles = (long long)base * se;
+    const long long waves = (tiles + DM_NUM_SMS - 1) / DM_NUM_SMS;
+    const double cost = (double)waves * (pps + tile_overhead_steps);
+    if (cost < best_cost * 0.999) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+bool g_attr_c = false;
+
 // dm_conv2d_wgrad: dWp[Cout][taps][Cin_k] (fp32, accumulated with red.add) += dY^T * im2col(X).
 // Same geometry arguments as dm_conv2d_fwd; dy is [N,Ho,Wo,Cout] bf16 with pitch lddy.
+// Two kernels: wgrad_gemm_kernel (M = Cout tiles of 128, for Cout a multiple of 128) and
+// wgrad2_gemm_kernel (M = im2col boxes, two accumulators per CTA; everything else).
 extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, int C1, int ld1, const void* dy, int lddy,
                                float* dwp, int N, int Hin, int Win, int Cout, int kh, int kw, int stride, int pad,
                                void* stream) {
@@ -747,50 +928,25 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
   if (stride == 2 && (x1 != nullptr || (Hin & 1) || (Win & 1))) { dm_set_error("dm_conv2d_wgrad: stride 2 needs one source, even H/W"); return DM_ERR_ARG; }
   if ((ld0 & 7) || (x1 && (ld1 & 7)) || (lddy & 7)) { dm_set_error("dm_conv2d_wgrad: channel pitch must be a multiple of 8"); return DM_ERR_ARG; }
   const int Ho = (Hin + 2 * pad - kh) / stride + 1, Wo = (Win + 2 * pad - kw) / stride + 1;
-  WgradParams P;
-  memset(&P, 0, sizeof P);
-  pick_patch(Wo, Ho, 64, P.log_bw, P.log_bh, P.log_bn);
-  const int bw = 1 << P.log_bw, bh = 1 << P.log_bh, bn = 1 << P.log_bn;
-  P.tiles_w = dm::cdiv(Wo, bw); P.tiles_h = dm::cdiv(Ho, bh); P.tiles_b = dm::cdiv(N, bn);
-  P.patches = P.tiles_w * P.tiles_h * P.tiles_b;
-  P.chunks0 = dm::cdiv(C0, 64);
-  P.chunks1 = x1 ? dm::cdiv(C1, 64) : 0;
-  P.dual = x1 ? 1 : 0;
-  P.num_taps = kh * kw;
-  const int chunks = P.chunks0 + P.chunks1;
-  P.cin_k = chunks * 64;
-  P.block_n = chunks >= 4 ? 256 : chunks * 64;
-  P.ci_tiles = dm::cdiv(P.cin_k, P.block_n);
-  P.co_tiles = dm::cdiv(Cout, 128);
-  P.Cout = Cout;
-  const int base_tiles = P.co_tiles * P.num_taps * P.ci_tiles;
-  // split-K over pixel patches: aim for >= 2 waves of CTAs, keep >= 8 patches per split
-  int splits = 1;
-  if (base_tiles < 2 * DM_NUM_SMS) {
-    splits = dm::cdiv(2 * DM_NUM_SMS, base_tiles);
-    int max_splits = P.patches / 8; if (max_splits < 1) max_splits = 1;
-    if (splits > max_splits) splits = max_splits;
-  }
-  if (g_debug[2] > 0) splits = (int)g_debug[2];
-  P.patches_per_split = dm::cdiv(P.patches, splits);
-  P.splits = dm::cdiv(P.patches, P.patches_per_split);
-  P.b_stage_bytes = (P.block_n / 64) * 8192;
-  P.dwp = dwp;
-  P.idesc = make_idesc(P.block_n, true, true);
-  P.desc_hi_a = kDescHiMN; P.desc_hi_b = kDescHiMN;
-  P.lbo_a = 8192 >> 4; P.lbo_b = 8192 >> 4;
-  if (g_debug[3] == 1) {   // probe: swap the roles of LBO / SBO
-    P.desc_hi_a = (512ull << 32) | (1ull << 46) | (2ull << 61); P.desc_hi_b = P.desc_hi_a;
-    P.lbo_a = 64; P.lbo_b = 64;
-  }
+  // ---- geometry shared by both kernels: 64-pixel patches, filter taps, activation maps
+  int log_bw, log_bh, log_bn;
+  pick_patch(Wo, Ho, 64, log_bw, log_bh, log_bn);
+  const int bw = 1 << log_bw, bh = 1 << log_bh, bn = 1 << log_bn;
+  const int tiles_w = dm::cdiv(Wo, bw), tiles_h = dm::cdiv(Ho, bh), tiles_b = dm::cdiv(N, bn);
+  const int patches = tiles_w * tiles_h * tiles_b;
+  const int chunks0 = dm::cdiv(C0, 64), chunks1 = x1 ? dm::cdiv(C1, 64) : 0;
+  const int chunks = chunks0 + chunks1;
+  const int num_taps = kh * kw;
+  TapInfo taps[16];
+  CUtensorMap tmX[4], tmDY;
   int rc;
   if (stride == 1) {
     for (int r = 0; r < kh; ++r)
-      for (int s = 0; s < kw; ++s) { TapInfo t = {(int8_t)(r - pad), (int8_t)(s - pad), 0, 0}; P.taps[r * kw + s] = t; }
-    rc = make_act_map(&P.tmX[0], x0, C0, Win, Hin, N, ld0, (long long)Win * ld0, (long long)Hin * Win * ld0, bw, bh, bn);
+      for (int s = 0; s < kw; ++s) { TapInfo t = {(int8_t)(r - pad), (int8_t)(s - pad), 0, 0}; taps[r * kw + s] = t; }
+    rc = make_act_map(&tmX[0], x0, C0, Win, Hin, N, ld0, (long long)Win * ld0, (long long)Hin * Win * ld0, bw, bh, bn);
     if (rc) return rc;
     if (x1) {
-      rc = make_act_map(&P.tmX[1], x1, C1, Win, Hin, N, ld1, (long long)Win * ld1, (long long)Hin * Win * ld1, bw, bh, bn);
+      rc = make_act_map(&tmX[1], x1, C1, Win, Hin, N, ld1, (long long)Win * ld1, (long long)Hin * Win * ld1, bw, bh, bn);
       if (rc) return rc;
     }
   } else {
@@ -799,18 +955,84 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
         const int a = r - pad, b = s - pad;
         const int pa = ((a % 2) + 2) % 2, pb = ((b % 2) + 2) % 2;
         TapInfo t = {(int8_t)((a - pa) / 2), (int8_t)((b - pb) / 2), (int8_t)(pa * 2 + pb), 0};
-        P.taps[r * kw + s] = t;
+        taps[r * kw + s] = t;
       }
     for (int pa = 0; pa < 2; ++pa)
       for (int pb = 0; pb < 2; ++pb) {
         const bf16* base = reinterpret_cast<const bf16*>(x0) + ((long long)pa * Win + pb) * ld0;
-        rc = make_act_map(&P.tmX[pa * 2 + pb], base, C0, Win / 2, Hin / 2, N, 2LL * ld0, 2LL * Win * ld0,
+        rc = make_act_map(&tmX[pa * 2 + pb], base, C0, Win / 2, Hin / 2, N, 2LL * ld0, 2LL * Win * ld0,
                           (long long)Hin * Win * ld0, bw, bh, bn);
         if (rc) return rc;
       }
   }
-  rc = make_act_map(&P.tmDY, dy, Cout, Wo, Ho, N, lddy, (long long)Wo * lddy, (long long)Ho * Wo * lddy, bw, bh, bn);
+  rc = make_act_map(&tmDY, dy, Cout, Wo, Ho, N, lddy, (long long)Wo * lddy, (long long)Ho * Wo * lddy, bw, bh, bn);
   if (rc) return rc;
+
+  bool use_v2 = (Cout % 128) != 0 || Cout <= 384;
+  if (g_debug[4] == 1) use_v2 = false;
+  if (g_debug[4] == 2) use_v2 = true;
+
+  if (use_v2) {
+    Wgrad2Params P;
+    memset(&P, 0, sizeof P);
+    memcpy(P.tmX, tmX, sizeof tmX); P.tmDY = tmDY; memcpy(P.taps, taps, sizeof taps);
+    P.num_taps = num_taps; P.chunks0 = chunks0; P.chunks1 = chunks1; P.dual = x1 ? 1 : 0;
+    P.log_bw = log_bw; P.log_bh = log_bh; P.log_bn = log_bn;
+    P.tiles_w = tiles_w; P.tiles_h = tiles_h; P.tiles_b = tiles_b; P.patches = patches;
+    P.total_boxes = num_taps * chunks;
+    P.m_tiles = dm::cdiv(P.total_boxes, 4);
+    P.n_tiles = dm::cdiv(Cout, 256);
+    P.nb = dm::cdiv(dm::cdiv(Cout, P.n_tiles), 64);
+    P.block_n = P.nb * 64;
+    P.Cout = Cout; P.cin_k = chunks * 64; P.C0 = C0; P.C1 = C1;
+    int splits = pick_splits(P.m_tiles * P.n_tiles, patches, 8);
+    if (g_debug[2] > 0) splits = (int)g_debug[2];
+    P.patches_per_split = dm::cdiv(patches, splits);
+    P.splits = dm::cdiv(patches, P.patches_per_split);
+    P.dwp = dwp;
+    P.idesc = make_idesc(P.block_n, true, true);
+    P.desc_hi = kDescHiMN; P.lbo = 8192 >> 4;
+    const int stage_bytes = (4 + P.nb) * 8192;
+    int stages = (kSmemBudget - 1024 - 512) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (g_debug[0] > 0 && g_debug[0] < stages) stages = (int)g_debug[0];
+    P.stages = stages;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
+    if (!g_attr_c) {
+      cudaError_t e = cudaFuncSetAttribute(wgrad2_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+      if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
+      g_attr_c = true;
+    }
+    const int tiles = P.m_tiles * P.n_tiles * P.splits;
+    int grid = tiles < DM_NUM_SMS ? tiles : DM_NUM_SMS;
+    if (g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
+    wgrad2_gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+  }
+
+  WgradParams P;
+  memset(&P, 0, sizeof P);
+  memcpy(P.tmX, tmX, sizeof tmX); P.tmDY = tmDY; memcpy(P.taps, taps, sizeof taps);
+  P.log_bw = log_bw; P.log_bh = log_bh; P.log_bn = log_bn;
+  P.tiles_w = tiles_w; P.tiles_h = tiles_h; P.tiles_b = tiles_b; P.patches = patches;
+  P.chunks0 = chunks0; P.chunks1 = chunks1; P.dual = x1 ? 1 : 0;
+  P.num_taps = num_taps;
+  P.cin_k = chunks * 64;
+  P.block_n = chunks >= 4 ? 256 : chunks * 64;
+  P.ci_tiles = dm::cdiv(P.cin_k, P.block_n);
+  P.co_tiles = dm::cdiv(Cout, 128);
+  P.Cout = Cout;
+  const int base_tiles = P.co_tiles * P.num_taps * P.ci_tiles;
+  int splits = pick_splits(base_tiles, patches, 3);
+  if (g_debug[2] > 0) splits = (int)g_debug[2];
+  P.patches_per_split = dm::cdiv(P.patches, splits);
+  P.splits = dm::cdiv(P.patches, P.patches_per_split);
+  P.b_stage_bytes = (P.block_n / 64) * 8192;
+  P.dwp = dwp;
+  P.idesc = make_idesc(P.block_n, true, true);
+  P.desc_hi_a = kDescHiMN; P.desc_hi_b = kDescHiMN;
+  P.lbo_a = 8192 >> 4; P.lbo_b = 8192 >> 4;
   int stage_bytes = kAStage + P.b_stage_bytes;
   int stages = (kSmemBudget - 1024 - kAuxBytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;

@@ -34,41 +34,50 @@ struct PackArgs {
   long long s_row, s_col, row_len;
 };
 
-__device__ __forceinline__ bool pack_decode(const PackArgs& A, long long i, long long& src) {
-  // i indexes the packed buffer: [row][k] with k in [0,row_len) (tap_major_rows=0) or [tap*rows+row][k]
-  const long long k = i % A.row_len;
-  long long r = i / A.row_len;
-  int tap, col_k;
-  if (A.tap_major_rows) { tap = (int)(r / A.rows); r = r % A.rows; col_k = (int)k; if (k >= A.cols_k) return false; }
-  else { tap = (int)(k / A.cols_k); col_k = (int)(k % A.cols_k); if (tap >= A.ntaps) return false; }
+// Both kernels run one thread per (row, packed column) and walk the taps, so the accesses to the packed
+// matrix (bf16 writes / fp32 reads) are coalesced across the warp and each thread touches ntaps
+// consecutive elements of the reference-layout tensor.
+__device__ __forceinline__ int pack_col(const PackArgs& A, int col_k) {
+  // packed column -> source column, or -1 for a zero pad column
   int col = col_k;
   if (A.c_split > 0) {
     const int s64 = (A.c_split + 63) / 64 * 64;
-    if (col_k < s64) { if (col_k >= A.c_split) return false; }
+    if (col_k < s64) { if (col_k >= A.c_split) return -1; }
     else col = col_k - s64 + A.c_split;
   }
-  if (col >= A.cols) return false;
-  src = r * A.s_row + (long long)col * A.s_col + A.tap_off[tap];
-  return true;
+  return col < A.cols ? col : -1;
 }
-__global__ void pack_weight_kernel(const float* w, bf16* out, PackArgs A, long long total) {
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, PackArgs A) {
+  const long long total = (long long)A.rows * A.cols_k;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long src;
-    out[i] = __float2bfloat16(pack_decode(A, i, src) ? w[src] : 0.0f);
+    const int col_k = (int)(i % A.cols_k);
+    const long long row = i / A.cols_k;
+    const int col = pack_col(A, col_k);
+    const float* src = w + row * A.s_row + (long long)(col < 0 ? 0 : col) * A.s_col;
+    for (int tap = 0; tap < A.ntaps; ++tap) {
+      const float v = col < 0 ? 0.0f : __ldg(src + A.tap_off[tap]);
+      const long long pk = A.tap_major_rows ? ((long long)tap * A.rows + row) * A.row_len + col_k
+                                            : row * A.row_len + (long long)tap * A.cols_k + col_k;
+      out[pk] = __float2bfloat16(v);
+    }
   }
 }
-// destination-major gather so the fp32 gradient writes are coalesced: one thread per (row, col, tap)
-__global__ void unpack_wgrad_kernel(const float* dwp, float* grad, PackArgs A, long long total) {
+// grad[...] += dwp[...] over the real (row, col, tap) entries; consume != 0 re-zeroes dwp in the same pass.
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(float* __restrict__ dwp, float* __restrict__ grad, PackArgs A,
+                                                            int consume) {
+  const long long total = (long long)A.rows * A.cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int tap = (int)(i % A.ntaps);
-    long long rc = i / A.ntaps;
-    long long row, col;
-    if (A.s_row >= A.s_col) { col = rc % A.cols; row = rc / A.cols; } else { row = rc % A.rows; col = rc / A.rows; }
-    int col_k = (int)col;
-    if (A.c_split > 0 && col >= A.c_split) col_k = (int)col - A.c_split + (A.c_split + 63) / 64 * 64;
-    const long long pk = A.tap_major_rows ? ((long long)tap * A.rows + row) * A.row_len + col_k
-                                          : row * A.row_len + (long long)tap * A.cols_k + col_k;
-    grad[row * A.s_row + col * A.s_col + A.tap_off[tap]] += dwp[pk];
+    const int col = (int)(i % A.cols);
+    const long long row = i / A.cols;
+    int col_k = col;
+    if (A.c_split > 0 && col >= A.c_split) col_k = col - A.c_split + (A.c_split + 63) / 64 * 64;
+    float* dst = grad + row * A.s_row + (long long)col * A.s_col;
+    for (int tap = 0; tap < A.ntaps; ++tap) {
+      const long long pk = A.tap_major_rows ? ((long long)tap * A.rows + row) * A.row_len + col_k
+                                            : row * A.row_len + (long long)tap * A.cols_k + col_k;
+      dst[A.tap_off[tap]] += dwp[pk];
+      if (consume) dwp[pk] = 0.0f;
+    }
   }
 }
 
@@ -231,18 +240,20 @@ extern "C" int dm_pack_weight(const float* w, void* out, int rows, int cols, int
                               int tap_major_rows, void* stream) {
   if (ntaps < 1 || ntaps > 64) { dm_set_error("dm_pack_weight: 1..64 taps"); return DM_ERR_ARG; }
   PackArgs A; fill_pack(A, rows, cols, ntaps, tap_off_host, s_row, s_col, c_split, cols_k, row_len, tap_major_rows);
-  const long long total = (tap_major_rows ? (long long)ntaps * rows : (long long)rows) * row_len;
-  pack_weight_kernel<<<grid_for(total), 256, 0, ST>>>(w, (bf16*)out, A, total);
+  if (!tap_major_rows && row_len > (long long)ntaps * cols_k) {      // zero the row tails the kernel never writes
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)rows * row_len * 2, ST);
+    if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
+  }
+  pack_weight_kernel<<<grid_for((long long)rows * cols_k), 256, 0, ST>>>(w, (bf16*)out, A);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
-extern "C" int dm_unpack_wgrad(const float* dwp, float* grad, int rows, int cols, int ntaps, const long long* tap_off_host,
+extern "C" int dm_unpack_wgrad(float* dwp, float* grad, int rows, int cols, int ntaps, const long long* tap_off_host,
                                long long s_row, long long s_col, int c_split, int cols_k, long long row_len,
-                               int tap_major_rows, void* stream) {
+                               int tap_major_rows, int consume, void* stream) {
   if (ntaps < 1 || ntaps > 64) { dm_set_error("dm_unpack_wgrad: 1..64 taps"); return DM_ERR_ARG; }
   PackArgs A; fill_pack(A, rows, cols, ntaps, tap_off_host, s_row, s_col, c_split, cols_k, row_len, tap_major_rows);
-  const long long total = (long long)rows * cols * ntaps;
-  unpack_wgrad_kernel<<<grid_for(total), 256, 0, ST>>>(dwp, grad, A, total);
+  unpack_wgrad_kernel<<<grid_for((long long)rows * cols), 256, 0, ST>>>(dwp, grad, A, consume);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }

@@ -42,8 +42,35 @@ int ew_launch(long long P, int C, F f, cudaStream_t st) {
 }
 
 __device__ __forceinline__ void ldp8(const float* p, int c0, int C, float (&o)[8]) {
+  if (c0 + 8 <= C && ((reinterpret_cast<uintptr_t>(p + c0) & 15) == 0)) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + c0)), b = __ldg(reinterpret_cast<const float4*>(p + c0) + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) o[j] = (c0 + j < C) ? __ldg(p + c0 + j) : 0.0f;
+}
+
+// Thread mapping of the channel-parameterised streaming kernels (BatchNorm apply / backward): a thread
+// keeps ONE 8-channel vector for its whole life, so the per-channel coefficients are loaded once into
+// registers and the inner loop is pure 16-byte loads -> math -> 16-byte stores.  A block is
+// VPB channel-vectors x R pixel rows; consecutive threads touch consecutive 16-byte chunks of a pixel.
+struct ChanMap { int Cv, VPB, R, cvt, threads; };
+inline ChanMap chan_map(int C, int vec = 8) {
+  ChanMap m;
+  m.Cv = (C + vec - 1) / vec;
+  m.VPB = m.Cv < 256 ? m.Cv : 256;
+  m.R = 256 / m.VPB; if (m.R < 1) m.R = 1;
+  m.cvt = (m.Cv + m.VPB - 1) / m.VPB;
+  m.threads = m.VPB * m.R;
+  return m;
+}
+inline int chan_grid_x(long long P, const ChanMap& m, int px_per_thread) {
+  long long want = (P + (long long)m.R * px_per_thread - 1) / ((long long)m.R * px_per_thread);
+  long long cap = (long long)DM_NUM_SMS * 8 / m.cvt; if (cap < 1) cap = 1;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
 }
 
 // ---------------------------------------------------------------------------------- reductions
@@ -92,6 +119,7 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(RedArgs A) {
     const int chunk = (A.count + gridDim.x - 1) / gridDim.x;
     const int i0 = blockIdx.x * chunk;
     const int i1 = min(A.count, i0 + chunk);
+#pragma unroll 4
     for (int i = i0 + r; i < i1; i += R) {
       float va[8], vb[8];
       load8(pa + (long long)i * A.a_ps, va);
@@ -195,42 +223,194 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* partials
   }
 }
 
-struct BnFwd {
-  const bf16* y; int ldy; const float *mean, *invstd, *gamma, *beta; bf16* z; int ldz; int C, act;
-  __device__ void operator()(unsigned p, int c0) const {
-    float v[8], mu[8], is[8], ga[8], be[8];
-    load8(y + (long long)p * ldy + c0, v);
-    ldp8(mean, c0, C, mu); ldp8(invstd, c0, C, is); ldp8(gamma, c0, C, ga); ldp8(beta, c0, C, be);
+// z = act(y * sc + sh), sc = invstd*gamma, sh = beta - mean*sc
+template <int ACT>
+__global__ void __launch_bounds__(256) bn_fwd_kernel(const bf16* __restrict__ y, int ldy, const float* __restrict__ mean,
+                                                      const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, bf16* __restrict__ z, int ldz,
+                                                      unsigned P, int C, int VPB, int R) {
+  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
+  const int c0 = (blockIdx.y * VPB + cvl) * 8;
+  if (c0 >= C) return;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? dm::act_f((v[j] - mu[j]) * is[j] * ga[j] + be[j], act) : 0.f;
-    store8(z + (long long)p * ldz + c0, v);
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float k = c < C ? __ldg(invstd + c) * __ldg(gamma + c) : 0.f;
+    sc[j] = k;
+    sh[j] = c < C ? __ldg(beta + c) - __ldg(mean + c) * k : 0.f;
   }
-};
-
-struct BnBwd {
-  const bf16* dz; int lddz; const bf16* y; int ldy; const float *mean, *invstd, *gamma, *beta;
-  const float* sums;   // [2][C]: sum g, sum g*xhat
-  bf16* dy; int lddy; int C, act, training; float invP;
-  __device__ void operator()(unsigned p, int c0) const {
-    float g[8], v[8], mu[8], is[8], ga[8], be[8], s1[8], s2[8];
-    load8(dz + (long long)p * lddz + c0, g);
-    load8(y + (long long)p * ldy + c0, v);
-    ldp8(mean, c0, C, mu); ldp8(invstd, c0, C, is); ldp8(gamma, c0, C, ga); ldp8(beta, c0, C, be);
-    ldp8(sums, c0, C, s1); ldp8(sums + C, c0, C, s2);
+  const unsigned step = gridDim.x * R;
+  for (unsigned p = blockIdx.x * R + r; p < P; p += 2 * step) {
+    const unsigned p1 = p + step;
+    const bool has1 = p1 < P;
+    float v0[8], v1[8];
+    load8(y + (long long)p * ldy + c0, v0);
+    if (has1) load8(y + (long long)p1 * ldy + c0, v1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (v[j] - mu[j]) * is[j];
-      const float gg = g[j] * dm::act_grad_f(xh * ga[j] + be[j], act);
-      const float t = training ? (gg - s1[j] * invP - xh * s2[j] * invP) : gg;
-      g[j] = (c0 + j < C) ? ga[j] * is[j] * t : 0.f;
+    for (int j = 0; j < 8; ++j) v0[j] = dm::act_f(fmaf(v0[j], sc[j], sh[j]), ACT);
+    store8(z + (long long)p * ldz + c0, v0);
+    if (has1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v1[j] = dm::act_f(fmaf(v1[j], sc[j], sh[j]), ACT);
+      store8(z + (long long)p1 * ldz + c0, v1);
     }
-    store8(dy + (long long)p * lddy + c0, g);
   }
-};
+}
 
-__global__ void accum2_kernel(const float* s, float* dgamma, float* dbeta, int C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) { dbeta[c] += s[c]; dgamma[c] += s[C + c]; }
+// BatchNorm + activation backward.  With xhat = a*y + b (a = invstd, b = -mean*invstd) and the
+// pre-activation u = A2*y + B2 (A2 = a*gamma, B2 = b*gamma + beta):
+//   g  = dz * act'(u)
+//   dy = gamma*invstd * (g - mean_p(g) - xhat*mean_p(g*xhat))  =  k0*g - K2*y - K1
+// so the streaming passes need only (A2, B2) resp. (A2, B2, k0, K1, K2) per channel; the sums over
+// xhat are recovered from sums over y in the finalize step (double precision).
+// Threads own 4 channels (8-byte vectors): half the coefficient registers of the 8-wide mapping, which
+// is what lets five 240-thread blocks live on an SM.
+//
+// pass 1: per-block partial sums of g, g*y and y, written (no atomics, no zeroing) to part[block][3][C].
+template <int ACT>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y,
+                                                             int ldy, const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* __restrict__ part,
+                                                             unsigned P, int C, int VPB, int R) {
+  extern __shared__ float sm[];          // [threads][12]
+  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
+  const int c0 = (blockIdx.y * VPB + cvl) * 4;
+  float s1[4], s2[4], s3[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { s1[j] = 0.f; s2[j] = 0.f; s3[j] = 0.f; }
+  if (c0 < C) {
+    float A2[4], B2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + j;
+      const bool ok = c < C;
+      const float a = ok ? __ldg(invstd + c) : 0.f, ga = ok ? __ldg(gamma + c) : 0.f;
+      A2[j] = a * ga;
+      B2[j] = ok ? fmaf(-__ldg(mean + c) * a, ga, __ldg(beta + c)) : 0.f;
+    }
+    const unsigned step = gridDim.x * R;
+    for (unsigned p = blockIdx.x * R + r; p < P; p += 2 * step) {
+      const unsigned p1 = p + step;
+      const bool has1 = p1 < P;
+      float g0[4], v0[4], g1[4], v1[4];
+      dm::load4(dz + (long long)p * lddz + c0, g0);
+      dm::load4(y + (long long)p * ldy + c0, v0);
+      if (has1) { dm::load4(dz + (long long)p1 * lddz + c0, g1); dm::load4(y + (long long)p1 * ldy + c0, v1); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gg = g0[j] * dm::act_grad_f(fmaf(v0[j], A2[j], B2[j]), ACT);
+        s1[j] += gg; s2[j] = fmaf(gg, v0[j], s2[j]); s3[j] += v0[j];
+      }
+      if (has1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float gg = g1[j] * dm::act_grad_f(fmaf(v1[j], A2[j], B2[j]), ACT);
+          s1[j] += gg; s2[j] = fmaf(gg, v1[j], s2[j]); s3[j] += v1[j];
+        }
+      }
+    }
+  }
+  float* mine = sm + threadIdx.x * 12;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { mine[j] = s1[j]; mine[4 + j] = s2[j]; mine[8 + j] = s3[j]; }
+  __syncthreads();
+  if (r == 0 && c0 < C) {
+    for (int rr = 1; rr < R; ++rr) {
+      const float* o = sm + (rr * VPB + cvl) * 12;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s1[j] += o[j]; s2[j] += o[4 + j]; s3[j] += o[8 + j]; }
+    }
+    float* g = part + (long long)blockIdx.x * 3 * C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c0 + j < C) { g[c0 + j] = s1[j]; g[C + c0 + j] = s2[j]; g[2 * C + c0 + j] = s3[j]; }
+  }
+}
+
+// pass 2: block partials -> per-channel coefficients coef[3][C] = (k0, K1, K2) of the apply pass;
+// dgamma += sum g*xhat, dbeta += sum g, and the bias gradient of the convolution feeding this norm:
+// sum_p dy = gamma*invstd * (training ? -(sum g*xhat / P) * sum xhat : sum g).
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, double P,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, float* __restrict__ coef,
+                                                                float* dgamma, float* dbeta, float* dbias, int training) {
+  __shared__ float sh[3][32][33];
+  const int cl = threadIdx.x & 31, rr = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+  if (c < C) {
+#pragma unroll 4
+    for (int t = rr; t < nblk; t += 32) {
+      const float* g = part + (long long)t * 3 * C;
+      f0 += g[c]; f1 += g[C + c]; f2 += g[2 * C + c];
+    }
+  }
+  sh[0][rr][cl] = f0; sh[1][rr][cl] = f1; sh[2][rr][cl] = f2;
+  __syncthreads();
+  if (rr == 0 && c < C) {
+    double sg = 0.0, sgy = 0.0, sy = 0.0;
+    for (int k = 0; k < 32; ++k) { sg += (double)sh[0][k][cl]; sgy += (double)sh[1][k][cl]; sy += (double)sh[2][k][cl]; }
+    const double a = (double)invstd[c], b = -(double)mean[c] * a, ga = (double)gamma[c];
+    const double sgx = a * sgy + b * sg;          // sum g*xhat
+    const double sx = a * sy + b * P;             // sum xhat
+    const double k0 = ga * a;
+    const double m1 = training ? sg / P : 0.0, m2 = training ? sgx / P : 0.0;
+    coef[c] = (float)k0;
+    coef[C + c] = (float)(k0 * (m1 + m2 * b));    // K1
+    coef[2 * C + c] = (float)(k0 * m2 * a);       // K2
+    dbeta[c] += (float)sg;
+    dgamma[c] += (float)sgx;
+    if (dbias) dbias[c] += (float)(training ? -k0 * m2 * sx : k0 * sg);
+  }
+}
+
+// pass 3: dy = k0*g - K2*y - K1
+template <int ACT>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y,
+                                                            int ldy, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const float* __restrict__ coef,
+                                                            bf16* __restrict__ dy, int lddy, unsigned P, int C, int VPB, int R) {
+  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
+  const int c0 = (blockIdx.y * VPB + cvl) * 4;
+  if (c0 >= C) return;
+  float A2[4], B2[4], k0[4], K1[4], K2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + j;
+    const bool ok = c < C;
+    const float a = ok ? __ldg(invstd + c) : 0.f, ga = ok ? __ldg(gamma + c) : 0.f;
+    A2[j] = a * ga;
+    B2[j] = ok ? fmaf(-__ldg(mean + c) * a, ga, __ldg(beta + c)) : 0.f;
+    k0[j] = ok ? __ldg(coef + c) : 0.f;
+    K1[j] = ok ? __ldg(coef + C + c) : 0.f;
+    K2[j] = ok ? __ldg(coef + 2 * C + c) : 0.f;
+  }
+  const unsigned step = gridDim.x * R;
+  for (unsigned p = blockIdx.x * R + r; p < P; p += 2 * step) {
+    const unsigned p1 = p + step;
+    const bool has1 = p1 < P;
+    float g0[4], v0[4], g1[4], v1[4];
+    dm::load4(dz + (long long)p * lddz + c0, g0);
+    dm::load4(y + (long long)p * ldy + c0, v0);
+    if (has1) { dm::load4(dz + (long long)p1 * lddz + c0, g1); dm::load4(y + (long long)p1 * ldy + c0, v1); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gg = g0[j] * dm::act_grad_f(fmaf(v0[j], A2[j], B2[j]), ACT);
+      g0[j] = fmaf(k0[j], gg, -fmaf(K2[j], v0[j], K1[j]));
+    }
+    dm::store4(dy + (long long)p * lddy + c0, g0);
+    if (has1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gg = g1[j] * dm::act_grad_f(fmaf(v1[j], A2[j], B2[j]), ACT);
+        g1[j] = fmaf(k0[j], gg, -fmaf(K2[j], v1[j], K1[j]));
+      }
+      dm::store4(dy + (long long)p1 * lddy + c0, g1);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------- GroupNorm
@@ -670,29 +850,49 @@ extern "C" int dm_bn_finalize(const float* partials, int m_tiles, int ld, int C,
 extern "C" int dm_bn_act_fwd(const void* y, int ldy, const float* mean, const float* invstd, const float* gamma,
                              const float* beta, void* z, int ldz, long long P, int C, int act, void* stream) {
   REQ8(ldy, "dm_bn_act_fwd"); REQ8(ldz, "dm_bn_act_fwd");
-  BnFwd f{(const bf16*)y, ldy, mean, invstd, gamma, beta, (bf16*)z, ldz, C, act};
-  return ew_launch(P, C, f, ST);
+  if (P <= 0) return DM_OK;
+  if (P >= (1ll << 31)) { dm_set_error("dm_bn_act_fwd: too many pixels"); return DM_ERR_ARG; }
+  const ChanMap m = chan_map(C);
+  dim3 grid(chan_grid_x(P, m, 4), m.cvt);
+#define BN_FWD(A) bn_fwd_kernel<A><<<grid, m.threads, 0, ST>>>((const bf16*)y, ldy, mean, invstd, gamma, beta, (bf16*)z, ldz, (unsigned)P, C, m.VPB, m.R)
+  if (act == 1) BN_FWD(1); else if (act == 2) BN_FWD(2); else BN_FWD(0);
+#undef BN_FWD
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+static int bn_bwd_blocks(long long P, int C) {
+  // one resident wave (4 blocks of <=256 threads per SM at 64 registers): few partial rows to finalize
+  const ChanMap m = chan_map(C, 4);
+  int b = chan_grid_x(P, m, 16);
+  const int cap = DM_NUM_SMS * 4 / m.cvt;
+  return b > cap ? (cap < 1 ? 1 : cap) : b;
+}
+extern "C" long long dm_bn_act_bwd_scratch(long long P, int C) {
+  return (long long)bn_bwd_blocks(P, C) * 3 * C + 3LL * C;
 }
 extern "C" int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, const float* mean, const float* invstd,
                              const float* gamma, const float* beta, void* dy, int lddy, float* dgamma, float* dbeta,
-                             float* scratch, long long P, int C, int act, int training, void* stream) {
+                             float* dbias, float* scratch, long long P, int C, int act, int training, void* stream) {
   REQ8(lddz, "dm_bn_act_bwd"); REQ8(ldy, "dm_bn_act_bwd"); REQ8(lddy, "dm_bn_act_bwd");
+  if (P <= 0) return DM_OK;
   if (P >= (1ll << 31)) { dm_set_error("dm_bn_act_bwd: too many pixels"); return DM_ERR_ARG; }
-  int rc = zero_f32(scratch, 2 * C, ST);
-  if (rc) return rc;
-  RedArgs A{};
-  A.a = (const bf16*)dz; A.b = (const bf16*)y;
-  A.a_hi = 0; A.a_lo = 0; A.a_ps = lddz; A.b_hi = 0; A.b_lo = 0; A.b_ps = ldy;
-  A.gdiv = 1; A.count = (int)P; A.C = C; A.mode = 3; A.act = act; A.G = 1; A.stat_div = 1;
-  A.mean = mean; A.invstd = invstd; A.gamma = gamma; A.beta = beta; A.scale = 1.f;
-  A.out1 = scratch; A.out2 = scratch + C;
-  rc = launch_reduce(A, 1, ST);
-  if (rc) return rc;
-  BnBwd f{(const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, scratch, (bf16*)dy, lddy, C, act,
-          training, (float)(1.0 / (double)P)};
-  rc = ew_launch(P, C, f, ST);
-  if (rc) return rc;
-  accum2_kernel<<<dm::cdiv(C, 256), 256, 0, ST>>>(scratch, dgamma, dbeta, C);
+  const ChanMap m = chan_map(C, 4);
+  const int nblk = bn_bwd_blocks(P, C);
+  float* coef = scratch;                    // [3][C]
+  float* part = scratch + 3LL * C;          // [nblk][3][C]
+  dim3 grid(nblk, m.cvt);
+  const size_t smem = (size_t)m.threads * 12 * sizeof(float);
+#define BN_RED(A) bn_bwd_reduce_kernel<A><<<grid, m.threads, smem, ST>>>((const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, part, (unsigned)P, C, m.VPB, m.R)
+  if (act == 1) BN_RED(1); else if (act == 2) BN_RED(2); else BN_RED(0);
+#undef BN_RED
+  DM_CHECK_LAUNCH();
+  bn_bwd_finalize_kernel<<<dm::cdiv(C, 32), 1024, 0, ST>>>(part, nblk, C, (double)P, mean, invstd, gamma, coef, dgamma, dbeta,
+                                                         dbias, training);
+  DM_CHECK_LAUNCH();
+  dim3 grid2(chan_grid_x(P, m, 4), m.cvt);
+#define BN_APP(A) bn_bwd_apply_kernel<A><<<grid2, m.threads, 0, ST>>>((const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, coef, (bf16*)dy, lddy, (unsigned)P, C, m.VPB, m.R)
+  if (act == 1) BN_APP(1); else if (act == 2) BN_APP(2); else BN_APP(0);
+#undef BN_APP
   DM_CHECK_LAUNCH();
   return DM_OK;
 }

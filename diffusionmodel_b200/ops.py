@@ -151,16 +151,93 @@ _PACKERS = {"fwd": _pack_fwd, "dgrad": _pack_dgrad, "s2dgrad": _pack_s2dgrad,
             "convt_fwd": _pack_convt_fwd, "convt_dgrad": _pack_convt_dgrad}
 
 
+# --------------------------------------------------------------------------------------- weight gradients
+class _PackedGrad:
+    """Persistent fp32 accumulator of one conv weight's gradient in the GEMM's packed layout.
+
+    The wgrad kernel red.adds into it on every micro-batch; ``flush`` scatters it into the parameter's
+    NCHW ``.grad`` (+=) and re-zeroes it in the same pass.  Owned by the optimizer (FusedAdamW), which
+    flushes once per optimizer step instead of once per backward (ACCUM_STEPS x fewer scatter passes and
+    no per-backward zero-fill of a weight-sized buffer)."""
+
+    __slots__ = ("weight", "dwp", "args", "dirty")
+
+    def __init__(self, weight, shape):
+        self.weight, self.args, self.dirty = weight, None, False
+        self.dwp = torch.zeros(shape, device=weight.device, dtype=torch.float32)
+
+    def flush(self):
+        if self.dirty:
+            call("dm_unpack_wgrad", _p(self.dwp), _p(grad_buf(self.weight)), *self.args, 1, _stream())
+            self.dirty = False
+
+
+_deferred = {}          # weight.data_ptr() -> [weakref(param), _PackedGrad | None]
+
+
+def defer_weight_grads(params):
+    """Register parameters whose conv weight gradients may stay packed until ``flush_weight_grads``."""
+    import weakref
+    for p in params:
+        if p.dim() == 4:
+            _deferred[p.data_ptr()] = [weakref.ref(p), None]
+
+
+def _live_entries():
+    for key in list(_deferred):
+        ref, e = _deferred[key]
+        p = ref()
+        if p is None or p.data_ptr() != key:
+            del _deferred[key]              # parameter gone or re-homed: forget it
+        elif e is not None:
+            yield e
+
+
+def flush_weight_grads():
+    for e in _live_entries():
+        e.flush()
+
+
+def discard_weight_grads():
+    """zero_grad(): drop packed gradients that were never flushed."""
+    for e in _live_entries():
+        if e.dirty:
+            e.dwp.zero_()
+            e.dirty = False
+
+
+def _wgrad_into(weight, shape, unpack_args, run):
+    """Run ``run(dwp)`` (the wgrad GEMM accumulating into ``dwp``) and deliver the result to weight.grad:
+    immediately, or -- for parameters registered by the optimizer -- at the next flush."""
+    key = weight.data_ptr()
+    slot = _deferred.get(key)
+    if slot is not None:
+        p = slot[0]()
+        if p is None or p.shape != weight.shape:
+            del _deferred[key]
+            slot = None
+    if slot is not None:
+        e = slot[1]
+        if e is None or e.dwp.shape != torch.Size(shape):
+            e = slot[1] = _PackedGrad(weight, shape)
+        run(e.dwp)
+        e.args, e.dirty = unpack_args, True
+        return
+    dwp = torch.zeros(shape, device=weight.device, dtype=torch.float32)
+    run(dwp)
+    call("dm_unpack_wgrad", _p(dwp), _p(grad_buf(weight)), *unpack_args, 0, _stream())
+
+
 # --------------------------------------------------------------------------------------- convolution
-def conv_mtiles(n, ho, wo):
-    return _lib.fn("dm_conv2d_fwd_mtiles")(n, ho, wo)
+def conv_stat_rows(n, ho, wo, cout):
+    return _lib.fn("dm_conv2d_fwd_stat_rows")(n, ho, wo, cout)
 
 
 class _Conv2d(torch.autograd.Function):
     """nn.Conv2d (new_scripy.py:184 etc.) on one or two channel-concatenated NHWC sources."""
 
     @staticmethod
-    def forward(ctx, x0, x1, weight, bias, pack, c0, c1, stride, pad, want_stats, out_f32):
+    def forward(ctx, x0, x1, weight, bias, pack, c0, c1, stride, pad, want_stats, out_f32, bias_grad_by_norm):
         ld0 = _chk(x0, "conv input")
         ld1 = _chk(x1, "conv input 2") if x1 is not None else 0
         n, hin, win, _ = x0.shape
@@ -175,19 +252,18 @@ class _Conv2d(torch.autograd.Function):
             y = new_act(n, ho, wo, cout, x0.device)
         stats = None
         if want_stats:
-            mt = conv_mtiles(n, ho, wo)
-            stats = torch.empty((mt, 2, cout), device=x0.device, dtype=torch.float32)
+            stats = torch.empty((conv_stat_rows(n, ho, wo, cout), 2, cout), device=x0.device, dtype=torch.float32)
         call("dm_conv2d_fwd", _p(x0), c0, ld0, _p(x1), c1, ld1, _p(wpk), _p(bias), _p(y), y.stride(2), int(out_f32),
              _p(stats), cout, n, hin, win, cout, kh, kw, stride, pad, _stream())
         ctx.save_for_backward(x0, x1, weight, bias)
-        ctx.pack, ctx.geom = pack, (c0, c1, stride, pad, out_f32)
+        ctx.pack, ctx.geom = pack, (c0, c1, stride, pad, out_f32, bias_grad_by_norm)
         ctx.mark_non_differentiable(*([stats] if stats is not None else []))
         return (y, stats) if want_stats else (y, None)
 
     @staticmethod
     def backward(ctx, dy, _dstats):
         x0, x1, weight, bias = ctx.saved_tensors
-        c0, c1, stride, pad, out_f32 = ctx.geom
+        c0, c1, stride, pad, out_f32, bias_grad_by_norm = ctx.geom
         cout, cin, kh, kw = weight.shape
         n, hin, win, _ = x0.shape
         ho, wo = dy.shape[1], dy.shape[2]
@@ -198,17 +274,16 @@ class _Conv2d(torch.autograd.Function):
             call("dm_cast_nhwc", _p(dy), dy.stride(2), _p(dyb), dyb.stride(2), n * ho * wo, cout, st)
             dy = dyb
         lddy = _chk(dy, "conv grad")
-        # bias gradient: column sums of dy
-        if bias is not None:
+        # bias gradient: column sums of dy (a following BatchNorm's backward produces it instead)
+        if bias is not None and not bias_grad_by_norm:
             call("dm_colsum", _p(dy), lddy, _p(grad_buf(bias)), n * ho * wo, cout, st)
-        # weight gradient: packed fp32 [Cout][taps][Cin_k] then scattered (+=) into the NCHW parameter grad
+        # weight gradient: packed fp32 [Cout][taps][Cin_k], scattered (+=) into the NCHW parameter grad
         ck = _cols_k(cin, c0 if x1 is not None else 0)
-        dwp = torch.zeros((cout, kh * kw * ck), device=dy.device, dtype=torch.float32)
-        call("dm_conv2d_wgrad", _p(x0), c0, x0.stride(2), _p(x1), c1, x1.stride(2) if x1 is not None else 0, _p(dy),
-             lddy, _p(dwp), n, hin, win, cout, kh, kw, stride, pad, st)
         offs = [r * kw + s for r in range(kh) for s in range(kw)]
-        call("dm_unpack_wgrad", _p(dwp), _p(grad_buf(weight)), cout, cin, kh * kw, _taps(offs), cin * kh * kw, kh * kw,
-             c0 if x1 is not None else 0, ck, kh * kw * ck, 0, st)
+        unpack = (cout, cin, kh * kw, _taps(offs), cin * kh * kw, kh * kw, c0 if x1 is not None else 0, ck, kh * kw * ck, 0)
+        _wgrad_into(weight, (cout, kh * kw * ck), unpack, lambda dwp: call(
+            "dm_conv2d_wgrad", _p(x0), c0, x0.stride(2), _p(x1), c1, x1.stride(2) if x1 is not None else 0, _p(dy),
+            lddy, _p(dwp), n, hin, win, cout, kh, kw, stride, pad, st))
         # data gradient
         dx0 = dx1 = None
         need0 = ctx.needs_input_grad[0]
@@ -228,14 +303,15 @@ class _Conv2d(torch.autograd.Function):
                 dx0 = dx
             else:
                 dx0, dx1 = dx[..., :c0], dx[..., c0:]
-        return dx0, dx1, None, None, None, None, None, None, None, None, None
+        return dx0, dx1, None, None, None, None, None, None, None, None, None, None
 
 
-def conv2d(x0, weight, bias, pack, *, x1=None, c0=None, c1=0, stride=1, pad=0, want_stats=False, out_f32=False):
+def conv2d(x0, weight, bias, pack, *, x1=None, c0=None, c1=0, stride=1, pad=0, want_stats=False, out_f32=False,
+           bias_grad_by_norm=False):
     c0 = weight.shape[1] - c1 if c0 is None else c0
     if x1 is not None and (c0 % 8 or x0.shape[3] != c0):
         raise _lib.DmB200Error("dual-source conv needs a tight first source with a multiple-of-8 channel count")
-    return _Conv2d.apply(x0, x1, weight, bias, pack, c0, c1, stride, pad, want_stats, out_f32)
+    return _Conv2d.apply(x0, x1, weight, bias, pack, c0, c1, stride, pad, want_stats, out_f32, bias_grad_by_norm)
 
 
 class _ConvT(torch.autograd.Function):
@@ -269,12 +345,11 @@ class _ConvT(torch.autograd.Function):
         call("dm_space_to_depth", _p(dy), lddy, _p(s2d), s2d.stride(2), n, hin, win, cout, k, st)
         # weight gradient: rows (tap, co), K columns ci
         ck = r64(cin)
-        dwp = torch.zeros((kc, ck), device=dy.device, dtype=torch.float32)
-        call("dm_conv2d_wgrad", _p(x), cin, x.stride(2), None, 0, 0, _p(s2d), s2d.stride(2), _p(dwp), n, hin, win, kc,
-             1, 1, 1, 0, st)
         offs = [t for t in range(k * k)]
-        call("dm_unpack_wgrad", _p(dwp), _p(grad_buf(weight)), cout, cin, k * k, _taps(offs), k * k, cout * k * k, 0,
-             ck, ck, 1, st)
+        unpack = (cout, cin, k * k, _taps(offs), k * k, cout * k * k, 0, ck, ck, 1)
+        _wgrad_into(weight, (kc, ck), unpack, lambda dwp: call(
+            "dm_conv2d_wgrad", _p(x), cin, x.stride(2), None, 0, 0, _p(s2d), s2d.stride(2), _p(dwp), n, hin, win, kc,
+            1, 1, 1, 0, st))
         dx = None
         if ctx.needs_input_grad[0]:
             wd = ctx.pack.get(weight, "convt_dgrad")
@@ -293,7 +368,7 @@ class _BnAct(torch.autograd.Function):
     """BatchNorm2d (eps 1e-5, momentum 0.1) + activation (new_scripy.py:185-186)."""
 
     @staticmethod
-    def forward(ctx, y, stats, gamma, beta, rmean, rvar, c, training, act, momentum, eps):
+    def forward(ctx, y, stats, gamma, beta, rmean, rvar, conv_bias, c, training, act, momentum, eps):
         ldy = _chk(y, "bn input")
         n, h, w, _ = y.shape
         mean = torch.empty(c, device=y.device, dtype=torch.float32)
@@ -307,30 +382,34 @@ class _BnAct(torch.autograd.Function):
         z = torch.empty_like(y)
         call("dm_bn_act_fwd", _p(y), ldy, _p(mean), _p(invstd), _p(gamma), _p(beta), _p(z), z.stride(2), n * h * w, c,
              act, st)
-        ctx.save_for_backward(y, mean, invstd, gamma, beta)
+        ctx.save_for_backward(y, mean, invstd, gamma, beta, conv_bias)
         ctx.cfg = (c, training, act)
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        y, mean, invstd, gamma, beta = ctx.saved_tensors
+        y, mean, invstd, gamma, beta, conv_bias = ctx.saved_tensors
         c, training, act = ctx.cfg
         lddz = _chk(dz, "bn grad")
         n, h, w, _ = y.shape
         dy = torch.empty_like(y)
-        scratch = torch.empty(2 * c, device=y.device, dtype=torch.float32)
+        npix = n * h * w
+        scratch = torch.empty(_lib.fn("dm_bn_act_bwd_scratch")(npix, c), device=y.device, dtype=torch.float32)
         call("dm_bn_act_bwd", _p(dz), lddz, _p(y), y.stride(2), _p(mean), _p(invstd), _p(gamma), _p(beta), _p(dy),
-             dy.stride(2), _p(grad_buf(gamma)), _p(grad_buf(beta)), _p(scratch), n * h * w, c, act, int(training),
+             dy.stride(2), _p(grad_buf(gamma)), _p(grad_buf(beta)),
+             _p(grad_buf(conv_bias)) if conv_bias is not None else None, _p(scratch), npix, c, act, int(training),
              _stream())
-        return dy, None, None, None, None, None, None, None, None, None, None
+        return dy, None, None, None, None, None, None, None, None, None, None, None
 
 
-def bn_act(y, stats, bn, act):
+def bn_act(y, stats, bn, act, conv_bias=None):
+    """``conv_bias``: bias parameter of the convolution that produced ``y`` (called with
+    ``bias_grad_by_norm=True``); its gradient is produced by this norm's backward."""
     training = bn.training
     if training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    return _BnAct.apply(y, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_features, training, act,
-                        float(bn.momentum), float(bn.eps))
+    return _BnAct.apply(y, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var, conv_bias, bn.num_features,
+                        training, act, float(bn.momentum), float(bn.eps))
 
 
 class _GnAct(torch.autograd.Function):

@@ -22,7 +22,8 @@ class FusedAdamW(torch.optim.Optimizer):
     """AdamW (decoupled weight decay, bias correction: torch.optim.AdamW semantics) with optional
     global-norm clipping folded into the update.  ``param_groups[0]['lr']`` stays schedulable."""
 
-    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=0.0):
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=0.0,
+                 defer_weight_grads=True):
         params = [p for p in params if p.requires_grad]
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.max_grad_norm = float(max_grad_norm)
@@ -48,6 +49,15 @@ class FusedAdamW(torch.optim.Optimizer):
                 view.copy_(p.data)
                 p.data = view
         self._attach_grads()
+        # conv weight gradients stay in the wgrad GEMM's packed layout across the accumulation window and
+        # are scattered into the flat gradient once per step (see ops._PackedGrad)
+        if defer_weight_grads:
+            ops.defer_weight_grads(params)
+
+    def flush(self):
+        """Make ``p.grad`` (the flat gradient buffer) complete: scatter any packed weight gradients."""
+        self._attach_grads()
+        ops.flush_weight_grads()
 
     def _attach_grads(self):
         for p, o in zip(self._params, self._offsets):
@@ -58,20 +68,21 @@ class FusedAdamW(torch.optim.Optimizer):
                 p.grad = gv
 
     def zero_grad(self, set_to_none: bool = False):
+        ops.discard_weight_grads()
         self.flat_grad.zero_()
         self._attach_grads()
 
     @torch.no_grad()
     def grad_norm(self):
         """Global L2 norm of the (flat) gradient as a device scalar."""
-        self._attach_grads()
+        self.flush()
         self._gnorm_sq.zero_()
         ops.call("dm_sumsq", _p(self.flat_grad), self._n, _p(self._gnorm_sq), ops._stream())
         return self._gnorm_sq.sqrt()
 
     @torch.no_grad()
     def step(self, closure=None):
-        self._attach_grads()
+        self.flush()
         g = self.param_groups[0]
         self._step += 1
         b1, b2 = g["betas"]

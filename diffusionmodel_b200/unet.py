@@ -30,17 +30,17 @@ def _pack_of(conv):
     return pk
 
 
-def conv(x, m, *, x1=None, c1=0, want_stats=False, out_f32=False):
+def conv(x, m, *, x1=None, c1=0, want_stats=False, out_f32=False, bias_grad_by_norm=False):
     """Run an nn.Conv2d container through the implicit-GEMM kernel."""
     return ops.conv2d(x, m.weight, m.bias, _pack_of(m), x1=x1, c1=c1, stride=m.stride[0], pad=m.padding[0],
-                      want_stats=want_stats, out_f32=out_f32)
+                      want_stats=want_stats, out_f32=out_f32, bias_grad_by_norm=bias_grad_by_norm)
 
 
 def conv_bn_act(x, seq, act=ACT_GELU, **kw):
     """Sequential(Conv2d, BatchNorm2d, GELU): conv with fused statistics, then one normalise+activate pass."""
     cv, bn = seq[0], seq[1]
-    y, stats = conv(x, cv, want_stats=bn.training, **kw)
-    return ops.bn_act(y, stats, bn, act)
+    y, stats = conv(x, cv, want_stats=bn.training, bias_grad_by_norm=cv.bias is not None, **kw)
+    return ops.bn_act(y, stats, bn, act, conv_bias=cv.bias)
 
 
 # ------------------------------------------------------------------------------------------ blocks

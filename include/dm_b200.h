@@ -30,13 +30,13 @@ long long dm_launch_count(void);   /* kernels launched by this library so far (b
  * nn.Conv2d forward: new_scripy.py:166,169,184,188,217,222,225,229,243,311,314; MNIST_script.py:42,46,149,152.
  * x0 (++ x1 concatenated on channels: replaces torch.cat new_scripy.py:355 / MNIST_script.py:186),
  * wpk = dm_pack_weight() output [Cout][kh*kw][Cin_k]; y bf16 (y_f32=0) or fp32 (y_f32=1, ldy%4==0);
- * stats (nullable): [dm_conv2d_fwd_mtiles()][2][stats_ld] per-tile sum / sum-of-squares of y for the
- * train-mode BatchNorm that follows.  The data gradient of a stride-1 conv is the same call with the
+ * stats (nullable): [dm_conv2d_fwd_stat_rows()][2][stats_ld] per-CTA sum / sum-of-squares of y for the
+ * train-mode BatchNorm that follows (accumulated across the CTA's tiles in shared memory).  The data gradient of a stride-1 conv is the same call with the
  * flipped/transposed weight pack and pad' = k-1-pad. */
 int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, int C1, int ld1, const void* wpk,
                   const float* bias, void* y, int ldy, int y_f32, float* stats, int stats_ld, int N, int Hin,
                   int Win, int Cout, int kh, int kw, int stride, int pad, void* stream);
-int dm_conv2d_fwd_mtiles(int N, int Ho, int Wo);
+int dm_conv2d_fwd_stat_rows(int N, int Ho, int Wo, int Cout);
 /* data gradient of Conv2d(k=4, s=2, p=1) (new_scripy.py:229); wpk = 4 phase packs, see weights.py */
 int dm_conv2d_s2_dgrad(const void* dy, int Cout, int lddy, const void* wpk, void* dx, int Cin, int lddx,
                        int N, int Ho, int Wo, void* stream);
@@ -55,10 +55,11 @@ int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, int C1, int
 int dm_pack_weight(const float* w, void* out, int rows, int cols, int ntaps, const long long* tap_off_host,
                    long long s_row, long long s_col, int c_split, int cols_k, long long row_len,
                    int tap_major_rows, void* stream);
-/* inverse gather: grad[...] += dwp[...] with the same addressing (fp32 -> fp32) */
-int dm_unpack_wgrad(const float* dwp, float* grad, int rows, int cols, int ntaps, const long long* tap_off_host,
+/* inverse scatter: grad[...] += dwp[...] with the same addressing (fp32 -> fp32); consume != 0 also
+ * re-zeroes the packed accumulator (persistent per-parameter accumulators, flushed once per optimizer step) */
+int dm_unpack_wgrad(float* dwp, float* grad, int rows, int cols, int ntaps, const long long* tap_off_host,
                     long long s_row, long long s_col, int c_split, int cols_k, long long row_len,
-                    int tap_major_rows, void* stream);
+                    int tap_major_rows, int consume, void* stream);
 
 /* ---- layout conversion --------------------------------------------------------------------------- */
 int dm_nchw_to_nhwc(const float* x, void* y, int ldy, int y_f32, int N, int C, int H, int W, void* stream);
@@ -73,10 +74,14 @@ int dm_bn_finalize(const float* partials, int m_tiles, int ld, int C, double cou
                    float* running_mean, float* running_var, float momentum, float eps, void* stream);
 int dm_bn_act_fwd(const void* y, int ldy, const float* mean, const float* invstd, const float* gamma,
                   const float* beta, void* z, int ldz, long long P, int C, int act, void* stream);
-/* dy = BN/act backward; dgamma/dbeta += ; scratch >= 2*C floats; training=0 drops the batch-stat terms */
+/* dy = BN/act backward (three launches: block partial sums -> finalize -> apply); dgamma/dbeta += ;
+ * dbias (nullable) += the bias gradient of the convolution that feeds this norm (sum_p dy, evaluated
+ * from the same sums instead of a separate pass over dy); scratch >= dm_bn_act_bwd_scratch(P, C)
+ * floats; training=0 drops the batch-statistic terms. */
+long long dm_bn_act_bwd_scratch(long long P, int C);
 int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, const float* mean, const float* invstd,
                   const float* gamma, const float* beta, void* dy, int lddy, float* dgamma, float* dbeta,
-                  float* scratch, long long P, int C, int act, int training, void* stream);
+                  float* dbias, float* scratch, long long P, int C, int act, int training, void* stream);
 
 /* ---- GroupNorm(8,C) + ReLU/GELU (new_scripy.py:167-168,299-300,312-313) --------------------------- */
 int dm_gn_act_fwd(const void* x, int ldx, const float* gamma, const float* beta, void* z, int ldz, float* mean,

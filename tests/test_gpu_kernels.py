@@ -118,6 +118,33 @@ def test_conv2d_f32_head_and_dual_source(dev):
     assert rel(wd.grad.cpu(), wr.grad) < F32_TOL
 
 
+@pytest.mark.parametrize("version", [1, 2])
+@pytest.mark.parametrize("case", [(2, 16, 16, 64, 512, 3, 1, 1), (1, 32, 32, 192, 192, 3, 1, 1), (2, 16, 16, 96, 128, 4, 2, 1),
+                                  (4, 8, 8, 320, 640, 1, 1, 0), (3, 10, 12, 40, 24, 3, 1, 1)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_wgrad_both_kernels(dev, case, version):
+    """Both weight-gradient kernels (M = Cout tiles / M = im2col boxes) on shapes either may be chosen for."""
+    from diffusionmodel_b200 import _lib, ops
+    n, h, w, cin, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(41)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    xr = x.clone()
+    wr = bf(wt).requires_grad_(True)
+    y_ref = F.conv2d(xr, wr, None, stride, pad)
+    dy = bf(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    wd = torch.nn.Parameter(wt.to(dev))
+    _lib.debug_set(4, version)
+    try:
+        y, _ = ops.conv2d(nhwc(x, dev), wd, None, ops.WeightPack(), stride=stride, pad=pad)
+        y.backward(nhwc(dy, dev))
+        torch.cuda.synchronize()
+    finally:
+        _lib.debug_set(4, 0)
+    assert rel(wd.grad.cpu(), wr.grad) < F32_TOL
+
+
 @pytest.mark.parametrize("case", [(4, 2, 2, 128, 128, 8), (3, 1, 1, 32, 32, 7), (2, 7, 7, 64, 16, 2)],
                          ids=lambda c: "x".join(map(str, c)))
 def test_conv_transpose(dev, case):

@@ -89,10 +89,17 @@ def test_against_golden(dev, tag):
                     worst = (r, k)
         return (num / den) ** 0.5, worst
 
+    # bar: 1e-2 where bf16 itself allows it; on configurations where PyTorch's own autocast(bfloat16) run
+    # of the reference is already beyond 0.8e-2 from fp32 (the floor from operand rounding alone is
+    # 0.86e-2 on rdd_f16_s128_b2), no farther than 1.25x that distance.
     _, g_eval = oracle_grads(False)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        _, g_eval_ac = oracle_grads(False)
     e_g, worst = agg_err(grads_of(ddpm), g_eval)
-    print(f"{tag}: eval-mode grad rel-L2 vs fp32 oracle = {e_g:.3e}; worst significant tensor {worst[1]} {worst[0]:.3e}")
-    assert e_g < BAR and worst[0] < 3e-2
+    e_ac_eval, _ = agg_err({k: v.float() for k, v in g_eval_ac.items()}, g_eval)
+    print(f"{tag}: eval-mode grad rel-L2 vs fp32 oracle = {e_g:.3e} (torch autocast(bf16): {e_ac_eval:.3e}); "
+          f"worst significant tensor {worst[1]} {worst[0]:.3e}")
+    assert e_g < max(BAR, 1.25 * e_ac_eval) and worst[0] < 3e-2
 
     # ---- train mode.  Batch-statistic BatchNorm amplifies bf16 rounding chaotically (SURVEY.md App. D:
     # PyTorch's own autocast(bf16) run of the reference is ~1e-1 from fp32), so the end-to-end train-mode
