@@ -254,6 +254,23 @@ def run_ours(args):
     if rank == 0 and os.environ.get("DM_BENCH_BREAKDOWN"):
         with open(os.environ["DM_BENCH_BREAKDOWN"], "w") as f:
             json.dump({k: v for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}, f, indent=1)
+    # ---- sampled img/s: the CFG reverse loop (new_scripy.py:441-477) on this rank's shard of trajectories:
+    # samples_per_class=3 x 5 classes (the CLI default --samples 3), guide_w=2.0, timed over a bounded number
+    # of the n_T=700 identical reverse steps; device-side noise (the reference's per-step CPU randn + H2D is
+    # kept as DDPM(sample_noise="reference") for parity runs)
+    ddpm.eval()
+    ddpm.sample_noise = "device"
+    n_samp, s_steps = 3 * CFG["n_classes"], max(args.steps, 5)
+    ddpm.sample(n_samp, (3, CFG["img"], CFG["img"]), dev, guide_w=2.0, steps=3)          # warm-up (packs, folds)
+    torch.cuda.synchronize()
+    ms_samp = timed(lambda: ddpm.sample(n_samp, (3, CFG["img"], CFG["img"]), dev, guide_w=2.0, steps=s_steps), 1) / s_steps
+    gf_exec = n_samp * (649.7 + 2 * (696.5 - 86.97))      # shared encoder once, decoder twice, LocalEnhancer(+0) skipped
+    sampling = {"n_sample_per_gpu": n_samp, "guide_w": 2.0, "n_T": CFG["n_T"], "steps_timed": s_steps,
+                "ms_per_reverse_step": ms_samp, "imgs_per_s": world * n_samp / (CFG["n_T"] * ms_samp * 1e-3),
+                "noise": "device", "shared_encoder_cfg": True, "executed_tflops": gf_exec / ms_samp / 1e3,
+                "reference_schedule_tflops": n_samp * 2 * 1346.17 / ms_samp / 1e3}
+    ddpm.train()
+
     # host-side enqueue cost of one step (Python + autograd + ctypes), kernels stubbed out
     real_call = ops.call
     ops.call = lambda *a, **k: 0
@@ -284,7 +301,8 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * accum,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof}
+                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof,
+                "sampling": sampling}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -296,7 +314,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -52,7 +52,7 @@ _D = ctypes.c_double
 
 # argument signatures, in header order (p = pointer, i = int, l = long long, f = float, d = double)
 _SIGS = {
-    "dm_conv2d_fwd": "pii pii p p pii pi iiiiiiii p",
+    "dm_conv2d_fwd": "pii pii p p pi pii pi iiiiiiii p",
     "dm_conv2d_fwd_stat_rows": "iiii",
     "dm_conv2d_s2_dgrad": "pii p pii iii p",
     "dm_convt_fwd": "pii p p pi iiiii p",

@@ -32,7 +32,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;        // bf16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kAStage = kBlockM * kBlockK * 2;       // 16 KB
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;        // weight-gradient kernels: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kConvThreads = 320;    // conv kernel: TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kAuxBytes = 512;                       // barriers + TMEM slot (the BN-statistics slab follows, sized per launch)
 constexpr int kMaxStatBytes = 48 * 1024;
@@ -57,6 +58,8 @@ struct ConvParams {
   int convt_k;
   long long sKy, sKx;
   const float* bias;
+  const float* scale;           // optional per-channel multiplier applied before the bias (folded eval-mode BatchNorm)
+  int act;                      // activation fused after scale/bias: 0 none, 1 GELU, 2 ReLU
   float* stats;
   int stats_ld;
   unsigned idesc;
@@ -215,7 +218,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, int stages, int stage_
 }
 
 // ------------------------------------------------------------------------------------------ kernel A
-__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stage_bytes = kAStage + p.b_stage_bytes;
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(L.full + 8 * s, 1); mbar_init(L.empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(L.tfull + 8 * s, 1); mbar_init(L.tempty + 8 * s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(L.tfull + 8 * s, 1); mbar_init(L.tempty + 8 * s, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     tma_prefetch_desc(&p.tmB);
   }
   float* const slab = reinterpret_cast<float*>(smem_raw + (L.stat - smem_u32(smem_raw)));
-  for (int i = threadIdx.x; i < 2 * p.stat_c; i += kThreads) slab[i] = 0.0f;
+  for (int i = threadIdx.x; i < 2 * p.stat_c; i += kConvThreads) slab[i] = 0.0f;
   if (warp == 1) tc_alloc(L.tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -292,8 +295,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31): they take alternate
+    // 32-column chunks, which hides the tcgen05.ld / shuffle latencies of this instruction-heavy stage.
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // 0: even chunks, 1: odd chunks
     const int row = q * 32 + lane;          // row of the 128-pixel tile
     const int bw = 1 << p.log_bw, bh = 1 << p.log_bh;
     int it = 0;
@@ -316,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       mbar_wait(L.tfull + 8 * as, aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
-      for (int cc = 0; cc < p.block_n; cc += 32) {
+      for (int cc = half * 32; cc < p.block_n; cc += 64) {
         float v[32];
         tc_ld32(t_row + (uint32_t)cc, v);
         const int cbase = co0 + cc;         // first output channel of this chunk
@@ -324,7 +330,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int j = 0; j < 32; ++j) {
           const int c = cbase + j;
           const float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.0f;
-          v[j] = (c < p.Cout && cc + j < p.block_n) ? v[j] + b : 0.0f;
+          const float sc = (p.scale != nullptr && c < p.Cout) ? __ldg(p.scale + c) : 1.0f;
+          v[j] = (c < p.Cout && cc + j < p.block_n) ? fmaf(v[j], sc, b) : 0.0f;
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = dm::gelu_f(v[j]);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
         }
         if (valid) {
           if (p.out_f32) {
@@ -362,10 +376,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     if (p.stats != nullptr) {
       // one partial row per CTA: [blockIdx.x][2][stats_ld]
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = threadIdx.x - 64;     // 0..127
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int e = threadIdx.x - 64;     // 0..255
       float* g = p.stats + (long long)blockIdx.x * 2 * p.stats_ld;
-      for (int c = e; c < p.Cout; c += 128) {
+      for (int c = e; c < p.Cout; c += 256) {
         g[c] = slab[c];
         g[p.stats_ld + c] = slab[p.stat_c + c];
       }
@@ -744,7 +758,7 @@ static int launch_conv(ConvParams& P, cudaStream_t st) {
   }
   int grid = conv_grid(P.m_tiles * P.n_tiles);
   if (!P.stats && g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
-  conv_gemm_kernel<<<grid, kThreads, smem, st>>>(P);
+  conv_gemm_kernel<<<grid, kConvThreads, smem, st>>>(P);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
@@ -764,12 +778,14 @@ static void fill_common(ConvParams& P, int N, int H, int W, int Cout_rows, int b
 }
 
 // ---------------------------------------------------------------------------------------------------
-// dm_conv2d_fwd: y[N,Ho,Wo,Cout] = conv(x0 (++ x1 on channels), Wp) + bias    (bf16 NHWC in, bf16/fp32 out)
+// dm_conv2d_fwd: y[N,Ho,Wo,Cout] = act(conv(x0 (++ x1 on channels), Wp) * scale + bias)   (bf16 NHWC in, bf16/fp32 out)
+// scale (nullable -> 1) and act (0 none / 1 GELU / 2 ReLU) fold an eval-mode BatchNorm + activation into the epilogue.
 // stride 1: any kh,kw,pad.  stride 2: even Hin,Win (parity views), single source.
 // stats (optional): per-CTA partial sums [dm_conv2d_fwd_stat_rows()][2][stats_ld] of y and y^2 for train-mode BatchNorm.
 extern "C" int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, int C1, int ld1, const void* wpk,
-                             const float* bias, void* y, int ldy, int y_f32, float* stats, int stats_ld, int N, int Hin,
-                             int Win, int Cout, int kh, int kw, int stride, int pad, void* stream) {
+                             const float* bias, const float* scale, int act, void* y, int ldy, int y_f32, float* stats,
+                             int stats_ld, int N, int Hin, int Win, int Cout, int kh, int kw, int stride, int pad,
+                             void* stream) {
   if (ensure_encode() != DM_OK) return DM_ERR_TMA;
   if (kh * kw > 16 || (stride != 1 && stride != 2)) { dm_set_error("dm_conv2d_fwd: unsupported kernel/stride"); return DM_ERR_ARG; }
   if (stride == 2 && (x1 != nullptr || (Hin & 1) || (Win & 1))) { dm_set_error("dm_conv2d_fwd: stride 2 needs one source, even H/W"); return DM_ERR_ARG; }
@@ -817,7 +833,8 @@ extern "C" int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, in
   P.out = y; P.out_f32 = y_f32;
   P.sN = (long long)Ho * Wo * ldy; P.sH = (long long)Wo * ldy; P.sW = ldy;
   P.Cout = Cout; P.ldc_pad = ldy;
-  P.bias = bias; P.stats = stats; P.stats_ld = stats_ld;
+  P.bias = bias; P.scale = scale; P.act = act; P.stats = stats; P.stats_ld = stats_ld;
+  if (stats && (scale || act)) { dm_set_error("dm_conv2d_fwd: statistics are taken of the plain conv output (no scale/act)"); return DM_ERR_ARG; }
   return launch_conv(P, (cudaStream_t)stream);
 }
 

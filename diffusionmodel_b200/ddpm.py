@@ -62,6 +62,7 @@ class DDPM(nn.Module):
         self.variant = getattr(nn_model, "variant", "rdd")
         self.enhance_with_attn_map = enhance_with_attn_map
         self.sample_noise = sample_noise
+        self.shared_encoder_cfg = True      # exact in eval mode (see sample()); False = the reference's 2n-batch encoder
         self._host_sched = None
 
     # ------------------------------------------------------------------ training
@@ -114,6 +115,7 @@ class DDPM(nn.Module):
         ctx_mask = torch.zeros_like(c_i)
         ctx_mask[n_sample:] = 1.0
         xt = ops.to_nhwc(torch.cat([x_i, x_i], 0))
+        shared = self.shared_encoder_cfg and not self.nn_model.training
         store = []
         done = 0
         for i in range(n_T, 0, -1):
@@ -123,7 +125,14 @@ class DDPM(nn.Module):
                 z = z.float().contiguous()
             else:
                 z = None
-            eps = self.nn_model.forward_nhwc(xt, c_i, t_is, ctx_mask)
+            if shared:
+                # eval mode: the encoder sees neither c nor ctx_mask and t is the same for both halves, so the
+                # two halves of the reference's doubled batch are identical up to up0 -- run it once
+                enc = self.nn_model.encode(xt[:n_sample])
+                enc = {k: torch.cat([v, v], 0) for k, v in enc.items()}
+                eps = self.nn_model.decode(enc, c_i, t_is, ctx_mask)
+            else:
+                eps = self.nn_model.forward_nhwc(xt, c_i, t_is, ctx_mask)
             x_i, xt = ops.cfg_reverse_step(eps, x_i, z, guide_w, sched["oneover_sqrta"][i],
                                            sched["mab_over_sqrtmab"][i], sched["sqrt_beta_t"][i])
             if self.variant == "mnist" and (i % 20 == 0 or i == n_T or i < 8):

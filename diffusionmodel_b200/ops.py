@@ -246,6 +246,7 @@ class _Conv2d(torch.autograd.Function):
         ho = (hin + 2 * pad - kh) // stride + 1
         wo = (win + 2 * pad - kw) // stride + 1
         wpk = pack.get(weight, "fwd", c_split=c0 if x1 is not None else 0)
+        scale, act = None, ACT_NONE
         if out_f32:
             y = torch.empty((n, ho, wo, (cout + 3) // 4 * 4), device=x0.device, dtype=torch.float32)
         else:
@@ -253,7 +254,7 @@ class _Conv2d(torch.autograd.Function):
         stats = None
         if want_stats:
             stats = torch.empty((conv_stat_rows(n, ho, wo, cout), 2, cout), device=x0.device, dtype=torch.float32)
-        call("dm_conv2d_fwd", _p(x0), c0, ld0, _p(x1), c1, ld1, _p(wpk), _p(bias), _p(y), y.stride(2), int(out_f32),
+        call("dm_conv2d_fwd", _p(x0), c0, ld0, _p(x1), c1, ld1, _p(wpk), _p(bias), _p(scale), act, _p(y), y.stride(2), int(out_f32),
              _p(stats), cout, n, hin, win, cout, kh, kw, stride, pad, _stream())
         ctx.save_for_backward(x0, x1, weight, bias)
         ctx.pack, ctx.geom = pack, (c0, c1, stride, pad, out_f32, bias_grad_by_norm)
@@ -294,7 +295,7 @@ class _Conv2d(torch.autograd.Function):
             dx = torch.empty((n, hin, win, width), device=dy.device, dtype=torch.bfloat16)
             if stride == 1:
                 wd = ctx.pack.get(weight, "dgrad")
-                call("dm_conv2d_fwd", _p(dy), cout, lddy, None, 0, 0, _p(wd), None, _p(dx), dx.stride(2), 0, None, 0,
+                call("dm_conv2d_fwd", _p(dy), cout, lddy, None, 0, 0, _p(wd), None, None, 0, _p(dx), dx.stride(2), 0, None, 0,
                      n, ho, wo, cin, kh, kw, 1, kh - 1 - pad, st)
             else:
                 wd = ctx.pack.get(weight, "s2dgrad")
@@ -304,6 +305,23 @@ class _Conv2d(torch.autograd.Function):
             else:
                 dx0, dx1 = dx[..., :c0], dx[..., c0:]
         return dx0, dx1, None, None, None, None, None, None, None, None, None, None
+
+
+def conv2d_fused_eval(x0, weight, pack, shift, scale, act, *, x1=None, c1=0, stride=1, pad=0):
+    """Inference-only conv with an eval-mode BatchNorm + activation folded into the epilogue:
+    act(conv(x) * scale + shift) in ONE kernel (sampling loop; no autograd tape)."""
+    c0 = weight.shape[1] - c1
+    ld0 = _chk(x0, "conv input")
+    ld1 = _chk(x1, "conv input 2") if x1 is not None else 0
+    n, hin, win, _ = x0.shape
+    cout, cin, kh, kw = weight.shape
+    ho = (hin + 2 * pad - kh) // stride + 1
+    wo = (win + 2 * pad - kw) // stride + 1
+    wpk = pack.get(weight, "fwd", c_split=c0 if x1 is not None else 0)
+    y = new_act(n, ho, wo, cout, x0.device)
+    call("dm_conv2d_fwd", _p(x0), c0, ld0, _p(x1), c1, ld1, _p(wpk), _p(shift), _p(scale), act, _p(y), y.stride(2), 0,
+         None, 0, n, hin, win, cout, kh, kw, stride, pad, _stream())
+    return y
 
 
 def conv2d(x0, weight, bias, pack, *, x1=None, c0=None, c1=0, stride=1, pad=0, want_stats=False, out_f32=False,
@@ -354,7 +372,7 @@ class _ConvT(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wd = ctx.pack.get(weight, "convt_dgrad")
             dx = new_act(n, hin, win, cin, dy.device)
-            call("dm_conv2d_fwd", _p(s2d), kc, s2d.stride(2), None, 0, 0, _p(wd), None, _p(dx), dx.stride(2), 0, None, 0,
+            call("dm_conv2d_fwd", _p(s2d), kc, s2d.stride(2), None, 0, 0, _p(wd), None, None, 0, _p(dx), dx.stride(2), 0, None, 0,
                  n, hin, win, cin, 1, 1, 1, 0, st)
         return dx, None, None, None, None
 
@@ -847,7 +865,7 @@ class _Profile:
     def _flops(name, a):
         if name in ("dm_conv2d_fwd", "dm_conv2d_wgrad"):
             if name == "dm_conv2d_fwd":
-                c0, c1, n, hin, win, cout, kh, kw, stride, pad = a[1], a[4], a[13], a[14], a[15], a[16], a[17], a[18], a[19], a[20]
+                c0, c1, n, hin, win, cout, kh, kw, stride, pad = a[1], a[4], a[15], a[16], a[17], a[18], a[19], a[20], a[21], a[22]
             else:
                 c0, c1, n, hin, win, cout, kh, kw, stride, pad = a[1], a[4], a[9], a[10], a[11], a[12], a[13], a[14], a[15], a[16]
             ho, wo = (hin + 2 * pad - kh) // stride + 1, (win + 2 * pad - kw) // stride + 1

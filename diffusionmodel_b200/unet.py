@@ -36,9 +36,32 @@ def conv(x, m, *, x1=None, c1=0, want_stats=False, out_f32=False, bias_grad_by_n
                       want_stats=want_stats, out_f32=out_f32, bias_grad_by_norm=bias_grad_by_norm)
 
 
+def _folded_bn(cv, bn):
+    """Eval-mode BatchNorm folded onto the conv output: y*scale + shift with the running statistics
+    (constants while sampling).  Cached per module until a parameter or buffer changes."""
+    ts = [bn.weight, bn.bias, bn.running_mean, bn.running_var] + ([cv.bias] if cv.bias is not None else [])
+    stamp = tuple(t._version for t in ts) + tuple(t.data_ptr() for t in ts) + (ops._weights_epoch,)
+    hit = bn.__dict__.get("_dm_fold")
+    if hit is not None and hit[0] == stamp:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        scale = (bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)).contiguous()
+        shift = bn.bias.float() - bn.running_mean.float() * scale
+        if cv.bias is not None:
+            shift = shift + cv.bias.float() * scale
+        shift = shift.contiguous()
+    bn.__dict__["_dm_fold"] = (stamp, scale, shift)
+    return scale, shift
+
+
 def conv_bn_act(x, seq, act=ACT_GELU, **kw):
-    """Sequential(Conv2d, BatchNorm2d, GELU): conv with fused statistics, then one normalise+activate pass."""
+    """Sequential(Conv2d, BatchNorm2d, GELU): conv with fused statistics, then one normalise+activate pass
+    (training / autograd); in no-grad eval mode the norm and activation ride in the conv epilogue."""
     cv, bn = seq[0], seq[1]
+    if not bn.training and not torch.is_grad_enabled():
+        scale, shift = _folded_bn(cv, bn)
+        return ops.conv2d_fused_eval(x, cv.weight, _pack_of(cv), shift, scale, act, stride=cv.stride[0],
+                                     pad=cv.padding[0], **kw)
     y, stats = conv(x, cv, want_stats=bn.training, bias_grad_by_norm=cv.bias is not None, **kw)
     return ops.bn_act(y, stats, bn, act, conv_bias=cv.bias)
 
@@ -258,8 +281,9 @@ class ContextUnet(nn.Module):
         self.out = nn.Sequential(nn.Conv2d(2 * f, f, 3, 1, 1), nn.GroupNorm(8, f), nn.ReLU(),
                                  nn.Conv2d(f, self.in_ch, 3, 1, 1))
 
-    def forward_nhwc(self, x, c, t, ctx_mask, attn_map=None):
-        """x: bf16 NHWC; returns eps as fp32 NHWC (pitch 4 for 3 channels)."""
+    def encode(self, x):
+        """Everything that does not depend on (c, t, ctx_mask): init_conv ... down4, CoordAttn, to_vec, up0
+        (new_scripy.py:318-332,347).  x: bf16 NHWC."""
         f = self.n_feat
         x0, x0_skip = ops.fork(self.init_conv(x), f)
         d1, d1s = ops.fork(self.ca1(self.down1(x0)), f)
@@ -268,23 +292,30 @@ class ContextUnet(nn.Module):
         d4 = self.ca4(self.down4(d3))
         d4, d4s = ops.fork(d4, 8 * f)
         hidden = ops.avgpool_act(d4, 8 * f, 8, ACT_GELU)
+        u1 = ops.conv_transpose(hidden, self.up0[0].weight, self.up0[0].bias, _pack_of(self.up0[0]), 8)
+        u1 = ops.gn_act(u1, self.up0[1], ACT_RELU)
+        return dict(x0=x0_skip, d1=d1s, d2=d2s, d3=d3s, d4=d4s, u1=u1)
 
+    def decode(self, enc, c, t, ctx_mask, attn_map=None):
+        """Embeddings, FiLM, up1..up4, LocalEnhancer, head (new_scripy.py:334-355) -> eps as fp32 NHWC."""
+        f = self.n_feat
         c1h = F.one_hot(c.long(), num_classes=self.n_classes).type(torch.float)
         c1h = c1h * ctx_mask[:, None].repeat(1, self.n_classes).to(c1h.dtype)     # no flip (new_scripy.py:337-340)
         t = t.to(torch.float32)
         cemb1, temb1 = self.ctx_emb1(c1h), self.time_emb1(t)
         cemb2, temb2 = self.ctx_emb2(c1h), self.time_emb2(t)
-
-        u1 = ops.conv_transpose(hidden, self.up0[0].weight, self.up0[0].bias, _pack_of(self.up0[0]), 8)
-        u1 = ops.gn_act(u1, self.up0[1], ACT_RELU)
-        u2 = self.up1(ops.film(u1, cemb1, temb1, 8 * f), d4s, 8 * f, 8 * f)
-        u3 = self.up2(ops.film(u2, cemb2, temb2, 4 * f), d3s, 4 * f, 4 * f)
-        u4 = self.up3(u3, d2s, 2 * f, 2 * f)
-        u5 = self.up4(u4, d1s, f, f)
+        u2 = self.up1(ops.film(enc["u1"], cemb1, temb1, 8 * f), enc["d4"], 8 * f, 8 * f)
+        u3 = self.up2(ops.film(u2, cemb2, temb2, 4 * f), enc["d3"], 4 * f, 4 * f)
+        u4 = self.up3(u3, enc["d2"], 2 * f, 2 * f)
+        u5 = self.up4(u4, enc["d1"], f, f)
         if attn_map is not None:
             u5 = self.local_enhance(u5, attn_map)
         # attn_map None: the shipped call site adds conv(...) * 0 -- identical output, no side effects
-        return _head(u5, x0_skip, self.out, f)
+        return _head(u5, enc["x0"], self.out, f)
+
+    def forward_nhwc(self, x, c, t, ctx_mask, attn_map=None):
+        """x: bf16 NHWC; returns eps as fp32 NHWC (pitch 4 for 3 channels)."""
+        return self.decode(self.encode(x), c, t, ctx_mask, attn_map)
 
     def forward(self, x, c, t, ctx_mask, attn_map=None):
         if x.shape[2] % 128 or x.shape[3] % 128:
@@ -371,23 +402,31 @@ class MnistContextUnet(nn.Module):
     def in_ch(self):
         return self.in_channels
 
-    def forward_nhwc(self, x, c, t, context_mask, attn_map=None):
+    def encode(self, x):
+        """init_conv, down1, down2, to_vec, up0 (MNIST_script.py:157-161,176): independent of (c, t, mask)."""
         f = self.n_feat
         x0, x0s = ops.fork(self.init_conv(x), f)
         d1, d1s = ops.fork(self.down1(x0), f)
         d2, d2s = ops.fork(self.down2(d1), 2 * f)
         hidden = ops.avgpool_act(d2, 2 * f, 7, ACT_GELU)
+        u1 = ops.conv_transpose(hidden, self.up0[0].weight, self.up0[0].bias, _pack_of(self.up0[0]), 7)
+        u1 = ops.gn_act(u1, self.up0[1], ACT_RELU)
+        return dict(x0=x0s, d1=d1s, d2=d2s, u1=u1)
+
+    def decode(self, enc, c, t, context_mask, attn_map=None):
+        f = self.n_feat
         c1h = F.one_hot(c.long(), num_classes=self.n_classes).type(torch.float)
         m = context_mask[:, None].repeat(1, self.n_classes).to(c1h.dtype)
         c1h = c1h * (-1 * (1 - m))                                     # flip and negate (MNIST_script.py:170)
         t = t.to(torch.float32)
         cemb1, temb1 = self.contextembed1(c1h), self.timeembed1(t)
         cemb2, temb2 = self.contextembed2(c1h), self.timeembed2(t)
-        u1 = ops.conv_transpose(hidden, self.up0[0].weight, self.up0[0].bias, _pack_of(self.up0[0]), 7)
-        u1 = ops.gn_act(u1, self.up0[1], ACT_RELU)
-        u2 = self.up1(ops.film(u1, cemb1, temb1, 2 * f), d2s, 2 * f, 2 * f)
-        u3 = self.up2(ops.film(u2, cemb2, temb2, f), d1s, f, f)
-        return _head(u3, x0s, self.out, f)
+        u2 = self.up1(ops.film(enc["u1"], cemb1, temb1, 2 * f), enc["d2"], 2 * f, 2 * f)
+        u3 = self.up2(ops.film(u2, cemb2, temb2, f), enc["d1"], f, f)
+        return _head(u3, enc["x0"], self.out, f)
+
+    def forward_nhwc(self, x, c, t, context_mask, attn_map=None):
+        return self.decode(self.encode(x), c, t, context_mask)
 
     def forward(self, x, c, t, context_mask):
         y = self.forward_nhwc(ops.to_nhwc(x), c, t, context_mask)

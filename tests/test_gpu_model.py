@@ -199,6 +199,28 @@ def test_blocks_vs_oracle(dev, block):
     assert e_out < BAR and e_dx < 1.5e-2 and e_dw < 1.5e-2
 
 
+def test_shared_encoder_cfg_matches_reference_schedule(dev):
+    """Eval mode: running the encoder once for the n trajectories and the decoder on the doubled batch is the
+    same computation as the reference's schedule (encoder on the doubled batch).  Exact in exact arithmetic;
+    the per-sample reductions (GroupNorm / SE / CoordAttn pooling) split differently for n and 2n samples, so
+    the two differ by fp32 summation order only."""
+    for variant, n_feat, size, in_ch in (("rdd", 16, 128, 3), ("mnist", 16, 28, 1)):
+        ddpm, _ = build(variant, n_feat, 5 if variant == "rdd" else 10, 400, 3, dev)
+        ddpm.eval()
+        ncls = 10 if variant == "mnist" else 5
+        gg = torch.Generator().manual_seed(5)
+        x_T = torch.randn(ncls, in_ch, size, size, generator=gg)
+        zs = {i: torch.randn(ncls, in_ch, size, size, generator=gg) for i in range(400, 397, -1)}
+        outs = []
+        for shared in (True, False):
+            ddpm.shared_encoder_cfg = shared
+            o = ddpm.sample(ncls, (in_ch, size, size), dev, guide_w=2.0, steps=3, noise=(x_T, zs))
+            outs.append((o[0] if variant == "mnist" else o).cpu())
+        e = P.rel_l2(outs[0], outs[1])
+        print(f"{variant}: shared-encoder vs doubled-batch sampling rel-L2 = {e:.3e}")
+        assert e < 2e-3
+
+
 def test_state_dict_roundtrip_and_fail_loudly(dev):
     import diffusionmodel_b200 as D
     from diffusionmodel_b200._lib import DmB200Error

@@ -73,14 +73,14 @@ def main():
             P_ = ops._p
 
             def fwd():
-                ops.call("dm_conv2d_fwd", P_(x), cin, x.stride(2), None, 0, 0, P_(wpk), P_(b), P_(y), y.stride(2), 0,
+                ops.call("dm_conv2d_fwd", P_(x), cin, x.stride(2), None, 0, 0, P_(wpk), P_(b), None, 0, P_(y), y.stride(2), 0,
                          P_(stats), cout, n, h, h, cout, k, k, s, p, st)
             dx = torch.empty_like(x)
             if s == 1:
                 wd = pack.get(w, "dgrad")
 
                 def dgrad():
-                    ops.call("dm_conv2d_fwd", P_(dy), cout, dy.stride(2), None, 0, 0, P_(wd), None, P_(dx), dx.stride(2), 0,
+                    ops.call("dm_conv2d_fwd", P_(dy), cout, dy.stride(2), None, 0, 0, P_(wd), None, None, 0, P_(dx), dx.stride(2), 0,
                              None, 0, n, ho, ho, cin, k, k, 1, k - 1 - p, st)
             else:
                 wd = pack.get(w, "s2dgrad")
