@@ -91,6 +91,49 @@ class DDPM(nn.Module):
         pred = self.nn_model.forward_nhwc(xt, c, ts / self.n_T, ctx_mask, **kw)
         return ops.ddpm_loss(pred, noise, attn_mask if self.variant == "rdd" else None)
 
+    def capture_train_step(self, x, c, attn_mask=None, loss_scale=1.0, warmup=2):
+        """CUDA-graph one training micro-step: ``loss = self(x, c, attn_mask) * loss_scale; loss.backward()``.
+
+        Returns ``step(x, c, attn_mask=None, randoms=None) -> loss`` (a static device scalar, valid until the
+        next call) that copies the batch into the graph's static inputs, draws the step's randoms exactly
+        like ``forward`` (new_scripy.py:405-413) and replays ~500 kernel launches with one graph launch.
+        Gradients accumulate into the parameters' ``.grad`` (the optimizer's flat buffer) as in eager mode.
+        The warm-up/capture passes accumulate gradients too: call ``optimizer.zero_grad()`` afterwards.
+        Shapes are fixed to those of the example batch; parameters must not be re-allocated afterwards."""
+        sx, sc = x.detach().clone().float().contiguous(), c.detach().clone()
+        sm = attn_mask.detach().clone().to(self.device) if attn_mask is not None else None
+        r = self.draw_randoms(sx, sc)
+        st = [t.detach().clone() for t in r]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                (self.forward(sx, sc, sm, randoms=tuple(st)) * loss_scale).backward()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        from . import _lib
+        k0 = _lib.launch_count()
+        with ops.capture_log() as touched, torch.cuda.graph(graph):
+            loss = self.forward(sx, sc, sm, randoms=tuple(st)) * loss_scale
+            loss.backward()
+        touched = list(touched)
+        kernels = _lib.launch_count() - k0          # library kernels recorded in the graph (run on every replay)
+
+        def step(x, c, attn_mask=None, randoms=None):
+            rr = randoms if randoms is not None else self.draw_randoms(x, c)
+            sx.copy_(x, non_blocking=True)
+            sc.copy_(c, non_blocking=True)
+            if sm is not None:
+                sm.copy_(attn_mask, non_blocking=True)
+            for dst, src in zip(st, rr):
+                dst.copy_(src, non_blocking=True)
+            graph.replay()
+            for e in touched:
+                e.dirty = True
+            return loss
+        step.graph, step.kernels_per_replay = graph, kernels
+        return step
+
     # ------------------------------------------------------------------ sampling
     def _sched(self):
         if self._host_sched is None:

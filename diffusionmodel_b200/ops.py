@@ -9,6 +9,7 @@ per backward pass.
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 import torch
 
@@ -65,11 +66,14 @@ def grad_buf(p):
 
 # --------------------------------------------------------------------------------------- weight packs
 class WeightPack:
-    """bf16 K-major packs of one conv weight for the implicit-GEMM kernels, rebuilt when the fp32
-    master parameter changes (torch-side in-place update or the fused optimizer epoch)."""
+    """bf16 K-major packs of one conv weight for the implicit-GEMM kernels, rebuilt IN PLACE when the fp32
+    master parameter changes (torch-side in-place update or the fused optimizer epoch), so their
+    addresses stay valid inside captured CUDA graphs."""
 
     def __init__(self):
         self.cache = {}
+        self.weight = None
+        _all_packs.add(self)
 
     def get(self, w, kind, **kw):
         key = (kind, tuple(sorted(kw.items())))
@@ -77,9 +81,26 @@ class WeightPack:
         hit = self.cache.get(key)
         if hit is not None and hit[0] == stamp:
             return hit[1]
-        out = _PACKERS[kind](w.detach(), **kw)
+        self.weight = weakref.ref(w)
+        out = _PACKERS[kind](w.detach(), hit[1] if hit is not None else None, **kw)
         self.cache[key] = (stamp, out)
         return out
+
+    def refresh(self):
+        w = self.weight() if self.weight is not None else None
+        if w is not None:
+            for kind, kw in list(self.cache):
+                self.get(w, kind, **dict(kw))
+
+
+_all_packs = weakref.WeakSet()
+
+
+def refresh_weight_packs():
+    """Re-pack every cached weight pack whose master changed (called by the optimizer right after its
+    update, so no pack kernel runs inside a later forward/backward -- or inside a replayed graph)."""
+    for pk in list(_all_packs):
+        pk.refresh()
 
 
 def _taps(offs):
@@ -87,9 +108,10 @@ def _taps(offs):
     return arr
 
 
-def _pack(w, rows, cols, tap_offs, s_row, s_col, c_split, cols_k, row_len, tap_major):
+def _pack(w, out, rows, cols, tap_offs, s_row, s_col, c_split, cols_k, row_len, tap_major):
     total_rows = rows * (len(tap_offs) if tap_major else 1)
-    out = torch.empty((total_rows, row_len), device=w.device, dtype=torch.bfloat16)
+    if out is None or tuple(out.shape) != (total_rows, row_len):
+        out = torch.empty((total_rows, row_len), device=w.device, dtype=torch.bfloat16)
     call("dm_pack_weight", _p(w), _p(out), rows, cols, len(tap_offs), _taps(tap_offs), s_row, s_col, c_split,
          cols_k, row_len, 1 if tap_major else 0, _stream())
     return out
@@ -105,46 +127,49 @@ def conv_geom(w, c_split=0):
     return cout, cin, kh, kw, ck
 
 
-def _pack_fwd(w, c_split=0):
+def _pack_fwd(w, out=None, c_split=0):
     cout, cin, kh, kw, ck = conv_geom(w, c_split)
     offs = [r * kw + s for r in range(kh) for s in range(kw)]
-    return _pack(w, cout, cin, offs, cin * kh * kw, kh * kw, c_split, ck, kh * kw * ck, False)
+    return _pack(w, out, cout, cin, offs, cin * kh * kw, kh * kw, c_split, ck, kh * kw * ck, False)
 
 
-def _pack_dgrad(w):
+def _pack_dgrad(w, out=None):
     """stride-1 data gradient = conv with the 180-degree rotated kernel and Cin/Cout swapped."""
     cout, cin, kh, kw = w.shape
     ck = r64(cout)
     offs = [(kh - 1 - r) * kw + (kw - 1 - s) for r in range(kh) for s in range(kw)]
-    return _pack(w, cin, cout, offs, kh * kw, cin * kh * kw, 0, ck, kh * kw * ck, False)
+    return _pack(w, out, cin, cout, offs, kh * kw, cin * kh * kw, 0, ck, kh * kw * ck, False)
 
 
-def _pack_s2dgrad(w):
+def _pack_s2dgrad(w, out=None):
     """k=4, s=2, p=1 data gradient: four output-parity phases of 2x2 taps (see dm_conv2d_s2_dgrad)."""
     cout, cin, kh, kw = w.shape
     assert kh == 4 and kw == 4
     ck = r64(cout)
     rsel = {0: (1, 3), 1: (0, 2)}
-    packs = []
+    if out is None or tuple(out.shape) != (4 * cin, 4 * ck):
+        out = torch.empty((4 * cin, 4 * ck), device=w.device, dtype=torch.bfloat16)
+    i = 0
     for ph in range(2):
         for pw in range(2):
             offs = [r * kw + s for r in rsel[ph] for s in rsel[pw]]
-            packs.append(_pack(w, cin, cout, offs, kh * kw, cin * kh * kw, 0, ck, 4 * ck, False))
-    return torch.cat(packs, 0)
+            _pack(w, out[i * cin:(i + 1) * cin], cin, cout, offs, kh * kw, cin * kh * kw, 0, ck, 4 * ck, False)
+            i += 1
+    return out
 
 
-def _pack_convt_fwd(w):
+def _pack_convt_fwd(w, out=None):
     """ConvTranspose2d weight [Cin, Cout, k, k] -> rows (tap, co), K = ci."""
     cin, cout, k, _ = w.shape
     offs = [t for t in range(k * k)]
-    return _pack(w, cout, cin, offs, k * k, cout * k * k, 0, r64(cin), r64(cin), True)
+    return _pack(w, out, cout, cin, offs, k * k, cout * k * k, 0, r64(cin), r64(cin), True)
 
 
-def _pack_convt_dgrad(w):
+def _pack_convt_dgrad(w, out=None):
     """rows ci, K = (tap, co): a 1x1 conv over the space-to-depth'd output gradient."""
     cin, cout, k, _ = w.shape
     offs = [t for t in range(k * k)]
-    return _pack(w, cin, cout, offs, cout * k * k, k * k, 0, cout, r64(k * k * cout), False)
+    return _pack(w, out, cin, cout, offs, cout * k * k, k * k, 0, cout, r64(k * k * cout), False)
 
 
 _PACKERS = {"fwd": _pack_fwd, "dgrad": _pack_dgrad, "s2dgrad": _pack_s2dgrad,
@@ -173,6 +198,7 @@ class _PackedGrad:
 
 
 _deferred = {}          # weight.data_ptr() -> [weakref(param), _PackedGrad | None]
+_capture_log = None     # while a train step is being captured: the _PackedGrad entries it accumulates into
 
 
 def defer_weight_grads(params):
@@ -191,6 +217,20 @@ def _live_entries():
             del _deferred[key]              # parameter gone or re-homed: forget it
         elif e is not None:
             yield e
+
+
+class capture_log:
+    """Context manager used while CUDA-graph capturing a backward pass: collects the packed-gradient
+    accumulators the captured kernels write, so each replay can mark them dirty again."""
+
+    def __enter__(self):
+        global _capture_log
+        _capture_log = []
+        return _capture_log
+
+    def __exit__(self, *exc):
+        global _capture_log
+        _capture_log = None
 
 
 def flush_weight_grads():
@@ -222,6 +262,8 @@ def _wgrad_into(weight, shape, unpack_args, run):
             e = slot[1] = _PackedGrad(weight, shape)
         run(e.dwp)
         e.args, e.dirty = unpack_args, True
+        if _capture_log is not None:
+            _capture_log.append(e)
         return
     dwp = torch.zeros(shape, device=weight.device, dtype=torch.float32)
     run(dwp)

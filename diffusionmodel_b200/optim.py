@@ -96,3 +96,4 @@ class FusedAdamW(torch.optim.Optimizer):
              float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
              1.0 - b1 ** self._step, 1.0 - b2 ** self._step, gn, self.max_grad_norm, st)
         ops.bump_weights_epoch()
+        ops.refresh_weight_packs()
