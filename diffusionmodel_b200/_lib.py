@@ -62,7 +62,10 @@ _SIGS = {
     "dm_nchw_to_nhwc": "p pi i iiii p",
     "dm_cast_nhwc": "pi pi l i p",
     "dm_nhwc_to_nchw": "pii p iiii p",
+    "dm_im2col3x3": "pi p iiii p",
     "dm_space_to_depth": "pi pi iiiii p",
+    "dm_bn_stats_rows": "li",
+    "dm_bn_stats": "pi pi l i p",
     "dm_bn_finalize": "p iii d pp pp ff p",
     "dm_bn_act_fwd": "pi pppp pi l ii p",
     "dm_bn_act_bwd": "pi pi pppp pi pp p p l iii p",

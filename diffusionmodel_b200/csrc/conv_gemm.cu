@@ -38,6 +38,13 @@ constexpr int kSmemBudget = 227 * 1024;
 constexpr int kAuxBytes = 512;                       // barriers + TMEM slot (the BN-statistics slab follows, sized per launch)
 constexpr int kMaxStatBytes = 48 * 1024;
 constexpr int kMaxStages = 8;
+// halo kernel: an 8 x 16 pixel tile's 3x3 neighbourhood = 10 x 18 pixels x 64 channels, loaded ONCE per
+// 64-channel chunk; the nine filter taps are nine shifted views of it (descriptor start + (dy*10+dx) rows,
+// 8-row groups 10 rows = 1280 B apart).
+constexpr int kHaloW = 10, kHaloH = 18;
+constexpr int kHaloBytes = kHaloW * kHaloH * 128;             // 23040
+constexpr int kHaloStage = (kHaloBytes + 1023) / 1024 * 1024; // 23552: keeps every patch 1024-aligned
+constexpr int kHaloAStages = 2;
 
 struct TapInfo { int8_t dy, dx, map, pad_; };
 
@@ -51,6 +58,7 @@ struct ConvParams {
   int N, H, W;
   int stages, b_stage_bytes;
   int stat_c;                   // channels covered by the statistics slab (n_tiles * block_n), 0 = no statistics
+  int stat_rows;                // rows of the caller's statistics buffer (>= grid; the surplus is zero-filled)
   void* out;
   int out_f32;
   long long sN, sH, sW;
@@ -64,6 +72,10 @@ struct ConvParams {
   int stats_ld;
   unsigned idesc;
   unsigned long long desc_hi;   // upper 32 bits of the smem descriptors (SBO / version / layout)
+  // halo kernel (3x3, stride 1): ring of input patches + ring of weight tiles
+  int a_stages, base_off_mode;
+  int ablate;                   // dev: bit0 no MMA issue, bit1 no TMA loads, bit2 no epilogue work (timing decomposition)
+  unsigned long long desc_hi_halo;
 };
 
 struct WgradParams {
@@ -218,6 +230,106 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, int stages, int stage_
 }
 
 // ------------------------------------------------------------------------------------------ kernel A
+// Epilogue shared by the conv kernels (warps 2..9): TMEM -> registers -> scale/bias/activation ->
+// bf16|fp32 global store, plus the per-CTA BatchNorm statistics.
+__device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t bar_tfull, uint32_t bar_tempty, uint32_t tmem_base,
+                                              float* slab, int warp, int lane, int total_tiles) {
+  struct { uint32_t tfull, tempty; } L = {bar_tfull, bar_tempty};
+  // ===================================================================== epilogue (warps 2..9)
+  // Two warps per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31): they take alternate
+  // 32-column chunks, which hides the tcgen05.ld / shuffle latencies of this instruction-heavy stage.
+  const int q = warp & 3;                 // TMEM lane quarter this warp may access
+  const int half = (warp - 2) >> 2;       // 0: even chunks, 1: odd chunks
+  const int row = q * 32 + lane;          // row of the 128-pixel tile
+  const int bw = 1 << p.log_bw, bh = 1 << p.log_bh;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+    const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+    const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+    const int w = (tw << p.log_bw) + (row & (bw - 1));
+    const int h = (th << p.log_bh) + ((row >> p.log_bw) & (bh - 1));
+    const int n = (tb << p.log_bn) + (row >> (p.log_bw + p.log_bh));
+    const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
+    const int n_base = nt * p.block_n;
+    int co0 = n_base;
+    long long off = (long long)n * p.sN + (long long)h * p.sH + (long long)w * p.sW;
+    if (p.convt_k) {
+      const int tap = n_base / p.Cout;
+      co0 = n_base - tap * p.Cout;
+      off += (long long)(tap / p.convt_k) * p.sKy + (long long)(tap % p.convt_k) * p.sKx;
+    }
+    mbar_wait(L.tfull + 8 * as, aph);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+    for (int cc = half * 32; cc < ((p.ablate & 4) ? 0 : p.block_n); cc += 64) {
+      float v[32];
+      tc_ld32(t_row + (uint32_t)cc, v);
+      const int cbase = co0 + cc;         // first output channel of this chunk
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = cbase + j;
+        const float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.0f;
+        const float sc = (p.scale != nullptr && c < p.Cout) ? __ldg(p.scale + c) : 1.0f;
+        v[j] = (c < p.Cout && cc + j < p.block_n) ? fmaf(v[j], sc, b) : 0.0f;
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = dm::gelu_f(v[j]);
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+      }
+      if (valid) {
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + off + cbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (cbase + j < p.ldc_pad && cc + j < p.block_n)
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          bf16* o = reinterpret_cast<bf16*>(p.out) + off + cbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            if (cbase + j < p.ldc_pad && cc + j < p.block_n) {
+              uint4 u;
+              u.x = dm::pack2(v[j], v[j + 1]); u.y = dm::pack2(v[j + 2], v[j + 3]);
+              u.z = dm::pack2(v[j + 4], v[j + 5]); u.w = dm::pack2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = u;
+            }
+        }
+      }
+      if (p.stats != nullptr) {
+        // per-channel sum and sum of squares over this warp's 32 rows -> combined over the 4 warps below
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float x = valid ? v[j] : 0.0f; s1[j] = x; s2[j] = x * x; }
+        const float a = warp_colsum32(s1, lane), b2 = warp_colsum32(s2, lane);
+        // accumulated over all of this CTA's tiles in shared memory (atomics: four warps share a column)
+        atomicAdd(slab + n_base + cc + lane, a);
+        atomicAdd(slab + p.stat_c + n_base + cc + lane, b2);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(L.tempty + 8 * as);
+  }
+  if (p.stats != nullptr) {
+    // one partial row per CTA: [blockIdx.x][2][stats_ld]
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int e = threadIdx.x - 64;     // 0..255
+    float* g = p.stats + (long long)blockIdx.x * 2 * p.stats_ld;
+    for (int c = e; c < p.Cout; c += 256) {
+      g[c] = slab[c];
+      g[p.stats_ld + c] = slab[p.stat_c + c];
+    }
+    for (int r = blockIdx.x + gridDim.x; r < p.stat_rows; r += gridDim.x) {     // rows no CTA owns: zero
+      float* z = p.stats + (long long)r * 2 * p.stats_ld;
+      for (int c = e; c < p.Cout; c += 256) { z[c] = 0.0f; z[p.stats_ld + c] = 0.0f; }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -295,95 +407,115 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..9)
-    // Two warps per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31): they take alternate
-    // 32-column chunks, which hides the tcgen05.ld / shuffle latencies of this instruction-heavy stage.
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // 0: even chunks, 1: odd chunks
-    const int row = q * 32 + lane;          // row of the 128-pixel tile
-    const int bw = 1 << p.log_bw, bh = 1 << p.log_bh;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
-      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
-      const int w = (tw << p.log_bw) + (row & (bw - 1));
-      const int h = (th << p.log_bh) + ((row >> p.log_bw) & (bh - 1));
-      const int n = (tb << p.log_bn) + (row >> (p.log_bw + p.log_bh));
-      const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
-      const int n_base = nt * p.block_n;
-      int co0 = n_base;
-      long long off = (long long)n * p.sN + (long long)h * p.sH + (long long)w * p.sW;
-      if (p.convt_k) {
-        const int tap = n_base / p.Cout;
-        co0 = n_base - tap * p.Cout;
-        off += (long long)(tap / p.convt_k) * p.sKy + (long long)(tap % p.convt_k) * p.sKx;
-      }
-      mbar_wait(L.tfull + 8 * as, aph);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
-      for (int cc = half * 32; cc < p.block_n; cc += 64) {
-        float v[32];
-        tc_ld32(t_row + (uint32_t)cc, v);
-        const int cbase = co0 + cc;         // first output channel of this chunk
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = cbase + j;
-          const float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.0f;
-          const float sc = (p.scale != nullptr && c < p.Cout) ? __ldg(p.scale + c) : 1.0f;
-          v[j] = (c < p.Cout && cc + j < p.block_n) ? fmaf(v[j], sc, b) : 0.0f;
-        }
-        if (p.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = dm::gelu_f(v[j]);
-        } else if (p.act == 2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        }
-        if (valid) {
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + off + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (cbase + j < p.ldc_pad && cc + j < p.block_n)
-                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + off + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              if (cbase + j < p.ldc_pad && cc + j < p.block_n) {
-                uint4 u;
-                u.x = dm::pack2(v[j], v[j + 1]); u.y = dm::pack2(v[j + 2], v[j + 3]);
-                u.z = dm::pack2(v[j + 4], v[j + 5]); u.w = dm::pack2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = u;
-              }
+    conv_epilogue(p, L.tfull, L.tempty, tmem_base, slab, warp, lane, total_tiles);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tc_fence_after(); tc_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------ kernel D
+// 3x3 / stride 1 / pad 1 convolution (forward and data gradient) with input-patch reuse: per tile and
+// 64-channel chunk ONE TMA box brings the 10 x 18 pixel halo patch into shared memory (SWIZZLE_128B,
+// one 128-byte row per pixel); the nine taps are issued as MMAs on nine shifted descriptor views of that
+// patch, so the activation operand crosses L2->SM once instead of nine times.  Weight tiles stream
+// through their own ring, one [block_n x 64] box per (tap, chunk).
+__global__ void __launch_bounds__(kConvThreads, 1) conv3x3_halo_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ringA = base;
+  const uint32_t ringB = ringA + (uint32_t)p.a_stages * kHaloStage;
+  const uint32_t bars = ringB + (uint32_t)p.stages * (uint32_t)p.b_stage_bytes;
+  const uint32_t fullB = bars, emptyB = fullB + 8 * kMaxStages, fullA = emptyB + 8 * kMaxStages, emptyA = fullA + 32,
+                 tfull = emptyA + 32, tempty = tfull + 16, tmem_slot = tempty + 16;
+  float* const slab = reinterpret_cast<float*>(smem_raw + (bars + kAuxBytes - smem_u32(smem_raw)));
+  const int chunks = p.chunks0 + p.chunks1;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 1); }
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(fullA + 8 * s, 1); mbar_init(emptyA + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + 8 * s, 1); mbar_init(tempty + 8 * s, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB); }
+  for (int i = threadIdx.x; i < 2 * p.stat_c; i += kConvThreads) slab[i] = 0.0f;
+  if (warp == 1) tc_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw << p.log_bw, h0 = th << p.log_bh;
+        const int n_base = nt * p.block_n;
+        for (int ch = 0; ch < chunks; ++ch) {
+          int map = 0, c0 = ch * kBlockK;
+          if (p.dual && ch >= p.chunks0) { map = 1; c0 = (ch - p.chunks0) * kBlockK; }
+          mbar_wait(emptyA + 8 * sa, pha ^ 1);
+          if (p.ablate & 2) mbar_arrive(fullA + 8 * sa);
+          else {
+            mbar_expect_tx(fullA + 8 * sa, kHaloBytes);
+            tma_load_4d(ringA + sa * kHaloStage, &p.tmA[map], c0, w0 - 1, h0 - 1, tb, fullA + 8 * sa);
+          }
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(emptyB + 8 * sb, phb ^ 1);
+            if (p.ablate & 2) mbar_arrive(fullB + 8 * sb);
+            else {
+              mbar_expect_tx(fullB + 8 * sb, p.b_stage_bytes);
+              tma_load_2d(ringB + sb * p.b_stage_bytes, &p.tmB, (tap * chunks + ch) * kBlockK, n_base, fullB + 8 * sb);
+            }
+            if (++sb == p.stages) { sb = 0; phb ^= 1; }
           }
         }
-        if (p.stats != nullptr) {
-          // per-channel sum and sum of squares over this warp's 32 rows -> combined over the 4 warps below
-          float s1[32], s2[32];
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(tempty + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(fullA + 8 * sa, pha);
+          const uint32_t a0 = ringA + sa * kHaloStage;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(fullB + 8 * sb, phb);
+            tc_fence_after();
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint32_t av = a0 + (uint32_t)((dy * kHaloW + dx) * 128);
+            const uint32_t bv = ringB + sb * p.b_stage_bytes;
+            uint64_t adesc = p.desc_hi_halo | (uint64_t)((av & 0x3FFFFu) >> 4);
+            if (p.base_off_mode == 1) adesc |= (uint64_t)((av >> 7) & 7u) << 49;
+            const uint64_t bdesc = p.desc_hi | (uint64_t)((bv & 0x3FFFFu) >> 4);
+            if (p.ablate & 1) mbar_arrive(emptyB + 8 * sb);
+            else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { const float x = valid ? v[j] : 0.0f; s1[j] = x; s2[j] = x * x; }
-          const float a = warp_colsum32(s1, lane), b2 = warp_colsum32(s2, lane);
-          // accumulated over all of this CTA's tiles in shared memory (atomics: four warps share a column)
-          atomicAdd(slab + n_base + cc + lane, a);
-          atomicAdd(slab + p.stat_c + n_base + cc + lane, b2);
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (ch | tap | k) != 0);
+              tc_commit(emptyB + 8 * sb);
+            }
+            if (++sb == p.stages) { sb = 0; phb ^= 1; }
+          }
+          if (p.ablate & 1) mbar_arrive(emptyA + 8 * sa); else tc_commit(emptyA + 8 * sa);
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(L.tempty + 8 * as);
-    }
-    if (p.stats != nullptr) {
-      // one partial row per CTA: [blockIdx.x][2][stats_ld]
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int e = threadIdx.x - 64;     // 0..255
-      float* g = p.stats + (long long)blockIdx.x * 2 * p.stats_ld;
-      for (int c = e; c < p.Cout; c += 256) {
-        g[c] = slab[c];
-        g[p.stats_ld + c] = slab[p.stat_c + c];
+        if (p.ablate & 1) mbar_arrive(tfull + 8 * as); else tc_commit(tfull + 8 * as);
       }
     }
+  } else {
+    conv_epilogue(p, tfull, tempty, tmem_base, slab, warp, lane, total_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -735,6 +867,7 @@ struct ConvGeom {
 
 }  // namespace
 
+extern "C" int dm_conv2d_fwd_stat_rows(int N, int Ho, int Wo, int Cout);
 extern "C" void dm_debug_set(int key, long long value) { if (key >= 0 && key < 8) g_debug[key] = value; }
 
 // Generic launcher for kernel A.  All geometry is resolved by the typed entry points below.
@@ -759,6 +892,35 @@ static int launch_conv(ConvParams& P, cudaStream_t st) {
   int grid = conv_grid(P.m_tiles * P.n_tiles);
   if (!P.stats && g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
   conv_gemm_kernel<<<grid, kConvThreads, smem, st>>>(P);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
+bool g_attr_d = false;
+// SBO = 1280 B: consecutive 8-pixel rows of the tile are one halo row (10 pixels) apart
+constexpr unsigned long long kDescHiHalo = ((unsigned long long)(kHaloW * 128 / 16) << 32) | (1ull << 46) | (2ull << 61) | (1ull << 16);
+
+static int launch_conv_halo(ConvParams& P, cudaStream_t st) {
+  P.stat_c = P.stats ? (P.n_tiles * P.block_n + 31) / 32 * 32 : 0;
+  const int stat_bytes = 8 * P.stat_c;
+  if (stat_bytes > kMaxStatBytes) { dm_set_error("conv_gemm: too many output channels for fused BatchNorm statistics"); return DM_ERR_ARG; }
+  P.a_stages = kHaloAStages;
+  int stages = (kSmemBudget - 1024 - kAuxBytes - stat_bytes - P.a_stages * kHaloStage) / P.b_stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (g_debug[0] > 0 && g_debug[0] < stages) stages = (int)g_debug[0];
+  if (stages < 2) { dm_set_error("conv3x3_halo: not enough shared memory"); return DM_ERR_ARG; }
+  P.stages = stages;
+  P.desc_hi_halo = kDescHiHalo;
+  P.base_off_mode = (int)g_debug[6];
+  P.ablate = (int)g_debug[7];
+  const size_t smem = 1024 + (size_t)P.a_stages * kHaloStage + (size_t)stages * P.b_stage_bytes + kAuxBytes + stat_bytes;
+  if (!g_attr_d) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
+    g_attr_d = true;
+  }
+  const int grid = conv_grid(P.m_tiles * P.n_tiles);
+  conv3x3_halo_kernel<<<grid, kConvThreads, smem, st>>>(P);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
@@ -799,7 +961,15 @@ extern "C" int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, in
   P.chunks1 = x1 ? dm::cdiv(C1, 64) : 0;
   P.dual = x1 ? 1 : 0;
   P.num_taps = kh * kw;
-  const int bw = 1 << P.log_bw, bh = 1 << P.log_bh, bn = 1 << P.log_bn;
+  // 3x3 / stride 1 / pad 1 on images that tile into 8 x 16 pixel patches: the halo kernel
+  bool halo = kh == 3 && kw == 3 && stride == 1 && pad == 1 && (Win % 8) == 0 && (Hin % 16) == 0;
+  if (g_debug[5] == 1) halo = false;
+  if (halo) {
+    P.log_bw = 3; P.log_bh = 4; P.log_bn = 0;
+    P.tiles_w = Wo / 8; P.tiles_h = Ho / 16; P.tiles_b = N;
+    P.m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
+  }
+  const int bw = halo ? kHaloW : 1 << P.log_bw, bh = halo ? kHaloH : 1 << P.log_bh, bn = 1 << P.log_bn;
   int rc;
   if (stride == 1) {
     for (int r = 0; r < kh; ++r)
@@ -834,15 +1004,21 @@ extern "C" int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, in
   P.sN = (long long)Ho * Wo * ldy; P.sH = (long long)Wo * ldy; P.sW = ldy;
   P.Cout = Cout; P.ldc_pad = ldy;
   P.bias = bias; P.scale = scale; P.act = act; P.stats = stats; P.stats_ld = stats_ld;
+  P.stat_rows = stats ? dm_conv2d_fwd_stat_rows(N, Ho, Wo, Cout) : 0;
   if (stats && (scale || act)) { dm_set_error("dm_conv2d_fwd: statistics are taken of the plain conv output (no scale/act)"); return DM_ERR_ARG; }
-  return launch_conv(P, (cudaStream_t)stream);
+  return halo ? launch_conv_halo(P, (cudaStream_t)stream) : launch_conv(P, (cudaStream_t)stream);
 }
 
 // rows of the statistics buffer dm_conv2d_fwd writes: one per CTA of the persistent grid
 extern "C" int dm_conv2d_fwd_stat_rows(int N, int Ho, int Wo, int Cout) {
+  // one row per CTA; the two tilings (generic 128-pixel patches / 8x16 halo tiles) can differ in tile
+  // count, so this is the larger of the two and the kernels zero-fill the rows beyond their grid
   int a, b, c; pick_patch(Wo, Ho, kBlockM, a, b, c);
-  const int m_tiles = dm::cdiv(Wo, 1 << a) * dm::cdiv(Ho, 1 << b) * dm::cdiv(N, 1 << c);
-  return conv_grid(m_tiles * dm::cdiv(Cout, pick_block_n(Cout)));
+  const int nt = dm::cdiv(Cout, pick_block_n(Cout));
+  const int m_generic = dm::cdiv(Wo, 1 << a) * dm::cdiv(Ho, 1 << b) * dm::cdiv(N, 1 << c);
+  const int m_halo = dm::cdiv(Wo, 8) * dm::cdiv(Ho, 16) * N;
+  const int m = m_generic > m_halo ? m_generic : m_halo;
+  return conv_grid(m * nt);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -178,6 +178,98 @@ int launch_reduce(RedArgs& A, int groups, cudaStream_t st) {
   return DM_OK;
 }
 
+// db[c] += sum_p dy[p][c]: the bias gradient of a convolution that is not followed by a BatchNorm.
+// Same thread mapping as the BatchNorm kernels (a thread owns 8 channels, 4 independent 16-byte loads in
+// flight), block-level reduction in shared memory, one atomicAdd per channel per block.
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, int lddy, float* __restrict__ db, unsigned P,
+                                                      int C, int VPB, int R) {
+  extern __shared__ float sm[];          // [threads][8]
+  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
+  const int c0 = (blockIdx.y * VPB + cvl) * 8;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (c0 < C) {
+    const unsigned step = gridDim.x * R;
+    for (unsigned p = blockIdx.x * R + r; p < P; p += 4 * step) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned pu = p + u * step;
+        if (pu < P) load8(dy + (long long)pu * lddy + c0, v[u]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += (v[0][j] + v[1][j]) + (v[2][j] + v[3][j]);
+    }
+  }
+  float* mine = sm + threadIdx.x * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mine[j] = s[j];
+  __syncthreads();
+  if (r == 0 && c0 < C) {
+    for (int rr = 1; rr < R; ++rr) {
+      const float* o = sm + (rr * VPB + cvl) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += o[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < C) atomicAdd(db + c0 + j, s[j]);
+  }
+}
+
+// Train-mode BatchNorm statistics of a stored (bf16) convolution output: per-block partial sums of y and
+// y^2, written without atomics to part[blockIdx.x][2][ld] -- the layout dm_bn_finalize consumes.  Fixed
+// grid + fixed summation order => bit-reproducible statistics (the conv-epilogue variant accumulates
+// through shared-memory atomics and costs ~20% of the GEMM's time in shuffles).
+__global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ y, int ldy, float* __restrict__ part, int ld,
+                                                        unsigned P, int C, int VPB, int R) {
+  extern __shared__ float sm[];          // [threads][16]
+  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
+  const int c0 = (blockIdx.y * VPB + cvl) * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  if (c0 < C) {
+    const unsigned step = gridDim.x * R;
+    for (unsigned p = blockIdx.x * R + r; p < P; p += 4 * step) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned pu = p + u * step;
+        if (pu < P) load8(y + (long long)pu * ldy + c0, v[u]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] += v[u][j]; s2[j] = fmaf(v[u][j], v[u][j], s2[j]); }
+    }
+  }
+  float* mine = sm + threadIdx.x * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mine[j] = s1[j]; mine[8 + j] = s2[j]; }
+  __syncthreads();
+  if (r == 0 && c0 < C) {
+    for (int rr = 1; rr < R; ++rr) {
+      const float* o = sm + (rr * VPB + cvl) * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1[j] += o[j]; s2[j] += o[8 + j]; }
+    }
+    float* g = part + (long long)blockIdx.x * 2 * ld;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < C) { g[c0 + j] = s1[j]; g[ld + c0 + j] = s2[j]; }
+  }
+}
+
 __global__ void zero_kernel(float* p, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = 0.f;
 }
@@ -764,6 +856,40 @@ struct S2D {
   }
 };
 
+// 3x3 / pad 1 im2col of a few-channel image (C*9 <= 32): out[p][ci*9 + r*3 + s] = x[p + (r-1, s-1)][ci],
+// zero outside the image and in the pad lanes.  Turns the K=27 first convolution of the U-Net into a 1x1
+// convolution with one 64-wide K block instead of nine (one per tap, 61 of 64 lanes zero).
+__global__ void im2col3x3_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ out, int N, int H, int W, int C) {
+  const long long P = (long long)N * H * W;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(p % W), yy = (int)((p / W) % H);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int y2 = yy + r - 1, x2 = xx + t - 1;
+        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
+          float f[8];
+          load8(x + (p + (long long)(r - 1) * W + (t - 1)) * ldx, f);
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci)
+            if (ci < C) v[ci * 9 + r * 3 + t] = f[ci];
+        }
+      }
+    bf16* o = out + p * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float t8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t8[i] = v[j + i];
+      store8(o + j, t8);
+    }
+  }
+}
+
 __global__ void nchw_to_nhwc_kernel(const float* x, bf16* y, int ldy, int N, int C, int HW) {
   const long long P = (long long)N * HW;
   const int Cv = ldy / 8;
@@ -834,6 +960,13 @@ extern "C" int dm_nhwc_to_nchw(const void* x, int x_f32, int ldx, float* y, int 
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
+extern "C" int dm_im2col3x3(const void* x, int ldx, void* out, int N, int H, int W, int C, void* stream) {
+  REQ8(ldx, "dm_im2col3x3");
+  if (C < 1 || C > 3) { dm_set_error("dm_im2col3x3: 1..3 channels"); return DM_ERR_ARG; }
+  im2col3x3_kernel<<<ew_grid((long long)N * H * W), kEwThreads, 0, ST>>>((const bf16*)x, ldx, (bf16*)out, N, H, W, C);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
 extern "C" int dm_space_to_depth(const void* x, int ldx, void* y, int ldy, int N, int H, int W, int C, int k, void* stream) {
   REQ8(ldx, "dm_space_to_depth"); REQ8(ldy, "dm_space_to_depth"); REQ8(C, "dm_space_to_depth");
   S2D f{(const bf16*)x, ldx, (bf16*)y, ldy, H, W, C, k};
@@ -844,6 +977,22 @@ extern "C" int dm_bn_finalize(const float* partials, int m_tiles, int ld, int C,
                               float* running_mean, float* running_var, float momentum, float eps, void* stream) {
   bn_finalize_kernel<<<dm::cdiv(C, 32), 1024, 0, ST>>>(partials, m_tiles, ld, C, count, mean, invstd, running_mean,
                                                        running_var, momentum, eps);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+static int bn_stats_blocks(long long P, int C) {
+  const ChanMap m = chan_map(C);
+  int gx = chan_grid_x(P, m, 16);
+  const int cap = DM_NUM_SMS * 4 / m.cvt;
+  return gx > cap ? (cap < 1 ? 1 : cap) : gx;
+}
+extern "C" int dm_bn_stats_rows(long long P, int C) { return bn_stats_blocks(P, C); }
+extern "C" int dm_bn_stats(const void* y, int ldy, float* part, int ld, long long P, int C, void* stream) {
+  REQ8(ldy, "dm_bn_stats");
+  if (P <= 0 || P >= (1ll << 31)) { dm_set_error("dm_bn_stats: bad pixel count"); return DM_ERR_ARG; }
+  const ChanMap m = chan_map(C);
+  dim3 grid(bn_stats_blocks(P, C), m.cvt);
+  bn_stats_kernel<<<grid, m.threads, (size_t)m.threads * 16 * sizeof(float), ST>>>((const bf16*)y, ldy, part, ld, (unsigned)P, C, m.VPB, m.R);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
@@ -958,11 +1107,16 @@ extern "C" int dm_pool_prod_nhw(const void* a, int lda, const void* b, int ldb, 
 }
 extern "C" int dm_colsum(const void* dy, int lddy, float* db, long long P, int C, void* stream) {
   REQ8(lddy, "dm_colsum");
+  if (P <= 0) return DM_OK;
   if (P >= (1ll << 31)) { dm_set_error("dm_colsum: too many pixels"); return DM_ERR_ARG; }
-  RedArgs A{};
-  A.a = (const bf16*)dy; A.a_ps = lddy; A.gdiv = 1; A.count = (int)P; A.C = C; A.mode = 0; A.scale = 1.f; A.out1 = db;
-  A.G = 1; A.stat_div = 1;
-  return launch_reduce(A, 1, ST);
+  const ChanMap m = chan_map(C);
+  int gx = chan_grid_x(P, m, 16);
+  const int cap = DM_NUM_SMS * 4 / m.cvt;
+  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  dim3 grid(gx, m.cvt);
+  colsum_kernel<<<grid, m.threads, (size_t)m.threads * 8 * sizeof(float), ST>>>((const bf16*)dy, lddy, db, (unsigned)P, C, m.VPB, m.R);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
 }
 extern "C" int dm_se_apply_fwd(const void* x2, int ld2, const float* gate, const void* res, int ldr, void* out, int ldo,
                                int N, int HW, int C, float scale, void* stream) {

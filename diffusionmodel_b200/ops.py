@@ -172,7 +172,14 @@ def _pack_convt_dgrad(w, out=None):
     return _pack(w, out, cin, cout, offs, cout * k * k, k * k, 0, cout, r64(k * k * cout), False)
 
 
-_PACKERS = {"fwd": _pack_fwd, "dgrad": _pack_dgrad, "s2dgrad": _pack_s2dgrad,
+def _pack_im2col(w, out=None):
+    """[Cout, Cin, 3, 3] with Cin*9 <= 32 as a 1x1 weight over the im2col'd input: K column = ci*9 + tap,
+    i.e. the parameter's own memory order, padded to one 64-wide K block."""
+    cout, cin, kh, kw = w.shape
+    return _pack(w, out, cout, cin * kh * kw, [0], cin * kh * kw, 1, 0, 64, 64, False)
+
+
+_PACKERS = {"im2col": _pack_im2col, "fwd": _pack_fwd, "dgrad": _pack_dgrad, "s2dgrad": _pack_s2dgrad,
             "convt_fwd": _pack_convt_fwd, "convt_dgrad": _pack_convt_dgrad}
 
 
@@ -349,6 +356,50 @@ class _Conv2d(torch.autograd.Function):
         return dx0, dx1, None, None, None, None, None, None, None, None, None, None
 
 
+class _Im2colConv3x3(torch.autograd.Function):
+    """3x3 / pad 1 convolution of a <=3-channel image (the U-Net's first conv) as im2col + 1x1 GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pack, want_stats, bias_grad_by_norm):
+        ldx = _chk(x, "conv input")
+        n, h, w, _ = x.shape
+        cout, cin = weight.shape[0], weight.shape[1]
+        st = _stream()
+        xi = torch.empty((n, h, w, 32), device=x.device, dtype=torch.bfloat16)
+        call("dm_im2col3x3", _p(x), ldx, _p(xi), n, h, w, cin, st)
+        wpk = pack.get(weight, "im2col")
+        y = new_act(n, h, w, cout, x.device)
+        stats = None
+        if want_stats:
+            stats = torch.empty((conv_stat_rows(n, h, w, cout), 2, cout), device=x.device, dtype=torch.float32)
+        call("dm_conv2d_fwd", _p(xi), cin * 9, 32, None, 0, 0, _p(wpk), _p(bias), None, 0, _p(y), y.stride(2), 0,
+             _p(stats), cout, n, h, w, cout, 1, 1, 1, 0, st)
+        ctx.save_for_backward(xi, weight, bias)
+        ctx.pack, ctx.cfg = pack, bias_grad_by_norm
+        ctx.mark_non_differentiable(*([stats] if stats is not None else []))
+        return (y, stats) if want_stats else (y, None)
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        xi, weight, bias = ctx.saved_tensors
+        cout, cin = weight.shape[0], weight.shape[1]
+        n, h, w, _ = xi.shape
+        lddy = _chk(dy, "conv grad")
+        st = _stream()
+        if bias is not None and not ctx.cfg:
+            call("dm_colsum", _p(dy), lddy, _p(grad_buf(bias)), n * h * w, cout, st)
+        unpack = (cout, cin * 9, 1, _taps([0]), cin * 9, 1, 0, 64, 64, 0)
+        _wgrad_into(weight, (cout, 64), unpack, lambda dwp: call(
+            "dm_conv2d_wgrad", _p(xi), cin * 9, 32, None, 0, 0, _p(dy), lddy, _p(dwp), n, h, w, cout, 1, 1, 1, 0, st))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wd = ctx.pack.get(weight, "dgrad")
+            dx = new_act(n, h, w, cin, dy.device)
+            call("dm_conv2d_fwd", _p(dy), cout, lddy, None, 0, 0, _p(wd), None, None, 0, _p(dx), dx.stride(2), 0, None, 0,
+                 n, h, w, cin, 3, 3, 1, 1, st)
+        return dx, None, None, None, None, None
+
+
 def conv2d_fused_eval(x0, weight, pack, shift, scale, act, *, x1=None, c1=0, stride=1, pad=0):
     """Inference-only conv with an eval-mode BatchNorm + activation folded into the epilogue:
     act(conv(x) * scale + shift) in ONE kernel (sampling loop; no autograd tape)."""
@@ -357,6 +408,13 @@ def conv2d_fused_eval(x0, weight, pack, shift, scale, act, *, x1=None, c1=0, str
     ld1 = _chk(x1, "conv input 2") if x1 is not None else 0
     n, hin, win, _ = x0.shape
     cout, cin, kh, kw = weight.shape
+    if x1 is None and cin <= 3 and (kh, kw, stride, pad) == (3, 3, 1, 1):       # first conv: im2col + 1x1
+        xi = torch.empty((n, hin, win, 32), device=x0.device, dtype=torch.bfloat16)
+        call("dm_im2col3x3", _p(x0), ld0, _p(xi), n, hin, win, cin, _stream())
+        y = new_act(n, hin, win, cout, x0.device)
+        call("dm_conv2d_fwd", _p(xi), cin * 9, 32, None, 0, 0, _p(pack.get(weight, "im2col")), _p(shift), _p(scale), act,
+             _p(y), y.stride(2), 0, None, 0, n, hin, win, cout, 1, 1, 1, 0, _stream())
+        return y
     ho = (hin + 2 * pad - kh) // stride + 1
     wo = (win + 2 * pad - kw) // stride + 1
     wpk = pack.get(weight, "fwd", c_split=c0 if x1 is not None else 0)
@@ -369,6 +427,9 @@ def conv2d_fused_eval(x0, weight, pack, shift, scale, act, *, x1=None, c1=0, str
 def conv2d(x0, weight, bias, pack, *, x1=None, c0=None, c1=0, stride=1, pad=0, want_stats=False, out_f32=False,
            bias_grad_by_norm=False):
     c0 = weight.shape[1] - c1 if c0 is None else c0
+    if (x1 is None and weight.shape[1] <= 3 and tuple(weight.shape[2:]) == (3, 3) and stride == 1 and pad == 1
+            and not out_f32):
+        return _Im2colConv3x3.apply(x0, weight, bias, pack, want_stats, bias_grad_by_norm)
     if x1 is not None and (c0 % 8 or x0.shape[3] != c0):
         raise _lib.DmB200Error("dual-source conv needs a tight first source with a multiple-of-8 channel count")
     return _Conv2d.apply(x0, x1, weight, bias, pack, c0, c1, stride, pad, want_stats, out_f32, bias_grad_by_norm)
@@ -462,12 +523,27 @@ class _BnAct(torch.autograd.Function):
         return dy, None, None, None, None, None, None, None, None, None, None, None
 
 
+FUSED_CONV_STATS = False      # True: BatchNorm statistics from the conv epilogue; False: a separate pass over y
+
+
+def bn_stats(y, c):
+    """Per-block partial sums of y and y^2 over all pixels (train-mode BatchNorm statistics)."""
+    ldy = _chk(y, "bn input")
+    n, h, w, _ = y.shape
+    rows = _lib.fn("dm_bn_stats_rows")(n * h * w, c)
+    part = torch.empty((rows, 2, c), device=y.device, dtype=torch.float32)
+    call("dm_bn_stats", _p(y), ldy, _p(part), c, n * h * w, c, _stream())
+    return part
+
+
 def bn_act(y, stats, bn, act, conv_bias=None):
     """``conv_bias``: bias parameter of the convolution that produced ``y`` (called with
     ``bias_grad_by_norm=True``); its gradient is produced by this norm's backward."""
     training = bn.training
     if training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
+    if training and stats is None:
+        stats = bn_stats(y, bn.num_features)
     return _BnAct.apply(y, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var, conv_bias, bn.num_features,
                         training, act, float(bn.momentum), float(bn.eps))
 

@@ -62,7 +62,7 @@ def conv_bn_act(x, seq, act=ACT_GELU, **kw):
         scale, shift = _folded_bn(cv, bn)
         return ops.conv2d_fused_eval(x, cv.weight, _pack_of(cv), shift, scale, act, stride=cv.stride[0],
                                      pad=cv.padding[0], **kw)
-    y, stats = conv(x, cv, want_stats=bn.training, bias_grad_by_norm=cv.bias is not None, **kw)
+    y, stats = conv(x, cv, want_stats=bn.training and ops.FUSED_CONV_STATS, bias_grad_by_norm=cv.bias is not None, **kw)
     return ops.bn_act(y, stats, bn, act, conv_bias=cv.bias)
 
 

@@ -67,11 +67,18 @@ int dm_unpack_wgrad(float* dwp, float* grad, int rows, int cols, int ntaps, cons
 int dm_nchw_to_nhwc(const float* x, void* y, int ldy, int y_f32, int N, int C, int H, int W, void* stream);
 int dm_cast_nhwc(const float* x, int ldx, void* y, int ldy, long long P, int C, void* stream);  /* fp32 -> bf16 NHWC */
 int dm_nhwc_to_nchw(const void* x, int x_f32, int ldx, float* y, int N, int C, int H, int W, void* stream);
+/* 3x3/pad-1 im2col of a <=3-channel image into [N,H,W,32] (column ci*9 + r*3 + s): the first U-Net conv
+ * (new_scripy.py:184 with in_ch=3, MNIST_script.py:42 with 1) then runs as a 1x1 convolution */
+int dm_im2col3x3(const void* x, int ldx, void* out, int N, int H, int W, int C, void* stream);
 int dm_space_to_depth(const void* x, int ldx, void* y, int ldy, int N, int H, int W, int C, int k, void* stream);
 
 /* ---- BatchNorm2d + GELU (new_scripy.py:185-186,189-190,218-219,226-227) ---------------------------
  * finalize: partial sums -> batch mean / invstd (+ running-stat update, momentum 0.1, unbiased var);
  * m_tiles == 0: eval mode, mean/invstd from the running buffers. */
+/* batch statistics of a stored conv output: part[dm_bn_stats_rows(P, C)][2][ld] partial sums of y, y^2
+ * (no atomics, fixed order: bit-reproducible); alternative to the conv epilogue's fused statistics */
+int dm_bn_stats_rows(long long P, int C);
+int dm_bn_stats(const void* y, int ldy, float* part, int ld, long long P, int C, void* stream);
 int dm_bn_finalize(const float* partials, int m_tiles, int ld, int C, double count, float* mean, float* invstd,
                    float* running_mean, float* running_var, float momentum, float eps, void* stream);
 int dm_bn_act_fwd(const void* y, int ldy, const float* mean, const float* invstd, const float* gamma,

@@ -118,6 +118,35 @@ def test_conv2d_f32_head_and_dual_source(dev):
     assert rel(wd.grad.cpu(), wr.grad) < F32_TOL
 
 
+@pytest.mark.parametrize("case", [(2, 16, 16, 64, 64), (1, 32, 32, 192, 192), (1, 48, 24, 40, 24), (3, 16, 8, 16, 16),
+                                  (1, 128, 128, 192, 192), (1, 64, 64, 320, 272)], ids=lambda c: "x".join(map(str, c)))
+def test_conv3x3_halo_kernel(dev, case):
+    """The input-patch-reuse 3x3 kernel (nine shifted descriptor views of one 10x18 halo patch) against the
+    fp32 CPU convolution and against the generic per-tap implicit-GEMM kernel (same products, accumulated
+    chunk-major instead of tap-major, so equal up to fp32 summation order / one bf16 rounding)."""
+    from diffusionmodel_b200 import _lib, ops
+    n, h, w, cin, cout = case
+    g = torch.Generator().manual_seed(43)
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    b = torch.randn(cout, generator=g) * 0.1
+    y_ref = F.conv2d(x, bf(wt), b, 1, 1)
+    wd, bd = torch.nn.Parameter(wt.to(dev)), torch.nn.Parameter(b.to(dev))
+    outs = {}
+    for name, key5 in (("halo", 0), ("generic", 1)):
+        _lib.debug_set(5, key5)
+        try:
+            with torch.no_grad():
+                y, stats = ops.conv2d(nhwc(x, dev), wd, bd, ops.WeightPack(), stride=1, pad=1, want_stats=True)
+            torch.cuda.synchronize()
+        finally:
+            _lib.debug_set(5, 0)
+        outs[name] = (y.clone(), stats.sum(0).cpu())
+        assert rel(nchw(y, cout), y_ref) < BF16_TOL, name
+    assert rel(outs["halo"][0].float(), outs["generic"][0].float()) < 1e-3
+    assert rel(outs["halo"][1], outs["generic"][1]) < 1e-5
+
+
 @pytest.mark.parametrize("version", [1, 2])
 @pytest.mark.parametrize("case", [(2, 16, 16, 64, 512, 3, 1, 1), (1, 32, 32, 192, 192, 3, 1, 1), (2, 16, 16, 96, 128, 4, 2, 1),
                                   (4, 8, 8, 320, 640, 1, 1, 0), (3, 10, 12, 40, 24, 3, 1, 1)],

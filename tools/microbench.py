@@ -50,6 +50,9 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--out", default="microbench.json")
+    ap.add_argument("--ablate", action="store_true", help="halo-kernel timing decomposition (no MMA / no TMA / no epilogue)")
+    ap.add_argument("--ab", action="store_true", help="also time the alternative kernels (generic conv, wgrad v1/v2)")
+    ap.add_argument("--shapes", type=int, default=0, help="only the first N conv shapes")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     n = a.batch
@@ -57,7 +60,7 @@ def main():
     rows = []
     g = torch.Generator(device=dev).manual_seed(0)
     if a.only in ("", "conv"):
-        for (h, cin, cout, k, s, p, cnt) in CONVS:
+        for (h, cin, cout, k, s, p, cnt) in (CONVS[:a.shapes] if a.shapes else CONVS):
             x = torch.randn(n, h, h, ops.r8(cin), device=dev, generator=g).to(torch.bfloat16)
             w = torch.nn.Parameter(torch.randn(cout, cin, k, k, device=dev, generator=g) / (cin * k * k) ** 0.5)
             b = torch.nn.Parameter(torch.zeros(cout, device=dev))
@@ -75,6 +78,9 @@ def main():
             def fwd():
                 ops.call("dm_conv2d_fwd", P_(x), cin, x.stride(2), None, 0, 0, P_(wpk), P_(b), None, 0, P_(y), y.stride(2), 0,
                          P_(stats), cout, n, h, h, cout, k, k, s, p, st)
+            def fwd_nostat():
+                ops.call("dm_conv2d_fwd", P_(x), cin, x.stride(2), None, 0, 0, P_(wpk), P_(b), None, 0, P_(y), y.stride(2), 0,
+                         None, 0, n, h, h, cout, k, k, s, p, st)
             dx = torch.empty_like(x)
             if s == 1:
                 wd = pack.get(w, "dgrad")
@@ -94,11 +100,24 @@ def main():
                 ops.call("dm_conv2d_wgrad", P_(x), cin, x.stride(2), None, 0, 0, P_(dy), dy.stride(2), P_(dwp), n, h, h,
                          cout, k, k, s, p, st)
             r = {"shape": f"{h}x{h} {cin}->{cout} k{k}s{s}", "count": cnt, "gflop": fl / 1e9}
-            for name, fn in (("fwd", fwd), ("dgrad", dgrad), ("wgrad", wgrad), ("wgrad_v1", wgrad), ("wgrad_v2", wgrad)):
+            variants = [("fwd", fwd), ("fwd_nostat", fwd_nostat), ("dgrad", dgrad), ("wgrad", wgrad)]
+            if a.ab:
+                variants += [("fwd_generic", fwd), ("fwd_nostat_generic", fwd_nostat), ("dgrad_generic", dgrad),
+                             ("wgrad_v1", wgrad), ("wgrad_v2", wgrad)]
+            if a.ablate and k == 3 and s == 1:
+                for mask in (0, 1, 2, 3, 4, 5, 6, 7):
+                    variants.append((f"dgrad_abl{mask}", dgrad))
+            for name, fn in variants:
                 if name.startswith("wgrad_v"):
                     _lib.debug_set(4, int(name[-1]))
+                if name.endswith("_generic"):
+                    _lib.debug_set(5, 1)
+                if "_abl" in name:
+                    _lib.debug_set(7, int(name[-1]))
                 ms = timer(fn, a.iters, flush)
                 _lib.debug_set(4, 0)
+                _lib.debug_set(5, 0)
+                _lib.debug_set(7, 0)
                 r[name + "_ms"] = round(ms, 4)
                 r[name + "_tflops"] = round(fl / ms / 1e9, 1)
             print(json.dumps(r), flush=True)
