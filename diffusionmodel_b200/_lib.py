@@ -66,7 +66,7 @@ _SIGS = {
     "dm_space_to_depth": "pi pi iiiii p",
     "dm_bn_stats_rows": "li",
     "dm_bn_stats": "pi pi l i p",
-    "dm_bn_finalize": "p iii d pp pp ff p",
+    "dm_bn_finalize": "p iii d pp pp ff p p",
     "dm_bn_act_fwd": "pi pppp pi l ii p",
     "dm_bn_act_bwd": "pi pi pppp pi pp p p l iii p",
     "dm_bn_act_bwd_scratch": "li",

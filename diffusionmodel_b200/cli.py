@@ -1,0 +1,154 @@
+"""`--mode train/generate` command line of the reference (new_scripy.py:1292-1321) over the B200 hot path.
+
+    python -m diffusionmodel_b200.cli --mode train [--epochs E --steps_per_epoch S]
+    python -m diffusionmodel_b200.cli --mode generate --ckpt CKPT --guide_scales 2 4 --samples 3 [--no_eval]
+    torchrun --nproc-per-node N -m diffusionmodel_b200.cli --mode train        # data parallel, one rank per GPU
+
+Flag names, defaults and the missing-checkpoint behaviour are the reference's.  The drivers are the thin
+caller contract of SURVEY.md 2.1 (train_model new_scripy.py:659-943, gen_samples :945-1108): accumulation
+over ACCUM_STEPS micro-batches, clip 1.0, AdamW(lr 1e-4, wd 1e-5), CosineAnnealingWarmRestarts(10, 2, 3e-5),
+checkpoints as ``{'epoch', 'model_state_dict', 'optimizer_state_dict', 'loss'}``.  The reference's dataset
+(./cropped_images, VOC XML) is not shipped with it, so batches are synthetic road-damage-shaped tensors
+(images in [-1,1], labels, attention map 0.5 / 1.0 lower half / 3.0 box, new_scripy.py:535-546); FID/SSIM
+evaluation (new_scripy.py:1111-1290) is out of scope, ``--no_eval`` is accepted and ignored.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+from . import DDPM, ContextUnet, FusedAdamW, parallel
+
+
+class Cfg:                      # new_scripy.py:22-67 (only what the drivers read)
+    N_FEAT, IN_CH, N_T, BETAS, DROP_PROB = 192, 3, 700, (1e-4, 0.02), 0.1
+    BATCH_SIZE, ACCUM_STEPS, LR, WD, N_EPOCH = 4, 4, 1e-4, 1e-5, 400
+    SAVE_DIR, SAMPLE_DIR = "./output/diffusion/", "./output/samples/"
+    GUIDE_SCALES, SAMPLES_PER_CLASS, IMG_SIZE = [2.0, 4.0], 3, 256
+
+
+def synth_batch(gen, batch, img, n_classes):
+    x = torch.rand(batch, 3, img, img, generator=gen) * 2 - 1
+    c = torch.randint(0, n_classes, (batch,), generator=gen)
+    m = torch.full((batch, img, img), 0.5)
+    m[:, img // 2:, :] = 1.0
+    for b in range(batch):
+        xs = torch.randint(0, img, (2,), generator=gen).sort().values
+        ys = torch.randint(0, img, (2,), generator=gen).sort().values
+        m[b, int(ys[0]):int(ys[1]) + 1, int(xs[0]):int(xs[1]) + 1] = 3.0
+    return x, c, m
+
+
+def build(n_classes, device, n_feat=Cfg.N_FEAT):
+    net = ContextUnet(in_ch=Cfg.IN_CH, n_feat=n_feat, n_classes=n_classes)
+    return DDPM(nn_model=net, betas=Cfg.BETAS, n_T=Cfg.N_T, device=device, drop_prob=Cfg.DROP_PROB,
+                enhance_with_attn_map=True).to(device)
+
+
+def train_model(args):
+    rank, local, world = parallel.init_from_env()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    torch.manual_seed(0)
+    ddpm = build(args.n_classes, device, args.n_feat).train()
+    optim = FusedAdamW(ddpm.parameters(), lr=Cfg.LR, weight_decay=Cfg.WD, max_grad_norm=1.0)
+    sched = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(optim, T_0=10, T_mult=2, eta_min=3e-5)
+    parallel.broadcast_parameters(optim.flat_param, list(ddpm.buffers()))
+    gen = torch.Generator().manual_seed(100 + rank)
+    torch.manual_seed(1234 + rank)
+    step_fn = None
+    os.makedirs(Cfg.SAVE_DIR, exist_ok=True)
+    for ep in range(args.epochs):
+        t0, ema, seen = time.time(), None, 0
+        for step in range(args.steps_per_epoch):
+            x, c, m = (t.to(device, non_blocking=True) for t in synth_batch(gen, Cfg.BATCH_SIZE, args.img, args.n_classes))
+            if step_fn is None and not args.no_graph:
+                step_fn = ddpm.capture_train_step(x, c, m, loss_scale=1.0 / Cfg.ACCUM_STEPS)
+                optim.zero_grad()
+            if step_fn is not None:
+                loss = step_fn(x, c, m)
+            else:
+                loss = ddpm(x, c, m) / Cfg.ACCUM_STEPS              # new_scripy.py:785-786
+                ddpm.scaler.scale(loss).backward()                 # :792 (disabled scaler: bf16)
+            li = loss.item() * Cfg.ACCUM_STEPS
+            ema = li if ema is None else 0.95 * ema + 0.05 * li    # :806-809
+            seen += Cfg.BATCH_SIZE * world
+            if (step + 1) % Cfg.ACCUM_STEPS == 0 or step + 1 == args.steps_per_epoch:     # :795
+                optim.flush()
+                parallel.allreduce_mean_(optim.flat_grad)
+                optim.step()                                       # unscale / clip 1.0 / AdamW, :797-801
+                optim.zero_grad()
+        sched.step()                                               # :848
+        if rank == 0:
+            dt = time.time() - t0
+            print(f"epoch {ep}: loss(ema) {ema:.4f}  lr {optim.param_groups[0]['lr']:.2e}  {seen / dt:.1f} img/s", flush=True)
+    if rank == 0:
+        path = os.path.join(Cfg.SAVE_DIR, "best_model.pt")
+        torch.save({"epoch": args.epochs, "model_state_dict": ddpm.state_dict(), "loss": ema}, path)   # :730-744
+        print(f"saved {path}")
+    return ddpm
+
+
+def gen_samples(ckpt, n_samples_per_class=3, guide_scales=(2.0, 4.0), eval_quality=True, n_classes=5, n_feat=Cfg.N_FEAT,
+                img=Cfg.IMG_SIZE):
+    rank, local, world = parallel.init_from_env()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    try:
+        checkpoint = torch.load(ckpt, map_location="cpu")          # new_scripy.py:966-969
+    except Exception as e:                                         # the reference swallows load errors and returns None
+        print(f"Error loading checkpoint: {e}")
+        return None
+    ddpm = build(n_classes, device, n_feat)
+    ddpm.drop_prob = 0.0
+    state = checkpoint["model_state_dict"] if isinstance(checkpoint, dict) and "model_state_dict" in checkpoint else checkpoint
+    ddpm.load_state_dict(state)                                    # :976-990 (raw-dict fallback)
+    ddpm.eval()
+    os.makedirs(Cfg.SAMPLE_DIR, exist_ok=True)
+    out = {}
+    for w in guide_scales:                                         # :1036
+        n_sample = parallel.shard_samples(n_samples_per_class * n_classes, n_classes, rank, world)
+        t0 = time.time()
+        x_gen = ddpm.sample(n_sample, (3, img, img), device, guide_w=w) if n_sample else None
+        torch.cuda.synchronize()
+        if x_gen is not None:
+            torch.save(x_gen.cpu(), os.path.join(Cfg.SAMPLE_DIR, f"samples_w{w}_rank{rank}.pt"))
+            out[w] = x_gen
+        if rank == 0:
+            print(f"guide_w={w}: {n_sample} samples/rank in {time.time() - t0:.1f}s", flush=True)
+    return out
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(description="Enhanced Diffusion Model Training/Generation")
+    parser.add_argument("--mode", type=str, default="train", choices=["train", "generate"],
+                        help="Mode: 'train' for training, 'generate' for sample generation")
+    parser.add_argument("--ckpt", type=str, default=None, help="Checkpoint path for generation mode")
+    parser.add_argument("--guide_scales", type=float, nargs="+", default=Cfg.GUIDE_SCALES, help="Guidance scales for generation")
+    parser.add_argument("--samples", type=int, default=Cfg.SAMPLES_PER_CLASS, help="Number of samples per class")
+    parser.add_argument("--no_eval", action="store_true", help="Skip image quality evaluation")
+    # additions (the reference hard-codes these in Cfg / the dataset)
+    parser.add_argument("--epochs", type=int, default=Cfg.N_EPOCH)
+    parser.add_argument("--steps_per_epoch", type=int, default=64)
+    parser.add_argument("--n_classes", type=int, default=5)
+    parser.add_argument("--n_feat", type=int, default=Cfg.N_FEAT)
+    parser.add_argument("--img", type=int, default=Cfg.IMG_SIZE)
+    parser.add_argument("--no_graph", action="store_true", help="eager launches instead of the CUDA-graphed micro-step")
+    args = parser.parse_args(argv)
+    if args.mode == "train":
+        train_model(args)
+    elif args.mode == "generate":
+        if args.ckpt is None:
+            print("Error: Checkpoint path required for generation mode")
+            parser.print_help()
+            sys.exit(1)
+        gen_samples(args.ckpt, n_samples_per_class=args.samples, guide_scales=args.guide_scales,
+                    eval_quality=not args.no_eval, n_classes=args.n_classes, n_feat=args.n_feat, img=args.img)
+
+
+if __name__ == "__main__":
+    main()

@@ -157,6 +157,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+// One lane of a fully converged warp.  The producer / MMA warps run their loops warp-uniformly and only the
+// issue statements sit under elect_one(): inside an `if (lane == 0)` region the compiler must wrap every
+// uniform-datapath instruction (UTCHMMA, UTMALDG, UTCBAR) in an ELECT / BRA.U.ANY waterfall, which made
+// the single issuing thread -- not the tensor pipe -- the bottleneck (~700 cycles per 64-wide K block).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -266,12 +279,22 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t bar_
       float v[32];
       tc_ld32(t_row + (uint32_t)cc, v);
       const int cbase = co0 + cc;         // first output channel of this chunk
+      // whole chunk inside the tile and the tensor (the common case): no per-element bounds selects
+      const bool full = (cbase + 32 <= p.Cout) && (cc + 32 <= p.block_n);
+      if (p.scale != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = cbase + j;
-        const float b = (p.bias != nullptr && c < p.Cout) ? __ldg(p.bias + c) : 0.0f;
-        const float sc = (p.scale != nullptr && c < p.Cout) ? __ldg(p.scale + c) : 1.0f;
-        v[j] = (c < p.Cout && cc + j < p.block_n) ? fmaf(v[j], sc, b) : 0.0f;
+        for (int j = 0; j < 32; ++j) {
+          const int c = min(cbase + j, p.Cout - 1);
+          v[j] = fmaf(v[j], __ldg(p.scale + c), p.bias != nullptr ? __ldg(p.bias + c) : 0.0f);
+        }
+      } else if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + min(cbase + j, p.Cout - 1));
+      }
+      if (!full) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (!(cbase + j < p.Cout && cc + j < p.block_n)) v[j] = 0.0f;
       }
       if (p.act == 1) {
 #pragma unroll
@@ -357,8 +380,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(L.tmem_slot));
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (warp-uniform loop)
+    {
       int stage = 0; uint32_t phase = 0;
       const int chunks = p.chunks0 + p.chunks1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -370,20 +393,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           mbar_wait(L.empty + 8 * stage, phase ^ 1);
           const uint32_t sa = L.base + stage * stage_bytes, sb = sa + kAStage;
           const uint32_t fb = L.full + 8 * stage;
-          mbar_expect_tx(fb, kAStage + p.b_stage_bytes);
           const int tap = kb / chunks, ch = kb - tap * chunks;
           const TapInfo t = p.taps[tap];
           int map = t.map, c0 = ch * kBlockK;
           if (p.dual && ch >= p.chunks0) { map = 1; c0 = (ch - p.chunks0) * kBlockK; }
-          tma_load_4d(sa, &p.tmA[map], c0, w0 + t.dx, h0 + t.dy, n0, fb);
-          tma_load_2d(sb, &p.tmB, kb * kBlockK, n_base, fb);
+          if (elect_one()) {
+            mbar_expect_tx(fb, kAStage + p.b_stage_bytes);
+            tma_load_4d(sa, &p.tmA[map], c0, w0 + t.dx, h0 + t.dy, n0, fb);
+            tma_load_2d(sb, &p.tmB, kb * kBlockK, n_base, fb);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (warp-uniform loop)
+    {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -397,13 +423,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
           const uint32_t sa = L.base + stage * stage_bytes, sb = sa + kAStage;
           const uint64_t adesc = p.desc_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
           const uint64_t bdesc = p.desc_hi | (uint64_t)((sb & 0x3FFFFu) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
-          tc_commit(L.empty + 8 * stage);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
+            tc_commit(L.empty + 8 * stage);
+            if (kb == num_kb - 1) tc_commit(L.tfull + 8 * as);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(L.tfull + 8 * as);
       }
     }
   } else {
@@ -449,7 +478,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_halo_kernel(const __g
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
@@ -460,26 +489,32 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_halo_kernel(const __g
           int map = 0, c0 = ch * kBlockK;
           if (p.dual && ch >= p.chunks0) { map = 1; c0 = (ch - p.chunks0) * kBlockK; }
           mbar_wait(emptyA + 8 * sa, pha ^ 1);
-          if (p.ablate & 2) mbar_arrive(fullA + 8 * sa);
-          else {
-            mbar_expect_tx(fullA + 8 * sa, kHaloBytes);
-            tma_load_4d(ringA + sa * kHaloStage, &p.tmA[map], c0, w0 - 1, h0 - 1, tb, fullA + 8 * sa);
+          if (elect_one()) {
+            if (p.ablate & 2) mbar_arrive(fullA + 8 * sa);
+            else {
+              mbar_expect_tx(fullA + 8 * sa, kHaloBytes);
+              tma_load_4d(ringA + sa * kHaloStage, &p.tmA[map], c0, w0 - 1, h0 - 1, tb, fullA + 8 * sa);
+            }
           }
+          __syncwarp();
           if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(emptyB + 8 * sb, phb ^ 1);
-            if (p.ablate & 2) mbar_arrive(fullB + 8 * sb);
-            else {
-              mbar_expect_tx(fullB + 8 * sb, p.b_stage_bytes);
-              tma_load_2d(ringB + sb * p.b_stage_bytes, &p.tmB, (tap * chunks + ch) * kBlockK, n_base, fullB + 8 * sb);
+            if (elect_one()) {
+              if (p.ablate & 2) mbar_arrive(fullB + 8 * sb);
+              else {
+                mbar_expect_tx(fullB + 8 * sb, p.b_stage_bytes);
+                tma_load_2d(ringB + sb * p.b_stage_bytes, &p.tmB, (tap * chunks + ch) * kBlockK, n_base, fullB + 8 * sb);
+              }
             }
+            __syncwarp();
             if (++sb == p.stages) { sb = 0; phb ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -499,19 +534,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_halo_kernel(const __g
             uint64_t adesc = p.desc_hi_halo | (uint64_t)((av & 0x3FFFFu) >> 4);
             if (p.base_off_mode == 1) adesc |= (uint64_t)((av >> 7) & 7u) << 49;
             const uint64_t bdesc = p.desc_hi | (uint64_t)((bv & 0x3FFFFu) >> 4);
-            if (p.ablate & 1) mbar_arrive(emptyB + 8 * sb);
-            else {
+            const bool last = (ch == chunks - 1) && (tap == 8);
+            if (elect_one()) {
+              if (p.ablate & 1) {
+                mbar_arrive(emptyB + 8 * sb);
+                if (tap == 8) mbar_arrive(emptyA + 8 * sa);
+                if (last) mbar_arrive(tfull + 8 * as);
+              } else {
 #pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (ch | tap | k) != 0);
-              tc_commit(emptyB + 8 * sb);
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  tc_mma_bf16((p.ablate & 8) ? tmem_base + (uint32_t)((k & 1) * 256) : d_tmem, adesc + (uint64_t)(k * 2),
+                              bdesc + (uint64_t)(k * 2), p.idesc, (ch | tap | k) != 0);   // ablate bit3: two independent chains
+                tc_commit(emptyB + 8 * sb);
+                if (tap == 8) tc_commit(emptyA + 8 * sa);
+                if (last) tc_commit(tfull + 8 * as);
+              }
             }
+            __syncwarp();
             if (++sb == p.stages) { sb = 0; phb ^= 1; }
           }
-          if (p.ablate & 1) mbar_arrive(emptyA + 8 * sa); else tc_commit(emptyA + 8 * sa);
           if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
         }
-        if (p.ablate & 1) mbar_arrive(tfull + 8 * as); else tc_commit(tfull + 8 * as);
       }
     }
   } else {
@@ -552,7 +595,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int cot, tap, cit, sp; decode(tile, cot, tap, cit, sp);
@@ -566,21 +609,24 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
           mbar_wait(L.empty + 8 * stage, phase ^ 1);
           const uint32_t sa = L.base + stage * stage_bytes, sb = sa + kAStage;
           const uint32_t fb = L.full + 8 * stage;
-          mbar_expect_tx(fb, 2 * 8192 + nch * 8192);
-          tma_load_4d(sa, &p.tmDY, cot * 128, w0, h0, n0, fb);
-          tma_load_4d(sa + 8192, &p.tmDY, cot * 128 + 64, w0, h0, n0, fb);
-          for (int j = 0; j < nch; ++j) {
-            const int ch = cit * cpt + j;
-            int map = t.map, c0 = ch * 64;
-            if (p.dual && ch >= p.chunks0) { map = 1; c0 = (ch - p.chunks0) * 64; }
-            tma_load_4d(sb + j * 8192, &p.tmX[map], c0, w0 + t.dx, h0 + t.dy, n0, fb);
+          if (elect_one()) {
+            mbar_expect_tx(fb, 2 * 8192 + nch * 8192);
+            tma_load_4d(sa, &p.tmDY, cot * 128, w0, h0, n0, fb);
+            tma_load_4d(sa + 8192, &p.tmDY, cot * 128 + 64, w0, h0, n0, fb);
+            for (int j = 0; j < nch; ++j) {
+              const int ch = cit * cpt + j;
+              int map = t.map, c0 = ch * 64;
+              if (p.dual && ch >= p.chunks0) { map = 1; c0 = (ch - p.chunks0) * 64; }
+              tma_load_4d(sb + j * 8192, &p.tmX[map], c0, w0 + t.dx, h0 + t.dy, n0, fb);
+            }
           }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -597,13 +643,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
           const uint32_t sa = L.base + stage * stage_bytes, sb = sa + kAStage;
           const uint64_t adesc = p.desc_hi_a | ((uint64_t)p.lbo_a << 16) | (uint64_t)((sa & 0x3FFFFu) >> 4);
           const uint64_t bdesc = p.desc_hi_b | ((uint64_t)p.lbo_b << 16) | (uint64_t)((sb & 0x3FFFFu) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)      // 16 pixels per MMA = two 8-row swizzle groups = 2048 B
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc, (pp != p0) | (k != 0));
-          tc_commit(L.empty + 8 * stage);
+            for (int k = 0; k < 4; ++k)      // 16 pixels per MMA = two 8-row swizzle groups = 2048 B
+              tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc, (pp != p0) | (k != 0));
+            tc_commit(L.empty + 8 * stage);
+            if (pp == p1 - 1) tc_commit(L.tfull + 8 * as);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(L.tfull + 8 * as);
       }
     }
   } else {
@@ -675,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2_gemm_kernel(const __grid_c
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int mt, nt, sp; decode(tile, mt, nt, sp);
@@ -696,17 +745,20 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2_gemm_kernel(const __grid_c
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
           const uint32_t fb = bar_full + 8 * stage;
-          mbar_expect_tx(fb, (nA + p.nb) * 8192);
-          for (int j = 0; j < p.nb; ++j) tma_load_4d(sb + j * 8192, &p.tmDY, nt * p.block_n + j * 64, w0, h0, n0, fb);
+          if (elect_one()) {
+            mbar_expect_tx(fb, (nA + p.nb) * 8192);
+            for (int j = 0; j < p.nb; ++j) tma_load_4d(sb + j * 8192, &p.tmDY, nt * p.block_n + j * 64, w0, h0, n0, fb);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j < nA) tma_load_4d(sa + j * 8192, &p.tmX[bmap[j]], bc0[j], w0 + bdx[j], h0 + bdy[j], n0, fb);
+            for (int j = 0; j < 4; ++j)
+              if (j < nA) tma_load_4d(sa + j * 8192, &p.tmX[bmap[j]], bc0[j], w0 + bdx[j], h0 + bdy[j], n0, fb);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -722,18 +774,21 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2_gemm_kernel(const __grid_c
           tc_fence_after();
           const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
           const uint64_t bdesc = p.desc_hi | ((uint64_t)p.lbo << 16) | (uint64_t)((sb & 0x3FFFFu) >> 4);
-          for (int h = 0; h < nh; ++h) {
-            const uint32_t sah = sa + h * 16384;
-            const uint64_t adesc = p.desc_hi | ((uint64_t)p.lbo << 16) | (uint64_t)((sah & 0x3FFFFu) >> 4);
+          const uint64_t adesc0 = p.desc_hi | ((uint64_t)p.lbo << 16) | (uint64_t)((sa & 0x3FFFFu) >> 4);
+          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)      // 16 pixels per MMA = two 8-row swizzle groups = 2048 B
-              tc_mma_bf16(tmem_base + (uint32_t)(h * 256), adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc,
-                          (pp != p0) | (k != 0));
+            for (int k = 0; k < 4; ++k) {    // 16 pixels per MMA = two 8-row swizzle groups = 2048 B
+              tc_mma_bf16(tmem_base, adesc0 + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc, (pp != p0) | (k != 0));
+              if (nh == 2)                   // second accumulator: boxes 2,3 (16 KB further = 1024 descriptor units)
+                tc_mma_bf16(tmem_base + 256u, adesc0 + (uint64_t)(1024 + k * 128), bdesc + (uint64_t)(k * 128), p.idesc,
+                            (pp != p0) | (k != 0));
+            }
+            tc_commit(bar_empty + 8 * stage);
+            if (pp == p1 - 1) tc_commit(bar_tfull);
           }
-          tc_commit(bar_empty + 8 * stage);
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(bar_tfull);
       }
     }
   } else {
@@ -780,7 +835,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad2_gemm_kernel(const __grid_c
 
 // ------------------------------------------------------------------------------------------ host side
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
-long long g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+long long g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 stages 1 grid 2 splits 3 block_n 4 wgrad kernel 5 no-halo 6 base-offset 7 ablation
 
 int ensure_encode() {
   if (g_encode) return DM_OK;
@@ -841,10 +896,30 @@ void pick_patch(int W, int H, int rows, int& lbw, int& lbh, int& lbn) {
 }
 
 int pick_block_n(int cout) {
+  if (g_debug[3] >= 16 && g_debug[3] <= 256 && (g_debug[3] % 16) == 0) return (int)g_debug[3];   // dev: forced tile width
   int c16 = (cout + 15) / 16 * 16;
   int nt = (c16 + 255) / 256;
   int bn = ((c16 + nt - 1) / nt + 15) / 16 * 16;
   return bn;
+}
+
+// Tile width for a conv with `m_tiles` 128-pixel tiles: the persistent grid runs ceil(tiles / #SMs) rounds of
+// (block_n + fixed) cost each, so for the small-spatial layers (32 M-tiles at 32x32, batch 4) a narrower
+// tile that fills the last round beats the widest one: Cout=1536 -> 9 x 176 (288 tiles, 1.95 rounds)
+// instead of 6 x 256 (192 tiles, 1.3 rounds); Cout=768 -> 4 x 192 instead of 3 x 256.
+int pick_block_n_tiles(int cout, int m_tiles) {
+  if (g_debug[3] >= 16 && g_debug[3] <= 256 && (g_debug[3] % 16) == 0) return (int)g_debug[3];
+  const int widest = pick_block_n(cout);
+  if (cout <= 256) return widest;
+  int best = widest; double best_cost = 1e30;
+  for (int bn = 256; bn >= 96; bn -= 16) {
+    const int nt = (cout + bn - 1) / bn;
+    const long long tiles = (long long)m_tiles * nt;
+    const long long rounds = (tiles + DM_NUM_SMS - 1) / DM_NUM_SMS;
+    const double cost = (double)rounds * (bn + 48);      // 48 ~ the per-tile share that does not shrink with N
+    if (cost < best_cost * 0.98) { best_cost = cost; best = bn; }
+  }
+  return best;
 }
 
 unsigned make_idesc(int n, bool a_mn, bool b_mn) {
@@ -955,7 +1030,7 @@ extern "C" int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, in
   const int Ho = (Hin + 2 * pad - kh) / stride + 1, Wo = (Win + 2 * pad - kw) / stride + 1;
   ConvParams P;
   memset(&P, 0, sizeof P);
-  const int block_n = pick_block_n(Cout);
+  const int block_n = pick_block_n_tiles(Cout, dm::cdiv((long)N * Ho * Wo, kBlockM));
   fill_common(P, N, Ho, Wo, Cout, block_n);
   P.chunks0 = dm::cdiv(C0, 64);
   P.chunks1 = x1 ? dm::cdiv(C1, 64) : 0;
@@ -1014,7 +1089,7 @@ extern "C" int dm_conv2d_fwd_stat_rows(int N, int Ho, int Wo, int Cout) {
   // one row per CTA; the two tilings (generic 128-pixel patches / 8x16 halo tiles) can differ in tile
   // count, so this is the larger of the two and the kernels zero-fill the rows beyond their grid
   int a, b, c; pick_patch(Wo, Ho, kBlockM, a, b, c);
-  const int nt = dm::cdiv(Cout, pick_block_n(Cout));
+  const int nt = dm::cdiv(Cout, pick_block_n_tiles(Cout, dm::cdiv((long)N * Ho * Wo, kBlockM)));
   const int m_generic = dm::cdiv(Wo, 1 << a) * dm::cdiv(Ho, 1 << b) * dm::cdiv(N, 1 << c);
   const int m_halo = dm::cdiv(Wo, 8) * dm::cdiv(Ho, 16) * N;
   const int m = m_generic > m_halo ? m_generic : m_halo;
@@ -1036,7 +1111,7 @@ extern "C" int dm_conv2d_s2_dgrad(const void* dy, int Cout, int lddy, const void
     for (int pw = 0; pw < 2; ++pw) {
       ConvParams P;
       memset(&P, 0, sizeof P);
-      const int block_n = pick_block_n(Cin);
+      const int block_n = pick_block_n_tiles(Cin, dm::cdiv((long)N * Ho * Wo, kBlockM));
       fill_common(P, N, Ho, Wo, Cin, block_n);
       P.chunks0 = chunks; P.num_taps = 4;
       // row i = 2Y+ph gets dy rows y with r = i + 1 - 2y in [0,3]:  ph=0: (y=Y, r=1), (y=Y-1, r=3);  ph=1: (y=Y+1, r=0), (y=Y, r=2)

@@ -283,7 +283,7 @@ int zero_f32(float* p, long long n, cudaStream_t st) {
 // ---------------------------------------------------------------------------------- BatchNorm
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* partials, int m_tiles, int ld, int C, double count,
                                                             float* mean, float* invstd, float* rmean, float* rvar,
-                                                            float momentum, float eps) {
+                                                            float momentum, float eps, const float* conv_bias) {
   __shared__ double s1[32][33], s2[32][33];
   const int cl = threadIdx.x & 31, rr = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* partials
       invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
       if (rmean) {
         const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-        rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mu;
+        // conv_bias: the producing conv left its bias out of y (the batch norm cancels it); the tracked mean is of conv + bias
+        rmean[c] = (1.f - momentum) * rmean[c] + momentum * ((float)mu + (conv_bias ? conv_bias[c] : 0.f));
         rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
       }
     } else {
@@ -974,9 +975,10 @@ extern "C" int dm_space_to_depth(const void* x, int ldx, void* y, int ldy, int N
 }
 
 extern "C" int dm_bn_finalize(const float* partials, int m_tiles, int ld, int C, double count, float* mean, float* invstd,
-                              float* running_mean, float* running_var, float momentum, float eps, void* stream) {
+                              float* running_mean, float* running_var, float momentum, float eps, const float* conv_bias,
+                              void* stream) {
   bn_finalize_kernel<<<dm::cdiv(C, 32), 1024, 0, ST>>>(partials, m_tiles, ld, C, count, mean, invstd, running_mean,
-                                                       running_var, momentum, eps);
+                                                       running_var, momentum, eps, conv_bias);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }

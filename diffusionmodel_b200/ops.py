@@ -286,7 +286,7 @@ class _Conv2d(torch.autograd.Function):
     """nn.Conv2d (new_scripy.py:184 etc.) on one or two channel-concatenated NHWC sources."""
 
     @staticmethod
-    def forward(ctx, x0, x1, weight, bias, pack, c0, c1, stride, pad, want_stats, out_f32, bias_grad_by_norm):
+    def forward(ctx, x0, x1, weight, bias, pack, c0, c1, stride, pad, want_stats, out_f32, bias_grad_by_norm, add_bias):
         ld0 = _chk(x0, "conv input")
         ld1 = _chk(x1, "conv input 2") if x1 is not None else 0
         n, hin, win, _ = x0.shape
@@ -303,8 +303,8 @@ class _Conv2d(torch.autograd.Function):
         stats = None
         if want_stats:
             stats = torch.empty((conv_stat_rows(n, ho, wo, cout), 2, cout), device=x0.device, dtype=torch.float32)
-        call("dm_conv2d_fwd", _p(x0), c0, ld0, _p(x1), c1, ld1, _p(wpk), _p(bias), _p(scale), act, _p(y), y.stride(2), int(out_f32),
-             _p(stats), cout, n, hin, win, cout, kh, kw, stride, pad, _stream())
+        call("dm_conv2d_fwd", _p(x0), c0, ld0, _p(x1), c1, ld1, _p(wpk), _p(bias) if add_bias else None, _p(scale), act,
+             _p(y), y.stride(2), int(out_f32), _p(stats), cout, n, hin, win, cout, kh, kw, stride, pad, _stream())
         ctx.save_for_backward(x0, x1, weight, bias)
         ctx.pack, ctx.geom = pack, (c0, c1, stride, pad, out_f32, bias_grad_by_norm)
         ctx.mark_non_differentiable(*([stats] if stats is not None else []))
@@ -353,14 +353,14 @@ class _Conv2d(torch.autograd.Function):
                 dx0 = dx
             else:
                 dx0, dx1 = dx[..., :c0], dx[..., c0:]
-        return dx0, dx1, None, None, None, None, None, None, None, None, None, None
+        return dx0, dx1, None, None, None, None, None, None, None, None, None, None, None
 
 
 class _Im2colConv3x3(torch.autograd.Function):
     """3x3 / pad 1 convolution of a <=3-channel image (the U-Net's first conv) as im2col + 1x1 GEMM."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, pack, want_stats, bias_grad_by_norm):
+    def forward(ctx, x, weight, bias, pack, want_stats, bias_grad_by_norm, add_bias):
         ldx = _chk(x, "conv input")
         n, h, w, _ = x.shape
         cout, cin = weight.shape[0], weight.shape[1]
@@ -372,8 +372,8 @@ class _Im2colConv3x3(torch.autograd.Function):
         stats = None
         if want_stats:
             stats = torch.empty((conv_stat_rows(n, h, w, cout), 2, cout), device=x.device, dtype=torch.float32)
-        call("dm_conv2d_fwd", _p(xi), cin * 9, 32, None, 0, 0, _p(wpk), _p(bias), None, 0, _p(y), y.stride(2), 0,
-             _p(stats), cout, n, h, w, cout, 1, 1, 1, 0, st)
+        call("dm_conv2d_fwd", _p(xi), cin * 9, 32, None, 0, 0, _p(wpk), _p(bias) if add_bias else None, None, 0, _p(y),
+             y.stride(2), 0, _p(stats), cout, n, h, w, cout, 1, 1, 1, 0, st)
         ctx.save_for_backward(xi, weight, bias)
         ctx.pack, ctx.cfg = pack, bias_grad_by_norm
         ctx.mark_non_differentiable(*([stats] if stats is not None else []))
@@ -397,7 +397,7 @@ class _Im2colConv3x3(torch.autograd.Function):
             dx = new_act(n, h, w, cin, dy.device)
             call("dm_conv2d_fwd", _p(dy), cout, lddy, None, 0, 0, _p(wd), None, None, 0, _p(dx), dx.stride(2), 0, None, 0,
                  n, h, w, cin, 3, 3, 1, 1, st)
-        return dx, None, None, None, None, None
+        return dx, None, None, None, None, None, None
 
 
 def conv2d_fused_eval(x0, weight, pack, shift, scale, act, *, x1=None, c1=0, stride=1, pad=0):
@@ -425,14 +425,14 @@ def conv2d_fused_eval(x0, weight, pack, shift, scale, act, *, x1=None, c1=0, str
 
 
 def conv2d(x0, weight, bias, pack, *, x1=None, c0=None, c1=0, stride=1, pad=0, want_stats=False, out_f32=False,
-           bias_grad_by_norm=False):
+           bias_grad_by_norm=False, add_bias=True):
     c0 = weight.shape[1] - c1 if c0 is None else c0
     if (x1 is None and weight.shape[1] <= 3 and tuple(weight.shape[2:]) == (3, 3) and stride == 1 and pad == 1
             and not out_f32):
-        return _Im2colConv3x3.apply(x0, weight, bias, pack, want_stats, bias_grad_by_norm)
+        return _Im2colConv3x3.apply(x0, weight, bias, pack, want_stats, bias_grad_by_norm, add_bias)
     if x1 is not None and (c0 % 8 or x0.shape[3] != c0):
         raise _lib.DmB200Error("dual-source conv needs a tight first source with a multiple-of-8 channel count")
-    return _Conv2d.apply(x0, x1, weight, bias, pack, c0, c1, stride, pad, want_stats, out_f32, bias_grad_by_norm)
+    return _Conv2d.apply(x0, x1, weight, bias, pack, c0, c1, stride, pad, want_stats, out_f32, bias_grad_by_norm, add_bias)
 
 
 class _ConvT(torch.autograd.Function):
@@ -489,7 +489,7 @@ class _BnAct(torch.autograd.Function):
     """BatchNorm2d (eps 1e-5, momentum 0.1) + activation (new_scripy.py:185-186)."""
 
     @staticmethod
-    def forward(ctx, y, stats, gamma, beta, rmean, rvar, conv_bias, c, training, act, momentum, eps):
+    def forward(ctx, y, stats, gamma, beta, rmean, rvar, conv_bias, c, training, act, momentum, eps, bias_outside):
         ldy = _chk(y, "bn input")
         n, h, w, _ = y.shape
         mean = torch.empty(c, device=y.device, dtype=torch.float32)
@@ -497,9 +497,9 @@ class _BnAct(torch.autograd.Function):
         st = _stream()
         if training:
             call("dm_bn_finalize", _p(stats), stats.shape[0], stats.shape[2], c, float(n * h * w), _p(mean), _p(invstd),
-                 _p(rmean), _p(rvar), momentum, eps, st)
+                 _p(rmean), _p(rvar), momentum, eps, _p(conv_bias) if bias_outside else None, st)
         else:
-            call("dm_bn_finalize", None, 0, 0, c, 1.0, _p(mean), _p(invstd), _p(rmean), _p(rvar), momentum, eps, st)
+            call("dm_bn_finalize", None, 0, 0, c, 1.0, _p(mean), _p(invstd), _p(rmean), _p(rvar), momentum, eps, None, st)
         z = torch.empty_like(y)
         call("dm_bn_act_fwd", _p(y), ldy, _p(mean), _p(invstd), _p(gamma), _p(beta), _p(z), z.stride(2), n * h * w, c,
              act, st)
@@ -520,7 +520,7 @@ class _BnAct(torch.autograd.Function):
              dy.stride(2), _p(grad_buf(gamma)), _p(grad_buf(beta)),
              _p(grad_buf(conv_bias)) if conv_bias is not None else None, _p(scratch), npix, c, act, int(training),
              _stream())
-        return dy, None, None, None, None, None, None, None, None, None, None, None
+        return dy, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 FUSED_CONV_STATS = False      # True: BatchNorm statistics from the conv epilogue; False: a separate pass over y
@@ -536,16 +536,18 @@ def bn_stats(y, c):
     return part
 
 
-def bn_act(y, stats, bn, act, conv_bias=None):
+def bn_act(y, stats, bn, act, conv_bias=None, bias_outside=False):
     """``conv_bias``: bias parameter of the convolution that produced ``y`` (called with
-    ``bias_grad_by_norm=True``); its gradient is produced by this norm's backward."""
+    ``bias_grad_by_norm=True``); its gradient is produced by this norm's backward.
+    ``bias_outside``: train mode only -- that conv did NOT add its bias to ``y`` (batch normalisation
+    cancels a per-channel constant exactly); the bias then only enters the tracked running mean."""
     training = bn.training
     if training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     if training and stats is None:
         stats = bn_stats(y, bn.num_features)
     return _BnAct.apply(y, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var, conv_bias, bn.num_features,
-                        training, act, float(bn.momentum), float(bn.eps))
+                        training, act, float(bn.momentum), float(bn.eps), bool(bias_outside and training))
 
 
 class _GnAct(torch.autograd.Function):

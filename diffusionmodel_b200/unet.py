@@ -30,10 +30,10 @@ def _pack_of(conv):
     return pk
 
 
-def conv(x, m, *, x1=None, c1=0, want_stats=False, out_f32=False, bias_grad_by_norm=False):
+def conv(x, m, *, x1=None, c1=0, want_stats=False, out_f32=False, bias_grad_by_norm=False, add_bias=True):
     """Run an nn.Conv2d container through the implicit-GEMM kernel."""
     return ops.conv2d(x, m.weight, m.bias, _pack_of(m), x1=x1, c1=c1, stride=m.stride[0], pad=m.padding[0],
-                      want_stats=want_stats, out_f32=out_f32, bias_grad_by_norm=bias_grad_by_norm)
+                      want_stats=want_stats, out_f32=out_f32, bias_grad_by_norm=bias_grad_by_norm, add_bias=add_bias)
 
 
 def _folded_bn(cv, bn):
@@ -62,8 +62,10 @@ def conv_bn_act(x, seq, act=ACT_GELU, **kw):
         scale, shift = _folded_bn(cv, bn)
         return ops.conv2d_fused_eval(x, cv.weight, _pack_of(cv), shift, scale, act, stride=cv.stride[0],
                                      pad=cv.padding[0], **kw)
-    y, stats = conv(x, cv, want_stats=bn.training and ops.FUSED_CONV_STATS, bias_grad_by_norm=cv.bias is not None, **kw)
-    return ops.bn_act(y, stats, bn, act, conv_bias=cv.bias)
+    # train mode: batch normalisation cancels the conv bias exactly, so the GEMM epilogue skips it
+    y, stats = conv(x, cv, want_stats=bn.training and ops.FUSED_CONV_STATS, bias_grad_by_norm=cv.bias is not None,
+                    add_bias=not bn.training, **kw)
+    return ops.bn_act(y, stats, bn, act, conv_bias=cv.bias, bias_outside=bn.training and cv.bias is not None)
 
 
 # ------------------------------------------------------------------------------------------ blocks

@@ -80,7 +80,9 @@ int dm_space_to_depth(const void* x, int ldx, void* y, int ldy, int N, int H, in
 int dm_bn_stats_rows(long long P, int C);
 int dm_bn_stats(const void* y, int ldy, float* part, int ld, long long P, int C, void* stream);
 int dm_bn_finalize(const float* partials, int m_tiles, int ld, int C, double count, float* mean, float* invstd,
-                   float* running_mean, float* running_var, float momentum, float eps, void* stream);
+                   float* running_mean, float* running_var, float momentum, float eps, const float* conv_bias,
+                   void* stream);   /* conv_bias (nullable): bias the producing conv left out of y (train mode: the
+                                       norm cancels it); it is added to the tracked running mean only */
 int dm_bn_act_fwd(const void* y, int ldy, const float* mean, const float* invstd, const float* gamma,
                   const float* beta, void* z, int ldz, long long P, int C, int act, void* stream);
 /* dy = BN/act backward (three launches: block partial sums -> finalize -> apply); dgamma/dbeta += ;

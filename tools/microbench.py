@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--out", default="microbench.json")
     ap.add_argument("--ablate", action="store_true", help="halo-kernel timing decomposition (no MMA / no TMA / no epilogue)")
+    ap.add_argument("--bn_sweep", action="store_true", help="forced tile widths, full kernel and MMA-only")
     ap.add_argument("--ab", action="store_true", help="also time the alternative kernels (generic conv, wgrad v1/v2)")
     ap.add_argument("--shapes", type=int, default=0, help="only the first N conv shapes")
     a = ap.parse_args()
@@ -105,19 +106,26 @@ def main():
                 variants += [("fwd_generic", fwd), ("fwd_nostat_generic", fwd_nostat), ("dgrad_generic", dgrad),
                              ("wgrad_v1", wgrad), ("wgrad_v2", wgrad)]
             if a.ablate and k == 3 and s == 1:
-                for mask in (0, 1, 2, 3, 4, 5, 6, 7):
+                for mask in (0, 6, 14):
                     variants.append((f"dgrad_abl{mask}", dgrad))
+            if a.bn_sweep and k == 3 and s == 1:
+                for bn_ in (64, 96, 128, 192, 256):
+                    if bn_ <= ops.r8(cin) * 2:
+                        variants += [(f"dgrad_bn{bn_}_abl6", dgrad), (f"dgrad_bn{bn_}_abl0", dgrad)]
             for name, fn in variants:
                 if name.startswith("wgrad_v"):
                     _lib.debug_set(4, int(name[-1]))
                 if name.endswith("_generic"):
                     _lib.debug_set(5, 1)
                 if "_abl" in name:
-                    _lib.debug_set(7, int(name[-1]))
+                    _lib.debug_set(7, int(name.split("_abl")[1]))
+                if "_bn" in name:
+                    _lib.debug_set(3, int(name.split("_bn")[1].split("_")[0]))
                 ms = timer(fn, a.iters, flush)
                 _lib.debug_set(4, 0)
                 _lib.debug_set(5, 0)
                 _lib.debug_set(7, 0)
+                _lib.debug_set(3, 0)
                 r[name + "_ms"] = round(ms, 4)
                 r[name + "_tflops"] = round(fl / ms / 1e9, 1)
             print(json.dumps(r), flush=True)
