@@ -70,6 +70,7 @@ _SIGS = {
     "dm_bn_act_fwd": "pi pppp pi l ii p",
     "dm_bn_act_bwd": "pi pi pppp pi pp p p l iii p",
     "dm_bn_act_bwd_scratch": "li",
+    "dm_gn_scratch": "iii",
     "dm_gn_act_fwd": "pi pp pi pp p iiii f i p",
     "dm_gn_act_bwd": "pi pi pppp pi pp p iiii i p",
     "dm_pool_nhw": "pi p iii f p",
@@ -97,7 +98,7 @@ _SIGS = {
     "dm_sumsq": "p l p p",
     "dm_adamw": "pppp l fffffff p f p",
 }
-_RET_LL = {"dm_bn_act_bwd_scratch"}          # size queries return long long, not a status
+_RET_LL = {"dm_bn_act_bwd_scratch", "dm_gn_scratch"}          # size queries return long long, not a status
 _CT = {"p": _P, "i": _I, "l": _L, "f": _F, "d": _D}
 _bound = {}
 

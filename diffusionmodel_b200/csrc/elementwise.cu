@@ -507,72 +507,272 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
 }
 
 // ---------------------------------------------------------------------------------- GroupNorm
-__global__ void gn_fold_fwd_kernel(const float* S, int N, int C, int G, double cnt, float eps, float* mean, float* rstd) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * G) return;
-  const int n = i / G, g = i % G, cg = C / G;
-  double a = 0, b = 0;
-  for (int c = g * cg; c < (g + 1) * cg; ++c) { a += S[(long long)n * C + c]; b += S[(long long)(N + n) * C + c]; }
-  const double mu = a / cnt;
-  double var = b / cnt - mu * mu; if (var < 0) var = 0;
-  mean[i] = (float)mu; rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
-}
-struct GnFwd {
-  const bf16* x; int ldx; const float *mean, *rstd, *gamma, *beta; bf16* z; int ldz; int C, G, HW, act;
-  __device__ void operator()(unsigned p, int c0) const {
-    float v[8], ga[8], be[8];
-    load8(x + (long long)p * ldx + c0, v);
-    ldp8(gamma, c0, C, ga); ldp8(beta, c0, C, be);
-    const int n = p / HW, cg = C / G;
+// Same streaming structure as the BatchNorm kernels, with one grid.z slice per sample and per-(sample,
+// channel) coefficient rows: the statistics of a (sample, group) fold into rows scale/shift[n][c] once, so
+// the big passes are load -> fma -> activation -> store with the coefficients in registers.
+//
+// pass 1 (forward): per-block partial sums of x and x^2 for one sample: part[n][blockIdx.x][2][C]
+__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, int ldx, float* __restrict__ part, unsigned HW,
+                                                        int C, int VPB, int R) {
+  extern __shared__ float sm[];          // [threads][16]
+  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
+  const int c0 = (blockIdx.y * VPB + cvl) * 8;
+  const int n = blockIdx.z;
+  x += (long long)n * HW * ldx;
+  float s1[8], s2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j < C ? c0 + j : C - 1;
-      const int si = n * G + c / cg;
-      v[j] = (c0 + j < C) ? dm::act_f((v[j] - __ldg(mean + si)) * __ldg(rstd + si) * ga[j] + be[j], act) : 0.f;
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  if (c0 < C) {
+    const unsigned step = gridDim.x * R;
+    for (unsigned p = blockIdx.x * R + r; p < HW; p += 4 * step) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned pu = p + u * step;
+        if (pu < HW) load8(x + (long long)pu * ldx + c0, v[u]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] += v[u][j]; s2[j] = fmaf(v[u][j], v[u][j], s2[j]); }
     }
-    store8(z + (long long)p * ldz + c0, v);
   }
-};
-// S = [2][N][C] sums (g, g*xhat) -> m[2][N*G] group means of (g*gamma), (g*gamma*xhat); dgamma/dbeta +=
-__global__ void gn_fold_bwd_kernel(const float* S, const float* gamma, int N, int C, int G, double cnt, float* m,
-                                   float* dgamma, float* dbeta) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N * G) {
-    const int n = i / G, g = i % G, cg = C / G;
-    double a = 0, b = 0;
-    for (int c = g * cg; c < (g + 1) * cg; ++c) {
-      a += (double)gamma[c] * S[(long long)n * C + c];
-      b += (double)gamma[c] * S[(long long)(N + n) * C + c];
+  float* mine = sm + threadIdx.x * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mine[j] = s1[j]; mine[8 + j] = s2[j]; }
+  __syncthreads();
+  if (r == 0 && c0 < C) {
+    for (int rr = 1; rr < R; ++rr) {
+      const float* o = sm + (rr * VPB + cvl) * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1[j] += o[j]; s2[j] += o[8 + j]; }
     }
-    m[i] = (float)(a / cnt); m[N * G + i] = (float)(b / cnt);
-  }
-  if (i < C) {
-    float a = 0, b = 0;
-    for (int n = 0; n < N; ++n) { a += S[(long long)n * C + i]; b += S[(long long)(N + n) * C + i]; }
-    dbeta[i] += a; dgamma[i] += b;
+    float* g = part + ((long long)n * gridDim.x + blockIdx.x) * 2 * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < C) { g[c0 + j] = s1[j]; g[C + c0 + j] = s2[j]; }
   }
 }
-struct GnBwd {
-  const bf16* dz; int lddz; const bf16* x; int ldx; const float *mean, *rstd, *gamma, *beta, *m;
-  bf16* dx; int lddx; int C, G, HW, N, act;
-  __device__ void operator()(unsigned p, int c0) const {
-    float g[8], v[8], ga[8], be[8];
-    load8(dz + (long long)p * lddz + c0, g);
-    load8(x + (long long)p * ldx + c0, v);
-    ldp8(gamma, c0, C, ga); ldp8(beta, c0, C, be);
-    const int n = p / HW, cg = C / G;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j < C ? c0 + j : C - 1;
-      const int si = n * G + c / cg;
-      const float rs = __ldg(rstd + si);
-      const float xh = (v[j] - __ldg(mean + si)) * rs;
-      const float gg = g[j] * dm::act_grad_f(xh * ga[j] + be[j], act);
-      g[j] = (c0 + j < C) ? rs * (gg * ga[j] - __ldg(m + si) - xh * __ldg(m + N * G + si)) : 0.f;
-    }
-    store8(dx + (long long)p * lddx + c0, g);
+// pass 2 (forward): one block per (sample, group): statistics -> mean/rstd and the coefficient rows
+// sc[n][c] = rstd*gamma, sh[n][c] = beta - mean*rstd*gamma
+__global__ void __launch_bounds__(256) gn_fold_fwd_kernel(const float* __restrict__ part, int nblk, int C, int G, double cnt,
+                                                           float eps, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* mean, float* rstd,
+                                                           float* sc, float* sh, float* sx) {
+  __shared__ double red[2][256];
+  const int n = blockIdx.x / G, g = blockIdx.x % G, cg = C / G;
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < cg * nblk; i += blockDim.x) {
+    const int c = g * cg + i % cg, t = i / cg;
+    const float* row = part + ((long long)n * nblk + t) * 2 * C;
+    a += (double)row[c]; b += (double)row[C + c];
   }
-};
+  red[0][threadIdx.x] = a; red[1][threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { red[0][threadIdx.x] += red[0][threadIdx.x + o]; red[1][threadIdx.x] += red[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  const double mu = red[0][0] / cnt;
+  double var = red[1][0] / cnt - mu * mu; if (var < 0) var = 0;
+  const double rs = 1.0 / sqrt(var + (double)eps);
+  if (threadIdx.x == 0) { mean[blockIdx.x] = (float)mu; rstd[blockIdx.x] = (float)rs; }
+  for (int i = threadIdx.x; i < cg; i += blockDim.x) {
+    const int c = g * cg + i;
+    const double k = rs * (double)gamma[c];
+    sc[(long long)n * C + c] = (float)k;
+    sh[(long long)n * C + c] = (float)((double)beta[c] - mu * k);
+  }
+  (void)sx;
+}
+// pass 3 (forward): z = act(x * sc[n][c] + sh[n][c])
+template <int ACT>
+__global__ void __launch_bounds__(256) gn_apply_fwd_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ sc,
+                                                            const float* __restrict__ sh, bf16* __restrict__ z, int ldz,
+                                                            unsigned HW, int C, int VPB, int R) {
+  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
+  const int c0 = (blockIdx.y * VPB + cvl) * 8;
+  if (c0 >= C) return;
+  const int n = blockIdx.z;
+  x += (long long)n * HW * ldx; z += (long long)n * HW * ldz;
+  float a[8], b[8];
+  ldp8(sc + (long long)n * C, c0, C, a); ldp8(sh + (long long)n * C, c0, C, b);
+  const unsigned step = gridDim.x * R;
+  for (unsigned p = blockIdx.x * R + r; p < HW; p += 2 * step) {
+    const unsigned p1 = p + step;
+    const bool has1 = p1 < HW;
+    float v0[8], v1[8];
+    load8(x + (long long)p * ldx + c0, v0);
+    if (has1) load8(x + (long long)p1 * ldx + c0, v1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v0[j] = (c0 + j < C) ? dm::act_f(fmaf(v0[j], a[j], b[j]), ACT) : 0.f;
+    store8(z + (long long)p * ldz + c0, v0);
+    if (has1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v1[j] = (c0 + j < C) ? dm::act_f(fmaf(v1[j], a[j], b[j]), ACT) : 0.f;
+      store8(z + (long long)p1 * ldz + c0, v1);
+    }
+  }
+}
+// backward pass 1: per-block partial sums of g = dz*act'(x*sc+sh) and g*x for one sample: part[n][blk][2][C]
+template <int ACT>
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ x,
+                                                             int ldx, const float* __restrict__ sc, const float* __restrict__ sh,
+                                                             float* __restrict__ part, unsigned HW, int C, int VPB, int R) {
+  extern __shared__ float sm[];          // [threads][8]
+  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
+  const int c0 = (blockIdx.y * VPB + cvl) * 4;
+  const int n = blockIdx.z;
+  dz += (long long)n * HW * lddz; x += (long long)n * HW * ldx;
+  float s1[4], s2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  if (c0 < C) {
+    float a[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool ok = c0 + j < C;
+      a[j] = ok ? __ldg(sc + (long long)n * C + c0 + j) : 0.f;
+      b[j] = ok ? __ldg(sh + (long long)n * C + c0 + j) : 0.f;
+    }
+    const unsigned step = gridDim.x * R;
+    for (unsigned p = blockIdx.x * R + r; p < HW; p += 2 * step) {
+      const unsigned p1 = p + step;
+      const bool has1 = p1 < HW;
+      float g0[4], v0[4], g1[4], v1[4];
+      dm::load4(dz + (long long)p * lddz + c0, g0);
+      dm::load4(x + (long long)p * ldx + c0, v0);
+      if (has1) { dm::load4(dz + (long long)p1 * lddz + c0, g1); dm::load4(x + (long long)p1 * ldx + c0, v1); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gg = g0[j] * dm::act_grad_f(fmaf(v0[j], a[j], b[j]), ACT);
+        s1[j] += gg; s2[j] = fmaf(gg, v0[j], s2[j]);
+      }
+      if (has1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float gg = g1[j] * dm::act_grad_f(fmaf(v1[j], a[j], b[j]), ACT);
+          s1[j] += gg; s2[j] = fmaf(gg, v1[j], s2[j]);
+        }
+      }
+    }
+  }
+  float* mine = sm + threadIdx.x * 8;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { mine[j] = s1[j]; mine[4 + j] = s2[j]; }
+  __syncthreads();
+  if (r == 0 && c0 < C) {
+    for (int rr = 1; rr < R; ++rr) {
+      const float* o = sm + (rr * VPB + cvl) * 8;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s1[j] += o[j]; s2[j] += o[4 + j]; }
+    }
+    float* g = part + ((long long)n * gridDim.x + blockIdx.x) * 2 * C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c0 + j < C) { g[c0 + j] = s1[j]; g[C + c0 + j] = s2[j]; }
+  }
+}
+// backward pass 2: one block per (sample, group).  With Sg = sum g, Sgx = sum g*x per channel:
+//   m1 = sum_c gamma*Sg / cnt,  m2 = sum_c gamma*rstd*(Sgx - mean*Sg) / cnt
+//   dx = (rstd*gamma)*g - (rstd^2*m2)*x - (rstd*m1 - rstd^2*m2*mean)        -> coef[n][3][C] = (k0, K1, K2)
+//   dgamma[c] += rstd*(Sgx - mean*Sg), dbeta[c] += Sg      (atomic across samples)
+__global__ void __launch_bounds__(256) gn_fold_bwd_kernel(const float* __restrict__ part, int nblk, int C, int G, double cnt,
+                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, float* __restrict__ coef,
+                                                           float* dgamma, float* dbeta) {
+  __shared__ double red[2][256];
+  const int n = blockIdx.x / G, g = blockIdx.x % G, cg = C / G;
+  const double mu = (double)mean[blockIdx.x], rs = (double)rstd[blockIdx.x];
+  // per-channel sums over the partial rows: (channel, row-slice) threads, then a fixed-order combine
+  __shared__ float ps[2][256];
+  const int slices = cg < 256 ? 256 / cg : 1;
+  double a = 0.0, b = 0.0;
+  for (int i0 = 0; i0 < cg; i0 += 256) {
+    const int i = i0 + (int)threadIdx.x % (cg < 256 ? cg : 256), sl = (int)threadIdx.x / (cg < 256 ? cg : 256);
+    float f0 = 0.f, f1 = 0.f;
+    if (i < cg && sl < slices) {
+      const int c = g * cg + i;
+      for (int q = sl; q < nblk; q += slices) {
+        const float* row = part + ((long long)n * nblk + q) * 2 * C;
+        f0 += row[c]; f1 += row[C + c];
+      }
+    }
+    ps[0][threadIdx.x] = f0; ps[1][threadIdx.x] = f1;
+    __syncthreads();
+    if (sl == 0 && i < cg) {
+      const int c = g * cg + i, stride = cg < 256 ? cg : 256;
+      double sg = 0.0, sgx = 0.0;
+      for (int k = 0; k < slices; ++k) { sg += (double)ps[0][k * stride + (i - i0)]; sgx += (double)ps[1][k * stride + (i - i0)]; }
+      const double ga = (double)gamma[c];
+      a += ga * sg; b += ga * rs * (sgx - mu * sg);
+      atomicAdd(dbeta + c, (float)sg);
+      atomicAdd(dgamma + c, (float)(rs * (sgx - mu * sg)));
+    }
+    __syncthreads();
+  }
+  red[0][threadIdx.x] = a; red[1][threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { red[0][threadIdx.x] += red[0][threadIdx.x + o]; red[1][threadIdx.x] += red[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  const double m1 = red[0][0] / cnt, m2 = red[1][0] / cnt;
+  for (int i = threadIdx.x; i < cg; i += blockDim.x) {
+    const int c = g * cg + i;
+    float* row = coef + (long long)n * 3 * C;
+    row[c] = (float)(rs * (double)gamma[c]);
+    row[C + c] = (float)(rs * m1 - rs * rs * m2 * mu);
+    row[2 * C + c] = (float)(rs * rs * m2);
+  }
+}
+// backward pass 3: dx = k0*g - K2*x - K1
+template <int ACT>
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ x,
+                                                            int ldx, const float* __restrict__ sc, const float* __restrict__ sh,
+                                                            const float* __restrict__ coef, bf16* __restrict__ dx, int lddx,
+                                                            unsigned HW, int C, int VPB, int R) {
+  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
+  const int c0 = (blockIdx.y * VPB + cvl) * 4;
+  if (c0 >= C) return;
+  const int n = blockIdx.z;
+  dz += (long long)n * HW * lddz; x += (long long)n * HW * ldx; dx += (long long)n * HW * lddx;
+  float a[4], b[4], k0[4], K1[4], K2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool ok = c0 + j < C;
+    const long long o = (long long)n * C + c0 + j, o3 = (long long)n * 3 * C + c0 + j;
+    a[j] = ok ? __ldg(sc + o) : 0.f; b[j] = ok ? __ldg(sh + o) : 0.f;
+    k0[j] = ok ? __ldg(coef + o3) : 0.f; K1[j] = ok ? __ldg(coef + o3 + C) : 0.f; K2[j] = ok ? __ldg(coef + o3 + 2 * C) : 0.f;
+  }
+  const unsigned step = gridDim.x * R;
+  for (unsigned p = blockIdx.x * R + r; p < HW; p += 2 * step) {
+    const unsigned p1 = p + step;
+    const bool has1 = p1 < HW;
+    float g0[4], v0[4], g1[4], v1[4];
+    dm::load4(dz + (long long)p * lddz + c0, g0);
+    dm::load4(x + (long long)p * ldx + c0, v0);
+    if (has1) { dm::load4(dz + (long long)p1 * lddz + c0, g1); dm::load4(x + (long long)p1 * ldx + c0, v1); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gg = g0[j] * dm::act_grad_f(fmaf(v0[j], a[j], b[j]), ACT);
+      g0[j] = fmaf(k0[j], gg, -fmaf(K2[j], v0[j], K1[j]));
+    }
+    dm::store4(dx + (long long)p * lddx + c0, g0);
+    if (has1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gg = g1[j] * dm::act_grad_f(fmaf(v1[j], a[j], b[j]), ACT);
+        g1[j] = fmaf(k0[j], gg, -fmaf(K2[j], v1[j], K1[j]));
+      }
+      dm::store4(dx + (long long)p1 * lddx + c0, g1);
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------- SE / residual
 struct SeFwd {
@@ -1048,43 +1248,63 @@ extern "C" int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, c
   return DM_OK;
 }
 
+static int gn_blocks(int N, long long HW, int C, int vec) {
+  // blocks per sample: enough CTAs in total for a full wave, but few partial rows to fold
+  const ChanMap m = chan_map(C, vec);
+  int b = chan_grid_x(HW, m, 16);
+  int cap = DM_NUM_SMS * 4 / (m.cvt * (N > 0 ? N : 1)); if (cap < 1) cap = 1;
+  return b > cap ? cap : b;
+}
+/* scratch layout (floats): sc[N*C] sh[N*C] sx[N*C] coef[3*N*C] part[N*blocks*2*C] */
+extern "C" long long dm_gn_scratch(int N, int HW, int C) {
+  const int b8 = gn_blocks(N, HW, C, 8), b4 = gn_blocks(N, HW, C, 4);
+  return 6LL * N * C + 2LL * N * (b8 > b4 ? b8 : b4) * C;
+}
 extern "C" int dm_gn_act_fwd(const void* x, int ldx, const float* gamma, const float* beta, void* z, int ldz, float* mean,
                              float* rstd, float* scratch, int N, int HW, int C, int G, float eps, int act, void* stream) {
   REQ8(ldx, "dm_gn_act_fwd"); REQ8(ldz, "dm_gn_act_fwd");
-  if (C % G) { dm_set_error("dm_gn_act_fwd: C must be divisible by G"); return DM_ERR_ARG; }
-  int rc = zero_f32(scratch, 2LL * N * C, ST);
-  if (rc) return rc;
-  RedArgs A{};
-  A.a = (const bf16*)x; A.b = nullptr; A.a_hi = (long long)HW * ldx; A.a_lo = 0; A.a_ps = ldx;
-  A.gdiv = 1; A.count = HW; A.C = C; A.mode = 1; A.scale = 1.f; A.G = G; A.stat_div = 1;
-  A.out1 = scratch; A.out2 = scratch + (long long)N * C;
-  rc = launch_reduce(A, N, ST);
-  if (rc) return rc;
-  gn_fold_fwd_kernel<<<dm::cdiv(N * G, 128), 128, 0, ST>>>(scratch, N, C, G, (double)HW * (C / G), eps, mean, rstd);
+  if (C % G || C / G > 512) { dm_set_error("dm_gn_act_fwd: C must be divisible by G with at most 512 channels per group"); return DM_ERR_ARG; }
+  if (N <= 0 || HW <= 0) return DM_OK;
+  if (N > 65535) { dm_set_error("dm_gn_act_fwd: batch too large"); return DM_ERR_ARG; }
+  float *sc = scratch, *sh = sc + (long long)N * C, *sx = sh + (long long)N * C, *part = scratch + 6LL * N * C;
+  const ChanMap m = chan_map(C);
+  const int nblk = gn_blocks(N, HW, C, 8);
+  gn_stats_kernel<<<dim3(nblk, m.cvt, N), m.threads, (size_t)m.threads * 16 * sizeof(float), ST>>>((const bf16*)x, ldx, part,
+                                                                                                  (unsigned)HW, C, m.VPB, m.R);
   DM_CHECK_LAUNCH();
-  GnFwd f{(const bf16*)x, ldx, mean, rstd, gamma, beta, (bf16*)z, ldz, C, G, HW, act};
-  return ew_launch((long long)N * HW, C, f, ST);
+  gn_fold_fwd_kernel<<<N * G, 256, 0, ST>>>(part, nblk, C, G, (double)HW * (C / G), eps, gamma, beta, mean, rstd, sc, sh, sx);
+  DM_CHECK_LAUNCH();
+  dim3 grid(chan_grid_x(HW, m, 4), m.cvt, N);
+  { int cap = DM_NUM_SMS * 8 / (m.cvt * N); if (cap < 1) cap = 1; if ((int)grid.x > cap) grid.x = cap; }
+#define GN_FWD(A) gn_apply_fwd_kernel<A><<<grid, m.threads, 0, ST>>>((const bf16*)x, ldx, sc, sh, (bf16*)z, ldz, (unsigned)HW, C, m.VPB, m.R)
+  if (act == 1) GN_FWD(1); else if (act == 2) GN_FWD(2); else GN_FWD(0);
+#undef GN_FWD
+  DM_CHECK_LAUNCH();
+  return DM_OK;
 }
+/* scratch: the forward call's buffer (sc/sh rows are read, coef/part are overwritten) */
 extern "C" int dm_gn_act_bwd(const void* dz, int lddz, const void* x, int ldx, const float* mean, const float* rstd,
                              const float* gamma, const float* beta, void* dx, int lddx, float* dgamma, float* dbeta,
                              float* scratch, int N, int HW, int C, int G, int act, void* stream) {
   REQ8(lddz, "dm_gn_act_bwd"); REQ8(ldx, "dm_gn_act_bwd"); REQ8(lddx, "dm_gn_act_bwd");
-  int rc = zero_f32(scratch, 2LL * N * C, ST);
-  if (rc) return rc;
-  RedArgs A{};
-  A.a = (const bf16*)dz; A.b = (const bf16*)x;
-  A.a_hi = (long long)HW * lddz; A.a_lo = 0; A.a_ps = lddz; A.b_hi = (long long)HW * ldx; A.b_lo = 0; A.b_ps = ldx;
-  A.gdiv = 1; A.count = HW; A.C = C; A.mode = 4; A.act = act; A.G = G; A.stat_div = 1;
-  A.mean = mean; A.invstd = rstd; A.gamma = gamma; A.beta = beta; A.scale = 1.f;
-  A.out1 = scratch; A.out2 = scratch + (long long)N * C;
-  rc = launch_reduce(A, N, ST);
-  if (rc) return rc;
-  float* m = scratch + 2LL * N * C;
-  int nt = N * G > C ? N * G : C;
-  gn_fold_bwd_kernel<<<dm::cdiv(nt, 128), 128, 0, ST>>>(scratch, gamma, N, C, G, (double)HW * (C / G), m, dgamma, dbeta);
+  if (N <= 0 || HW <= 0) return DM_OK;
+  float *sc = scratch, *sh = sc + (long long)N * C, *coef = scratch + 3LL * N * C, *part = scratch + 6LL * N * C;
+  const ChanMap m = chan_map(C, 4);
+  const int nblk = gn_blocks(N, HW, C, 4);
+#define GN_RED(A) gn_bwd_reduce_kernel<A><<<dim3(nblk, m.cvt, N), m.threads, (size_t)m.threads * 8 * sizeof(float), ST>>>((const bf16*)dz, lddz, (const bf16*)x, ldx, sc, sh, part, (unsigned)HW, C, m.VPB, m.R)
+  if (act == 1) GN_RED(1); else if (act == 2) GN_RED(2); else GN_RED(0);
+#undef GN_RED
   DM_CHECK_LAUNCH();
-  GnBwd f{(const bf16*)dz, lddz, (const bf16*)x, ldx, mean, rstd, gamma, beta, m, (bf16*)dx, lddx, C, G, HW, N, act};
-  return ew_launch((long long)N * HW, C, f, ST);
+  gn_fold_bwd_kernel<<<N * G, 256, 0, ST>>>(part, nblk, C, G, (double)HW * (C / G), gamma, mean, rstd, coef, dgamma, dbeta);
+  DM_CHECK_LAUNCH();
+  dim3 grid(chan_grid_x(HW, m, 4), m.cvt, N);
+  { int cap = DM_NUM_SMS * 8 / (m.cvt * N); if (cap < 1) cap = 1; if ((int)grid.x > cap) grid.x = cap; }
+#define GN_APP(A) gn_bwd_apply_kernel<A><<<grid, m.threads, 0, ST>>>((const bf16*)dz, lddz, (const bf16*)x, ldx, sc, sh, coef, (bf16*)dx, lddx, (unsigned)HW, C, m.VPB, m.R)
+  if (act == 1) GN_APP(1); else if (act == 2) GN_APP(2); else GN_APP(0);
+#undef GN_APP
+  DM_CHECK_LAUNCH();
+  (void)beta;
+  return DM_OK;
 }
 
 extern "C" int dm_pool_nhw(const void* x, int ldx, float* out, int N, int HW, int C, float scale, void* stream) {

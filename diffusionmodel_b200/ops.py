@@ -559,22 +559,21 @@ class _GnAct(torch.autograd.Function):
         n, h, w, _ = x.shape
         mean = torch.empty(n * groups, device=x.device, dtype=torch.float32)
         rstd = torch.empty(n * groups, device=x.device, dtype=torch.float32)
-        scratch = torch.empty(2 * n * c, device=x.device, dtype=torch.float32)
+        scratch = torch.empty(_lib.fn("dm_gn_scratch")(n, h * w, c), device=x.device, dtype=torch.float32)
         z = torch.empty_like(x)
         call("dm_gn_act_fwd", _p(x), ldx, _p(gamma), _p(beta), _p(z), z.stride(2), _p(mean), _p(rstd), _p(scratch), n,
              h * w, c, groups, eps, act, _stream())
-        ctx.save_for_backward(x, mean, rstd, gamma, beta)
+        ctx.save_for_backward(x, mean, rstd, gamma, beta, scratch)
         ctx.cfg = (c, groups, act)
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        x, mean, rstd, gamma, beta = ctx.saved_tensors
+        x, mean, rstd, gamma, beta, scratch = ctx.saved_tensors
         c, groups, act = ctx.cfg
         lddz = _chk(dz, "gn grad")
         n, h, w, _ = x.shape
         dx = torch.empty_like(x)
-        scratch = torch.empty(2 * n * c + 2 * n * groups, device=x.device, dtype=torch.float32)
         call("dm_gn_act_bwd", _p(dz), lddz, _p(x), x.stride(2), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dx),
              dx.stride(2), _p(grad_buf(gamma)), _p(grad_buf(beta)), _p(scratch), n, h * w, c, groups, act, _stream())
         return dx, None, None, None, None, None, None

@@ -94,7 +94,11 @@ int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, const float*
                   const float* gamma, const float* beta, void* dy, int lddy, float* dgamma, float* dbeta,
                   float* dbias, float* scratch, long long P, int C, int act, int training, void* stream);
 
-/* ---- GroupNorm(8,C) + ReLU/GELU (new_scripy.py:167-168,299-300,312-313) --------------------------- */
+/* ---- GroupNorm(8,C) + ReLU/GELU (new_scripy.py:167-168,299-300,312-313) ---------------------------
+ * Three launches each way (per-sample partial sums -> fold to per-(sample,channel) coefficient rows ->
+ * streaming apply).  scratch >= dm_gn_scratch(N, HW, C) floats; the backward call must receive the SAME
+ * scratch buffer the forward call filled (it holds the coefficient rows). */
+long long dm_gn_scratch(int N, int HW, int C);
 int dm_gn_act_fwd(const void* x, int ldx, const float* gamma, const float* beta, void* z, int ldz, float* mean,
                   float* rstd, float* scratch, int N, int HW, int C, int G, float eps, int act, void* stream);
 int dm_gn_act_bwd(const void* dz, int lddz, const void* x, int ldx, const float* mean, const float* rstd,
