@@ -958,6 +958,7 @@ static int launch_conv(ConvParams& P, cudaStream_t st) {
   if (g_debug[0] > 0 && g_debug[0] < stages) stages = (int)g_debug[0];
   if (stages < 2) { dm_set_error("conv_gemm: not enough shared memory for 2 stages"); return DM_ERR_ARG; }
   P.stages = stages;
+  P.ablate = (int)g_debug[7] & 4;          // generic kernel: only the epilogue switch
   size_t smem = 1024 + (size_t)stages * stage_bytes + kAuxBytes + stat_bytes;
   if (!g_attr_a) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);

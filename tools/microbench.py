@@ -106,8 +106,10 @@ def main():
                 variants += [("fwd_generic", fwd), ("fwd_nostat_generic", fwd_nostat), ("dgrad_generic", dgrad),
                              ("wgrad_v1", wgrad), ("wgrad_v2", wgrad)]
             if a.ablate and k == 3 and s == 1:
-                for mask in (0, 6, 14):
+                for mask in (0, 2, 4, 6):
                     variants.append((f"dgrad_abl{mask}", dgrad))
+            if a.ablate:
+                variants += [("fwd_nostat_abl4", fwd_nostat), ("dgrad_abl4", dgrad)]
             if a.bn_sweep and k == 3 and s == 1:
                 for bn_ in (64, 96, 128, 192, 256):
                     if bn_ <= ops.r8(cin) * 2:
