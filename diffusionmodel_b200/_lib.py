@@ -95,6 +95,7 @@ _SIGS = {
     "dm_ddpm_loss_fwd": "pi p p p p iiii ffffff p",
     "dm_ddpm_loss_bwd": "pi p p p pi iiii ffffff p",
     "dm_cfg_reverse_step": "pi p p p pi ffff iiii p",
+    "dm_cfg_reverse_step_dev": "pi p p p pi p iiii p",
     "dm_sumsq": "p l p p",
     "dm_adamw": "pppp l fffffff p f p",
 }

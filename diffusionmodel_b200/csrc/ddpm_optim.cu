@@ -160,7 +160,8 @@ __global__ void loss_bwd_kernel(const float* pred, int ldp, const float* noise, 
 }
 
 __global__ void cfg_reverse_kernel(const float* eps, int ldp, const float* x, const float* z, float* x_out, bf16* xt_next,
-                                   int ldo, float gw, float a, float b, float s, int n, int C, int HW) {
+                                   int ldo, float gw, float a, float b, float s, const float* coef, int n, int C, int HW) {
+  if (coef != nullptr) { gw = coef[0]; a = coef[1]; b = coef[2]; s = coef[3]; }     // graph-replayable: scalars from device memory
   const long long P = (long long)n * HW;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
     const long long i = p / HW, hw = p % HW;
@@ -291,7 +292,16 @@ extern "C" int dm_cfg_reverse_step(const float* eps, int ldp, const float* x, co
                                    int n, int C, int H, int W, void* stream) {
   if (ldo & 7) { dm_set_error("dm_cfg_reverse_step: pitch must be a multiple of 8"); return DM_ERR_ARG; }
   cfg_reverse_kernel<<<grid_for((long long)n * H * W), 256, 0, ST>>>(eps, ldp, x, z, x_out, (bf16*)xt_next, ldo, guide_w,
-                                                                    oneover_sqrta, mab_over_sqrtmab, sqrt_beta, n, C, H * W);
+                                                                    oneover_sqrta, mab_over_sqrtmab, sqrt_beta, nullptr, n, C, H * W);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+extern "C" int dm_cfg_reverse_step_dev(const float* eps, int ldp, const float* x, const float* z, float* x_out, void* xt_next,
+                                       int ldo, const float* coef4, int n, int C, int H, int W, void* stream) {
+  if (ldo & 7) { dm_set_error("dm_cfg_reverse_step_dev: pitch must be a multiple of 8"); return DM_ERR_ARG; }
+  if (coef4 == nullptr) { dm_set_error("dm_cfg_reverse_step_dev: coefficient buffer required"); return DM_ERR_ARG; }
+  cfg_reverse_kernel<<<grid_for((long long)n * H * W), 256, 0, ST>>>(eps, ldp, x, z, x_out, (bf16*)xt_next, ldo, 0.f, 0.f, 0.f, 0.f,
+                                                                    coef4, n, C, H * W);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }

@@ -63,7 +63,9 @@ class DDPM(nn.Module):
         self.enhance_with_attn_map = enhance_with_attn_map
         self.sample_noise = sample_noise
         self.shared_encoder_cfg = True      # exact in eval mode (see sample()); False = the reference's 2n-batch encoder
+        self.graph_sampling = True          # one CUDA graph of the reverse step, replayed n_T times
         self._host_sched = None
+        self._sample_graphs = {}
 
     # ------------------------------------------------------------------ training
     def draw_randoms(self, x, c):
@@ -130,11 +132,77 @@ class DDPM(nn.Module):
             graph.replay()
             for e in touched:
                 e.dirty = True
+            ops.bump_bn_stats_epoch()         # the replay updated BatchNorm running statistics in place
             return loss
         step.graph, step.kernels_per_replay = graph, kernels
         return step
 
     # ------------------------------------------------------------------ sampling
+    def _reverse_step_graph(self, n_sample, size, c_i, ctx_mask, shared):
+        """Capture eps = U-Net(x_t) -> CFG combine + reverse step on static buffers (one graph per batch shape)."""
+        dev = c_i.device
+        key = (n_sample, tuple(size), bool(shared), str(dev))
+        g = self._sample_graphs.get(key)
+        if g is not None:
+            return g
+        st = dict(x=torch.zeros((n_sample, *size), device=dev), z=torch.zeros((n_sample, *size), device=dev),
+                  t=torch.zeros(2 * n_sample, device=dev), coef=torch.zeros(4, device=dev), c=c_i.clone(), m=ctx_mask.clone())
+        st["xt"] = ops.new_act(2 * n_sample, size[1], size[2], size[0], dev).zero_()
+        st["x_out"], st["xt_out"] = torch.empty_like(st["x"]), torch.empty_like(st["xt"])
+
+        def body():
+            if shared:
+                enc = self.nn_model.encode(st["xt"][:n_sample])
+                enc = {k: torch.cat([v, v], 0) for k, v in enc.items()}
+                eps = self.nn_model.decode(enc, st["c"], st["t"], st["m"])
+            else:
+                eps = self.nn_model.forward_nhwc(st["xt"], st["c"], st["t"], st["m"])
+            ops.cfg_reverse_step_dev(eps, st["x"], st["z"], st["coef"], st["x_out"], st["xt_out"])
+            st["x"].copy_(st["x_out"])
+            st["xt"].copy_(st["xt_out"])
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            body(); body()                                  # warm-up: weight packs, folded norms, allocator
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        st["graph"] = graph
+        st["sched"] = torch.stack([self.oneover_sqrta, self.mab_over_sqrtmab, self.sqrt_beta_t], 1).to(dev).contiguous()
+        self._sample_graphs[key] = st
+        return st
+
+    def _sample_graphed(self, x_i, xt, c_i, ctx_mask, n_sample, size, guide_w, steps, noise, shared):
+        st = self._reverse_step_graph(n_sample, size, c_i, ctx_mask, shared)
+        from . import unet
+        unet.refresh_folded_norms()          # weights / running statistics may have changed since the capture
+        st["x"].copy_(x_i); st["xt"].copy_(xt); st["c"].copy_(c_i); st["m"].copy_(ctx_mask)
+        st["coef"][0] = float(guide_w)
+        store, done, n_T = [], 0, self.n_T
+        for i in range(n_T, 0, -1):
+            st["t"].fill_(i / n_T)
+            st["coef"][1:].copy_(st["sched"][i])
+            if i > 1:
+                if noise is not None:
+                    st["z"].copy_(noise[1][i])
+                elif self.sample_noise == "reference":
+                    st["z"].copy_(torch.randn(n_sample, *size))          # CPU generator, like new_scripy.py:465
+                else:
+                    st["z"].normal_()
+            else:
+                st["z"].zero_()                                           # i == 1: z = 0, no RNG draw
+            st["graph"].replay()
+            if self.variant == "mnist" and (i % 20 == 0 or i == n_T or i < 8):
+                store.append(st["x"].detach().cpu().numpy())
+            done += 1
+            if steps is not None and done >= steps:
+                break
+        x_fin = st["x"].clone()
+        if self.variant == "mnist":
+            return x_fin, np.array(store)
+        return x_fin
+
     def _sched(self):
         if self._host_sched is None:
             self._host_sched = {k: getattr(self, k).detach().cpu().tolist()
@@ -161,6 +229,8 @@ class DDPM(nn.Module):
         shared = self.shared_encoder_cfg and not self.nn_model.training
         store = []
         done = 0
+        if self.graph_sampling and not self.nn_model.training and x_i.is_cuda:
+            return self._sample_graphed(x_i, xt, c_i, ctx_mask, n_sample, size, guide_w, steps, noise, shared)
         for i in range(n_T, 0, -1):
             t_is = torch.full((2 * n_sample,), i / n_T, device=device, dtype=torch.float32)
             if i > 1:

@@ -18,11 +18,17 @@ from ._lib import call
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 _weights_epoch = 0            # bumped by the fused optimizer (it writes parameters behind torch's back)
+_bn_stats_epoch = 0           # bumped whenever kernels may have updated BatchNorm running statistics in place
 
 
 def bump_weights_epoch():
     global _weights_epoch
     _weights_epoch += 1
+
+
+def bump_bn_stats_epoch():
+    global _bn_stats_epoch
+    _bn_stats_epoch += 1
 
 
 def _stream():
@@ -544,6 +550,8 @@ def bn_act(y, stats, bn, act, conv_bias=None, bias_outside=False):
     training = bn.training
     if training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
+    if training:
+        bump_bn_stats_epoch()
     if training and stats is None:
         stats = bn_stats(y, bn.num_features)
     return _BnAct.apply(y, stats, bn.weight, bn.bias, bn.running_mean, bn.running_var, conv_bias, bn.num_features,
@@ -971,6 +979,14 @@ def cfg_reverse_step(eps_nhwc_f32, x, z, guide_w, a, b, s, want_next=True):
     call("dm_cfg_reverse_step", _p(eps_nhwc_f32), eps_nhwc_f32.stride(2), _p(x), _p(z), _p(x_out), _p(xt),
          xt.stride(2) if xt is not None else 8, float(guide_w), float(a), float(b), float(s), n, c, h, w, _stream())
     return x_out, xt
+
+
+def cfg_reverse_step_dev(eps_nhwc_f32, x, z, coef4, x_out, xt_out):
+    """Graph-capturable reverse step: (guide_w, oneover_sqrta, mab_over_sqrtmab, sqrt_beta) come from the 4-float
+    device tensor ``coef4``; writes ``x_out`` (fp32 NCHW) and ``xt_out`` (doubled bf16 NHWC batch)."""
+    n, c, h, w = x.shape
+    call("dm_cfg_reverse_step_dev", _p(eps_nhwc_f32), eps_nhwc_f32.stride(2), _p(x), _p(z), _p(x_out), _p(xt_out),
+         xt_out.stride(2), _p(coef4), n, c, h, w, _stream())
 
 
 # --------------------------------------------------------------------------------------- profiling hook

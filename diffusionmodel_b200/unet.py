@@ -11,6 +11,8 @@ own ``forward`` (aten/cuDNN) is never called on the hot path, and there is no CP
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -40,7 +42,7 @@ def _folded_bn(cv, bn):
     """Eval-mode BatchNorm folded onto the conv output: y*scale + shift with the running statistics
     (constants while sampling).  Cached per module until a parameter or buffer changes."""
     ts = [bn.weight, bn.bias, bn.running_mean, bn.running_var] + ([cv.bias] if cv.bias is not None else [])
-    stamp = tuple(t._version for t in ts) + tuple(t.data_ptr() for t in ts) + (ops._weights_epoch,)
+    stamp = tuple(t._version for t in ts) + tuple(t.data_ptr() for t in ts) + (ops._weights_epoch, ops._bn_stats_epoch)
     hit = bn.__dict__.get("_dm_fold")
     if hit is not None and hit[0] == stamp:
         return hit[1], hit[2]
@@ -49,9 +51,23 @@ def _folded_bn(cv, bn):
         shift = bn.bias.float() - bn.running_mean.float() * scale
         if cv.bias is not None:
             shift = shift + cv.bias.float() * scale
-        shift = shift.contiguous()
+        if hit is not None and hit[1].shape == scale.shape and hit[1].device == scale.device:
+            hit[1].copy_(scale); hit[2].copy_(shift)      # in place: captured sampling graphs keep their pointers
+            scale, shift = hit[1], hit[2]
+        else:
+            shift = shift.contiguous()
     bn.__dict__["_dm_fold"] = (stamp, scale, shift)
+    _FOLDED[bn] = cv
     return scale, shift
+
+
+_FOLDED = weakref.WeakKeyDictionary()        # BatchNorm -> its conv, for every folded pair seen so far
+
+
+def refresh_folded_norms():
+    """Bring every cached folded scale/shift up to date IN PLACE (captured sampling graphs read them)."""
+    for bn, cv in list(_FOLDED.items()):
+        _folded_bn(cv, bn)
 
 
 def conv_bn_act(x, seq, act=ACT_GELU, **kw):

@@ -168,6 +168,11 @@ int dm_cfg_reverse_step(const float* eps, int ldp, const float* x, const float* 
                         int ldo, float guide_w, float oneover_sqrta, float mab_over_sqrtmab, float sqrt_beta, int n,
                         int C, int H, int W, void* stream);
 
+/* same step with (guide_w, oneover_sqrta, mab_over_sqrtmab, sqrt_beta) read from a 4-float DEVICE buffer, so one
+ * captured CUDA graph of the reverse step serves all n_T iterations (z must be a valid buffer: zeros at i == 1) */
+int dm_cfg_reverse_step_dev(const float* eps, int ldp, const float* x, const float* z, float* x_out, void* xt_next,
+                            int ldo, const float* coef4, int n, int C, int H, int W, void* stream);
+
 /* ---- optimizer side (new_scripy.py:797-803) --------------------------------------------------------- */
 int dm_sumsq(const float* g, long long n, float* out, void* stream);          /* *out += sum g^2 */
 int dm_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
