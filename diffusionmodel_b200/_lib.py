@@ -114,7 +114,23 @@ def fn(name):
     return f
 
 
+_workspace = None
+
+
+def _ensure_workspace():
+    """One 32 MiB device scratch buffer for the reduction kernels' partial sums (dm_set_workspace)."""
+    global _workspace
+    if _workspace is None:
+        import torch
+        _workspace = torch.empty(32 << 20, dtype=torch.uint8, device="cuda")
+        f = lib().dm_set_workspace
+        f.argtypes, f.restype = [_P, _L], _I
+        f(ctypes.c_void_p(_workspace.data_ptr()), _workspace.numel())
+
+
 def call(name, *args):
+    if _workspace is None:
+        _ensure_workspace()
     rc = fn(name)(*args)
     if rc != 0:
         msg = lib().dm_last_error().decode(errors="replace")

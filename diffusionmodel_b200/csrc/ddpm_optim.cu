@@ -81,6 +81,45 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(float* __restrict__ d
   }
 }
 
+// ConvTranspose2d(k == s) weights [Cin][Cout][k*k]: the 151 M-parameter up0 layer dominates the generic
+// kernels' time (each thread walks 64 taps, lanes 393 KB apart), so its two pack layouts are produced by
+// shared-memory tile transposes with contiguous segments on both sides.
+//   src S[ci][j], j = co*T + tap  (T = k*k taps, L = Cout*T contiguous)
+// K1  forward pack   out[(tap*Cout + co)][ci]      (tap-major rows, K = ci)
+__global__ void __launch_bounds__(256) convt_pack_fwd_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cin, int Cout,
+                                                              int T, int cin_k) {
+  __shared__ float tile[32][33];
+  const long long L = (long long)Cout * T;
+  const long long j0 = (long long)blockIdx.x * 32;
+  const int ci0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int ci = ci0 + r; const long long j = j0 + tx;
+    tile[r][tx] = (ci < Cin && j < L) ? __ldg(w + (long long)ci * L + j) : 0.0f;
+  }
+  __syncthreads();
+  for (int c = ty; c < 32; c += 8) {
+    const long long j = j0 + c;
+    if (j < L && ci0 + tx < cin_k) {
+      const int co = (int)(j / T), tap = (int)(j - (long long)co * T);
+      out[((long long)tap * Cout + co) * cin_k + ci0 + tx] = __float2bfloat16(ci0 + tx < Cin ? tile[tx][c] : 0.0f);
+    }
+  }
+}
+// K2  data-gradient pack   out[ci][tap*Cout + co]    (row_len >= T*Cout)
+__global__ void __launch_bounds__(256) convt_pack_dgrad_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int T,
+                                                                long long row_len) {
+  extern __shared__ float sm[];                     // [32 co][T + 1]
+  const int ci = blockIdx.y, co0 = blockIdx.x * 32;
+  const int nco = min(32, Cout - co0);
+  const float* src = w + ((long long)ci * Cout + co0) * T;
+  for (int i = threadIdx.x; i < nco * T; i += 256) { const int c = i / T, t = i - c * T; sm[c * (T + 1) + t] = __ldg(src + i); }
+  __syncthreads();
+  bf16* dst = out + (long long)ci * row_len + co0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = warp; t < T; t += 8)
+    if (lane < nco) dst[(long long)t * Cout + lane] = __float2bfloat16(sm[lane * (T + 1) + t]);
+}
 // ------------------------------------------------------------------------------------------ DDPM
 __global__ void q_sample_kernel(const float* x, const float* noise, const float* sqrtab, const float* sqrtmab,
                                 const long long* ts, bf16* xt, int ldo, int N, int C, int HW) {
@@ -241,6 +280,27 @@ extern "C" int dm_pack_weight(const float* w, void* out, int rows, int cols, int
                               int tap_major_rows, void* stream) {
   if (ntaps < 1 || ntaps > 64) { dm_set_error("dm_pack_weight: 1..64 taps"); return DM_ERR_ARG; }
   PackArgs A; fill_pack(A, rows, cols, ntaps, tap_off_host, s_row, s_col, c_split, cols_k, row_len, tap_major_rows);
+  bool ident = true;
+  for (int i = 0; i < ntaps; ++i) ident = ident && tap_off_host[i] == i;
+  // ConvTranspose2d weight [Cin][Cout][T]: tiled transposes (see convt_pack_*_kernel)
+  if (ident && c_split == 0 && tap_major_rows && s_row == ntaps && s_col == (long long)rows * ntaps && row_len == cols_k &&
+      (long long)rows * cols >= 4096) {
+    dim3 grid(dm::cdiv((long long)rows * ntaps, 32), dm::cdiv(cols_k, 32));
+    convt_pack_fwd_kernel<<<grid, 256, 0, ST>>>(w, (bf16*)out, cols, rows, ntaps, cols_k);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+  }
+  if (ident && c_split == 0 && !tap_major_rows && s_col == ntaps && s_row == (long long)cols * ntaps && cols_k == cols &&
+      ntaps > 16 && (long long)rows * cols >= 4096) {
+    if (row_len > (long long)ntaps * cols_k) {
+      cudaError_t e = cudaMemsetAsync(out, 0, (size_t)rows * row_len * 2, ST);
+      if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
+    }
+    dim3 grid(dm::cdiv(cols, 32), rows);
+    convt_pack_dgrad_kernel<<<grid, 256, (size_t)32 * (ntaps + 1) * sizeof(float), ST>>>(w, (bf16*)out, cols, ntaps, row_len);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+  }
   if (!tap_major_rows && row_len > (long long)ntaps * cols_k) {      // zero the row tails the kernel never writes
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)rows * row_len * 2, ST);
     if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }

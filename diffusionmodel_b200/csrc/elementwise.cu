@@ -82,6 +82,7 @@ struct RedArgs {
   const float *mean, *invstd, *gamma, *beta;
   float scale;
   float *out1, *out2;
+  float* part;          // workspace for the per-split partial sums (splits > 1)
 };
 // mode 0: s1 = sum a            1: s1 = sum a, s2 = sum a^2        2: s1 = sum a*b, s2 = sum a
 // mode 3: BN bwd   g = a*act'(xhat*gamma+beta), xhat = (b-mean[c])*invstd[c];  s1 = sum g, s2 = sum g*xhat
@@ -153,34 +154,73 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(RedArgs A) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s1[j] += o[j]; s2[j] += o[8 + j]; }
     }
+    // no atomics: a single split writes the result, several splits write partial rows that
+    // reduce_finalize_kernel adds in a fixed order (bit-reproducible, and no same-address contention)
+    if (gridDim.x == 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (c0 + j < A.C) {
-        atomicAdd(A.out1 + (long long)g * A.C + c0 + j, s1[j] * A.scale);
-        if (A.out2) atomicAdd(A.out2 + (long long)g * A.C + c0 + j, s2[j] * A.scale);
-      }
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < A.C) {
+          A.out1[(long long)g * A.C + c0 + j] = s1[j] * A.scale;
+          if (A.out2) A.out2[(long long)g * A.C + c0 + j] = s2[j] * A.scale;
+        }
+    } else {
+      float* row = A.part + ((long long)blockIdx.x * gridDim.z + g) * 2 * A.C;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < A.C) { row[c0 + j] = s1[j]; row[A.C + c0 + j] = s2[j]; }
     }
   }
 }
+__global__ void reduce_finalize_kernel(const float* __restrict__ part, int splits, int groups, int C, float scale,
+                                       float* __restrict__ out1, float* __restrict__ out2, int accumulate) {
+  const long long total = (long long)groups * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long g = i / C; const int c = (int)(i - g * C);
+    float a = 0.f, b = 0.f;
+    for (int sp = 0; sp < splits; ++sp) {
+      const float* row = part + ((long long)sp * groups + g) * 2 * C;
+      a += row[c];
+      if (out2) b += row[C + c];
+    }
+    if (accumulate) { out1[i] += a * scale; if (out2) out2[i] += b * scale; }
+    else { out1[i] = a * scale; if (out2) out2[i] = b * scale; }
+  }
+}
+
+float* g_ws = nullptr;          // caller-provided scratch for partial sums (dm_set_workspace)
+long long g_ws_floats = 0;
 
 int launch_reduce(RedArgs& A, int groups, cudaStream_t st) {
   const int Cv = (A.C + 7) / 8;
   const int VPB = Cv < 256 ? Cv : 256;
   const int R = 256 / VPB;
   const int cvt = (Cv + VPB - 1) / VPB;
-  long long want = (long long)DM_NUM_SMS * 6 / ((long long)groups * cvt);
-  int maxs = A.count / (R * 4); if (maxs < 1) maxs = 1;
+  long long want = (long long)DM_NUM_SMS * 4 / ((long long)groups * cvt);
+  int maxs = A.count / (R * 8); if (maxs < 1) maxs = 1;
+  if (maxs > 64) maxs = 64;                       // few partial rows: the finalize pass stays trivial
   int splits = (int)(want < 1 ? 1 : (want > maxs ? maxs : want));
   if (groups > 65535) { dm_set_error("reduce: too many groups"); return DM_ERR_ARG; }
+  if (splits > 1 && (long long)splits * groups * 2 * A.C > g_ws_floats) {
+    if (g_ws_floats == 0) { dm_set_error("reduction kernels need scratch: call dm_set_workspace() first"); return DM_ERR_ARG; }
+    splits = (int)(g_ws_floats / ((long long)groups * 2 * A.C));
+    if (splits < 1) splits = 1;
+  }
+  A.part = g_ws;
   dim3 grid(splits, cvt, groups);
   nc_reduce_kernel<<<grid, 256, 0, st>>>(A);
   DM_CHECK_LAUNCH();
+  if (splits > 1) {
+    const long long total = (long long)groups * A.C;
+    reduce_finalize_kernel<<<(int)((total + 255) / 256 > 592 ? 592 : (total + 255) / 256), 256, 0, st>>>(g_ws, splits, groups, A.C, A.scale,
+                                                                                                     A.out1, A.out2, 0);
+    DM_CHECK_LAUNCH();
+  }
   return DM_OK;
 }
 
 // db[c] += sum_p dy[p][c]: the bias gradient of a convolution that is not followed by a BatchNorm.
 // Same thread mapping as the BatchNorm kernels (a thread owns 8 channels, 4 independent 16-byte loads in
-// flight), block-level reduction in shared memory, one atomicAdd per channel per block.
+// flight), block-level reduction in shared memory, per-block partial rows added by reduce_finalize_kernel.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy, int lddy, float* __restrict__ db, unsigned P,
                                                       int C, int VPB, int R) {
   extern __shared__ float sm[];          // [threads][8]
@@ -217,8 +257,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
       for (int j = 0; j < 8; ++j) s[j] += o[j];
     }
 #pragma unroll
+    float* row = db + (long long)blockIdx.x * 2 * C;          // db = partial workspace here: [blocks][2][C], second half unused
+#pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (c0 + j < C) atomicAdd(db + c0 + j, s[j]);
+      if (c0 + j < C) row[c0 + j] = s[j];
   }
 }
 
@@ -1309,8 +1351,6 @@ extern "C" int dm_gn_act_bwd(const void* dz, int lddz, const void* x, int ldx, c
 
 extern "C" int dm_pool_nhw(const void* x, int ldx, float* out, int N, int HW, int C, float scale, void* stream) {
   REQ8(ldx, "dm_pool_nhw");
-  int rc = zero_f32(out, (long long)N * C, ST);
-  if (rc) return rc;
   RedArgs A{};
   A.a = (const bf16*)x; A.a_hi = (long long)HW * ldx; A.a_ps = ldx; A.gdiv = 1; A.count = HW; A.C = C; A.mode = 0;
   A.scale = scale; A.out1 = out; A.G = 1; A.stat_div = 1;
@@ -1319,8 +1359,6 @@ extern "C" int dm_pool_nhw(const void* x, int ldx, float* out, int N, int HW, in
 extern "C" int dm_pool_prod_nhw(const void* a, int lda, const void* b, int ldb, float* out, int N, int HW, int C,
                                 float scale, void* stream) {
   REQ8(lda, "dm_pool_prod_nhw"); REQ8(ldb, "dm_pool_prod_nhw");
-  int rc = zero_f32(out, (long long)N * C, ST);
-  if (rc) return rc;
   RedArgs A{};
   A.a = (const bf16*)a; A.b = (const bf16*)b;
   A.a_hi = (long long)HW * lda; A.a_ps = lda; A.b_hi = (long long)HW * ldb; A.b_ps = ldb;
@@ -1332,12 +1370,23 @@ extern "C" int dm_colsum(const void* dy, int lddy, float* db, long long P, int C
   if (P <= 0) return DM_OK;
   if (P >= (1ll << 31)) { dm_set_error("dm_colsum: too many pixels"); return DM_ERR_ARG; }
   const ChanMap m = chan_map(C);
-  int gx = chan_grid_x(P, m, 16);
-  const int cap = DM_NUM_SMS * 4 / m.cvt;
-  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  int gx = chan_grid_x(P, m, 32);
+  int cap = DM_NUM_SMS * 2 / m.cvt; if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  if ((long long)gx * 2 * C > g_ws_floats) {
+    if (g_ws_floats < 2LL * C) { dm_set_error("dm_colsum needs scratch: call dm_set_workspace() first"); return DM_ERR_ARG; }
+    gx = (int)(g_ws_floats / (2LL * C));
+  }
   dim3 grid(gx, m.cvt);
-  colsum_kernel<<<grid, m.threads, (size_t)m.threads * 8 * sizeof(float), ST>>>((const bf16*)dy, lddy, db, (unsigned)P, C, m.VPB, m.R);
+  colsum_kernel<<<grid, m.threads, (size_t)m.threads * 8 * sizeof(float), ST>>>((const bf16*)dy, lddy, g_ws, (unsigned)P, C, m.VPB, m.R);
   DM_CHECK_LAUNCH();
+  reduce_finalize_kernel<<<dm::cdiv(C, 256), 256, 0, ST>>>(g_ws, gx, 1, C, 1.0f, db, nullptr, 1);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+extern "C" int dm_set_workspace(void* ptr, long long bytes) {
+  g_ws = reinterpret_cast<float*>(ptr);
+  g_ws_floats = ptr ? bytes / 4 : 0;
   return DM_OK;
 }
 extern "C" int dm_se_apply_fwd(const void* x2, int ld2, const float* gate, const void* res, int ldr, void* out, int ldo,
@@ -1356,8 +1405,7 @@ extern "C" int dm_se_apply_bwd(const void* dout, int lddo, const float* gate, co
 extern "C" int dm_ca_pool(const void* a, int lda, const void* b, int ldb, float* oh, float* ow, int N, int H, int W, int C,
                           float scale_h, float scale_w, void* stream) {
   REQ8(lda, "dm_ca_pool"); if (b) REQ8(ldb, "dm_ca_pool");
-  int rc = zero_f32(oh, (long long)N * H * C, ST); if (rc) return rc;
-  rc = zero_f32(ow, (long long)N * W * C, ST); if (rc) return rc;
+  int rc;
   RedArgs A{};
   A.a = (const bf16*)a; A.b = (const bf16*)b; A.C = C; A.mode = b ? 2 : 0; A.G = 1; A.stat_div = 1;
   // rows: group g = n*H + h, pixels along w
@@ -1406,8 +1454,7 @@ extern "C" int dm_film_fwd(const void* x, int ldx, const float* ce, const float*
 extern "C" int dm_film_bwd(const void* dout, int lddo, const void* x, int ldx, const float* ce, void* dx, int lddx,
                            float* dce, float* dte, int N, int HW, int C, void* stream) {
   REQ8(lddo, "dm_film_bwd"); REQ8(ldx, "dm_film_bwd"); REQ8(lddx, "dm_film_bwd");
-  int rc = zero_f32(dce, (long long)N * C, ST); if (rc) return rc;
-  rc = zero_f32(dte, (long long)N * C, ST); if (rc) return rc;
+  int rc;
   RedArgs A{};
   A.a = (const bf16*)dout; A.b = (const bf16*)x;
   A.a_hi = (long long)HW * lddo; A.a_ps = lddo; A.b_hi = (long long)HW * ldx; A.b_ps = ldx;

@@ -25,6 +25,9 @@ const char* dm_last_error(void);
 int dm_version(void);
 void dm_debug_set(int key, long long value);
 long long dm_launch_count(void);   /* kernels launched by this library so far (bench.py's gpu_launches) */
+/* Device scratch (>= 16 MiB recommended) for the partial sums of the reduction kernels (pooling, colsum, FiLM
+ * gradients): used in stream order by every call, so one buffer per stream; must outlive captured graphs. */
+int dm_set_workspace(void* ptr, long long bytes);
 
 /* ---- tcgen05 implicit-GEMM convolutions (conv_gemm.cu) ------------------------------------------
  * nn.Conv2d forward: new_scripy.py:166,169,184,188,217,222,225,229,243,311,314; MNIST_script.py:42,46,149,152.
