@@ -63,7 +63,7 @@ _SIGS = {
     "dm_cast_nhwc": "pi pi l i p",
     "dm_nhwc_to_nchw": "pii p iiii p",
     "dm_im2col3x3": "pi p iiii p",
-    "dm_space_to_depth": "pi pi iiiii p",
+    "dm_space_to_depth": "pi pi iiiii i p",
     "dm_bn_stats_rows": "li",
     "dm_bn_stats": "pi pi l i p",
     "dm_bn_finalize": "p iii d pp pp ff p p",

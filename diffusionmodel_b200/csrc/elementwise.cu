@@ -1088,14 +1088,23 @@ struct Axpby {
   }
 };
 struct S2D {
-  const bf16* x; int ldx; bf16* y; int ldy; int H, W, C, k;    // x [N,H*k,W*k,C] -> y [N,H,W,k*k*C]
+  const bf16* x; int ldx; bf16* y; int ldy; int H, W, C, k, chan_major;    // x [N,H*k,W*k,C] -> y [N,H,W,k*k*C]
   __device__ void operator()(unsigned p, int c0) const {
-    // p indexes INPUT pixels of x
+    // p indexes INPUT pixels of x.  Output channel = tap*C + c (tap-major) or c*k*k + tap (channel-major: the
+    // ConvTranspose2d parameter's own [Cout][k][k] order, so its weight gradient is a plain GEMM output)
     const int Wi = W * k, Hi = H * k;
     const int xx = p % Wi, yy = (p / Wi) % Hi, n = p / (Wi * Hi);
     const int ow = xx / k, kx = xx % k, oh = yy / k, ky = yy % k;
-    uint4 v = *reinterpret_cast<const uint4*>(x + (long long)p * ldx + c0);
-    *reinterpret_cast<uint4*>(y + (((long long)n * H + oh) * W + ow) * ldy + (ky * k + kx) * C + c0) = v;
+    const uint4 v = *reinterpret_cast<const uint4*>(x + (long long)p * ldx + c0);
+    bf16* dst = y + (((long long)n * H + oh) * W + ow) * ldy;
+    if (!chan_major) {
+      *reinterpret_cast<uint4*>(dst + (ky * k + kx) * C + c0) = v;
+    } else {
+      const bf16* e = reinterpret_cast<const bf16*>(&v);
+      const int kk = k * k, tap = ky * k + kx;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[(long long)(c0 + j) * kk + tap] = e[j];
+    }
   }
 };
 
@@ -1210,9 +1219,10 @@ extern "C" int dm_im2col3x3(const void* x, int ldx, void* out, int N, int H, int
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
-extern "C" int dm_space_to_depth(const void* x, int ldx, void* y, int ldy, int N, int H, int W, int C, int k, void* stream) {
+extern "C" int dm_space_to_depth(const void* x, int ldx, void* y, int ldy, int N, int H, int W, int C, int k, int chan_major,
+                                 void* stream) {
   REQ8(ldx, "dm_space_to_depth"); REQ8(ldy, "dm_space_to_depth"); REQ8(C, "dm_space_to_depth");
-  S2D f{(const bf16*)x, ldx, (bf16*)y, ldy, H, W, C, k};
+  S2D f{(const bf16*)x, ldx, (bf16*)y, ldy, H, W, C, k, chan_major};
   return ew_launch((long long)N * H * k * W * k, C, f, ST);
 }
 

@@ -466,20 +466,29 @@ class _ConvT(torch.autograd.Function):
         st = _stream()
         if bias is not None:
             call("dm_colsum", _p(dy), lddy, _p(grad_buf(bias)), n * hin * k * win * k, cout, st)
-        # gather the k x k output blocks onto channels: [N, hin, win, k*k*cout]
         kc = k * k * cout
-        s2d = new_act(n, hin, win, kc, dy.device)
-        call("dm_space_to_depth", _p(dy), lddy, _p(s2d), s2d.stride(2), n, hin, win, cout, k, st)
-        # weight gradient: rows (tap, co), K columns ci
-        ck = r64(cin)
-        offs = [t for t in range(k * k)]
-        unpack = (cout, cin, k * k, _taps(offs), k * k, cout * k * k, 0, ck, ck, 1)
-        _wgrad_into(weight, (kc, ck), unpack, lambda dwp: call(
-            "dm_conv2d_wgrad", _p(x), cin, x.stride(2), None, 0, 0, _p(s2d), s2d.stride(2), _p(dwp), n, hin, win, kc,
-            1, 1, 1, 0, st))
+        # weight gradient.  With the k x k output blocks gathered onto channels in the PARAMETER's order
+        # (co*k*k + tap) and the GEMM roles swapped (rows = ci, columns = (co, tap)), the product
+        # dW[ci][(co, tap)] = sum_pixels x[ci] * dy[(co, tap)] lands in the [Cin, Cout, k, k] gradient itself:
+        # the wgrad kernel red.adds straight into p.grad -- no packed detour for the 151 M-parameter up0.
+        s2c = new_act(n, hin, win, kc, dy.device)
+        call("dm_space_to_depth", _p(dy), lddy, _p(s2c), s2c.stride(2), n, hin, win, cout, k, 1, st)
+        if kc % 64 == 0:
+            call("dm_conv2d_wgrad", _p(s2c), kc, s2c.stride(2), None, 0, 0, _p(x), x.stride(2), _p(grad_buf(weight)),
+                 n, hin, win, cin, 1, 1, 1, 0, st)
+        else:                       # K columns not a multiple of 64 (e.g. 7x7x16): padded staging buffer
+            ckc = r64(kc)
+            unpack = (cin, kc, 1, _taps([0]), kc, 1, 0, ckc, ckc, 0)
+            _wgrad_into(weight, (cin, ckc), unpack, lambda dwp: call(
+                "dm_conv2d_wgrad", _p(s2c), kc, s2c.stride(2), None, 0, 0, _p(x), x.stride(2), _p(dwp), n, hin, win, cin,
+                1, 1, 1, 0, st))
+        del s2c
         dx = None
         if ctx.needs_input_grad[0]:
+            # data gradient: a 1x1 conv over the tap-major gather [N, hin, win, (tap, co)]
             wd = ctx.pack.get(weight, "convt_dgrad")
+            s2d = new_act(n, hin, win, kc, dy.device)
+            call("dm_space_to_depth", _p(dy), lddy, _p(s2d), s2d.stride(2), n, hin, win, cout, k, 0, st)
             dx = new_act(n, hin, win, cin, dy.device)
             call("dm_conv2d_fwd", _p(s2d), kc, s2d.stride(2), None, 0, 0, _p(wd), None, None, 0, _p(dx), dx.stride(2), 0, None, 0,
                  n, hin, win, cin, 1, 1, 1, 0, st)

@@ -73,7 +73,8 @@ int dm_nhwc_to_nchw(const void* x, int x_f32, int ldx, float* y, int N, int C, i
 /* 3x3/pad-1 im2col of a <=3-channel image into [N,H,W,32] (column ci*9 + r*3 + s): the first U-Net conv
  * (new_scripy.py:184 with in_ch=3, MNIST_script.py:42 with 1) then runs as a 1x1 convolution */
 int dm_im2col3x3(const void* x, int ldx, void* out, int N, int H, int W, int C, void* stream);
-int dm_space_to_depth(const void* x, int ldx, void* y, int ldy, int N, int H, int W, int C, int k, void* stream);
+int dm_space_to_depth(const void* x, int ldx, void* y, int ldy, int N, int H, int W, int C, int k, int chan_major,
+                      void* stream);   /* out channel = tap*C + c, or c*k*k + tap when chan_major */
 
 /* ---- BatchNorm2d + GELU (new_scripy.py:185-186,189-190,218-219,226-227) ---------------------------
  * finalize: partial sums -> batch mean / invstd (+ running-stat update, momentum 0.1, unbiased var);
