@@ -283,15 +283,6 @@ def run_ours(args):
                 "reference_schedule_tflops": n_samp * 2 * 1346.17 / ms_samp / 1e3}
     ddpm.train()
 
-    # host-side enqueue cost of one step (Python + autograd + ctypes), kernels stubbed out
-    real_call = ops.call
-    ops.call = lambda *a, **k: 0
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    step_resident()
-    host_ms = (time.perf_counter() - t0) * 1e3
-    ops.call = real_call
-    torch.cuda.synchronize()
     pk, src = peaks()
     line = None
     if rank == 0:
@@ -318,7 +309,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * accum,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms, "clocks": clocks, "roofline": roof,
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
                 "sampling": sampling}
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -538,7 +538,28 @@ class _BnAct(torch.autograd.Function):
         return dy, None, None, None, None, None, None, None, None, None, None, None, None
 
 
+_counters_batched = False     # True while a model forward bumps all num_batches_tracked buffers in one launch
 FUSED_CONV_STATS = False      # True: BatchNorm statistics from the conv epilogue; False: a separate pass over y
+
+
+class batched_counters:
+    """Inside this context ``bn_act`` leaves ``num_batches_tracked`` alone: the caller has already advanced
+    every train-mode BatchNorm's counter with one multi-tensor add (41 single-element kernels otherwise)."""
+
+    def __init__(self, module):
+        self.bufs = [m.num_batches_tracked for m in module.modules()
+                     if isinstance(m, torch.nn.BatchNorm2d) and m.training and m.num_batches_tracked is not None
+                     and not getattr(m, "_dm_counts_itself", False)]
+
+    def __enter__(self):
+        global _counters_batched
+        if self.bufs:
+            torch._foreach_add_(self.bufs, 1)
+        self.prev, _counters_batched = _counters_batched, True
+
+    def __exit__(self, *exc):
+        global _counters_batched
+        _counters_batched = self.prev
 
 
 def bn_stats(y, c):
@@ -557,7 +578,7 @@ def bn_act(y, stats, bn, act, conv_bias=None, bias_outside=False):
     ``bias_outside``: train mode only -- that conv did NOT add its bias to ``y`` (batch normalisation
     cancels a per-channel constant exactly); the bias then only enters the tracked running mean."""
     training = bn.training
-    if training and bn.num_batches_tracked is not None:
+    if training and bn.num_batches_tracked is not None and not _counters_batched:
         bn.num_batches_tracked.add_(1)
     if training:
         bump_bn_stats_epoch()
@@ -613,9 +634,12 @@ def _run_small(fn_small, inputs, params):
 def _small_backward(ins, outs, grads, params):
     live = [p for p in params if p.requires_grad]
     res = torch.autograd.grad(outs, ins + live, grads, allow_unused=True)
+    bufs, gs = [], []
     for p, g in zip(live, res[len(ins):]):
         if g is not None:
-            grad_buf(p).add_(g)
+            bufs.append(grad_buf(p)); gs.append(g)
+    if bufs:
+        torch._foreach_add_(bufs, gs)            # one multi-tensor launch instead of one add per parameter
     return res[:len(ins)]
 
 

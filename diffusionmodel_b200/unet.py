@@ -139,6 +139,7 @@ class CoordAttn(nn.Module):
         self.conv1_w = nn.Conv2d(channel, mid, kernel_size=1)
         self.bn1_h = nn.BatchNorm2d(mid)
         self.bn1_w = nn.BatchNorm2d(mid)
+        self.bn1_h._dm_counts_itself = self.bn1_w._dm_counts_itself = True     # advanced in _bn below
         self.act = nn.GELU()
         self.h2w_proj = nn.Conv2d(mid, mid, kernel_size=1)
         self.w2h_proj = nn.Conv2d(mid, mid, kernel_size=1)
@@ -333,7 +334,8 @@ class ContextUnet(nn.Module):
 
     def forward_nhwc(self, x, c, t, ctx_mask, attn_map=None):
         """x: bf16 NHWC; returns eps as fp32 NHWC (pitch 4 for 3 channels)."""
-        return self.decode(self.encode(x), c, t, ctx_mask, attn_map)
+        with ops.batched_counters(self):
+            return self.decode(self.encode(x), c, t, ctx_mask, attn_map)
 
     def forward(self, x, c, t, ctx_mask, attn_map=None):
         if x.shape[2] % 128 or x.shape[3] % 128:
@@ -444,7 +446,8 @@ class MnistContextUnet(nn.Module):
         return _head(u3, enc["x0"], self.out, f)
 
     def forward_nhwc(self, x, c, t, context_mask, attn_map=None):
-        return self.decode(self.encode(x), c, t, context_mask)
+        with ops.batched_counters(self):
+            return self.decode(self.encode(x), c, t, context_mask)
 
     def forward(self, x, c, t, context_mask):
         y = self.forward_nhwc(ops.to_nhwc(x), c, t, context_mask)
