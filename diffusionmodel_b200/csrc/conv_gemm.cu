@@ -74,6 +74,8 @@ struct ConvParams {
   unsigned long long desc_hi;   // upper 32 bits of the smem descriptors (SBO / version / layout)
   // halo kernel (3x3, stride 1): ring of input patches + ring of weight tiles
   int a_stages, base_off_mode;
+  CUtensorMap tmB2;             // CTA-pair kernel: half-height weight box (block_n/2 rows)
+  int pair_tiles;               // CTA-pair kernel: number of (two M tiles) x (N tile) work items
   int ablate;                   // dev: bit0 no MMA issue, bit1 no TMA loads, bit2 no epilogue work (timing decomposition)
   unsigned long long desc_hi_halo;
 };
@@ -157,6 +159,51 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in the executing CTA's shared memory, the transaction bytes are
+// signalled on the LEADER CTA's mbarrier (a shared::cluster address).
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {     // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_alloc2(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
 // One lane of a fully converged warp.  The producer / MMA warps run their loops warp-uniformly and only the
 // issue statements sit under elect_one(): inside an `if (lane == 0)` region the compiler must wrap every
 // uniform-datapath instruction (UTCHMMA, UTMALDG, UTCBAR) in an ELECT / BRA.U.ANY waterfall, which made
@@ -245,9 +292,14 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, int stages, int stage_
 // ------------------------------------------------------------------------------------------ kernel A
 // Epilogue shared by the conv kernels (warps 2..9): TMEM -> registers -> scale/bias/activation ->
 // bf16|fp32 global store, plus the per-CTA BatchNorm statistics.
+// pair_rank < 0: one CTA per tile (tile = blockIdx.x, += gridDim.x).  pair_rank in {0,1}: CTA pairs
+// (cta_group::2): work item pt = blockIdx.x/2 (+= gridDim.x/2) is two M tiles x one N tile, this CTA owns
+// M tile 2*(pt/n_tiles)+rank, and the accumulator-free signal goes to the leader's barrier (cluster address).
 __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t bar_tfull, uint32_t bar_tempty, uint32_t tmem_base,
-                                              float* slab, int warp, int lane, int total_tiles) {
+                                              float* slab, int warp, int lane, int total_tiles, int pair_rank = -1) {
   struct { uint32_t tfull, tempty; } L = {bar_tfull, bar_tempty};
+  const int t_first = pair_rank < 0 ? (int)blockIdx.x : (int)(blockIdx.x >> 1);
+  const int t_step = pair_rank < 0 ? (int)gridDim.x : (int)(gridDim.x >> 1);
   // ===================================================================== epilogue (warps 2..9)
   // Two warps per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31): they take alternate
   // 32-column chunks, which hides the tcgen05.ld / shuffle latencies of this instruction-heavy stage.
@@ -256,9 +308,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t bar_
   const int row = q * 32 + lane;          // row of the 128-pixel tile
   const int bw = 1 << p.log_bw, bh = 1 << p.log_bh;
   int it = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+  for (int tile = t_first; tile < total_tiles; tile += t_step, ++it) {
     const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
-    const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+    const int nt = tile % p.n_tiles, mt = pair_rank < 0 ? tile / p.n_tiles : 2 * (tile / p.n_tiles) + pair_rank;
     const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
     const int w = (tw << p.log_bw) + (row & (bw - 1));
     const int h = (th << p.log_bh) + ((row >> p.log_bw) & (bh - 1));
@@ -335,7 +387,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t bar_
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(L.tempty + 8 * as);
+    if (lane == 0) { if (pair_rank < 0) mbar_arrive(L.tempty + 8 * as); else mbar_arrive_cluster(L.tempty + 8 * as); }
   }
   if (p.stats != nullptr) {
     // one partial row per CTA: [blockIdx.x][2][stats_ld]
@@ -563,6 +615,120 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_halo_kernel(const __g
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { __syncwarp(); tc_fence_after(); tc_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------ kernel E
+// CTA-pair version of kernel D (tcgen05.mma.cta_group::2, M = 256 per instruction).  A single-CTA 128 x N MMA
+// stream is capped by the MMA issue rate (~167 cycles per instruction whatever N: 1.48 PFLOP/s at N=192 with
+// loads and epilogue switched off); a pair instruction does twice the work, and each CTA stages only HALF of
+// the weight tile.  Two CTAs of a cluster take two M tiles with the same N tile: each loads its own halo
+// patch and block_n/2 weight rows (TMA with the LEADER's mbarrier as completion target), the leader's MMA
+// warp issues for both, tcgen05.commit multicasts the stage-free / accumulator-ready arrivals to both CTAs,
+// and both CTAs run the epilogue on their own 128 TMEM lanes.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv3x3_halo2_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int b_half = p.b_stage_bytes >> 1;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ringA = base;
+  const uint32_t ringB = ringA + (uint32_t)p.a_stages * kHaloStage;
+  const uint32_t bars = ringB + (uint32_t)p.stages * (uint32_t)b_half;
+  const uint32_t fullB = bars, emptyB = fullB + 8 * kMaxStages, fullA = emptyB + 8 * kMaxStages, emptyA = fullA + 32,
+                 tfull = emptyA + 32, tempty = tfull + 16, tmem_slot = tempty + 16;
+  float* const slab = reinterpret_cast<float*>(smem_raw + (bars + kAuxBytes - smem_u32(smem_raw)));
+  const int chunks = p.chunks0 + p.chunks1;
+  const int total = p.pair_tiles;
+  const int t_first = blockIdx.x >> 1, t_step = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 1); }
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(fullA + 8 * s, 1); mbar_init(emptyA + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + 8 * s, 1); mbar_init(tempty + 8 * s, 16); }   // 8 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB2); }
+  for (int i = threadIdx.x; i < 2 * p.stat_c; i += kConvThreads) slab[i] = 0.0f;
+  if (warp == 1) tc_alloc2(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();                      // both CTAs' barriers initialised and TMEM allocated
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // the leader's (rank 0) barriers as shared::cluster addresses
+  const uint32_t l_fullA = mapa_shared(fullA, 0), l_fullB = mapa_shared(fullB, 0), l_tempty = mapa_shared(tempty, 0);
+
+  if (warp == 0) {
+    int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+    for (int pt = t_first; pt < total; pt += t_step) {
+      const int nt = pt % p.n_tiles, mt = 2 * (pt / p.n_tiles) + (int)rank;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+      const int w0 = tw << p.log_bw, h0 = th << p.log_bh;
+      const int n_row = nt * p.block_n + (int)rank * (p.block_n >> 1);
+      for (int ch = 0; ch < chunks; ++ch) {
+        int map = 0, c0 = ch * kBlockK;
+        if (p.dual && ch >= p.chunks0) { map = 1; c0 = (ch - p.chunks0) * kBlockK; }
+        mbar_wait(emptyA + 8 * sa, pha ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(fullA + 8 * sa, 2 * kHaloBytes);
+          tma_load_4d_2sm(ringA + sa * kHaloStage, &p.tmA[map], c0, w0 - 1, h0 - 1, tb, l_fullA + 8 * sa);
+        }
+        __syncwarp();
+        if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(emptyB + 8 * sb, phb ^ 1);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(fullB + 8 * sb, 2 * b_half);
+            tma_load_2d_2sm(ringB + sb * b_half, &p.tmB2, (tap * chunks + ch) * kBlockK, n_row, l_fullB + 8 * sb);
+          }
+          __syncwarp();
+          if (++sb == p.stages) { sb = 0; phb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+      int it = 0;
+      for (int pt = t_first; pt < total; pt += t_step, ++it) {
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(tempty + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(fullA + 8 * sa, pha);
+          const uint32_t a0 = ringA + sa * kHaloStage;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(fullB + 8 * sb, phb);
+            tc_fence_after();
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint32_t av = a0 + (uint32_t)((dy * kHaloW + dx) * 128);
+            const uint32_t bv = ringB + sb * b_half;
+            const uint64_t adesc = p.desc_hi_halo | (uint64_t)((av & 0x3FFFFu) >> 4);
+            const uint64_t bdesc = p.desc_hi | (uint64_t)((bv & 0x3FFFFu) >> 4);
+            const bool last = (ch == chunks - 1) && (tap == 8);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                tc_mma2_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (ch | tap | k) != 0);
+              tc_commit2(emptyB + 8 * sb);
+              if (tap == 8) tc_commit2(emptyA + 8 * sa);
+              if (last) tc_commit2(tfull + 8 * as);
+            }
+            __syncwarp();
+            if (++sb == p.stages) { sb = 0; phb ^= 1; }
+          }
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+        }
+      }
+    }
+  } else {
+    conv_epilogue(p, tfull, l_tempty, tmem_base, slab, warp, lane, total, (int)rank);
+  }
+  tc_fence_before();
+  cluster_sync_all();                      // nobody leaves while the peer may still read its smem / signal its barriers
+  if (warp == 1) { tc_fence_after(); tc_dealloc2(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------------ kernel B
@@ -1001,6 +1167,35 @@ static int launch_conv_halo(ConvParams& P, cudaStream_t st) {
   return DM_OK;
 }
 
+bool g_attr_e = false;
+static int launch_conv_halo2(ConvParams& P, const void* wpk, long long w_rows, long long ktot, cudaStream_t st) {
+  P.stat_c = P.stats ? (P.n_tiles * P.block_n + 31) / 32 * 32 : 0;
+  const int stat_bytes = 8 * P.stat_c;
+  if (stat_bytes > kMaxStatBytes) { dm_set_error("conv_gemm: too many output channels for fused BatchNorm statistics"); return DM_ERR_ARG; }
+  int rc = make_w_map(&P.tmB2, wpk, w_rows, ktot, P.block_n / 2);
+  if (rc) return rc;
+  P.a_stages = kHaloAStages;
+  const int b_half = P.b_stage_bytes / 2;
+  int stages = (kSmemBudget - 1024 - kAuxBytes - stat_bytes - P.a_stages * kHaloStage) / b_half;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (g_debug[0] > 0 && g_debug[0] < stages) stages = (int)g_debug[0];
+  P.stages = stages;
+  P.desc_hi_halo = kDescHiHalo;
+  P.base_off_mode = 0; P.ablate = 0;
+  P.idesc = (P.idesc & ~(0x1Fu << 24)) | ((256u >> 4) << 24);       // M = 256 across the CTA pair
+  P.pair_tiles = dm::cdiv(P.m_tiles, 2) * P.n_tiles;
+  const size_t smem = 1024 + (size_t)P.a_stages * kHaloStage + (size_t)stages * b_half + kAuxBytes + stat_bytes;
+  if (!g_attr_e) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
+    g_attr_e = true;
+  }
+  const int clusters = P.pair_tiles < DM_NUM_SMS / 2 ? P.pair_tiles : DM_NUM_SMS / 2;
+  conv3x3_halo2_kernel<<<2 * clusters, kConvThreads, smem, st>>>(P);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
 static void fill_common(ConvParams& P, int N, int H, int W, int Cout_rows, int block_n) {
   pick_patch(W, H, kBlockM, P.log_bw, P.log_bh, P.log_bn);
   P.tiles_w = dm::cdiv(W, 1 << P.log_bw);
@@ -1082,6 +1277,8 @@ extern "C" int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, in
   P.bias = bias; P.scale = scale; P.act = act; P.stats = stats; P.stats_ld = stats_ld;
   P.stat_rows = stats ? dm_conv2d_fwd_stat_rows(N, Ho, Wo, Cout) : 0;
   if (stats && (scale || act)) { dm_set_error("dm_conv2d_fwd: statistics are taken of the plain conv output (no scale/act)"); return DM_ERR_ARG; }
+  // CTA pairs when the tile width splits into two halves of whole 8-row swizzle groups (always: block_n % 16 == 0)
+  if (halo && g_debug[5] != 2 && (block_n % 32) == 0) return launch_conv_halo2(P, wpk, Cout, ktot, (cudaStream_t)stream);
   return halo ? launch_conv_halo(P, (cudaStream_t)stream) : launch_conv(P, (cudaStream_t)stream);
 }
 
@@ -1094,7 +1291,7 @@ extern "C" int dm_conv2d_fwd_stat_rows(int N, int Ho, int Wo, int Cout) {
   const int m_generic = dm::cdiv(Wo, 1 << a) * dm::cdiv(Ho, 1 << b) * dm::cdiv(N, 1 << c);
   const int m_halo = dm::cdiv(Wo, 8) * dm::cdiv(Ho, 16) * N;
   const int m = m_generic > m_halo ? m_generic : m_halo;
-  return conv_grid(m * nt);
+  return conv_grid(m * nt + 1);         // +1: the CTA-pair kernel rounds an odd tile count up to whole pairs
 }
 
 // ---------------------------------------------------------------------------------------------------

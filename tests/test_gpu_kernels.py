@@ -133,7 +133,7 @@ def test_conv3x3_halo_kernel(dev, case):
     y_ref = F.conv2d(x, bf(wt), b, 1, 1)
     wd, bd = torch.nn.Parameter(wt.to(dev)), torch.nn.Parameter(b.to(dev))
     outs = {}
-    for name, key5 in (("halo", 0), ("generic", 1)):
+    for name, key5 in (("halo", 0), ("halo_single_cta", 2), ("generic", 1)):   # 0: CTA pairs where the tile width allows
         _lib.debug_set(5, key5)
         try:
             with torch.no_grad():
@@ -143,8 +143,9 @@ def test_conv3x3_halo_kernel(dev, case):
             _lib.debug_set(5, 0)
         outs[name] = (y.clone(), stats.sum(0).cpu())
         assert rel(nchw(y, cout), y_ref) < BF16_TOL, name
-    assert rel(outs["halo"][0].float(), outs["generic"][0].float()) < 1e-3
-    assert rel(outs["halo"][1], outs["generic"][1]) < 1e-5
+    for name in ("halo", "halo_single_cta"):
+        assert rel(outs[name][0].float(), outs["generic"][0].float()) < 1e-3, name
+        assert rel(outs[name][1], outs["generic"][1]) < 1e-5, name
 
 
 @pytest.mark.parametrize("version", [1, 2])

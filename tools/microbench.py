@@ -103,7 +103,8 @@ def main():
             r = {"shape": f"{h}x{h} {cin}->{cout} k{k}s{s}", "count": cnt, "gflop": fl / 1e9}
             variants = [("fwd", fwd), ("fwd_nostat", fwd_nostat), ("dgrad", dgrad), ("wgrad", wgrad)]
             if a.ab:
-                variants += [("fwd_generic", fwd), ("fwd_nostat_generic", fwd_nostat), ("dgrad_generic", dgrad),
+                variants += [("fwd_nostat_single", fwd_nostat), ("dgrad_single", dgrad),
+                             ("fwd_generic", fwd), ("fwd_nostat_generic", fwd_nostat), ("dgrad_generic", dgrad),
                              ("wgrad_v1", wgrad), ("wgrad_v2", wgrad)]
             if a.ablate and k == 3 and s == 1:
                 for mask in (0, 2, 4, 6):
@@ -119,6 +120,8 @@ def main():
                     _lib.debug_set(4, int(name[-1]))
                 if name.endswith("_generic"):
                     _lib.debug_set(5, 1)
+                if name.endswith("_single"):
+                    _lib.debug_set(5, 2)
                 if "_abl" in name:
                     _lib.debug_set(7, int(name.split("_abl")[1]))
                 if "_bn" in name:
