@@ -105,7 +105,7 @@ def main():
             if a.ab:
                 variants += [("fwd_nostat_single", fwd_nostat), ("dgrad_single", dgrad),
                              ("fwd_generic", fwd), ("fwd_nostat_generic", fwd_nostat), ("dgrad_generic", dgrad),
-                             ("wgrad_v1", wgrad), ("wgrad_v2", wgrad)]
+                             ("wgrad_v1", wgrad), ("wgrad_v2", wgrad), ("wgrad_v3", wgrad)]
             if a.ablate and k == 3 and s == 1:
                 for mask in (0, 2, 4, 6):
                     variants.append((f"dgrad_abl{mask}", dgrad))
