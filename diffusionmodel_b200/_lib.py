@@ -11,7 +11,7 @@ import os
 import re
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libdm_b200.so")
+LIB_PATH = os.environ.get("DM_B200_LIB") or os.path.join(_PKG, "libdm_b200.so")    # env override: A/B runs of two builds
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "dm_b200.h")
 
 _lib = None

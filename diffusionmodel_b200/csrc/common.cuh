@@ -18,6 +18,7 @@
 
 void dm_set_error(const char* msg);
 void dm_count_launch();
+long long dm_debug_value(int key);      // dev switches set through dm_debug_set (conv_gemm.cu)
 
 #define DM_NUM_SMS 148
 
@@ -27,16 +28,36 @@ typedef __nv_bfloat16 bf16;
 
 struct __align__(16) bf16x8 { __nv_bfloat162 v[4]; };
 
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// one 16-byte load / store (a struct copy of four bf16x2 compiles to four 4-byte accesses)
 __device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
-  bf16x8 r = *reinterpret_cast<const bf16x8*>(p);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(r.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  f[0] = bf_lo(r.x); f[1] = bf_hi(r.x); f[2] = bf_lo(r.y); f[3] = bf_hi(r.y);
+  f[4] = bf_lo(r.z); f[5] = bf_hi(r.z); f[6] = bf_lo(r.w); f[7] = bf_hi(r.w);
 }
+// Batched streaming loads: `volatile` keeps a group of these in program order, so the N loads of an unrolled
+// "load N pixels, then do the math" loop really are in flight together (left alone, ptxas may interleave each
+// load with the previous one's consumers and serialise the round trips).
+__device__ __forceinline__ uint4 ldg16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  f[0] = bf_lo(r.x); f[1] = bf_hi(r.x); f[2] = bf_lo(r.y); f[3] = bf_hi(r.y);
+  f[4] = bf_lo(r.z); f[5] = bf_hi(r.z); f[6] = bf_lo(r.w); f[7] = bf_hi(r.w);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b);
 __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
-  bf16x8 r;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) r.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  *reinterpret_cast<bf16x8*>(p) = r;
+  uint4 r;
+  r.x = pack2(f[0], f[1]); r.y = pack2(f[2], f[3]); r.z = pack2(f[4], f[5]); r.w = pack2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = r;
 }
 __device__ __forceinline__ void load4(const bf16* p, float (&f)[4]) {
   const uint2 r = *reinterpret_cast<const uint2*>(p);
@@ -89,6 +110,68 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   const GeluParts g = gelu_parts(x);
   return fmaf(x * 0.3989422804014327f, g.pdf_e, g.cdf);
 }
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): one issue slot does two lanes' worth of work.  The
+// streaming norm kernels are issue-bound on the GELU evaluation, so everything that is not a MUFU or an integer
+// op is done on register pairs; constants broadcast as immediates.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 bc2(float c) { return pk2(c, c); }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// bf16x2 word <-> packed pair (element 0 in the low half)
+__device__ __forceinline__ f32x2 bf2_to_f2(uint32_t w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+__device__ __forceinline__ uint32_t f2_to_bf2(f32x2 v) { float a, b; upk2(v, a, b); return pack2(a, b); }
+
+// Abramowitz-Stegun 7.1.26 on pairs, in the variable u (x = u/sqrt2 folded into the constants), coefficients
+// halved: poly(t) * t * exp(-u^2/2) = 0.5*erfc(|u|/sqrt2) = Phi(-|u|).
+constexpr float kAsP = 0.3275911f * 0.70710678118654752f;
+struct AsPair { f32x2 poly, T, D, E; };       // poly(t) (without the final *t), t, d = 1 + p|u|, exp(-u^2/2)
+__device__ __forceinline__ AsPair as_pair(f32x2 U, float u0, float u1) {
+  AsPair r;
+  const float d0 = fmaf(fabsf(u0), kAsP, 1.0f), d1 = fmaf(fabsf(u1), kAsP, 1.0f);
+  r.D = pk2(d0, d1);
+  r.T = pk2(rcp_approx(d0), rcp_approx(d1));
+  f32x2 poly = fma2(r.T, bc2(0.5307027145f), bc2(-0.7265760135f));
+  poly = fma2(poly, r.T, bc2(0.7107068705f));
+  poly = fma2(poly, r.T, bc2(-0.142248368f));
+  r.poly = fma2(poly, r.T, bc2(0.127414796f));
+  float m0, m1;
+  upk2(mul2(mul2(U, U), bc2(-0.72134752044448170f)), m0, m1);
+  r.E = pk2(ex2_approx(m0), ex2_approx(m1));
+  return r;
+}
+// gelu(u) = u*Phi(u) = max(u,0) - |u| * Phi(-|u|)
+__device__ __forceinline__ f32x2 gelu2(f32x2 U) {
+  float u0, u1; upk2(U, u0, u1);
+  const AsPair a = as_pair(U, u0, u1);
+  float q0, q1; upk2(mul2(mul2(a.poly, a.T), a.E), q0, q1);
+  return pk2(fmaf(-fabsf(u0), q0, fmaxf(u0, 0.0f)), fmaf(-fabsf(u1), q1, fmaxf(u1, 0.0f)));
+}
+// gelu'(u) = Phi(u) + u*phi(u).  With r = exp(-u^2/2) * (poly(t)*t - c|u|), c = 1/sqrt(2 pi):  gelu' = r for u < 0
+// and 1 - r for u >= 0, i.e. 0.5 + copysign(0.5 - r, u) (0.5 - r >= 0 everywhere).  c|u| = (c/p)*(d - 1).
+__device__ __forceinline__ f32x2 gelu_grad2(f32x2 U) {
+  float u0, u1; upk2(U, u0, u1);
+  const AsPair a = as_pair(U, u0, u1);
+  constexpr float kc = 0.3989422804014327f / kAsP;
+  const f32x2 V = fma2(a.D, bc2(-kc), fma2(a.poly, a.T, bc2(kc)));
+  float h0, h1; upk2(fma2(mul2(V, a.E), bc2(-1.0f), bc2(0.5f)), h0, h1);
+  h0 = __uint_as_float((__float_as_uint(h0) & 0x7fffffffu) | (__float_as_uint(u0) & 0x80000000u));
+  h1 = __uint_as_float((__float_as_uint(h1) & 0x7fffffffu) | (__float_as_uint(u1) & 0x80000000u));
+  return add2(pk2(h0, h1), bc2(0.5f));
+}
+template <int ACT> __device__ __forceinline__ f32x2 act2(f32x2 U) {        // ACT: 0 none, 1 GELU, 2 ReLU
+  if (ACT == 1) return gelu2(U);
+  if (ACT == 2) { float a, b; upk2(U, a, b); return pk2(fmaxf(a, 0.0f), fmaxf(b, 0.0f)); }
+  return U;
+}
+template <int ACT> __device__ __forceinline__ f32x2 act_grad2(f32x2 U) {
+  if (ACT == 1) return gelu_grad2(U);
+  if (ACT == 2) { float a, b; upk2(U, a, b); return pk2(a > 0.0f ? 1.0f : 0.0f, b > 0.0f ? 1.0f : 0.0f); }
+  return bc2(1.0f);
+}
+
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 // act: 0 none, 1 GELU, 2 ReLU

@@ -85,9 +85,9 @@ struct RedArgs {
   float *out1, *out2;
   float* part;          // workspace for the per-split partial sums (splits > 1)
 };
-// mode 0: s1 = sum a            1: s1 = sum a, s2 = sum a^2        2: s1 = sum a*b, s2 = sum a
-// mode 3: BN bwd   g = a*act'(xhat*gamma+beta), xhat = (b-mean[c])*invstd[c];  s1 = sum g, s2 = sum g*xhat
-// mode 4: GN bwd   same with mean/invstd per (sample, group)
+// MODE 0: s1 = sum a            MODE 2: s1 = sum a*b, s2 = sum a
+// Four pixels' 16-byte loads in flight per thread and operand.
+template <int MODE>
 __global__ void __launch_bounds__(256) nc_reduce_kernel(RedArgs A) {
   __shared__ float sm[256 * 16];
   const int Cv = (A.C + 7) / 8;
@@ -103,46 +103,40 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(RedArgs A) {
   const bool live = (r < R) && (cv < Cv);
   if (live) {
     const bf16* pa = A.a + (long long)(g / A.gdiv) * A.a_hi + (long long)(g % A.gdiv) * A.a_lo + c0;
-    const bf16* pb = A.b ? A.b + (long long)(g / A.gdiv) * A.b_hi + (long long)(g % A.gdiv) * A.b_lo + c0 : nullptr;
-    float mu[8], is[8], ga[8], be[8];
-    if (A.mode >= 3) {
-      ldp8(A.gamma, c0, A.C, ga); ldp8(A.beta, c0, A.C, be);
-      if (A.mode == 3) { ldp8(A.mean, c0, A.C, mu); ldp8(A.invstd, c0, A.C, is); }
-      else {
-        const int cg = A.C / A.G;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = c0 + j < A.C ? c0 + j : A.C - 1;
-          const int si = (g / A.stat_div) * A.G + c / cg;
-          mu[j] = __ldg(A.mean + si); is[j] = __ldg(A.invstd + si);
-        }
-      }
-    }
+    const bf16* pb = MODE == 2 ? A.b + (long long)(g / A.gdiv) * A.b_hi + (long long)(g % A.gdiv) * A.b_lo + c0 : nullptr;
     const int chunk = (A.count + gridDim.x - 1) / gridDim.x;
     const int i0 = blockIdx.x * chunk;
     const int i1 = min(A.count, i0 + chunk);
-#pragma unroll 4
-    for (int i = i0 + r; i < i1; i += R) {
-      float va[8], vb[8];
-      load8(pa + (long long)i * A.a_ps, va);
-      if (pb) load8(pb + (long long)i * A.b_ps, vb);
-      if (A.mode == 0) {
+    constexpr int NB = MODE == 2 ? 4 : 1;
+    uint4 wa[4], wb[NB];
+    auto fetch = [&](int i, uint4 (&xa)[4], uint4 (&xb)[NB]) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s1[j] += va[j];
-      } else if (A.mode == 1) {
+      for (int u = 0; u < 4; ++u) {
+        const int ii = i + u * R;
+        const bool ok = ii < i1;
+        xa[u] = ok ? dm::ldg16(pa + (long long)ii * A.a_ps) : make_uint4(0u, 0u, 0u, 0u);
+        if (MODE == 2) xb[MODE == 2 ? u : 0] = ok ? dm::ldg16(pb + (long long)ii * A.b_ps) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    int i = i0 + r;
+    fetch(i, wa, wb);
+    while (i < i1) {                                  // software pipeline, see bn_stats_kernel
+      uint4 na[4], nb[NB];
+      fetch(i + 4 * R, na, nb);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += va[j]; s2[j] += va[j] * va[j]; }
-      } else if (A.mode == 2) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += va[j] * vb[j]; s2[j] += va[j]; }
-      } else {
+      for (int u = 0; u < 4; ++u) {
+        float va[8], vb[8];
+        dm::unpack8(wa[u], va);
+        if (MODE == 2) dm::unpack8(wb[MODE == 2 ? u : 0], vb);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xh = (vb[j] - mu[j]) * is[j];
-          const float gg = va[j] * dm::act_grad_f(xh * ga[j] + be[j], A.act);
-          s1[j] += gg; s2[j] += gg * xh;
+          if (MODE == 0) s1[j] += va[j];
+          else { s1[j] = fmaf(va[j], vb[j], s1[j]); s2[j] += va[j]; }
         }
+        wa[u] = na[u];
+        if (MODE == 2) wb[MODE == 2 ? u : 0] = nb[MODE == 2 ? u : 0];
       }
+      i += 4 * R;
     }
   }
   // reduce over the R pixel rows of the block
@@ -172,21 +166,45 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(RedArgs A) {
     }
   }
 }
-__global__ void reduce_finalize_kernel(const float* __restrict__ part, int splits, int groups, int C, float scale,
-                                       float* __restrict__ out1, float* __restrict__ out2, int accumulate) {
+// Second stage of the deterministic reductions: out[i] = scale * sum_sp part[sp][i] over `splits` partial rows.
+// 32 outputs x 32 row slices per block; each thread issues its rows' loads four at a time (a plain dependent
+// loop pays one L2 round trip per partial row -- 130 us for the 296 rows of a column sum).  Fixed summation
+// order => bit-reproducible.
+__global__ void __launch_bounds__(1024) reduce_finalize_kernel(const float* __restrict__ part, int splits, int groups, int C,
+                                                                float scale, float* __restrict__ out1, float* __restrict__ out2,
+                                                                int accumulate) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const long long total = (long long)groups * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const long long i = (long long)blockIdx.x * 32 + cl;
+  float a = 0.f, b = 0.f;
+  if (i < total) {
     const long long g = i / C; const int c = (int)(i - g * C);
-    float a = 0.f, b = 0.f;
-    for (int sp = 0; sp < splits; ++sp) {
-      const float* row = part + ((long long)sp * groups + g) * 2 * C;
-      a += row[c];
-      if (out2) b += row[C + c];
+    const float* base = part + g * 2 * C + c;
+    const long long stride = (long long)groups * 2 * C;
+    for (int sp = sl; sp < splits; sp += 128) {
+      float x[4], y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int s = sp + 32 * u;
+        const bool ok = s < splits;
+        const float* row = base + (long long)(ok ? s : sp) * stride;
+        x[u] = ok ? __ldg(row) : 0.f;
+        y[u] = (ok && out2) ? __ldg(row + C) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a += x[u]; b += y[u]; }
     }
+  }
+  sa[sl][cl] = a; sb[sl][cl] = b;
+  __syncthreads();
+  if (sl == 0 && i < total) {
+    for (int k = 1; k < 32; ++k) { a += sa[k][cl]; b += sb[k][cl]; }
     if (accumulate) { out1[i] += a * scale; if (out2) out2[i] += b * scale; }
     else { out1[i] = a * scale; if (out2) out2[i] = b * scale; }
   }
 }
+static inline int finalize_grid(long long total) { return (int)((total + 31) / 32); }
 
 float* g_ws = nullptr;          // caller-provided scratch for partial sums (dm_set_workspace)
 long long g_ws_floats = 0;
@@ -196,9 +214,9 @@ int launch_reduce(RedArgs& A, int groups, cudaStream_t st) {
   const int VPB = Cv < 256 ? Cv : 256;
   const int R = 256 / VPB;
   const int cvt = (Cv + VPB - 1) / VPB;
-  long long want = (long long)DM_NUM_SMS * 4 / ((long long)groups * cvt);
+  long long want = (long long)DM_NUM_SMS * 6 / ((long long)groups * cvt);      // ~1400 resident threads per SM
   int maxs = A.count / (R * 8); if (maxs < 1) maxs = 1;
-  if (maxs > 64) maxs = 64;                       // few partial rows: the finalize pass stays trivial
+  if (maxs > 512) maxs = 512;
   int splits = (int)(want < 1 ? 1 : (want > maxs ? maxs : want));
   if (groups > 65535) { dm_set_error("reduce: too many groups"); return DM_ERR_ARG; }
   if (splits > 1 && (long long)splits * groups * 2 * A.C > g_ws_floats) {
@@ -208,12 +226,11 @@ int launch_reduce(RedArgs& A, int groups, cudaStream_t st) {
   }
   A.part = g_ws;
   dim3 grid(splits, cvt, groups);
-  nc_reduce_kernel<<<grid, 256, 0, st>>>(A);
+  if (A.mode == 2) nc_reduce_kernel<2><<<grid, 256, 0, st>>>(A); else nc_reduce_kernel<0><<<grid, 256, 0, st>>>(A);
   DM_CHECK_LAUNCH();
   if (splits > 1) {
     const long long total = (long long)groups * A.C;
-    reduce_finalize_kernel<<<(int)((total + 255) / 256 > 592 ? 592 : (total + 255) / 256), 256, 0, st>>>(g_ws, splits, groups, A.C, A.scale,
-                                                                                                     A.out1, A.out2, 0);
+    reduce_finalize_kernel<<<finalize_grid(total), 1024, 0, st>>>(g_ws, splits, groups, A.C, A.scale, A.out1, A.out2, 0);
     DM_CHECK_LAUNCH();
   }
   return DM_OK;
@@ -232,19 +249,27 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
   for (int j = 0; j < 8; ++j) s[j] = 0.f;
   if (c0 < C) {
     const unsigned step = gridDim.x * R;
-    for (unsigned p = blockIdx.x * R + r; p < P; p += 4 * step) {
-      float v[4][8];
+    unsigned p = blockIdx.x * R + r;
+    uint4 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned pu = p + u * step;
+      w[u] = pu < P ? dm::ldg16(dy + (long long)pu * lddy + c0) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    while (p < P) {                                   // software pipeline, see bn_stats_kernel
+      const unsigned pn = p + 4 * step;
+      uint4 wn[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const unsigned pu = p + u * step;
-        if (pu < P) load8(dy + (long long)pu * lddy + c0, v[u]);
-        else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
-        }
+        const unsigned pu = pn + u * step;
+        wn[u] = pu < P ? dm::ldg16(dy + (long long)pu * lddy + c0) : make_uint4(0u, 0u, 0u, 0u);
       }
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { dm::unpack8(w[u], v[u]); w[u] = wn[u]; }
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j] += (v[0][j] + v[1][j]) + (v[2][j] + v[3][j]);
+      p = pn;
     }
   }
   float* mine = sm + threadIdx.x * 8;
@@ -278,22 +303,33 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ 
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   if (c0 < C) {
+    // software pipeline: the next four pixels' loads are issued before this round's math, so eight 16-byte loads
+    // per thread are in flight (ptxas otherwise interleaves each load with the previous one's consumers)
     const unsigned step = gridDim.x * R;
-    for (unsigned p = blockIdx.x * R + r; p < P; p += 4 * step) {
-      float v[4][8];
+    unsigned p = blockIdx.x * R + r;
+    uint4 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned pu = p + u * step;
+      w[u] = pu < P ? dm::ldg16(y + (long long)pu * ldy + c0) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    while (p < P) {
+      const unsigned pn = p + 4 * step;
+      uint4 wn[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const unsigned pu = p + u * step;
-        if (pu < P) load8(y + (long long)pu * ldy + c0, v[u]);
-        else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
-        }
+        const unsigned pu = pn + u * step;
+        wn[u] = pu < P ? dm::ldg16(y + (long long)pu * ldy + c0) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        dm::unpack8(w[u], v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += v[u][j]; s2[j] = fmaf(v[u][j], v[u][j], s2[j]); }
+        for (int j = 0; j < 8; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
+        w[u] = wn[u];
+      }
+      p = pn;
     }
   }
   float* mine = sm + threadIdx.x * 16;
@@ -332,9 +368,17 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* partials
   const int c = blockIdx.x * 32 + cl;
   double a = 0.0, b = 0.0;
   if (c < C)
-    for (int t = rr; t < m_tiles; t += 32) {
-      a += (double)partials[(long long)t * 2 * ld + c];
-      b += (double)partials[(long long)t * 2 * ld + ld + c];
+    for (int t = rr; t < m_tiles; t += 128) {          // four rows' loads in flight per thread
+      float x[4], y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tt = t + 32 * u;
+        const bool ok = tt < m_tiles;
+        const float* row = partials + (long long)(ok ? tt : t) * 2 * ld;
+        x[u] = ok ? __ldg(row + c) : 0.f; y[u] = ok ? __ldg(row + ld + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a += (double)x[u]; b += (double)y[u]; }
     }
   s1[rr][cl] = a; s2[rr][cl] = b;
   __syncthreads();
@@ -359,83 +403,50 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* partials
   }
 }
 
-// GELU through a shared-memory table.  The BatchNorm kernels are issue-bound on the erf evaluation (~15 of
-// their ~30 instructions per element), not on HBM; a 1024-entry table of (value, forward difference) over
-// [-8, 8] with linear interpolation replaces it by ~8 instructions and one LDS.64.  Step 1/64: the
-// interpolation error is h^2/8 * max|f''| < 8e-6 for Phi and < 4e-5 for d/dx GELU -- two orders under the bf16
-// rounding (4e-3 relative) of the stored result.  Tables are built once, in double precision.
-constexpr int kLutN = 1024;
-__device__ float2 g_lut_cdf[kLutN];      // Phi(x)
-__device__ float2 g_lut_dgelu[kLutN];    // Phi(x) + x*phi(x)
-__global__ void lut_init_kernel() {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= kLutN) return;
-  auto cdf = [](double x) { return 0.5 * erfc(-x * 0.70710678118654752440); };
-  auto dg = [&](double x) { return cdf(x) + x * 0.39894228040143267794 * exp(-0.5 * x * x); };
-  const double x0 = -8.0 + i / 64.0, x1 = -8.0 + (i + 1) / 64.0;
-  g_lut_cdf[i] = make_float2((float)cdf(x0), (float)(cdf(x1) - cdf(x0)));
-  g_lut_dgelu[i] = make_float2((float)dg(x0), (float)(dg(x1) - dg(x0)));
-}
-__device__ __forceinline__ float lut_eval(const float2* lut, float u) {
-  float t = fmaf(u, 64.0f, 512.0f);
-  t = fminf(fmaxf(t, 0.0f), 1022.999f);
-  const float fl = floorf(t);
-  const float2 e = lut[(int)fl];
-  return fmaf(t - fl, e.y, e.x);
-}
-// ACT: 0 none, 1 GELU (analytic erf), 2 ReLU, 3 GELU (table)
-template <int ACT> __device__ __forceinline__ float actv(float u, const float2* lut) {
-  if (ACT == 3) return u * lut_eval(lut, u);
-  return dm::act_f(u, ACT);
-}
-template <int ACT> __device__ __forceinline__ float actg(float u, const float2* lut) {
-  if (ACT == 3) return lut_eval(lut, u);
-  return dm::act_grad_f(u, ACT);
-}
-template <int ACT> __device__ __forceinline__ void lut_load(float2* dst, const float2* src) {
-  if (ACT == 3) {
-    for (int i = threadIdx.x; i < kLutN; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-  }
+// z = act(y * sc + sh), sc = invstd*gamma, sh = beta - mean*sc.
+// The streaming BatchNorm kernels are issue-bound on the GELU, not on HBM, so their inner loops run on packed
+// fp32 pairs (dm::f32x2: FFMA2/FMUL2, see common.cuh): ~11 issue slots per element forward and ~14 backward
+// instead of 24-30.  A thread owns 4 channels (8-byte vectors, two pairs) for its whole life -- coefficients in
+// registers -- and keeps four pixels' loads in flight.
+using dm::f32x2; using dm::pk2; using dm::bc2; using dm::upk2; using dm::fma2; using dm::mul2; using dm::add2;
+using dm::bf2_to_f2; using dm::f2_to_bf2;
+
+struct ChanCoef2 { f32x2 v[2]; };
+__device__ __forceinline__ f32x2 coef_pair(const float* __restrict__ p, int c, int C) {
+  return pk2(c < C ? __ldg(p + c) : 0.f, c + 1 < C ? __ldg(p + c + 1) : 0.f);
 }
 
-// z = act(y * sc + sh), sc = invstd*gamma, sh = beta - mean*sc
-template <int ACT>
+template <int ACT, int U>
 __global__ void __launch_bounds__(256) bn_fwd_kernel(const bf16* __restrict__ y, int ldy, const float* __restrict__ mean,
                                                       const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, bf16* __restrict__ z, int ldz,
                                                       unsigned P, int C, int VPB, int R) {
-  // 4 channels per thread (8-byte vectors), four pixels in flight: 8 coefficient registers instead of 16, so
-  // more warps stay resident to cover the load latency of this issue-bound (erf) kernel
-  __shared__ float2 lut[ACT == 3 ? kLutN : 1];
-  lut_load<ACT>(lut, g_lut_cdf);
   const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
   const int c0 = (blockIdx.y * VPB + cvl) * 4;
   if (c0 >= C) return;
-  float sc[4], sh[4];
+  f32x2 sc[2], sh[2];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + j;
-    const float k = c < C ? __ldg(invstd + c) * __ldg(gamma + c) : 0.f;
-    sc[j] = k;
-    sh[j] = c < C ? __ldg(beta + c) - __ldg(mean + c) * k : 0.f;
+  for (int j = 0; j < 2; ++j) {
+    const int c = c0 + 2 * j;
+    sc[j] = mul2(coef_pair(invstd, c, C), coef_pair(gamma, c, C));
+    sh[j] = fma2(mul2(coef_pair(mean, c, C), bc2(-1.0f)), sc[j], coef_pair(beta, c, C));
   }
   const unsigned step = gridDim.x * R;
-  for (unsigned p = blockIdx.x * R + r; p < P; p += 4 * step) {
-    float v[4][4];
-    bool ok[4];
+  for (unsigned p = blockIdx.x * R + r; p < P; p += U * step) {
+    uint2 w[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const unsigned pu = p + u * step;
-      ok[u] = pu < P;
-      if (ok[u]) dm::load4(y + (long long)pu * ldy + c0, v[u]);
+      if (pu < P) w[u] = dm::ldg8(y + (long long)pu * ldy + c0);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (!ok[u]) continue;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[u][j] = actv<ACT>(fmaf(v[u][j], sc[j], sh[j]), lut);
-      dm::store4(z + (long long)(p + u * step) * ldz + c0, v[u]);
+    for (int u = 0; u < U; ++u) {
+      const unsigned pu = p + u * step;
+      if (pu >= P) break;
+      uint2 o;
+      o.x = f2_to_bf2(dm::act2<ACT>(fma2(bf2_to_f2(w[u].x), sc[0], sh[0])));
+      o.y = f2_to_bf2(dm::act2<ACT>(fma2(bf2_to_f2(w[u].y), sc[1], sh[1])));
+      *reinterpret_cast<uint2*>(z + (long long)pu * ldz + c0) = o;
     }
   }
 }
@@ -446,155 +457,155 @@ __global__ void __launch_bounds__(256) bn_fwd_kernel(const bf16* __restrict__ y,
 //   dy = gamma*invstd * (g - mean_p(g) - xhat*mean_p(g*xhat))  =  k0*g - K2*y - K1
 // so the streaming passes need only (A2, B2) resp. (A2, B2, k0, K1, K2) per channel; the sums over
 // xhat are recovered from sums over y in the finalize step (double precision).
-// Threads own 4 channels (8-byte vectors): half the coefficient registers of the 8-wide mapping, which
-// is what lets five 240-thread blocks live on an SM.
 //
-// pass 1: per-block partial sums of g, g*y and y, written (no atomics, no zeroing) to part[block][3][C].
+// pass 1: per-block partial sums of g and g*y, written (no atomics, no zeroing) to part[block][2][C].
+// (sum y is not needed: in training mode it is count*mean by construction, so sum xhat = 0 and the gradient of a
+// convolution bias feeding a batch-statistics norm is exactly zero.)
 template <int ACT>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y,
                                                              int ldy, const float* __restrict__ mean,
                                                              const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* __restrict__ part,
                                                              unsigned P, int C, int VPB, int R) {
-  extern __shared__ float sm[];          // [threads][12]
-  __shared__ float2 lut[ACT == 3 ? kLutN : 1];
-  lut_load<ACT>(lut, g_lut_dgelu);
+  extern __shared__ float sm[];          // [threads][8]
   const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
   const int c0 = (blockIdx.y * VPB + cvl) * 4;
-  float s1[4], s2[4], s3[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { s1[j] = 0.f; s2[j] = 0.f; s3[j] = 0.f; }
+  f32x2 s1[2], s2[2];
+  s1[0] = s1[1] = s2[0] = s2[1] = bc2(0.f);
   if (c0 < C) {
-    float A2[4], B2[4];
+    f32x2 A2[2], B2[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = c0 + j;
-      const bool ok = c < C;
-      const float a = ok ? __ldg(invstd + c) : 0.f, ga = ok ? __ldg(gamma + c) : 0.f;
-      A2[j] = a * ga;
-      B2[j] = ok ? fmaf(-__ldg(mean + c) * a, ga, __ldg(beta + c)) : 0.f;
+    for (int j = 0; j < 2; ++j) {
+      const int c = c0 + 2 * j;
+      const f32x2 a = coef_pair(invstd, c, C), ga = coef_pair(gamma, c, C);
+      A2[j] = mul2(a, ga);
+      B2[j] = fma2(mul2(coef_pair(mean, c, C), bc2(-1.0f)), A2[j], coef_pair(beta, c, C));
     }
     const unsigned step = gridDim.x * R;
-    for (unsigned p = blockIdx.x * R + r; p < P; p += 2 * step) {
-      const unsigned p1 = p + step;
-      const bool has1 = p1 < P;
-      float g0[4], v0[4], g1[4], v1[4];
-      dm::load4(dz + (long long)p * lddz + c0, g0);
-      dm::load4(y + (long long)p * ldy + c0, v0);
-      if (has1) { dm::load4(dz + (long long)p1 * lddz + c0, g1); dm::load4(y + (long long)p1 * ldy + c0, v1); }
+    for (unsigned p = blockIdx.x * R + r; p < P; p += 4 * step) {
+      uint2 wg[4], wy[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float gg = g0[j] * actg<ACT>(fmaf(v0[j], A2[j], B2[j]), lut);
-        s1[j] += gg; s2[j] = fmaf(gg, v0[j], s2[j]); s3[j] += v0[j];
-      }
-      if (has1) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float gg = g1[j] * actg<ACT>(fmaf(v1[j], A2[j], B2[j]), lut);
-          s1[j] += gg; s2[j] = fmaf(gg, v1[j], s2[j]); s3[j] += v1[j];
+      for (int u = 0; u < 4; ++u) {
+        const unsigned pu = p + u * step;
+        if (pu < P) {
+          wg[u] = dm::ldg8(dz + (long long)pu * lddz + c0);
+          wy[u] = dm::ldg8(y + (long long)pu * ldy + c0);
         }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p + u * step >= P) break;
+        const f32x2 y0 = bf2_to_f2(wy[u].x), y1 = bf2_to_f2(wy[u].y);
+        const f32x2 g0 = mul2(bf2_to_f2(wg[u].x), dm::act_grad2<ACT>(fma2(y0, A2[0], B2[0])));
+        const f32x2 g1 = mul2(bf2_to_f2(wg[u].y), dm::act_grad2<ACT>(fma2(y1, A2[1], B2[1])));
+        s1[0] = add2(s1[0], g0); s2[0] = fma2(g0, y0, s2[0]);
+        s1[1] = add2(s1[1], g1); s2[1] = fma2(g1, y1, s2[1]);
       }
     }
   }
-  float* mine = sm + threadIdx.x * 12;
+  float s[8];
+  upk2(s1[0], s[0], s[1]); upk2(s1[1], s[2], s[3]); upk2(s2[0], s[4], s[5]); upk2(s2[1], s[6], s[7]);
+  float* mine = sm + threadIdx.x * 8;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { mine[j] = s1[j]; mine[4 + j] = s2[j]; mine[8 + j] = s3[j]; }
+  for (int j = 0; j < 8; ++j) mine[j] = s[j];
   __syncthreads();
   if (r == 0 && c0 < C) {
     for (int rr = 1; rr < R; ++rr) {
-      const float* o = sm + (rr * VPB + cvl) * 12;
+      const float* o = sm + (rr * VPB + cvl) * 8;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { s1[j] += o[j]; s2[j] += o[4 + j]; s3[j] += o[8 + j]; }
+      for (int j = 0; j < 8; ++j) s[j] += o[j];
     }
-    float* g = part + (long long)blockIdx.x * 3 * C;
+    float* g = part + (long long)blockIdx.x * 2 * C;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (c0 + j < C) { g[c0 + j] = s1[j]; g[C + c0 + j] = s2[j]; g[2 * C + c0 + j] = s3[j]; }
+      if (c0 + j < C) { g[c0 + j] = s[j]; g[C + c0 + j] = s[4 + j]; }
   }
 }
 
 // pass 2: block partials -> per-channel coefficients coef[3][C] = (k0, K1, K2) of the apply pass;
-// dgamma += sum g*xhat, dbeta += sum g, and the bias gradient of the convolution feeding this norm:
-// sum_p dy = gamma*invstd * (training ? -(sum g*xhat / P) * sum xhat : sum g).
+// dgamma += sum g*xhat, dbeta += sum g, and (eval mode) the bias gradient of the convolution feeding this norm.
+// 32 channels x 32 row slices per block; each thread issues its partial-row loads four at a time (a plain
+// dependent loop costs one L2 round trip per row: 13 us for 600 rows).
 __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, double P,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 const float* __restrict__ gamma, float* __restrict__ coef,
                                                                 float* dgamma, float* dbeta, float* dbias, int training) {
-  __shared__ float sh[3][32][33];
+  __shared__ float sh[2][32][33];
   const int cl = threadIdx.x & 31, rr = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+  float f0 = 0.f, f1 = 0.f;
   if (c < C) {
-#pragma unroll 4
-    for (int t = rr; t < nblk; t += 32) {
-      const float* g = part + (long long)t * 3 * C;
-      f0 += g[c]; f1 += g[C + c]; f2 += g[2 * C + c];
+    for (int t = rr; t < nblk; t += 128) {
+      float x0[4], x1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tt = t + 32 * u;
+        const bool ok = tt < nblk;
+        const float* g = part + (long long)(ok ? tt : t) * 2 * C;
+        x0[u] = ok ? __ldg(g + c) : 0.f; x1[u] = ok ? __ldg(g + C + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { f0 += x0[u]; f1 += x1[u]; }
     }
   }
-  sh[0][rr][cl] = f0; sh[1][rr][cl] = f1; sh[2][rr][cl] = f2;
+  sh[0][rr][cl] = f0; sh[1][rr][cl] = f1;
   __syncthreads();
   if (rr == 0 && c < C) {
-    double sg = 0.0, sgy = 0.0, sy = 0.0;
-    for (int k = 0; k < 32; ++k) { sg += (double)sh[0][k][cl]; sgy += (double)sh[1][k][cl]; sy += (double)sh[2][k][cl]; }
+    double sg = 0.0, sgy = 0.0;
+    for (int k = 0; k < 32; ++k) { sg += (double)sh[0][k][cl]; sgy += (double)sh[1][k][cl]; }
     const double a = (double)invstd[c], b = -(double)mean[c] * a, ga = (double)gamma[c];
     const double sgx = a * sgy + b * sg;          // sum g*xhat
-    const double sx = a * sy + b * P;             // sum xhat
     const double k0 = ga * a;
     const double m1 = training ? sg / P : 0.0, m2 = training ? sgx / P : 0.0;
     coef[c] = (float)k0;
-    coef[C + c] = (float)(k0 * (m1 + m2 * b));    // K1
-    coef[2 * C + c] = (float)(k0 * m2 * a);       // K2
+    coef[C + c] = (float)(-k0 * (m1 + m2 * b));   // -K1
+    coef[2 * C + c] = (float)(-k0 * m2 * a);      // -K2
     dbeta[c] += (float)sg;
     dgamma[c] += (float)sgx;
-    if (dbias) dbias[c] += (float)(training ? -k0 * m2 * sx : k0 * sg);
+    if (dbias && !training) dbias[c] += (float)(k0 * sg);
   }
 }
 
-// pass 3: dy = k0*g - K2*y - K1
+// pass 3: dy = k0*g - K2*y - K1   (coef rows hold k0, -K1, -K2)
 template <int ACT>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ y,
                                                             int ldy, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, const float* __restrict__ coef,
                                                             bf16* __restrict__ dy, int lddy, unsigned P, int C, int VPB, int R) {
-  __shared__ float2 lut[ACT == 3 ? kLutN : 1];
-  lut_load<ACT>(lut, g_lut_dgelu);
   const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
   const int c0 = (blockIdx.y * VPB + cvl) * 4;
   if (c0 >= C) return;
-  float A2[4], B2[4], k0[4], K1[4], K2[4];
+  f32x2 A2[2], B2[2], k0[2], nK1[2], nK2[2];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + j;
-    const bool ok = c < C;
-    const float a = ok ? __ldg(invstd + c) : 0.f, ga = ok ? __ldg(gamma + c) : 0.f;
-    A2[j] = a * ga;
-    B2[j] = ok ? fmaf(-__ldg(mean + c) * a, ga, __ldg(beta + c)) : 0.f;
-    k0[j] = ok ? __ldg(coef + c) : 0.f;
-    K1[j] = ok ? __ldg(coef + C + c) : 0.f;
-    K2[j] = ok ? __ldg(coef + 2 * C + c) : 0.f;
+  for (int j = 0; j < 2; ++j) {
+    const int c = c0 + 2 * j;
+    A2[j] = mul2(coef_pair(invstd, c, C), coef_pair(gamma, c, C));
+    B2[j] = fma2(mul2(coef_pair(mean, c, C), bc2(-1.0f)), A2[j], coef_pair(beta, c, C));
+    k0[j] = coef_pair(coef, c, C); nK1[j] = coef_pair(coef + C, c, C); nK2[j] = coef_pair(coef + 2 * C, c, C);
   }
   const unsigned step = gridDim.x * R;
-  for (unsigned p = blockIdx.x * R + r; p < P; p += 2 * step) {
-    const unsigned p1 = p + step;
-    const bool has1 = p1 < P;
-    float g0[4], v0[4], g1[4], v1[4];
-    dm::load4(dz + (long long)p * lddz + c0, g0);
-    dm::load4(y + (long long)p * ldy + c0, v0);
-    if (has1) { dm::load4(dz + (long long)p1 * lddz + c0, g1); dm::load4(y + (long long)p1 * ldy + c0, v1); }
+  for (unsigned p = blockIdx.x * R + r; p < P; p += 4 * step) {
+    uint2 wg[4], wy[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float gg = g0[j] * actg<ACT>(fmaf(v0[j], A2[j], B2[j]), lut);
-      g0[j] = fmaf(k0[j], gg, -fmaf(K2[j], v0[j], K1[j]));
-    }
-    dm::store4(dy + (long long)p * lddy + c0, g0);
-    if (has1) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float gg = g1[j] * actg<ACT>(fmaf(v1[j], A2[j], B2[j]), lut);
-        g1[j] = fmaf(k0[j], gg, -fmaf(K2[j], v1[j], K1[j]));
+    for (int u = 0; u < 4; ++u) {
+      const unsigned pu = p + u * step;
+      if (pu < P) {
+        wg[u] = dm::ldg8(dz + (long long)pu * lddz + c0);
+        wy[u] = dm::ldg8(y + (long long)pu * ldy + c0);
       }
-      dm::store4(dy + (long long)p1 * lddy + c0, g1);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned pu = p + u * step;
+      if (pu >= P) break;
+      const f32x2 y0 = bf2_to_f2(wy[u].x), y1 = bf2_to_f2(wy[u].y);
+      const f32x2 g0 = mul2(bf2_to_f2(wg[u].x), dm::act_grad2<ACT>(fma2(y0, A2[0], B2[0])));
+      const f32x2 g1 = mul2(bf2_to_f2(wg[u].y), dm::act_grad2<ACT>(fma2(y1, A2[1], B2[1])));
+      uint2 o;
+      o.x = f2_to_bf2(fma2(k0[0], g0, fma2(nK2[0], y0, nK1[0])));
+      o.y = f2_to_bf2(fma2(k0[1], g1, fma2(nK2[1], y1, nK1[1])));
+      *reinterpret_cast<uint2*>(dy + (long long)pu * lddy + c0) = o;
     }
   }
 }
@@ -618,20 +629,19 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
   if (c0 < C) {
     const unsigned step = gridDim.x * R;
     for (unsigned p = blockIdx.x * R + r; p < HW; p += 4 * step) {
-      float v[4][8];
+      uint4 w[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const unsigned pu = p + u * step;
-        if (pu < HW) load8(x + (long long)pu * ldx + c0, v[u]);
-        else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
-        }
+        w[u] = pu < HW ? dm::ldg16(x + (long long)pu * ldx + c0) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        dm::unpack8(w[u], v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += v[u][j]; s2[j] = fmaf(v[u][j], v[u][j], s2[j]); }
+        for (int j = 0; j < 8; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
+      }
     }
   }
   float* mine = sm + threadIdx.x * 16;
@@ -1285,17 +1295,6 @@ extern "C" int dm_bn_finalize(const float* partials, int m_tiles, int ld, int C,
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
-// GELU tables: built on first use (before any graph capture: the warm-up pass), DM_GELU_LUT=0 keeps the analytic erf
-static bool ensure_lut(cudaStream_t st) {
-  static int state = -1;       // -1 unknown, 0 disabled, 1 ready
-  if (state < 0) {
-    const char* e = getenv("DM_GELU_LUT");
-    if (e && e[0] == '0') state = 0;
-    else { lut_init_kernel<<<kLutN / 256, 256, 0, st>>>(); state = cudaGetLastError() == cudaSuccess ? 1 : 0; }
-  }
-  return state == 1;
-}
-
 static int bn_stats_blocks(long long P, int C) {
   const ChanMap m = chan_map(C);
   int gx = chan_grid_x(P, m, 16);
@@ -1318,11 +1317,14 @@ extern "C" int dm_bn_act_fwd(const void* y, int ldy, const float* mean, const fl
   if (P <= 0) return DM_OK;
   if (P >= (1ll << 31)) { dm_set_error("dm_bn_act_fwd: too many pixels"); return DM_ERR_ARG; }
   const ChanMap m = chan_map(C, 4);
-  dim3 grid(chan_grid_x(P, m, 8), m.cvt);
-#define BN_FWD(A) bn_fwd_kernel<A><<<grid, m.threads, 0, ST>>>((const bf16*)y, ldy, mean, invstd, gamma, beta, (bf16*)z, ldz, (unsigned)P, C, m.VPB, m.R)
-  // (the table variant, ACT=3, measured slower than the analytic erf here: 88 vs 68 us on 4x256x256x192 -- one
-  //  lookup per element is LDS-conflict bound; it pays off only in the backward kernels, see dm_bn_act_bwd)
-  if (act == 1) BN_FWD(1); else if (act == 2) BN_FWD(2); else BN_FWD(0);
+  // eight pixels in flight per thread once every resident thread has at least two rounds of them (4.1 vs 3.8 TB/s
+  // on 4x256x256x192); dm_debug_set(8, 1|2) forces 8|4
+  int variant = (int)dm_debug_value(8);
+  if (variant == 0) variant = P * m.Cv >= (long long)DM_NUM_SMS * 1024 * 16 ? 1 : 2;
+  dim3 grid(chan_grid_x(P, m, variant == 1 ? 16 : 8), m.cvt);
+#define BN_FWD(A, U) bn_fwd_kernel<A, U><<<grid, m.threads, 0, ST>>>((const bf16*)y, ldy, mean, invstd, gamma, beta, (bf16*)z, ldz, (unsigned)P, C, m.VPB, m.R)
+  if (variant == 1) { if (act == 1) BN_FWD(1, 8); else if (act == 2) BN_FWD(2, 8); else BN_FWD(0, 8); }
+  else { if (act == 1) BN_FWD(1, 4); else if (act == 2) BN_FWD(2, 4); else BN_FWD(0, 4); }
 #undef BN_FWD
   DM_CHECK_LAUNCH();
   return DM_OK;
@@ -1335,7 +1337,7 @@ static int bn_bwd_blocks(long long P, int C) {
   return b > cap ? (cap < 1 ? 1 : cap) : b;
 }
 extern "C" long long dm_bn_act_bwd_scratch(long long P, int C) {
-  return (long long)bn_bwd_blocks(P, C) * 3 * C + 3LL * C;
+  return (long long)bn_bwd_blocks(P, C) * 2 * C + 3LL * C;
 }
 extern "C" int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, const float* mean, const float* invstd,
                              const float* gamma, const float* beta, void* dy, int lddy, float* dgamma, float* dbeta,
@@ -1346,12 +1348,11 @@ extern "C" int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, c
   const ChanMap m = chan_map(C, 4);
   const int nblk = bn_bwd_blocks(P, C);
   float* coef = scratch;                    // [3][C]
-  float* part = scratch + 3LL * C;          // [nblk][3][C]
+  float* part = scratch + 3LL * C;          // [nblk][2][C]
   dim3 grid(nblk, m.cvt);
-  const size_t smem = (size_t)m.threads * 12 * sizeof(float);
+  const size_t smem = (size_t)m.threads * 8 * sizeof(float);
 #define BN_RED(A) bn_bwd_reduce_kernel<A><<<grid, m.threads, smem, ST>>>((const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, part, (unsigned)P, C, m.VPB, m.R)
-  const bool use_lut = act == 1 && ensure_lut(ST);
-  if (use_lut) BN_RED(3); else if (act == 1) BN_RED(1); else if (act == 2) BN_RED(2); else BN_RED(0);
+  if (act == 1) BN_RED(1); else if (act == 2) BN_RED(2); else BN_RED(0);
 #undef BN_RED
   DM_CHECK_LAUNCH();
   bn_bwd_finalize_kernel<<<dm::cdiv(C, 32), 1024, 0, ST>>>(part, nblk, C, (double)P, mean, invstd, gamma, coef, dgamma, dbeta,
@@ -1359,7 +1360,7 @@ extern "C" int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, c
   DM_CHECK_LAUNCH();
   dim3 grid2(chan_grid_x(P, m, 4), m.cvt);
 #define BN_APP(A) bn_bwd_apply_kernel<A><<<grid2, m.threads, 0, ST>>>((const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, coef, (bf16*)dy, lddy, (unsigned)P, C, m.VPB, m.R)
-  if (use_lut) BN_APP(3); else if (act == 1) BN_APP(1); else if (act == 2) BN_APP(2); else BN_APP(0);
+  if (act == 1) BN_APP(1); else if (act == 2) BN_APP(2); else BN_APP(0);
 #undef BN_APP
   DM_CHECK_LAUNCH();
   return DM_OK;
@@ -1445,8 +1446,8 @@ extern "C" int dm_colsum(const void* dy, int lddy, float* db, long long P, int C
   if (P <= 0) return DM_OK;
   if (P >= (1ll << 31)) { dm_set_error("dm_colsum: too many pixels"); return DM_ERR_ARG; }
   const ChanMap m = chan_map(C);
-  int gx = chan_grid_x(P, m, 32);
-  int cap = DM_NUM_SMS * 2 / m.cvt; if (cap < 1) cap = 1;
+  int gx = chan_grid_x(P, m, 16);
+  int cap = DM_NUM_SMS * 5 / m.cvt; if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
   if ((long long)gx * 2 * C > g_ws_floats) {
     if (g_ws_floats < 2LL * C) { dm_set_error("dm_colsum needs scratch: call dm_set_workspace() first"); return DM_ERR_ARG; }
@@ -1455,7 +1456,7 @@ extern "C" int dm_colsum(const void* dy, int lddy, float* db, long long P, int C
   dim3 grid(gx, m.cvt);
   colsum_kernel<<<grid, m.threads, (size_t)m.threads * 8 * sizeof(float), ST>>>((const bf16*)dy, lddy, g_ws, (unsigned)P, C, m.VPB, m.R);
   DM_CHECK_LAUNCH();
-  reduce_finalize_kernel<<<dm::cdiv(C, 256), 256, 0, ST>>>(g_ws, gx, 1, C, 1.0f, db, nullptr, 1);
+  reduce_finalize_kernel<<<finalize_grid(C), 1024, 0, ST>>>(g_ws, gx, 1, C, 1.0f, db, nullptr, 1);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }

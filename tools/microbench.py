@@ -105,7 +105,7 @@ def main():
             if a.ab:
                 variants += [("fwd_nostat_single", fwd_nostat), ("dgrad_single", dgrad),
                              ("fwd_generic", fwd), ("fwd_nostat_generic", fwd_nostat), ("dgrad_generic", dgrad),
-                             ("wgrad_v1", wgrad), ("wgrad_v2", wgrad), ("wgrad_v3", wgrad)]
+                             ("wgrad_v1", wgrad), ("wgrad_v2", wgrad), ("wgrad_v3", wgrad), ("wgrad_v4", wgrad)]
             if a.ablate and k == 3 and s == 1:
                 for mask in (0, 2, 4, 6):
                     variants.append((f"dgrad_abl{mask}", dgrad))
@@ -162,8 +162,26 @@ def main():
 
             def axpby():
                 ops.call("dm_axpby", P_(y), c, P_(dz), c, P_(z), c, P, c, 1.0, 1.0, st)
-            for name, fn, nb in (("bn_act_fwd", bn_fwd, 2), ("bn_act_bwd", bn_bwd, 5), ("colsum", colsum, 1), ("axpby", axpby, 3)):
+            rows_ = _lib.fn("dm_bn_stats_rows")(P, c)
+            part = torch.empty((rows_, 2, c), device=dev)
+            rm = torch.zeros(c, device=dev); rv = torch.ones(c, device=dev)
+            pooled = torch.empty((n, c), device=dev)
+
+            def bn_stats():
+                ops.call("dm_bn_stats", P_(y), c, P_(part), c, P, c, st)
+
+            def bn_finalize():
+                ops.call("dm_bn_finalize", P_(part), rows_, c, c, float(P), P_(mean), P_(inv), P_(rm), P_(rv), 0.1, 1e-5, None, st)
+
+            def pool():
+                ops.call("dm_pool_nhw", P_(y), c, P_(pooled), n, h * h, c, 1.0 / (h * h), st)
+            for name, fn, nb in (("bn_stats", bn_stats, 1), ("bn_finalize", bn_finalize, 0), ("bn_act_fwd", bn_fwd, 2),
+                                 ("bn_act_fwd_v1", bn_fwd, 2),
+                                 ("bn_act_bwd", bn_bwd, 5), ("colsum", colsum, 1), ("pool_nhw", pool, 1), ("axpby", axpby, 3)):
+                if "_v" in name:
+                    _lib.debug_set(8, int(name.split("_v")[1]))
                 ms = timer(fn, a.iters, flush)
+                _lib.debug_set(8, 0)
                 r = {"kernel": name, "shape": f"{h}x{h}x{c}", "ms": round(ms, 4), "GBps": round(nb * bytes_el / ms / 1e6, 1)}
                 print(json.dumps(r), flush=True)
                 rows.append(r)
