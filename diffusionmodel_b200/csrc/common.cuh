@@ -49,6 +49,22 @@ __device__ __forceinline__ uint2 ldg8(const void* p) {
   asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Per-thread asynchronous 16-byte copies global -> shared (LDGSTS): the memory-level parallelism of a streaming
+// kernel then no longer depends on how ptxas schedules register loads against their consumers.  `pred` false
+// zero-fills the slot without touching global memory.  A thread only ever reads back its own slots, so
+// cp.async.wait_group is the only synchronisation needed.
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* g, bool pred) {
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds16(uint32_t smem_addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_addr) : "memory");
+  return r;
+}
 __device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
   f[0] = bf_lo(r.x); f[1] = bf_hi(r.x); f[2] = bf_lo(r.y); f[3] = bf_hi(r.y);
   f[4] = bf_lo(r.z); f[5] = bf_hi(r.z); f[6] = bf_lo(r.w); f[7] = bf_hi(r.w);

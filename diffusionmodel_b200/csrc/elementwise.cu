@@ -411,44 +411,69 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* partials
 using dm::f32x2; using dm::pk2; using dm::bc2; using dm::upk2; using dm::fma2; using dm::mul2; using dm::add2;
 using dm::bf2_to_f2; using dm::f2_to_bf2;
 
-struct ChanCoef2 { f32x2 v[2]; };
 __device__ __forceinline__ f32x2 coef_pair(const float* __restrict__ p, int c, int C) {
   return pk2(c < C ? __ldg(p + c) : 0.f, c + 1 < C ? __ldg(p + c + 1) : 0.f);
 }
+// Streaming skeleton shared by the three kernels below: thread (cvl, r) of block b owns the 8 channels c0..c0+7
+// (one 16-byte vector; pad lanes carry zero coefficients, so they stay zero) of the pixels p0, p0+step, ...;
+// pointers advance by a constant byte stride, rounds of U pixels run without bounds checks except on the
+// prefetch of the following round, whose loads are issued before this round's math.
+struct PixRun { unsigned p0, n, step; };
+constexpr int kRingS = 3, kRingU = 2;      // cp.async ring of the two-operand kernels: 3 rounds x 2 pixels x 2 operands x 16 B per thread
+__device__ __forceinline__ PixRun pix_run(unsigned P, int R, int r) {
+  PixRun q;
+  q.step = gridDim.x * R; q.p0 = blockIdx.x * R + r;
+  q.n = q.p0 < P ? (P - q.p0 + q.step - 1) / q.step : 0u;
+  return q;
+}
+__device__ __forceinline__ uint4 zero4() { return make_uint4(0u, 0u, 0u, 0u); }
 
-template <int ACT, int U>
+template <int ACT>
 __global__ void __launch_bounds__(256) bn_fwd_kernel(const bf16* __restrict__ y, int ldy, const float* __restrict__ mean,
                                                       const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, bf16* __restrict__ z, int ldz,
                                                       unsigned P, int C, int VPB, int R) {
   const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
-  const int c0 = (blockIdx.y * VPB + cvl) * 4;
-  if (c0 >= C) return;
-  f32x2 sc[2], sh[2];
+  const int c0 = (blockIdx.y * VPB + cvl) * 8;
+  PixRun q = pix_run(P, R, r);
+  if (c0 >= C || q.n == 0) return;
+  f32x2 sc[4], sh[4];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < 4; ++j) {
     const int c = c0 + 2 * j;
     sc[j] = mul2(coef_pair(invstd, c, C), coef_pair(gamma, c, C));
     sh[j] = fma2(mul2(coef_pair(mean, c, C), bc2(-1.0f)), sc[j], coef_pair(beta, c, C));
   }
-  const unsigned step = gridDim.x * R;
-  for (unsigned p = blockIdx.x * R + r; p < P; p += U * step) {
-    uint2 w[U];
+  constexpr int U = 4;
+  const char* src = reinterpret_cast<const char*>(y + (long long)q.p0 * ldy + c0);
+  char* dst = reinterpret_cast<char*>(z + (long long)q.p0 * ldz + c0);
+  const long long ss = (long long)q.step * ldy * 2, ds = (long long)q.step * ldz * 2;
+  auto emit = [&](const uint4& w, char* o) {
+    uint4 v;
+    v.x = f2_to_bf2(dm::act2<ACT>(fma2(bf2_to_f2(w.x), sc[0], sh[0])));
+    v.y = f2_to_bf2(dm::act2<ACT>(fma2(bf2_to_f2(w.y), sc[1], sh[1])));
+    v.z = f2_to_bf2(dm::act2<ACT>(fma2(bf2_to_f2(w.z), sc[2], sh[2])));
+    v.w = f2_to_bf2(dm::act2<ACT>(fma2(bf2_to_f2(w.w), sc[3], sh[3])));
+    *reinterpret_cast<uint4*>(o) = v;
+  };
+  uint4 w[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned pu = p + u * step;
-      if (pu < P) w[u] = dm::ldg8(y + (long long)pu * ldy + c0);
-    }
+  for (int u = 0; u < U; ++u) w[u] = (unsigned)u < q.n ? dm::ldg16(src + u * ss) : zero4();
+  unsigned n = q.n;
+  while (n >= (unsigned)U) {
+    src += U * ss;
+    const unsigned rem = n - U;
+    uint4 wn[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned pu = p + u * step;
-      if (pu >= P) break;
-      uint2 o;
-      o.x = f2_to_bf2(dm::act2<ACT>(fma2(bf2_to_f2(w[u].x), sc[0], sh[0])));
-      o.y = f2_to_bf2(dm::act2<ACT>(fma2(bf2_to_f2(w[u].y), sc[1], sh[1])));
-      *reinterpret_cast<uint2*>(z + (long long)pu * ldz + c0) = o;
-    }
+    for (int u = 0; u < U; ++u) wn[u] = (unsigned)u < rem ? dm::ldg16(src + u * ss) : zero4();
+#pragma unroll
+    for (int u = 0; u < U; ++u) { emit(w[u], dst + u * ds); w[u] = wn[u]; }
+    dst += U * ds;
+    n = rem;
   }
+#pragma unroll
+  for (int u = 0; u < U - 1; ++u)
+    if ((unsigned)u < n) emit(w[u], dst + u * ds);
 }
 
 // BatchNorm + activation backward.  With xhat = a*y + b (a = invstd, b = -mean*invstd) and the
@@ -467,58 +492,77 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
                                                              const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* __restrict__ part,
                                                              unsigned P, int C, int VPB, int R) {
-  extern __shared__ float sm[];          // [threads][8]
+  extern __shared__ float sm[];          // [threads][16]
   const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
-  const int c0 = (blockIdx.y * VPB + cvl) * 4;
-  f32x2 s1[2], s2[2];
-  s1[0] = s1[1] = s2[0] = s2[1] = bc2(0.f);
-  if (c0 < C) {
-    f32x2 A2[2], B2[2];
+  const int c0 = (blockIdx.y * VPB + cvl) * 8;
+  f32x2 s1[4], s2[4];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < 4; ++j) s1[j] = s2[j] = bc2(0.f);
+  PixRun q = pix_run(P, R, r);
+  if (c0 < C && q.n > 0) {
+    f32x2 A2[4], B2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
       const int c = c0 + 2 * j;
-      const f32x2 a = coef_pair(invstd, c, C), ga = coef_pair(gamma, c, C);
-      A2[j] = mul2(a, ga);
+      A2[j] = mul2(coef_pair(invstd, c, C), coef_pair(gamma, c, C));
       B2[j] = fma2(mul2(coef_pair(mean, c, C), bc2(-1.0f)), A2[j], coef_pair(beta, c, C));
     }
-    const unsigned step = gridDim.x * R;
-    for (unsigned p = blockIdx.x * R + r; p < P; p += 4 * step) {
-      uint2 wg[4], wy[4];
+    const char* pg = reinterpret_cast<const char*>(dz + (long long)q.p0 * lddz + c0);
+    const char* py = reinterpret_cast<const char*>(y + (long long)q.p0 * ldy + c0);
+    const long long sg = (long long)q.step * lddz * 2, sy = (long long)q.step * ldy * 2;
+    auto accum = [&](const uint4& g, const uint4& v) {     // dz = 0 (tail padding) contributes nothing
+      const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, vw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const unsigned pu = p + u * step;
-        if (pu < P) {
-          wg[u] = dm::ldg8(dz + (long long)pu * lddz + c0);
-          wy[u] = dm::ldg8(y + (long long)pu * ldy + c0);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const f32x2 yy = bf2_to_f2(vw[j]);
+        const f32x2 gg = mul2(bf2_to_f2(gw[j]), dm::act_grad2<ACT>(fma2(yy, A2[j], B2[j])));
+        s1[j] = add2(s1[j], gg); s2[j] = fma2(gg, yy, s2[j]);
       }
+    };
+    // ring of kRingS rounds x kRingU pixels x 2 operands, 16 bytes per (slot, thread)
+    const uint32_t ring = dm::smem_u32(sm) + threadIdx.x * 16u, slot = blockDim.x * 16u;
+    const unsigned rounds = (q.n + kRingU - 1) / kRingU;
+    auto issue = [&](unsigned rd) {
+      const uint32_t base = ring + (rd % kRingS) * (kRingU * 2) * slot;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (p + u * step >= P) break;
-        const f32x2 y0 = bf2_to_f2(wy[u].x), y1 = bf2_to_f2(wy[u].y);
-        const f32x2 g0 = mul2(bf2_to_f2(wg[u].x), dm::act_grad2<ACT>(fma2(y0, A2[0], B2[0])));
-        const f32x2 g1 = mul2(bf2_to_f2(wg[u].y), dm::act_grad2<ACT>(fma2(y1, A2[1], B2[1])));
-        s1[0] = add2(s1[0], g0); s2[0] = fma2(g0, y0, s2[0]);
-        s1[1] = add2(s1[1], g1); s2[1] = fma2(g1, y1, s2[1]);
+      for (int u = 0; u < kRingU; ++u) {
+        const unsigned k = rd * kRingU + u;
+        const bool ok = k < q.n;
+        const long long kk = ok ? (long long)k : 0;
+        dm::cp_async16(base + (2 * u) * slot, pg + kk * sg, ok);
+        dm::cp_async16(base + (2 * u + 1) * slot, py + kk * sy, ok);
       }
+    };
+#pragma unroll
+    for (int s = 0; s < kRingS - 1; ++s) { if ((unsigned)s < rounds) issue(s); dm::cp_async_commit(); }
+    for (unsigned rd = 0; rd < rounds; ++rd) {
+      if (rd + kRingS - 1 < rounds) issue(rd + kRingS - 1);
+      dm::cp_async_commit();
+      dm::cp_async_wait<kRingS - 1>();
+      const uint32_t base = ring + (rd % kRingS) * (kRingU * 2) * slot;
+#pragma unroll
+      for (int u = 0; u < kRingU; ++u) accum(dm::lds16(base + (2 * u) * slot), dm::lds16(base + (2 * u + 1) * slot));
     }
+    dm::cp_async_wait<0>();
   }
-  float s[8];
-  upk2(s1[0], s[0], s[1]); upk2(s1[1], s[2], s[3]); upk2(s2[0], s[4], s[5]); upk2(s2[1], s[6], s[7]);
-  float* mine = sm + threadIdx.x * 8;
+  __syncthreads();                       // the ring is reused for the block reduction
+  float s[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) mine[j] = s[j];
+  for (int j = 0; j < 4; ++j) { upk2(s1[j], s[2 * j], s[2 * j + 1]); upk2(s2[j], s[8 + 2 * j], s[8 + 2 * j + 1]); }
+  float* mine = sm + threadIdx.x * 16;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) mine[j] = s[j];
   __syncthreads();
   if (r == 0 && c0 < C) {
     for (int rr = 1; rr < R; ++rr) {
-      const float* o = sm + (rr * VPB + cvl) * 8;
+      const float* o = sm + (rr * VPB + cvl) * 16;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s[j] += o[j];
+      for (int j = 0; j < 16; ++j) s[j] += o[j];
     }
     float* g = part + (long long)blockIdx.x * 2 * C;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (c0 + j < C) { g[c0 + j] = s[j]; g[C + c0 + j] = s[4 + j]; }
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < C) { g[c0 + j] = s[j]; g[C + c0 + j] = s[8 + j]; }
   }
 }
 
@@ -574,40 +618,60 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
                                                             const float* __restrict__ beta, const float* __restrict__ coef,
                                                             bf16* __restrict__ dy, int lddy, unsigned P, int C, int VPB, int R) {
   const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
-  const int c0 = (blockIdx.y * VPB + cvl) * 4;
-  if (c0 >= C) return;
-  f32x2 A2[2], B2[2], k0[2], nK1[2], nK2[2];
+  const int c0 = (blockIdx.y * VPB + cvl) * 8;
+  PixRun q = pix_run(P, R, r);
+  if (c0 >= C || q.n == 0) return;
+  f32x2 A2[4], B2[4], k0[4], nK1[4], nK2[4];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < 4; ++j) {
     const int c = c0 + 2 * j;
     A2[j] = mul2(coef_pair(invstd, c, C), coef_pair(gamma, c, C));
     B2[j] = fma2(mul2(coef_pair(mean, c, C), bc2(-1.0f)), A2[j], coef_pair(beta, c, C));
     k0[j] = coef_pair(coef, c, C); nK1[j] = coef_pair(coef + C, c, C); nK2[j] = coef_pair(coef + 2 * C, c, C);
   }
-  const unsigned step = gridDim.x * R;
-  for (unsigned p = blockIdx.x * R + r; p < P; p += 4 * step) {
-    uint2 wg[4], wy[4];
+  extern __shared__ float sm[];
+  const char* pg = reinterpret_cast<const char*>(dz + (long long)q.p0 * lddz + c0);
+  const char* py = reinterpret_cast<const char*>(y + (long long)q.p0 * ldy + c0);
+  char* dst = reinterpret_cast<char*>(dy + (long long)q.p0 * lddy + c0);
+  const long long sg = (long long)q.step * lddz * 2, sy = (long long)q.step * ldy * 2, ds = (long long)q.step * lddy * 2;
+  auto emit = [&](const uint4& g, const uint4& v, char* o) {
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, vw[4] = {v.x, v.y, v.z, v.w};
+    uint32_t ow[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const unsigned pu = p + u * step;
-      if (pu < P) {
-        wg[u] = dm::ldg8(dz + (long long)pu * lddz + c0);
-        wy[u] = dm::ldg8(y + (long long)pu * ldy + c0);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const f32x2 yy = bf2_to_f2(vw[j]);
+      const f32x2 gg = mul2(bf2_to_f2(gw[j]), dm::act_grad2<ACT>(fma2(yy, A2[j], B2[j])));
+      ow[j] = f2_to_bf2(fma2(k0[j], gg, fma2(nK2[j], yy, nK1[j])));
     }
+    *reinterpret_cast<uint4*>(o) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  };
+  const uint32_t ring = dm::smem_u32(sm) + threadIdx.x * 16u, slot = blockDim.x * 16u;
+  const unsigned rounds = (q.n + kRingU - 1) / kRingU;
+  auto issue = [&](unsigned rd) {
+    const uint32_t base = ring + (rd % kRingS) * (kRingU * 2) * slot;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const unsigned pu = p + u * step;
-      if (pu >= P) break;
-      const f32x2 y0 = bf2_to_f2(wy[u].x), y1 = bf2_to_f2(wy[u].y);
-      const f32x2 g0 = mul2(bf2_to_f2(wg[u].x), dm::act_grad2<ACT>(fma2(y0, A2[0], B2[0])));
-      const f32x2 g1 = mul2(bf2_to_f2(wg[u].y), dm::act_grad2<ACT>(fma2(y1, A2[1], B2[1])));
-      uint2 o;
-      o.x = f2_to_bf2(fma2(k0[0], g0, fma2(nK2[0], y0, nK1[0])));
-      o.y = f2_to_bf2(fma2(k0[1], g1, fma2(nK2[1], y1, nK1[1])));
-      *reinterpret_cast<uint2*>(dy + (long long)pu * lddy + c0) = o;
+    for (int u = 0; u < kRingU; ++u) {
+      const unsigned k = rd * kRingU + u;
+      const bool ok = k < q.n;
+      const long long kk = ok ? (long long)k : 0;
+      dm::cp_async16(base + (2 * u) * slot, pg + kk * sg, ok);
+      dm::cp_async16(base + (2 * u + 1) * slot, py + kk * sy, ok);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < kRingS - 1; ++s) { if ((unsigned)s < rounds) issue(s); dm::cp_async_commit(); }
+  for (unsigned rd = 0; rd < rounds; ++rd) {
+    if (rd + kRingS - 1 < rounds) issue(rd + kRingS - 1);
+    dm::cp_async_commit();
+    dm::cp_async_wait<kRingS - 1>();
+    const uint32_t base = ring + (rd % kRingS) * (kRingU * 2) * slot;
+#pragma unroll
+    for (int u = 0; u < kRingU; ++u) {
+      const unsigned k = rd * kRingU + u;
+      if (k < q.n) emit(dm::lds16(base + (2 * u) * slot), dm::lds16(base + (2 * u + 1) * slot), dst + (long long)k * ds);
     }
   }
+  dm::cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------- GroupNorm
@@ -1316,22 +1380,17 @@ extern "C" int dm_bn_act_fwd(const void* y, int ldy, const float* mean, const fl
   REQ8(ldy, "dm_bn_act_fwd"); REQ8(ldz, "dm_bn_act_fwd");
   if (P <= 0) return DM_OK;
   if (P >= (1ll << 31)) { dm_set_error("dm_bn_act_fwd: too many pixels"); return DM_ERR_ARG; }
-  const ChanMap m = chan_map(C, 4);
-  // eight pixels in flight per thread once every resident thread has at least two rounds of them (4.1 vs 3.8 TB/s
-  // on 4x256x256x192); dm_debug_set(8, 1|2) forces 8|4
-  int variant = (int)dm_debug_value(8);
-  if (variant == 0) variant = P * m.Cv >= (long long)DM_NUM_SMS * 1024 * 16 ? 1 : 2;
-  dim3 grid(chan_grid_x(P, m, variant == 1 ? 16 : 8), m.cvt);
-#define BN_FWD(A, U) bn_fwd_kernel<A, U><<<grid, m.threads, 0, ST>>>((const bf16*)y, ldy, mean, invstd, gamma, beta, (bf16*)z, ldz, (unsigned)P, C, m.VPB, m.R)
-  if (variant == 1) { if (act == 1) BN_FWD(1, 8); else if (act == 2) BN_FWD(2, 8); else BN_FWD(0, 8); }
-  else { if (act == 1) BN_FWD(1, 4); else if (act == 2) BN_FWD(2, 4); else BN_FWD(0, 4); }
+  const ChanMap m = chan_map(C);
+  dim3 grid(chan_grid_x(P, m, 8), m.cvt);
+#define BN_FWD(A) bn_fwd_kernel<A><<<grid, m.threads, 0, ST>>>((const bf16*)y, ldy, mean, invstd, gamma, beta, (bf16*)z, ldz, (unsigned)P, C, m.VPB, m.R)
+  if (act == 1) BN_FWD(1); else if (act == 2) BN_FWD(2); else BN_FWD(0);
 #undef BN_FWD
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
 static int bn_bwd_blocks(long long P, int C) {
-  // one resident wave (4 blocks of <=256 threads per SM at 64 registers): few partial rows to finalize
-  const ChanMap m = chan_map(C, 4);
+  // about one resident wave: few partial rows to finalize
+  const ChanMap m = chan_map(C);
   int b = chan_grid_x(P, m, 16);
   const int cap = DM_NUM_SMS * 4 / m.cvt;
   return b > cap ? (cap < 1 ? 1 : cap) : b;
@@ -1345,12 +1404,12 @@ extern "C" int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, c
   REQ8(lddz, "dm_bn_act_bwd"); REQ8(ldy, "dm_bn_act_bwd"); REQ8(lddy, "dm_bn_act_bwd");
   if (P <= 0) return DM_OK;
   if (P >= (1ll << 31)) { dm_set_error("dm_bn_act_bwd: too many pixels"); return DM_ERR_ARG; }
-  const ChanMap m = chan_map(C, 4);
+  const ChanMap m = chan_map(C);
   const int nblk = bn_bwd_blocks(P, C);
   float* coef = scratch;                    // [3][C]
   float* part = scratch + 3LL * C;          // [nblk][2][C]
   dim3 grid(nblk, m.cvt);
-  const size_t smem = (size_t)m.threads * 8 * sizeof(float);
+  const size_t smem = (size_t)m.threads * 16 * kRingS * kRingU * 2;       // cp.async ring (>= 64 B per thread for the block reduction)
 #define BN_RED(A) bn_bwd_reduce_kernel<A><<<grid, m.threads, smem, ST>>>((const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, part, (unsigned)P, C, m.VPB, m.R)
   if (act == 1) BN_RED(1); else if (act == 2) BN_RED(2); else BN_RED(0);
 #undef BN_RED
@@ -1359,7 +1418,7 @@ extern "C" int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, c
                                                          dbias, training);
   DM_CHECK_LAUNCH();
   dim3 grid2(chan_grid_x(P, m, 4), m.cvt);
-#define BN_APP(A) bn_bwd_apply_kernel<A><<<grid2, m.threads, 0, ST>>>((const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, coef, (bf16*)dy, lddy, (unsigned)P, C, m.VPB, m.R)
+#define BN_APP(A) bn_bwd_apply_kernel<A><<<grid2, m.threads, smem, ST>>>((const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, coef, (bf16*)dy, lddy, (unsigned)P, C, m.VPB, m.R)
   if (act == 1) BN_APP(1); else if (act == 2) BN_APP(2); else BN_APP(0);
 #undef BN_APP
   DM_CHECK_LAUNCH();
