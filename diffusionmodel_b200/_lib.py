@@ -97,7 +97,9 @@ _SIGS = {
     "dm_cfg_reverse_step": "pi p p p pi ffff iiii p",
     "dm_cfg_reverse_step_dev": "pi p p p pi p iiii p",
     "dm_sumsq": "p l p p",
+    "dm_pack_transpose": "pp iii p l p",
     "dm_adamw": "pppp l fffffff p f p",
+    "dm_adamw_bf16": "ppppp l fffffff p f p",
 }
 _RET_LL = {"dm_bn_act_bwd_scratch", "dm_gn_scratch"}          # size queries return long long, not a status
 _CT = {"p": _P, "i": _I, "l": _L, "f": _F, "d": _D}

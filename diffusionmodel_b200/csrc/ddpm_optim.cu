@@ -265,6 +265,56 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* p, const float* g, fl
   }
 }
 
+// Same update on float4 vectors, additionally writing a bf16 copy of the new parameters: for convolution weights
+// stored in the GEMM's own [Cout][tap][Cin] order that copy IS the forward weight pack, so no pack kernel runs.
+__global__ void __launch_bounds__(256) adamw_bf16_kernel(float4* p, const float4* g, float4* m, float4* v, uint2* pb,
+                                                          long long n4, float lr, float b1, float b2, float eps, float wd,
+                                                          float bc1, float bc2, const float* gnorm_sq, float max_norm) {
+  float clip = 1.f;
+  if (gnorm_sq != nullptr && max_norm > 0.f) {
+    const float c = max_norm / (sqrtf(gnorm_sq[0]) + 1e-6f);
+    clip = c < 1.f ? c : 1.f;
+  }
+  const float step = lr / bc1, rs2 = 1.0f / sqrtf(bc2), decay = 1.f - lr * wd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = g[i]; float4 p4 = p[i], m4 = m[i], v4 = v[i];
+    float* pp = reinterpret_cast<float*>(&p4); float* mm = reinterpret_cast<float*>(&m4); float* vv = reinterpret_cast<float*>(&v4);
+    const float* gg = reinterpret_cast<const float*>(&g4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gi = gg[j] * clip;
+      float pi = pp[j] * decay;
+      const float mi = mm[j] + (1.f - b1) * (gi - mm[j]);
+      const float vi = b2 * vv[j] + (1.f - b2) * gi * gi;
+      pi -= step * mi / (sqrtf(vi) * rs2 + eps);
+      pp[j] = pi; mm[j] = mi; vv[j] = vi;
+    }
+    p[i] = p4; m[i] = m4; v[i] = v4;
+    pb[i] = make_uint2(dm::pack2(p4.x, p4.y), dm::pack2(p4.z, p4.w));
+  }
+}
+
+// Data-gradient packs from the bf16 forward pack of a GEMM-native weight: per filter tap a [Cout x Cin] ->
+// [Cin x Cout] transpose through a 64x64 shared-memory tile (128-byte contiguous segments on both sides), the tap
+// landing at dst_off[tap] (180-degree rotation for stride 1, the four parity phases for 4x4/s2).
+//   src[co][tap][ci] (pitch ntaps*cin)   ->   dst[ci * dst_pitch + dst_off[tap] + co], co < ck (zero beyond Cout)
+struct TransArgs { long long dst_off[16]; };
+__global__ void __launch_bounds__(256) pack_transpose_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int cout,
+                                                              int cin, int ntaps, long long dst_pitch, TransArgs A) {
+  __shared__ bf16 tile[64][66];
+  const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64, tap = blockIdx.z;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int r = ty; r < 64; r += 4) {
+    const int co = co0 + r, ci = ci0 + tx;
+    tile[r][tx] = (co < cout && ci < cin) ? src[((long long)co * ntaps + tap) * cin + ci] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int r = ty; r < 64; r += 4) {
+    const int ci = ci0 + r;
+    if (ci < cin) dst[(long long)ci * dst_pitch + A.dst_off[tap] + co0 + tx] = tile[tx][r];
+  }
+}
+
 }  // namespace
 
 static void fill_pack(PackArgs& A, int rows, int cols, int ntaps, const long long* tap_off, long long s_row, long long s_col,
@@ -374,6 +424,30 @@ extern "C" int dm_sumsq(const float* g, long long n, float* out, void* stream) {
 extern "C" int dm_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                         float eps, float wd, float bc1, float bc2, const float* gnorm_sq, float max_norm, void* stream) {
   adamw_kernel<<<grid_for(n), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2, gnorm_sq, max_norm);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
+/* dm_adamw plus a bf16 shadow copy of the updated parameters (n a multiple of 4, all pointers 16-byte aligned) */
+extern "C" int dm_adamw_bf16(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                             float beta2, float eps, float wd, float bc1, float bc2, const float* gnorm_sq, float max_norm,
+                             void* stream) {
+  if (n & 3) { dm_set_error("dm_adamw_bf16: element count must be a multiple of 4"); return DM_ERR_ARG; }
+  adamw_bf16_kernel<<<grid_for(n / 4), 256, 0, ST>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, (uint2*)p_bf16, n / 4,
+                                                     lr, beta1, beta2, eps, wd, bc1, bc2, gnorm_sq, max_norm);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
+
+/* bf16 [Cout][ntaps][Cin] -> dst[ci*dst_pitch + dst_off[tap] + co] for co < ck = ceil64(Cout) (zeros beyond Cout) */
+extern "C" int dm_pack_transpose(const void* src, void* dst, int cout, int cin, int ntaps, const long long* dst_off_host,
+                                 long long dst_pitch, void* stream) {
+  if (ntaps < 1 || ntaps > 16) { dm_set_error("dm_pack_transpose: 1..16 taps"); return DM_ERR_ARG; }
+  TransArgs A;
+  for (int i = 0; i < 16; ++i) A.dst_off[i] = i < ntaps ? dst_off_host[i] : 0;
+  dim3 grid(dm::cdiv(cin, 64), dm::cdiv(cout, 64), ntaps);
+  pack_transpose_kernel<<<grid, 256, 0, ST>>>((const bf16*)src, (bf16*)dst, cout, cin, ntaps, dst_pitch, A);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }

@@ -35,6 +35,68 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# --------------------------------------------------------------------------------------- GEMM-native weight storage
+# The fused optimizer may store a Conv2d weight [Cout, Cin, kh, kw] in the implicit GEMM's own order
+# [Cout][kh][kw][Cin] (the parameter becomes a permuted view: same shape, same values, same state_dict).  Then
+# the wgrad GEMM accumulates straight into ``param.grad``'s memory, and the bf16 copy the optimizer writes next
+# to the update IS the forward weight pack -- no scatter and no pack kernel per step for those weights.
+_conv2d_weights = {}                    # id(param) -> weakref: parameters known to be nn.Conv2d weights (ConvTranspose2d
+                                        # weights are [Cin, Cout, k, k]); keyed by id because tensors compare elementwise
+_native = {}                            # weight.data_ptr() -> _NativeWeight
+
+
+class _NativeWeight:
+    __slots__ = ("ref", "shadow", "stamp")
+
+    def __init__(self, param, shadow):
+        self.ref, self.shadow, self.stamp = weakref.ref(param), shadow, None
+
+
+def mark_conv2d_weights(module):
+    """Tell the optimizer which 4-D parameters are Conv2d weights (called by the U-Net constructors)."""
+    for m in module.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            _conv2d_weights[id(m.weight)] = weakref.ref(m.weight)
+
+
+def native_strides(shape):
+    cout, cin, kh, kw = shape
+    return (kh * kw * cin, 1, kw * cin, cin)
+
+
+def wants_native(p):
+    """Conv2d weights with a multiple of 64 input channels and a real filter footprint: the packed GEMM layout
+    then has no padding, i.e. it is a permutation of the parameter."""
+    r = _conv2d_weights.get(id(p))
+    return r is not None and r() is p and p.dim() == 4 and p.shape[1] % 64 == 0 and p.shape[2] * p.shape[3] > 1
+
+
+def register_native(param, shadow2d):
+    _native[param.data_ptr()] = _NativeWeight(param, shadow2d)
+
+
+def _native_of(w):
+    e = _native.get(w.data_ptr())
+    if e is None:
+        return None
+    p = e.ref()
+    if p is None or p.shape != w.shape or tuple(w.stride()) != native_strides(w.shape):
+        del _native[w.data_ptr()]
+        return None
+    return e
+
+
+def natives_fresh():
+    """The optimizer has just written every registered shadow together with its update."""
+    for key in list(_native):
+        e = _native[key]
+        p = e.ref()
+        if p is None or p.data_ptr() != key:
+            del _native[key]
+        else:
+            e.stamp = (p._version, _weights_epoch)
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -133,18 +195,47 @@ def conv_geom(w, c_split=0):
     return cout, cin, kh, kw, ck
 
 
+def _fresh_shadow(w, e):
+    """bf16 [Cout, kh*kw*Cin] copy of a GEMM-native weight, re-cast only when the parameter changed behind the
+    optimizer's back (load_state_dict, broadcast, manual edits)."""
+    stamp = (w._version, _weights_epoch)
+    if e.stamp != stamp:
+        cout, cin, kh, kw = w.shape
+        e.shadow.copy_(w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin))
+        e.stamp = stamp
+    return e.shadow
+
+
+def _pack_transposed(w, e, out, rows_out, row_len, dst_offs):
+    cout, cin, kh, kw = w.shape
+    if out is None or tuple(out.shape) != (rows_out, row_len):
+        out = torch.empty((rows_out, row_len), device=w.device, dtype=torch.bfloat16)
+    call("dm_pack_transpose", _p(_fresh_shadow(w, e)), _p(out), cout, cin, kh * kw, _taps(dst_offs), row_len, _stream())
+    return out
+
+
 def _pack_fwd(w, out=None, c_split=0):
     cout, cin, kh, kw, ck = conv_geom(w, c_split)
-    offs = [r * kw + s for r in range(kh) for s in range(kw)]
-    return _pack(w, out, cout, cin, offs, cin * kh * kw, kh * kw, c_split, ck, kh * kw * ck, False)
+    e = _native_of(w)
+    if e is not None and ck == cin:
+        return _fresh_shadow(w, e)      # GEMM-native storage: the forward pack is the optimizer's bf16 shadow
+    s0, s1, s2, s3 = w.stride()
+    offs = [r * s2 + s * s3 for r in range(kh) for s in range(kw)]
+    return _pack(w, out, cout, cin, offs, s0, s1, c_split, ck, kh * kw * ck, False)
 
 
 def _pack_dgrad(w, out=None):
     """stride-1 data gradient = conv with the 180-degree rotated kernel and Cin/Cout swapped."""
     cout, cin, kh, kw = w.shape
     ck = r64(cout)
-    offs = [(kh - 1 - r) * kw + (kw - 1 - s) for r in range(kh) for s in range(kw)]
-    return _pack(w, out, cin, cout, offs, kh * kw, cin * kh * kw, 0, ck, kh * kw * ck, False)
+    e = _native_of(w)
+    if e is not None:
+        # source tap (r, s) lands at rotated position (kh-1-r, kw-1-s) of the data-gradient filter
+        dst = [((kh - 1 - r) * kw + (kw - 1 - s)) * ck for r in range(kh) for s in range(kw)]
+        return _pack_transposed(w, e, out, cin, kh * kw * ck, dst)
+    s0, s1, s2, s3 = w.stride()
+    offs = [(kh - 1 - r) * s2 + (kw - 1 - s) * s3 for r in range(kh) for s in range(kw)]
+    return _pack(w, out, cin, cout, offs, s1, s0, 0, ck, kh * kw * ck, False)
 
 
 def _pack_s2dgrad(w, out=None):
@@ -152,14 +243,23 @@ def _pack_s2dgrad(w, out=None):
     cout, cin, kh, kw = w.shape
     assert kh == 4 and kw == 4
     ck = r64(cout)
+    s0, s1, s2, s3 = w.stride()
     rsel = {0: (1, 3), 1: (0, 2)}
+    e = _native_of(w)
+    if e is not None:
+        dst = [0] * 16
+        for ph in range(2):
+            for pw in range(2):
+                for j, (r, s_) in enumerate((r, s_) for r in rsel[ph] for s_ in rsel[pw]):
+                    dst[r * kw + s_] = (ph * 2 + pw) * cin * 4 * ck + j * ck
+        return _pack_transposed(w, e, out, 4 * cin, 4 * ck, dst)
     if out is None or tuple(out.shape) != (4 * cin, 4 * ck):
         out = torch.empty((4 * cin, 4 * ck), device=w.device, dtype=torch.bfloat16)
     i = 0
     for ph in range(2):
         for pw in range(2):
-            offs = [r * kw + s for r in rsel[ph] for s in rsel[pw]]
-            _pack(w, out[i * cin:(i + 1) * cin], cin, cout, offs, kh * kw, cin * kh * kw, 0, ck, 4 * ck, False)
+            offs = [r * s2 + s * s3 for r in rsel[ph] for s in rsel[pw]]
+            _pack(w, out[i * cin:(i + 1) * cin], cin, cout, offs, s1, s0, 0, ck, 4 * ck, False)
             i += 1
     return out
 
@@ -335,11 +435,18 @@ class _Conv2d(torch.autograd.Function):
             call("dm_colsum", _p(dy), lddy, _p(grad_buf(bias)), n * ho * wo, cout, st)
         # weight gradient: packed fp32 [Cout][taps][Cin_k], scattered (+=) into the NCHW parameter grad
         ck = _cols_k(cin, c0 if x1 is not None else 0)
-        offs = [r * kw + s for r in range(kh) for s in range(kw)]
-        unpack = (cout, cin, kh * kw, _taps(offs), cin * kh * kw, kh * kw, c0 if x1 is not None else 0, ck, kh * kw * ck, 0)
-        _wgrad_into(weight, (cout, kh * kw * ck), unpack, lambda dwp: call(
-            "dm_conv2d_wgrad", _p(x0), c0, x0.stride(2), _p(x1), c1, x1.stride(2) if x1 is not None else 0, _p(dy),
-            lddy, _p(dwp), n, hin, win, cout, kh, kw, stride, pad, st))
+
+        def run_wgrad(dwp):
+            call("dm_conv2d_wgrad", _p(x0), c0, x0.stride(2), _p(x1), c1, x1.stride(2) if x1 is not None else 0, _p(dy),
+                 lddy, _p(dwp), n, hin, win, cout, kh, kw, stride, pad, st)
+        gw = grad_buf(weight)
+        if ck == cin and _native_of(weight) is not None and tuple(gw.stride()) == native_strides(weight.shape):
+            run_wgrad(gw)                 # GEMM-native storage: param.grad's memory is the packed accumulator
+        else:
+            s0, s1, s2, s3 = gw.stride()
+            offs = [r * s2 + s * s3 for r in range(kh) for s in range(kw)]
+            unpack = (cout, cin, kh * kw, _taps(offs), s0, s1, c0 if x1 is not None else 0, ck, kh * kw * ck, 0)
+            _wgrad_into(weight, (cout, kh * kw * ck), unpack, run_wgrad)
         # data gradient
         dx0 = dx1 = None
         need0 = ctx.needs_input_grad[0]

@@ -23,7 +23,7 @@ class FusedAdamW(torch.optim.Optimizer):
     global-norm clipping folded into the update.  ``param_groups[0]['lr']`` stays schedulable."""
 
     def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=0.0,
-                 defer_weight_grads=True):
+                 defer_weight_grads=True, gemm_native_weights=True):
         params = [p for p in params if p.requires_grad]
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.max_grad_norm = float(max_grad_norm)
@@ -35,24 +35,38 @@ class FusedAdamW(torch.optim.Optimizer):
         off = 0
         for p in params:
             self._offsets.append(off)
-            off += (p.numel() + 3) // 4 * 4
+            off += (p.numel() + 7) // 8 * 8          # 16-byte aligned slots in the fp32 AND the bf16 shadow buffer (TMA)
         self._n = off
+        # Conv2d weights the GEMMs can use as stored (ops.wants_native): kept in [Cout][kh][kw][Cin] order inside the
+        # flat buffers; the parameter, its gradient and its state_dict entry are permuted views of that memory
+        self._native = [bool(gemm_native_weights and ops.wants_native(p)) for p in params]
         self.flat_param = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.flat_bf16 = torch.zeros(off, device=dev, dtype=torch.bfloat16) if any(self._native) else None
         self.flat_grad = torch.zeros(off, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(off, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(off, device=dev, dtype=torch.float32)
         self._gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
         self._step = 0
         with torch.no_grad():
-            for p, o in zip(params, self._offsets):
-                view = self.flat_param[o:o + p.numel()].view_as(p)
+            for p, o, nat in zip(params, self._offsets, self._native):
+                view = self._view(self.flat_param, o, p, nat)
                 view.copy_(p.data)
                 p.data = view
+                if nat:
+                    cout, cin, kh, kw = p.shape
+                    ops.register_native(p, self.flat_bf16[o:o + p.numel()].view(cout, kh * kw * cin))
         self._attach_grads()
         # conv weight gradients stay in the wgrad GEMM's packed layout across the accumulation window and
         # are scattered into the flat gradient once per step (see ops._PackedGrad)
         if defer_weight_grads:
             ops.defer_weight_grads(params)
+
+    @staticmethod
+    def _view(flat, o, p, native):
+        if native:
+            cout, cin, kh, kw = p.shape
+            return flat[o:o + p.numel()].view(cout, kh, kw, cin).permute(0, 3, 1, 2)
+        return flat[o:o + p.numel()].view_as(p)
 
     def flush(self):
         """Make ``p.grad`` (the flat gradient buffer) complete: scatter any packed weight gradients."""
@@ -60,8 +74,8 @@ class FusedAdamW(torch.optim.Optimizer):
         ops.flush_weight_grads()
 
     def _attach_grads(self):
-        for p, o in zip(self._params, self._offsets):
-            gv = self.flat_grad[o:o + p.numel()].view_as(p)
+        for p, o, nat in zip(self._params, self._offsets, self._native):
+            gv = self._view(self.flat_grad, o, p, nat)
             if p.grad is None or p.grad.data_ptr() != gv.data_ptr():
                 if p.grad is not None:
                     gv.copy_(p.grad)
@@ -92,8 +106,14 @@ class FusedAdamW(torch.optim.Optimizer):
             self._gnorm_sq.zero_()
             ops.call("dm_sumsq", _p(self.flat_grad), self._n, _p(self._gnorm_sq), st)
             gn = _p(self._gnorm_sq)
-        ops.call("dm_adamw", _p(self.flat_param), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq), self._n,
-             float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
-             1.0 - b1 ** self._step, 1.0 - b2 ** self._step, gn, self.max_grad_norm, st)
+        hyper = (float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
+                 1.0 - b1 ** self._step, 1.0 - b2 ** self._step, gn, self.max_grad_norm, st)
+        if self.flat_bf16 is not None:
+            ops.call("dm_adamw_bf16", _p(self.flat_param), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq),
+                     _p(self.flat_bf16), self._n, *hyper)
+        else:
+            ops.call("dm_adamw", _p(self.flat_param), _p(self.flat_grad), _p(self.exp_avg), _p(self.exp_avg_sq), self._n,
+                     *hyper)
         ops.bump_weights_epoch()
+        ops.natives_fresh()
         ops.refresh_weight_packs()

@@ -40,6 +40,9 @@ def broadcast_parameters(flat_param: torch.Tensor, buffers=()):
     dist.broadcast(flat_param, 0)
     for b in buffers:
         dist.broadcast(b, 0)
+    if flat_param.is_cuda:                       # parameters changed behind the weight-pack caches' back
+        from . import ops
+        ops.bump_weights_epoch()
 
 
 def allreduce_mean_(flat_grad: torch.Tensor, bucket_elems: int = 0):

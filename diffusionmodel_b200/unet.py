@@ -299,6 +299,7 @@ class ContextUnet(nn.Module):
         self.local_enhance = LocalEnhancer(f)
         self.out = nn.Sequential(nn.Conv2d(2 * f, f, 3, 1, 1), nn.GroupNorm(8, f), nn.ReLU(),
                                  nn.Conv2d(f, self.in_ch, 3, 1, 1))
+        ops.mark_conv2d_weights(self)
 
     def encode(self, x):
         """Everything that does not depend on (c, t, ctx_mask): init_conv ... down4, CoordAttn, to_vec, up0
@@ -417,6 +418,7 @@ class MnistContextUnet(nn.Module):
         self.up2 = MnistUnetUp(2 * f, f)
         self.out = nn.Sequential(nn.Conv2d(2 * f, f, 3, 1, 1), nn.GroupNorm(8, f), nn.ReLU(),
                                  nn.Conv2d(f, self.in_channels, 3, 1, 1))
+        ops.mark_conv2d_weights(self)
 
     @property
     def in_ch(self):

@@ -62,6 +62,11 @@ int dm_pack_weight(const float* w, void* out, int rows, int cols, int ntaps, con
                    int tap_major_rows, void* stream);
 /* inverse scatter: grad[...] += dwp[...] with the same addressing (fp32 -> fp32); consume != 0 also
  * re-zeroes the packed accumulator (persistent per-parameter accumulators, flushed once per optimizer step) */
+/* data-gradient packs of a weight whose bf16 forward pack is [Cout][ntaps][Cin]: per tap a tiled transpose to
+ * dst[ci*dst_pitch + dst_off[tap] + co], co < ceil64(Cout) (zeros beyond Cout); replaces the strided gather of
+ * dm_pack_weight for weights stored GEMM-natively by the optimizer */
+int dm_pack_transpose(const void* src, void* dst, int cout, int cin, int ntaps, const long long* dst_off,
+                      long long dst_pitch, void* stream);
 int dm_unpack_wgrad(float* dwp, float* grad, int rows, int cols, int ntaps, const long long* tap_off_host,
                     long long s_row, long long s_col, int c_split, int cols_k, long long row_len,
                     int tap_major_rows, int consume, void* stream);
@@ -181,6 +186,11 @@ int dm_cfg_reverse_step_dev(const float* eps, int ldp, const float* x, const flo
 int dm_sumsq(const float* g, long long n, float* out, void* stream);          /* *out += sum g^2 */
 int dm_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
              float eps, float wd, float bc1, float bc2, const float* gnorm_sq, float max_norm, void* stream);
+/* dm_adamw that also writes a bf16 copy of the updated parameters (the forward weight pack of convolution weights
+ * the optimizer stores in [Cout][tap][Cin] order); n % 4 == 0. */
+int dm_adamw_bf16(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                  float beta2, float eps, float wd, float bc1, float bc2, const float* gnorm_sq, float max_norm,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -272,3 +272,57 @@ def test_state_dict_roundtrip_and_fail_loudly(dev):
     ddpm2.load_state_dict(sd)
     with pytest.raises(DmB200Error):
         net(torch.zeros(1, 3, 128, 128), torch.zeros(1, dtype=torch.long), torch.ones(1), torch.ones(1))
+
+
+def test_gemm_native_weight_storage(dev):
+    """FusedAdamW stores Conv2d weights with Cin % 64 == 0 in the GEMM's [Cout][kh][kw][Cin] order (permuted views:
+    same names, shapes and values), so wgrad accumulates straight into ``.grad`` and the optimizer's bf16 shadow is
+    the forward pack.  Two optimizer steps (eval-mode norms: deterministic forward) must match the plain layout:
+    gradients, updated parameters, the packs used by the next forward, and a state_dict round trip."""
+    import diffusionmodel_b200 as D
+    from diffusionmodel_b200 import ops
+    inp = make_inputs("rdd", 1, 3, 128, 5, 700, 5)
+    x, c, attn, ts, noise, ctx = (inp[k].to(dev) for k in ("x", "c", "attn_mask", "ts", "noise", "ctx_mask"))
+    outs = []
+    for native in (False, True):
+        ddpm, _ = build("rdd", 64, 5, 700, 5, dev, enhance_with_attn_map=True)
+        ddpm.eval()
+        opt = D.FusedAdamW(ddpm.parameters(), lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0, gemm_native_weights=native)
+        n_native = sum(opt._native)
+        assert (n_native > 20) == native
+        losses, g_first = [], None
+        for _ in range(2):
+            lo = ddpm(x, c, attn, randoms=(ts, noise, ctx))
+            lo.backward()
+            losses.append(float(lo))
+            opt.flush()
+            if g_first is None:
+                g_first = grads_of(ddpm)
+            opt.step()
+            opt.zero_grad()
+        sd = {k: v.detach().cpu().clone() for k, v in ddpm.state_dict().items()}
+        outs.append((losses, g_first, sd))
+        if native:
+            w = ddpm.nn_model.down1.down[0].weight
+            assert not w.is_contiguous() and tuple(w.stride()) == ops.native_strides(w.shape)
+            idx = [i for i, q in enumerate(opt._params) if q is w][0]
+            assert w.grad.data_ptr() == opt.flat_grad.data_ptr() + 4 * opt._offsets[idx]
+            # a reference-layout checkpoint loads into the permuted storage and comes back unchanged
+            with torch.no_grad():
+                l_before = float(ddpm(x, c, attn, randoms=(ts, noise, ctx)))
+                ddpm.load_state_dict({k: v.clone() for k, v in outs[0][2].items()})      # the plain run's weights
+                l_other = float(ddpm(x, c, attn, randoms=(ts, noise, ctx)))
+                ddpm.load_state_dict({k: v.clone() for k, v in sd.items()})
+                back = ddpm.state_dict()
+                assert all(torch.equal(back[k].cpu(), sd[k]) for k in sd)
+                l_after = float(ddpm(x, c, attn, randoms=(ts, noise, ctx)))
+            assert l_after == pytest.approx(l_before, rel=1e-5) and l_other == pytest.approx(l_before, rel=5e-3)
+    (l0, g0, s0), (l1, g1, s1) = outs
+    print(f"plain losses {l0}  native losses {l1}")
+    assert abs(l0[0] - l1[0]) < 1e-5 * abs(l0[0]) and abs(l0[1] - l1[1]) < 2e-3 * abs(l0[1])
+    for k in g0:
+        assert g0[k].shape == g1[k].shape
+        assert P.rel_l2(g1[k], g0[k]) < 1e-4 or float(g0[k].abs().max()) < 1e-7, k
+    for k in s0:
+        if s0[k].is_floating_point():
+            assert P.rel_l2(s1[k], s0[k]) < 1e-3, k
