@@ -301,17 +301,21 @@ __global__ void __launch_bounds__(256) adamw_bf16_kernel(float4* p, const float4
 struct TransArgs { long long dst_off[16]; };
 __global__ void __launch_bounds__(256) pack_transpose_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int cout,
                                                               int cin, int ntaps, long long dst_pitch, TransArgs A) {
-  __shared__ bf16 tile[64][66];
+  // cin is a multiple of 64 (GEMM-native weights) and dst rows are ceil64(cout) wide: 4-byte accesses throughout
+  __shared__ __align__(4) bf16 tile[64][66];
   const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64, tap = blockIdx.z;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  for (int r = ty; r < 64; r += 4) {
-    const int co = co0 + r, ci = ci0 + tx;
-    tile[r][tx] = (co < cout && ci < cin) ? src[((long long)co * ntaps + tap) * cin + ci] : __float2bfloat16(0.f);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 64; r += 8) {
+    const int co = co0 + r;
+    uint32_t v = 0u;
+    if (co < cout) v = *reinterpret_cast<const uint32_t*>(src + ((long long)co * ntaps + tap) * cin + ci0 + 2 * tx);
+    *reinterpret_cast<uint32_t*>(&tile[r][2 * tx]) = v;
   }
   __syncthreads();
-  for (int r = ty; r < 64; r += 4) {
-    const int ci = ci0 + r;
-    if (ci < cin) dst[(long long)ci * dst_pitch + A.dst_off[tap] + co0 + tx] = tile[tx][r];
+  const unsigned short* t16 = reinterpret_cast<const unsigned short*>(&tile[0][0]);
+  for (int r = ty; r < 64; r += 8) {
+    const uint32_t lo = t16[(2 * tx) * 66 + r], hi = t16[(2 * tx + 1) * 66 + r];
+    *reinterpret_cast<uint32_t*>(dst + (long long)(ci0 + r) * dst_pitch + A.dst_off[tap] + co0 + 2 * tx) = lo | (hi << 16);
   }
 }
 
@@ -446,7 +450,8 @@ extern "C" int dm_pack_transpose(const void* src, void* dst, int cout, int cin, 
   if (ntaps < 1 || ntaps > 16) { dm_set_error("dm_pack_transpose: 1..16 taps"); return DM_ERR_ARG; }
   TransArgs A;
   for (int i = 0; i < 16; ++i) A.dst_off[i] = i < ntaps ? dst_off_host[i] : 0;
-  dim3 grid(dm::cdiv(cin, 64), dm::cdiv(cout, 64), ntaps);
+  if (cin % 64) { dm_set_error("dm_pack_transpose: Cin must be a multiple of 64"); return DM_ERR_ARG; }
+  dim3 grid(cin / 64, dm::cdiv(cout, 64), ntaps);
   pack_transpose_kernel<<<grid, 256, 0, ST>>>((const bf16*)src, (bf16*)dst, cout, cin, ntaps, dst_pitch, A);
   DM_CHECK_LAUNCH();
   return DM_OK;

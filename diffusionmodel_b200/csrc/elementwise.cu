@@ -173,38 +173,38 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(RedArgs A) {
 __global__ void __launch_bounds__(1024) reduce_finalize_kernel(const float* __restrict__ part, int splits, int groups, int C,
                                                                 float scale, float* __restrict__ out1, float* __restrict__ out2,
                                                                 int accumulate) {
-  __shared__ float sa[32][33], sb[32][33];
-  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  __shared__ float sa[64][17], sb[64][17];
+  const int cl = threadIdx.x & 15, sl = threadIdx.x >> 4;          // 16 outputs x 64 row slices
   const long long total = (long long)groups * C;
-  const long long i = (long long)blockIdx.x * 32 + cl;
+  const long long i = (long long)blockIdx.x * 16 + cl;
   float a = 0.f, b = 0.f;
   if (i < total) {
     const long long g = i / C; const int c = (int)(i - g * C);
     const float* base = part + g * 2 * C + c;
     const long long stride = (long long)groups * 2 * C;
-    for (int sp = sl; sp < splits; sp += 128) {
-      float x[4], y[4];
+    for (int sp = sl; sp < splits; sp += 512) {
+      float x[8], y[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int s = sp + 32 * u;
+      for (int u = 0; u < 8; ++u) {
+        const int s = sp + 64 * u;
         const bool ok = s < splits;
         const float* row = base + (long long)(ok ? s : sp) * stride;
         x[u] = ok ? __ldg(row) : 0.f;
         y[u] = (ok && out2) ? __ldg(row + C) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { a += x[u]; b += y[u]; }
+      for (int u = 0; u < 8; ++u) { a += x[u]; b += y[u]; }
     }
   }
   sa[sl][cl] = a; sb[sl][cl] = b;
   __syncthreads();
   if (sl == 0 && i < total) {
-    for (int k = 1; k < 32; ++k) { a += sa[k][cl]; b += sb[k][cl]; }
+    for (int k = 1; k < 64; ++k) { a += sa[k][cl]; b += sb[k][cl]; }
     if (accumulate) { out1[i] += a * scale; if (out2) out2[i] += b * scale; }
     else { out1[i] = a * scale; if (out2) out2[i] = b * scale; }
   }
 }
-static inline int finalize_grid(long long total) { return (int)((total + 31) / 32); }
+static inline int finalize_grid(long long total) { return (int)((total + 15) / 16); }
 
 float* g_ws = nullptr;          // caller-provided scratch for partial sums (dm_set_workspace)
 long long g_ws_floats = 0;
@@ -363,28 +363,37 @@ int zero_f32(float* p, long long n, cudaStream_t st) {
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* partials, int m_tiles, int ld, int C, double count,
                                                             float* mean, float* invstd, float* rmean, float* rvar,
                                                             float momentum, float eps, const float* conv_bias) {
-  __shared__ double s1[32][33], s2[32][33];
-  const int cl = threadIdx.x & 31, rr = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  // 16 channels x 64 row slices per block, eight partial rows' loads in flight per thread: the kernel is a chain of
+  // dependent round trips to L2/DRAM otherwise (13 us for 592 rows in the 32-slice, 4-row version)
+  __shared__ double s1[64][17], s2[64][17];
+  const int cl = threadIdx.x & 15, rr = threadIdx.x >> 4;
+  const int c = blockIdx.x * 16 + cl;
   double a = 0.0, b = 0.0;
   if (c < C)
-    for (int t = rr; t < m_tiles; t += 128) {          // four rows' loads in flight per thread
-      float x[4], y[4];
+    for (int t = rr; t < m_tiles; t += 512) {
+      float x[8], y[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int tt = t + 32 * u;
+      for (int u = 0; u < 8; ++u) {
+        const int tt = t + 64 * u;
         const bool ok = tt < m_tiles;
         const float* row = partials + (long long)(ok ? tt : t) * 2 * ld;
         x[u] = ok ? __ldg(row + c) : 0.f; y[u] = ok ? __ldg(row + ld + c) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { a += (double)x[u]; b += (double)y[u]; }
+      for (int u = 0; u < 8; ++u) { a += (double)x[u]; b += (double)y[u]; }
     }
   s1[rr][cl] = a; s2[rr][cl] = b;
   __syncthreads();
+  if (rr < 8) {                                   // two-level fixed-order combine: 8 slices each, then 8 partials
+    a = 0.0; b = 0.0;
+    for (int k = 0; k < 8; ++k) { a += s1[rr * 8 + k][cl]; b += s2[rr * 8 + k][cl]; }
+  }
+  __syncthreads();
+  if (rr < 8) { s1[rr][cl] = a; s2[rr][cl] = b; }
+  __syncthreads();
   if (rr == 0 && c < C) {
     if (m_tiles > 0) {
-      for (int k = 1; k < 32; ++k) { a += s1[k][cl]; b += s2[k][cl]; }
+      for (int k = 1; k < 8; ++k) { a += s1[k][cl]; b += s2[k][cl]; }
       const double mu = a / count;
       double var = b / count - mu * mu;
       if (var < 0.0) var = 0.0;
@@ -574,29 +583,29 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 const float* __restrict__ gamma, float* __restrict__ coef,
                                                                 float* dgamma, float* dbeta, float* dbias, int training) {
-  __shared__ float sh[2][32][33];
-  const int cl = threadIdx.x & 31, rr = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  __shared__ float sh[2][64][17];
+  const int cl = threadIdx.x & 15, rr = threadIdx.x >> 4;          // 16 channels x 64 row slices, see bn_finalize_kernel
+  const int c = blockIdx.x * 16 + cl;
   float f0 = 0.f, f1 = 0.f;
   if (c < C) {
-    for (int t = rr; t < nblk; t += 128) {
-      float x0[4], x1[4];
+    for (int t = rr; t < nblk; t += 512) {
+      float x0[8], x1[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int tt = t + 32 * u;
+      for (int u = 0; u < 8; ++u) {
+        const int tt = t + 64 * u;
         const bool ok = tt < nblk;
         const float* g = part + (long long)(ok ? tt : t) * 2 * C;
         x0[u] = ok ? __ldg(g + c) : 0.f; x1[u] = ok ? __ldg(g + C + c) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { f0 += x0[u]; f1 += x1[u]; }
+      for (int u = 0; u < 8; ++u) { f0 += x0[u]; f1 += x1[u]; }
     }
   }
   sh[0][rr][cl] = f0; sh[1][rr][cl] = f1;
   __syncthreads();
   if (rr == 0 && c < C) {
     double sg = 0.0, sgy = 0.0;
-    for (int k = 0; k < 32; ++k) { sg += (double)sh[0][k][cl]; sgy += (double)sh[1][k][cl]; }
+    for (int k = 0; k < 64; ++k) { sg += (double)sh[0][k][cl]; sgy += (double)sh[1][k][cl]; }
     const double a = (double)invstd[c], b = -(double)mean[c] * a, ga = (double)gamma[c];
     const double sgx = a * sgy + b * sg;          // sum g*xhat
     const double k0 = ga * a;
@@ -1354,7 +1363,7 @@ extern "C" int dm_space_to_depth(const void* x, int ldx, void* y, int ldy, int N
 extern "C" int dm_bn_finalize(const float* partials, int m_tiles, int ld, int C, double count, float* mean, float* invstd,
                               float* running_mean, float* running_var, float momentum, float eps, const float* conv_bias,
                               void* stream) {
-  bn_finalize_kernel<<<dm::cdiv(C, 32), 1024, 0, ST>>>(partials, m_tiles, ld, C, count, mean, invstd, running_mean,
+  bn_finalize_kernel<<<dm::cdiv(C, 16), 1024, 0, ST>>>(partials, m_tiles, ld, C, count, mean, invstd, running_mean,
                                                        running_var, momentum, eps, conv_bias);
   DM_CHECK_LAUNCH();
   return DM_OK;
@@ -1414,7 +1423,7 @@ extern "C" int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, c
   if (act == 1) BN_RED(1); else if (act == 2) BN_RED(2); else BN_RED(0);
 #undef BN_RED
   DM_CHECK_LAUNCH();
-  bn_bwd_finalize_kernel<<<dm::cdiv(C, 32), 1024, 0, ST>>>(part, nblk, C, (double)P, mean, invstd, gamma, coef, dgamma, dbeta,
+  bn_bwd_finalize_kernel<<<dm::cdiv(C, 16), 1024, 0, ST>>>(part, nblk, C, (double)P, mean, invstd, gamma, coef, dgamma, dbeta,
                                                          dbias, training);
   DM_CHECK_LAUNCH();
   dim3 grid2(chan_grid_x(P, m, 4), m.cvt);

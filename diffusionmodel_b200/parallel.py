@@ -52,14 +52,18 @@ def allreduce_mean_(flat_grad: torch.Tensor, bucket_elems: int = 0):
     n = world_size()
     if n == 1:
         return flat_grad
+    # NCCL averages inside the collective (no extra 2.8 GB scaling pass over the gradient); gloo only sums
+    avg = dist.get_backend() == "nccl"
+    op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
     if bucket_elems and bucket_elems < flat_grad.numel():
-        works = [dist.all_reduce(flat_grad[o:o + bucket_elems], op=dist.ReduceOp.SUM, async_op=True)
+        works = [dist.all_reduce(flat_grad[o:o + bucket_elems], op=op, async_op=True)
                  for o in range(0, flat_grad.numel(), bucket_elems)]
         for w in works:
             w.wait()
     else:
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
-    flat_grad.mul_(1.0 / n)
+        dist.all_reduce(flat_grad, op=op)
+    if not avg:
+        flat_grad.mul_(1.0 / n)
     return flat_grad
 
 

@@ -323,6 +323,8 @@ def test_gemm_native_weight_storage(dev):
     for k in g0:
         assert g0[k].shape == g1[k].shape
         assert P.rel_l2(g1[k], g0[k]) < 1e-4 or float(g0[k].abs().max()) < 1e-7, k
+    # parameters after two Adam steps: the first update is lr*sign(g), so reduction-order noise on near-zero gradient
+    # entries flips individual updates (2*lr each); the gradients above are the tight check
     for k in s0:
         if s0[k].is_floating_point():
-            assert P.rel_l2(s1[k], s0[k]) < 1e-3, k
+            assert P.rel_l2(s1[k], s0[k]) < 1e-2, k
