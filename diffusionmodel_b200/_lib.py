@@ -96,6 +96,9 @@ _SIGS = {
     "dm_ddpm_loss_bwd": "pi p p p pi iiii ffffff p",
     "dm_cfg_reverse_step": "pi p p p pi ffff iiii p",
     "dm_cfg_reverse_step_dev": "pi p p p pi p iiii p",
+    "dm_ca_gates_rows_per_block": "",
+    "dm_ca_gates_fwd": "p p",
+    "dm_ca_gates_bwd": "p p p",
     "dm_sumsq": "p l p p",
     "dm_pack_transpose": "pp iii p l p",
     "dm_adamw": "pppp l fffffff p f p",

@@ -205,6 +205,28 @@ __global__ void __launch_bounds__(1024) reduce_finalize_kernel(const float* __re
   }
 }
 static inline int finalize_grid(long long total) { return (int)((total + 15) / 16); }
+// few partial rows (<= 8) but possibly many outputs (CoordAttn row / column means): one thread per output
+__global__ void __launch_bounds__(256) reduce_finalize_small_kernel(const float* __restrict__ part, int splits, long long total,
+                                                                     int C, float scale, float* __restrict__ out1,
+                                                                     float* __restrict__ out2, int accumulate) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const long long g = i / C; const int c = (int)(i - g * C);
+  const float* base = part + g * 2 * C + c;
+  const long long stride = (total / C) * 2 * C;
+  float x[8], y[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const bool ok = u < splits;
+    x[u] = ok ? __ldg(base + u * stride) : 0.f;
+    y[u] = (ok && out2) ? __ldg(base + u * stride + C) : 0.f;
+  }
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { a += x[u]; b += y[u]; }
+  if (accumulate) { out1[i] += a * scale; if (out2) out2[i] += b * scale; }
+  else { out1[i] = a * scale; if (out2) out2[i] = b * scale; }
+}
 
 float* g_ws = nullptr;          // caller-provided scratch for partial sums (dm_set_workspace)
 long long g_ws_floats = 0;
@@ -230,7 +252,10 @@ int launch_reduce(RedArgs& A, int groups, cudaStream_t st) {
   DM_CHECK_LAUNCH();
   if (splits > 1) {
     const long long total = (long long)groups * A.C;
-    reduce_finalize_kernel<<<finalize_grid(total), 1024, 0, st>>>(g_ws, splits, groups, A.C, A.scale, A.out1, A.out2, 0);
+    if (splits <= 8)
+      reduce_finalize_small_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(g_ws, splits, total, A.C, A.scale, A.out1, A.out2, 0);
+    else
+      reduce_finalize_kernel<<<finalize_grid(total), 1024, 0, st>>>(g_ws, splits, groups, A.C, A.scale, A.out1, A.out2, 0);
     DM_CHECK_LAUNCH();
   }
   return DM_OK;

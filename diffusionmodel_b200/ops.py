@@ -844,7 +844,106 @@ class _CoordAttn(torch.autograd.Function):
         return (dx, None, None) + (None,) * len(params)
 
 
-def coord_attn(x, c, gates, params):
+class _CaGatesC(ctypes.Structure):
+    """DmCaGates (include/dm_b200.h)."""
+    _PTRS = ("xh xw w1_h w1_w b1_h b1_w bn_g_h bn_g_w bn_b_h bn_b_w bn_rm_h bn_rm_w bn_rv_h bn_rv_w wp_h2w wp_w2h "
+             "bp_h2w bp_w2h wc_h wc_w bc_h bc_w gamma_h gamma_w alpha beta u part stat t ah aw").split()
+    _fields_ = [(k, ctypes.c_void_p) for k in _PTRS] + [(k, ctypes.c_int) for k in ("R", "C", "m", "nblk", "training")] + [
+        ("eps", ctypes.c_float), ("momentum", ctypes.c_float)]
+
+
+class _CaGatesGradC(ctypes.Structure):
+    """DmCaGatesGrad (include/dm_b200.h)."""
+    _PTRS = ("d_ah d_aw d_xh d_xw dh dt du dz part scal g_w1_h g_w1_w g_b1_h g_b1_w g_bn_g_h g_bn_g_w g_bn_b_h g_bn_b_w g_wp_h2w "
+             "g_wp_w2h g_bp_h2w g_bp_w2h g_wc_h g_wc_w g_bc_h g_bc_w g_gamma_h g_gamma_w g_alpha g_beta").split()
+    _fields_ = [(k, ctypes.c_void_p) for k in _PTRS]
+
+
+def _ca_param_map(mod):
+    """struct field stem -> parameter of a unet.CoordAttn module."""
+    return {"w1_h": mod.conv1_h.weight, "w1_w": mod.conv1_w.weight, "b1_h": mod.conv1_h.bias, "b1_w": mod.conv1_w.bias,
+            "bn_g_h": mod.bn1_h.weight, "bn_g_w": mod.bn1_w.weight, "bn_b_h": mod.bn1_h.bias, "bn_b_w": mod.bn1_w.bias,
+            "wp_h2w": mod.h2w_proj.weight, "wp_w2h": mod.w2h_proj.weight, "bp_h2w": mod.h2w_proj.bias,
+            "bp_w2h": mod.w2h_proj.bias, "wc_h": mod.conv_h.weight, "wc_w": mod.conv_w.weight, "bc_h": mod.conv_h.bias,
+            "bc_w": mod.conv_w.bias, "gamma_h": mod.gamma_h, "gamma_w": mod.gamma_w, "alpha": mod.alpha, "beta": mod.beta}
+
+
+class _CoordAttnFused(torch.autograd.Function):
+    """Same operator with the gate network on the dm_ca_gates kernels (H == W): 2 + 7 launches per call instead of
+    ~90 tiny library kernels."""
+
+    @staticmethod
+    def forward(ctx, x, c, mod, *params):
+        ldx = _chk(x, "coordattn input")
+        n, h, w, _ = x.shape
+        st = _stream()
+        dev = x.device
+        m, r = mod.conv1_h.weight.shape[0], n * h
+        f32 = dict(device=dev, dtype=torch.float32)
+        xh, xw = torch.empty((n, h, c), **f32), torch.empty((n, w, c), **f32)
+        call("dm_ca_pool", _p(x), ldx, None, 0, _p(xh), _p(xw), n, h, w, c, 1.0 / w, 1.0 / h, st)
+        nblk = -(-r // _lib.fn("dm_ca_gates_rows_per_block")())
+        training = mod.bn1_h.training
+        work = {"u": torch.empty((2, r, m), **f32), "part": torch.empty((nblk, 2, 2, m), **f32),
+                "stat": torch.empty((2, 2, m), **f32), "t": torch.empty((2, r, m), **f32),
+                "ah": torch.empty((n, h, c), **f32), "aw": torch.empty((n, w, c), **f32), "xh": xh, "xw": xw}
+        pm = _ca_param_map(mod)
+        for k, v in pm.items():
+            if v.dtype != torch.float32 or not v.is_contiguous():
+                raise _lib.DmB200Error(f"CoordAttn parameter {k}: expected contiguous fp32")
+        S = _CaGatesC()
+        for k, v in {**pm, **work, "bn_rm_h": mod.bn1_h.running_mean, "bn_rm_w": mod.bn1_w.running_mean,
+                     "bn_rv_h": mod.bn1_h.running_var, "bn_rv_w": mod.bn1_w.running_var}.items():
+            setattr(S, k, v.data_ptr())
+        S.R, S.C, S.m, S.nblk, S.training = r, c, m, nblk, int(training)
+        S.eps, S.momentum = float(mod.bn1_h.eps), float(mod.bn1_h.momentum)
+        if training:
+            bump_bn_stats_epoch()
+            if not _counters_batched:
+                torch._foreach_add_([mod.bn1_h.num_batches_tracked, mod.bn1_w.num_batches_tracked], 1)
+        call("dm_ca_gates_fwd", ctypes.addressof(S), st)
+        out = torch.empty_like(x)
+        call("dm_ca_gate_fwd", _p(x), ldx, _p(work["ah"]), _p(work["aw"]), _p(out), out.stride(2), n, h, w, c, st)
+        ctx.save_for_backward(x)
+        ctx.ca = (c, mod, S, work, pm)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        c, mod, S, work, pm = ctx.ca
+        lddo = _chk(dout, "coordattn grad")
+        n, h, w, _ = x.shape
+        st = _stream()
+        f32 = dict(device=x.device, dtype=torch.float32)
+        dah, daw = torch.empty((n, h, c), **f32), torch.empty((n, w, c), **f32)
+        call("dm_ca_pool", _p(dout), lddo, _p(x), x.stride(2), _p(dah), _p(daw), n, h, w, c, 1.0, 1.0, st)
+        scal = mod.__dict__.get("_dm_ca_scal")
+        if scal is None or scal.device != x.device:
+            scal = mod.__dict__["_dm_ca_scal"] = torch.zeros(4, **f32)      # the backward kernels re-arm it
+        G = _CaGatesGradC()
+        tmp = {"d_ah": dah, "d_aw": daw, "d_xh": torch.empty((n, h, c), **f32), "d_xw": torch.empty((n, w, c), **f32),
+               "dh": torch.empty_like(work["u"]), "dt": torch.empty_like(work["u"]), "du": torch.empty_like(work["u"]),
+               "dz": torch.empty((2, n * h, c), **f32),
+               "part": torch.empty_like(work["part"]), "scal": scal}
+        for k, v in tmp.items():
+            setattr(G, k, v.data_ptr())
+        for k, v in pm.items():
+            setattr(G, "g_" + k, grad_buf(v).data_ptr())
+        call("dm_ca_gates_bwd", ctypes.addressof(S), ctypes.addressof(G), st)
+        dx = torch.empty_like(x)
+        call("dm_ca_gate_bwd", _p(dout), lddo, _p(work["ah"]), _p(work["aw"]), _p(tmp["d_xh"]), _p(tmp["d_xw"]), _p(dx),
+             dx.stride(2), n, h, w, c, st)
+        return (dx, None, None) + (None,) * len(pm)
+
+
+FUSED_CA_GATES = True         # False: the gate network as a torch sub-graph (the fallback for H != W)
+
+
+def coord_attn(x, c, gates, params, mod=None):
+    if FUSED_CA_GATES and mod is not None and x.shape[1] == x.shape[2]:
+        pm = _ca_param_map(mod)
+        return _CoordAttnFused.apply(x, c, mod, *pm.values())
     return _CoordAttn.apply(x, c, gates, *params)
 
 

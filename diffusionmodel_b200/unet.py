@@ -139,7 +139,6 @@ class CoordAttn(nn.Module):
         self.conv1_w = nn.Conv2d(channel, mid, kernel_size=1)
         self.bn1_h = nn.BatchNorm2d(mid)
         self.bn1_w = nn.BatchNorm2d(mid)
-        self.bn1_h._dm_counts_itself = self.bn1_w._dm_counts_itself = True     # advanced in _bn below
         self.act = nn.GELU()
         self.h2w_proj = nn.Conv2d(mid, mid, kernel_size=1)
         self.w2h_proj = nn.Conv2d(mid, mid, kernel_size=1)
@@ -159,7 +158,7 @@ class CoordAttn(nn.Module):
         shp = v.shape
         out = F.batch_norm(v.reshape(-1, shp[-1]), bn.running_mean, bn.running_var, bn.weight, bn.bias,
                            bn.training, bn.momentum, bn.eps)
-        if bn.training:
+        if bn.training and not ops._counters_batched:
             bn.num_batches_tracked.add_(1)
         return out.reshape(shp)
 
@@ -183,7 +182,7 @@ class CoordAttn(nn.Module):
 
     def forward(self, x):
         params = [p for p in self.parameters()]
-        return ops.coord_attn(x, self.channel, self._gates, params)
+        return ops.coord_attn(x, self.channel, self._gates, params, mod=self)
 
 
 class LocalEnhancer(nn.Module):

@@ -182,6 +182,39 @@ int dm_cfg_reverse_step(const float* eps, int ldp, const float* x, const float* 
 int dm_cfg_reverse_step_dev(const float* eps, int ldp, const float* x, const float* z, float* x_out, void* xt_next,
                             int ldo, const float* coef4, int n, int C, int H, int W, void* stream);
 
+/* ---- CoordAttn gate network (new_scripy.py:97-140): everything between the directional pooling and the gating pass,
+ * forward in two launches and backward in six (+ one memset).  R = N*L rows per direction (H == W == L), C channels, m = C/16.
+ * All tensors fp32 and contiguous: xh/xw/ah/aw [R][C]; conv1_* weight [m][C]; h2w/w2h projections [m][m]; conv_h/conv_w
+ * weight [C][m]; u/t/dh [2][R][m]; part [nblk][2][2][m] with nblk = ceil(R / dm_ca_gates_rows_per_block()); stat [2][2][m]
+ * (mean, rstd per direction: written by the forward, read by the backward).  training != 0: batch statistics and the
+ * running-statistics update of both BatchNorms (momentum, unbiased variance); 0: running statistics. */
+typedef struct DmCaGates {
+  const float *xh, *xw;
+  const float *w1_h, *w1_w, *b1_h, *b1_w;
+  const float *bn_g_h, *bn_g_w, *bn_b_h, *bn_b_w;
+  float *bn_rm_h, *bn_rm_w, *bn_rv_h, *bn_rv_w;
+  const float *wp_h2w, *wp_w2h, *bp_h2w, *bp_w2h;
+  const float *wc_h, *wc_w, *bc_h, *bc_w;
+  const float *gamma_h, *gamma_w, *alpha, *beta;
+  float *u, *part, *stat, *t, *ah, *aw;
+  int R, C, m, nblk, training;
+  float eps, momentum;
+} DmCaGates;
+/* gradients: d_ah/d_aw in, d_xh/d_xw out, g_* accumulated (+=) with fp32 atomics; scal = 4 zero-initialised floats the
+ * backward re-arms itself; part as in the forward (separate buffer) */
+typedef struct DmCaGatesGrad {
+  const float *d_ah, *d_aw;
+  float *d_xh, *d_xw, *dh, *dt, *du, *dz, *part, *scal;          /* dh, dt, du [2][R][m], dz [2][R][C]: work buffers */
+  float *g_w1_h, *g_w1_w, *g_b1_h, *g_b1_w;
+  float *g_bn_g_h, *g_bn_g_w, *g_bn_b_h, *g_bn_b_w;
+  float *g_wp_h2w, *g_wp_w2h, *g_bp_h2w, *g_bp_w2h;
+  float *g_wc_h, *g_wc_w, *g_bc_h, *g_bc_w;
+  float *g_gamma_h, *g_gamma_w, *g_alpha, *g_beta;
+} DmCaGatesGrad;
+int dm_ca_gates_rows_per_block(void);
+int dm_ca_gates_fwd(const DmCaGates* p, void* stream);
+int dm_ca_gates_bwd(const DmCaGates* p, const DmCaGatesGrad* q, void* stream);
+
 /* ---- optimizer side (new_scripy.py:797-803) --------------------------------------------------------- */
 int dm_sumsq(const float* g, long long n, float* out, void* stream);          /* *out += sum g^2 */
 int dm_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

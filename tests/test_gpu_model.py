@@ -328,3 +328,44 @@ def test_gemm_native_weight_storage(dev):
     for k in s0:
         if s0[k].is_floating_point():
             assert P.rel_l2(s1[k], s0[k]) < 1e-2, k
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("shape", [(4, 192, 16), (2, 64, 12), (3, 32, 7)])
+def test_coordattn_fused_gates_match_torch_subgraph(dev, shape, training):
+    """dm_ca_gates_fwd/bwd (the CoordAttn gate network as five kernels) against the same network run as a torch
+    fp32 sub-graph with autograd: output, dx, every parameter gradient, BatchNorm running statistics + counters."""
+    import copy
+    from diffusionmodel_b200 import ops, unet as U
+    from tests.test_gpu_kernels import bf, nhwc
+    n, c, s = shape
+    g = torch.Generator().manual_seed(5)
+    base = U.CoordAttn(c)
+    sd = {k: v.clone() for k, v in base.state_dict().items()}
+    fill_state_dict_(sd, 9)
+    for k in ("gamma_h", "gamma_w", "alpha", "beta"):
+        sd[k] = torch.randn(1, generator=g) * 0.7
+    base.load_state_dict(sd)
+    x = bf(torch.randn(n, c, s, s, generator=g))
+    dy = bf(torch.randn(n, c, s, s, generator=g))
+    res = []
+    for fused in (False, True):
+        mod = copy.deepcopy(base).to(dev).train(training)
+        ops.FUSED_CA_GATES = fused
+        try:
+            xd = nhwc(x, dev).requires_grad_(True)
+            y = mod(xd)
+            y.backward(nhwc(dy, dev))
+        finally:
+            ops.FUSED_CA_GATES = True
+        torch.cuda.synchronize()
+        res.append((y.detach().float().cpu(), xd.grad.float().cpu(), {k: p.grad.cpu() for k, p in mod.named_parameters()},
+                    {k: v.cpu().clone() for k, v in mod.state_dict().items() if "running" in k or "tracked" in k}))
+    (y0, dx0, g0, b0), (y1, dx1, g1, b1) = res
+    assert P.rel_l2(y1, y0) < 3e-4 and P.rel_l2(dx1, dx0) < 5e-4          # bf16 outputs: isolated one-ulp flips
+    scale = max(float(v.abs().max()) for v in g0.values())
+    for k in g0:      # (a bias in front of a batch-statistics BatchNorm has zero gradient: rounding noise on both sides)
+        noise = float(g0[k].abs().max()) < 1e-4 * scale and float(g1[k].abs().max()) < 1e-4 * scale
+        assert noise or P.rel_l2(g1[k], g0[k]) < 2e-4, (k, g0[k].flatten()[:4], g1[k].flatten()[:4])
+    for k in b0:
+        assert torch.equal(b0[k], b1[k]) if "tracked" in k else P.rel_l2(b1[k], b0[k]) < 1e-5, k

@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--bn_sweep", action="store_true", help="forced tile widths, full kernel and MMA-only")
     ap.add_argument("--ab", action="store_true", help="also time the alternative kernels (generic conv, wgrad v1/v2)")
     ap.add_argument("--shapes", type=int, default=0, help="only the first N conv shapes")
+    ap.add_argument("--pick", default="", help="comma-separated indices into the conv shape table")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     n = a.batch
@@ -61,7 +62,8 @@ def main():
     rows = []
     g = torch.Generator(device=dev).manual_seed(0)
     if a.only in ("", "conv"):
-        for (h, cin, cout, k, s, p, cnt) in (CONVS[:a.shapes] if a.shapes else CONVS):
+        picked = [CONVS[int(i)] for i in a.pick.split(",")] if a.pick else (CONVS[:a.shapes] if a.shapes else CONVS)
+        for (h, cin, cout, k, s, p, cnt) in picked:
             x = torch.randn(n, h, h, ops.r8(cin), device=dev, generator=g).to(torch.bfloat16)
             w = torch.nn.Parameter(torch.randn(cout, cin, k, k, device=dev, generator=g) / (cin * k * k) ** 0.5)
             b = torch.nn.Parameter(torch.zeros(cout, device=dev))
@@ -175,7 +177,13 @@ def main():
 
             def pool():
                 ops.call("dm_pool_nhw", P_(y), c, P_(pooled), n, h * h, c, 1.0 / (h * h), st)
+            def chain_sf():                 # statistics then apply, back to back: does the second read of y hit L2?
+                bn_stats(); bn_finalize(); bn_fwd()
+
+            def chain_bwd2():               # two backward calls back to back on the same tensors (dz, y in L2 for the 2nd?)
+                bn_bwd(); bn_bwd()
             for name, fn, nb in (("bn_stats", bn_stats, 1), ("bn_finalize", bn_finalize, 0), ("bn_act_fwd", bn_fwd, 2),
+                                 ("chain_stats_fwd", chain_sf, 3), ("chain_bwd_x2", chain_bwd2, 10),
                                  ("bn_act_fwd_v1", bn_fwd, 2),
                                  ("bn_act_bwd", bn_bwd, 5), ("colsum", colsum, 1), ("pool_nhw", pool, 1), ("axpby", axpby, 3)):
                 if "_v" in name:

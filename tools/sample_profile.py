@@ -1,5 +1,5 @@
 import sys, os, json, time, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import diffusionmodel_b200 as D
 from diffusionmodel_b200 import ops
 dev = torch.device('cuda:0')
@@ -16,6 +16,8 @@ real = ops.call; ops.call = lambda *a, **k: 0
 t0 = time.perf_counter(); ddpm.sample(15, (3, 256, 256), dev, guide_w=2.0, steps=10); torch.cuda.synchronize(); t1 = time.perf_counter()
 ops.call = real
 print("host enqueue ms per reverse step", (t1 - t0) * 100)
+ddpm.graph_sampling = False      # CUDA events cannot be recorded inside a graph replay
+ddpm.sample(15, (3, 256, 256), dev, guide_w=2.0, steps=2)
 prof = ops.enable_profile()
 ddpm.sample(15, (3, 256, 256), dev, guide_w=2.0, steps=2)
 torch.cuda.synchronize(); ops.disable_profile()
