@@ -300,12 +300,12 @@ def run_ours(args):
         ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
         roof = {"bound": "tensor",
-                "kernel": "conv3x3_halo_kernel + conv_gemm_kernel (fwd + data-gradient implicit GEMMs, all layers of one step)",
+                "kernel": "conv3x3_halo2_kernel (CTA pairs) + conv3x3_halo_kernel + conv_gemm_kernel: fwd + data-gradient implicit GEMMs, all layers of one step",
                 "achieved": ach, "peak": peak, "peak_source": f"{src} bf16_tflops_sustained", "unit": "TFLOP/s",
                 "frac": ach / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch on the dominant layer (3x3, 192->192,
                 # 4x256x256: 100.7 MB in, 100.7 MB out algorithmic), profiles/r01_gemm_kernels_ncu_full.txt
-                "traffic": 152.8e6, "traffic_unit": "B/launch (ncu --set full, dominant layer)",
+                "traffic": 154.7e6, "traffic_unit": "B/launch (ncu --set full, dominant layer: dram read 101.4 MB + write 53.3 MB, the rest of the 100.7 MB output still in L2)",
                 "launches": conv["n"], "ms_per_step": conv["ms"],
                 "wgrad": {"achieved": wg["flops"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] > 0 else 0.0,
                           "ms_per_step": wg["ms"], "launches": wg["n"]},
