@@ -156,6 +156,7 @@ __device__ __forceinline__ void gate_front(const DmCaGates& p, const GateSmem& g
       t0 = gelu_exact(hh);
     }
     g.hh[idx] = hh; g.t0[idx] = t0;
+    if (write_stats && blockIdx.y == 0 && r0 + r < R) p.t0[((long long)d * R + r0 + r) * m + j] = t0;
   }
   __syncthreads();
   // P_d[r][j] = bp_d[j] + sum_k T0_d[r][k] * wp_d[j][k]: a warp per (d, j), lanes over k (coalesced weight rows; one
@@ -189,7 +190,7 @@ __device__ __forceinline__ void gate_front(const DmCaGates& p, const GateSmem& g
 
 // ---- forward 2: statistics, gelu, cross interaction, output gates.  grid (nblk, ceil(C/256)): the small front part
 // is recomputed per channel chunk, each block reads only its 256 rows of the output weights
-__global__ void __launch_bounds__(kThreads) ca_gate_fwd_kernel(const DmCaGates p) {
+__global__ void __launch_bounds__(kThreads) ca_gate_fwd_kernel(const DmCaGates p, const int use_slab) {
   extern __shared__ float sm[];
   const int m = p.m, C = p.C, R = p.R, r0 = blockIdx.x * kRows;
   const GateSmem g = carve_gate(sm, m);
@@ -208,18 +209,28 @@ __global__ void __launch_bounds__(kThreads) ca_gate_fwd_kernel(const DmCaGates p
     const float* bc = d ? p.bc_w : p.bc_h;
     float* out = d ? p.aw : p.ah;
     const float* t = ts + d * kRows * m;
-    // a thread per output channel (its weight row is m contiguous floats; measured faster than a warp per channel with
-    // lanes over j for every m of the model)
+    // a thread per output channel.  Its weight row (m contiguous floats) is first staged by the whole warp with
+    // coalesced loads into a padded shared-memory slab: read straight from global, every load instruction of the
+    // j loop would touch 32 different rows = 32 L1 wavefronts
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.y * kThreads + threadIdx.x;
+    const float* w = wc + (long long)c * m;
+    float* slab = ts + 2 * kRows * m + warp * 32 * (m + 1);
+    if (use_slab) {
+      const int cb = blockIdx.y * kThreads + warp * 32;
+      for (int row = 0; row < 32 && cb + row < C; ++row)
+        for (int j = lane; j < m; j += 32) slab[row * (m + 1) + j] = __ldg(wc + (long long)(cb + row) * m + j);
+      __syncwarp();
+    }
     if (c < C) {
       float acc[kRows];
       const float b = bc[c];
 #pragma unroll
       for (int r = 0; r < kRows; ++r) acc[r] = b;
-      const float* w = wc + (long long)c * m;
+      const float* ws = slab + lane * (m + 1);
 #pragma unroll 4
       for (int j = 0; j < m; ++j) {
-        const float wv = __ldg(w + j);
+        const float wv = use_slab ? ws[j] : __ldg(w + j);
 #pragma unroll
         for (int r = 0; r < kRows; ++r) acc[r] = fmaf(t[r * m + j], wv, acc[r]);
       }
@@ -227,6 +238,7 @@ __global__ void __launch_bounds__(kThreads) ca_gate_fwd_kernel(const DmCaGates p
       for (int r = 0; r < kRows; ++r)
         if (r0 + r < R) out[(long long)(r0 + r) * C + c] = s.k[d] * sigmoidf_(acc[r]);
     }
+    __syncwarp();
   }
 }
 
@@ -317,24 +329,23 @@ __global__ void __launch_bounds__(kThreads) ca_gate_bwd_b_kernel(const DmCaGates
     for (int k = 0; k < m; ++k) acc = fmaf(dto[k], __ldg(wp + (long long)k * m + j), acc);
     dt0[idx] = dts[idx] + s.sg[1 - d] * acc;
   }
-  // projection parameter gradients and the gamma sums
-  for (int idx = threadIdx.x; idx < 2 * m * m; idx += kThreads) {
-    const int d = idx / (m * m), kj = idx - d * m * m, k = kj / m, j = kj - k * m;
-    float acc = 0.0f;
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) acc = fmaf(dts[(1 - d) * km + r * m + k], g.t0[d * km + r * m + j], acc);
-    atomicAdd((d ? q.g_wp_w2h : q.g_wp_h2w) + kj, s.sg[1 - d] * acc);
-  }
-  for (int idx = threadIdx.x; idx < 2 * m; idx += kThreads) {
-    const int d = idx / m, k = idx - d * m;
-    float sb = 0.0f, sg = 0.0f;
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const float v = dts[(1 - d) * km + r * m + k];
-      sb += v; sg = fmaf(v, g.pp[d * km + r * m + k], sg);
+  // the gamma sums (the projection weight / bias gradients come from ca_wgrad_kernel over dT and T0)
+  {
+    // per-direction totals: threads stride over (r, k), block reduction, one atomic per direction
+    __shared__ float red2[2][kThreads / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int d = 0; d < 2; ++d) {
+      float part = 0.0f;
+      for (int i = threadIdx.x; i < km; i += kThreads) part = fmaf(dts[(1 - d) * km + i], g.pp[d * km + i], part);
+      part = dm::warp_sum(part);
+      if (lane == 0) red2[d][warp] = part;
     }
-    atomicAdd((d ? q.g_bp_w2h : q.g_bp_h2w) + k, s.sg[1 - d] * sb);
-    atomicAdd(q.scal + 2 + (1 - d), sg);          // scal[2] = d sg_h (uses pp[1]), scal[3] = d sg_w (uses pp[0])
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      float tot = 0.0f;
+      for (int w = 0; w < kThreads / 32; ++w) tot += red2[threadIdx.x][w];
+      atomicAdd(q.scal + 2 + (1 - threadIdx.x), tot);     // scal[2] = d sg_h (uses pp[1]), scal[3] = d sg_w (uses pp[0])
+    }
   }
   __syncthreads();
   // through the gelu: dHhat, and the BatchNorm-backward partial sums of this block
@@ -416,7 +427,11 @@ __global__ void __launch_bounds__(kThreads) ca_lin1_bwd_kernel(const DmCaGates p
 
 // ---- weight gradients, parallel over outputs (no atomics): out[c*so_c + j*so_j] += sum_r A[r][c] * B[r][j], and
 // bias[c] += sum_r A[r][c].  grid (ceil(C/32), ceil(m/8), 2); block = 32 c lanes x 32 row slices.
-struct WgArgs { const float* A[2]; const float* B[2]; float* out[2]; float* bias[2]; int R, C, m; long long so_c, so_j; };
+struct WgArgs {
+  const float* A[2]; const float* B[2]; float* out[2]; float* bias[2];
+  const float* gate[2];          // optional: the sums are scaled by sigmoid(*gate[d])
+  int R, C, m; long long so_c, so_j;
+};
 __global__ void __launch_bounds__(1024) ca_wgrad_kernel(const WgArgs a) {
   __shared__ float red[32][32][9];
   const int d = blockIdx.z, cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
@@ -446,18 +461,19 @@ __global__ void __launch_bounds__(1024) ca_wgrad_kernel(const WgArgs a) {
   for (int jj = 0; jj < 8; ++jj) red[sl][cl][jj] = acc[jj];
   red[sl][cl][8] = sb;
   __syncthreads();
+  const float scale = a.gate[d] != nullptr ? sigmoidf_(a.gate[d][0]) : 1.0f;
   if (sl == 0 && c < a.C) {
     for (int jj = 0; jj < nj; ++jj) {
       float tot = 0.0f;
 #pragma unroll
       for (int s2 = 0; s2 < 32; ++s2) tot += red[s2][cl][jj];
-      a.out[d][(long long)c * a.so_c + (long long)(j0 + jj) * a.so_j] += tot;
+      a.out[d][(long long)c * a.so_c + (long long)(j0 + jj) * a.so_j] += scale * tot;
     }
     if (a.bias[d] != nullptr && blockIdx.y == 0) {
       float tot = 0.0f;
 #pragma unroll
       for (int s2 = 0; s2 < 32; ++s2) tot += red[s2][cl][8];
-      a.bias[d][c] += tot;
+      a.bias[d][c] += scale * tot;
     }
   }
 }
@@ -506,9 +522,12 @@ extern "C" int dm_ca_gates_fwd(const DmCaGates* p, void* stream) {
   if (int rc = set_smem((const void*)ca_lin1_kernel, s1, a1, h1)) return rc;
   ca_lin1_kernel<<<dim3(p->nblk, 2, dm::cdiv(p->m, kThreads / 32)), kThreads, s1, st>>>(*p);
   DM_CHECK_LAUNCH();
-  const size_t s2 = gate_smem_floats(p->m, 2) * sizeof(float);
+  size_t s2 = gate_smem_floats(p->m, 2) * sizeof(float);
+  const size_t slab = (size_t)kThreads * (p->m + 1) * sizeof(float);
+  const int use_slab = 0 * (s2 + slab <= 200 * 1024);      // measured slower than the direct reads (the staging loads serialise)
+  if (use_slab) s2 += slab;
   if (int rc = set_smem((const void*)ca_gate_fwd_kernel, s2, a2, h2)) return rc;
-  ca_gate_fwd_kernel<<<dim3(p->nblk, dm::cdiv(p->C, kThreads)), kThreads, s2, st>>>(*p);
+  ca_gate_fwd_kernel<<<dim3(p->nblk, dm::cdiv(p->C, kThreads)), kThreads, s2, st>>>(*p, use_slab);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
@@ -530,15 +549,20 @@ extern "C" int dm_ca_gates_bwd(const DmCaGates* p, const DmCaGatesGrad* q, void*
   ca_gate_bwd_b_kernel<<<p->nblk, kThreads, sb, st>>>(*p, *q);
   DM_CHECK_LAUNCH();
   const dim3 wg_grid(dm::cdiv(p->C, 32), dm::cdiv(p->m, 8), 2);
-  WgArgs wc = {{q->dz, q->dz + RC}, {p->t, p->t + Rm}, {q->g_wc_h, q->g_wc_w}, {q->g_bc_h, q->g_bc_w}, p->R, p->C, p->m,
-               (long long)p->m, 1};
+  WgArgs wc = {{q->dz, q->dz + RC}, {p->t, p->t + Rm}, {q->g_wc_h, q->g_wc_w}, {q->g_bc_h, q->g_bc_w}, {nullptr, nullptr},
+               p->R, p->C, p->m, (long long)p->m, 1};
   ca_wgrad_kernel<<<wg_grid, 1024, 0, st>>>(wc);
+  DM_CHECK_LAUNCH();
+  // projection gradients: d wp_e[k][j] = sg[1-e] * sum_r dT_{1-e}[r][k] * T0_e[r][j]  (wp_0 = h2w, wp_1 = w2h)
+  WgArgs wpj = {{q->dt + Rm, q->dt}, {p->t0, p->t0 + Rm}, {q->g_wp_h2w, q->g_wp_w2h}, {q->g_bp_h2w, q->g_bp_w2h},
+                {p->gamma_w, p->gamma_h}, p->R, p->m, p->m, (long long)p->m, 1};
+  ca_wgrad_kernel<<<dim3(dm::cdiv(p->m, 32), dm::cdiv(p->m, 8), 2), 1024, 0, st>>>(wpj);
   DM_CHECK_LAUNCH();
   const size_t s2 = ((size_t)kRows * p->m + 2 * p->m) * sizeof(float);
   ca_lin1_bwd_kernel<<<dim3(p->nblk, csplit, 2), kThreads, s2, st>>>(*p, *q);
   DM_CHECK_LAUNCH();
-  WgArgs w1 = {{p->xh, p->xw}, {q->du, q->du + Rm}, {q->g_w1_h, q->g_w1_w}, {nullptr, nullptr}, p->R, p->C, p->m, 1,
-               (long long)p->C};
+  WgArgs w1 = {{p->xh, p->xw}, {q->du, q->du + Rm}, {q->g_w1_h, q->g_w1_w}, {nullptr, nullptr}, {nullptr, nullptr},
+               p->R, p->C, p->m, 1, (long long)p->C};
   ca_wgrad_kernel<<<wg_grid, 1024, 0, st>>>(w1);
   DM_CHECK_LAUNCH();
   ca_scalars_bwd_kernel<<<1, 32, 0, st>>>(*p, *q);

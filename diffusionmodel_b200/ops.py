@@ -847,7 +847,7 @@ class _CoordAttn(torch.autograd.Function):
 class _CaGatesC(ctypes.Structure):
     """DmCaGates (include/dm_b200.h)."""
     _PTRS = ("xh xw w1_h w1_w b1_h b1_w bn_g_h bn_g_w bn_b_h bn_b_w bn_rm_h bn_rm_w bn_rv_h bn_rv_w wp_h2w wp_w2h "
-             "bp_h2w bp_w2h wc_h wc_w bc_h bc_w gamma_h gamma_w alpha beta u part stat t ah aw").split()
+             "bp_h2w bp_w2h wc_h wc_w bc_h bc_w gamma_h gamma_w alpha beta u part stat t t0 ah aw").split()
     _fields_ = [(k, ctypes.c_void_p) for k in _PTRS] + [(k, ctypes.c_int) for k in ("R", "C", "m", "nblk", "training")] + [
         ("eps", ctypes.c_float), ("momentum", ctypes.c_float)]
 
@@ -885,7 +885,7 @@ class _CoordAttnFused(torch.autograd.Function):
         nblk = -(-r // _lib.fn("dm_ca_gates_rows_per_block")())
         training = mod.bn1_h.training
         work = {"u": torch.empty((2, r, m), **f32), "part": torch.empty((nblk, 2, 2, m), **f32),
-                "stat": torch.empty((2, 2, m), **f32), "t": torch.empty((2, r, m), **f32),
+                "stat": torch.empty((2, 2, m), **f32), "t": torch.empty((2, r, m), **f32), "t0": torch.empty((2, r, m), **f32),
                 "ah": torch.empty((n, h, c), **f32), "aw": torch.empty((n, w, c), **f32), "xh": xh, "xw": xw}
         pm = _ca_param_map(mod)
         for k, v in pm.items():
@@ -937,7 +937,8 @@ class _CoordAttnFused(torch.autograd.Function):
         return (dx, None, None) + (None,) * len(pm)
 
 
-FUSED_CA_GATES = True         # False: the gate network as a torch sub-graph (the fallback for H != W)
+import os as _os
+FUSED_CA_GATES = _os.environ.get("DM_FUSED_CA", "1") != "0"         # False: the gate network as a torch sub-graph (the fallback for H != W)
 
 
 def coord_attn(x, c, gates, params, mod=None):

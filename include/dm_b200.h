@@ -196,7 +196,7 @@ typedef struct DmCaGates {
   const float *wp_h2w, *wp_w2h, *bp_h2w, *bp_w2h;
   const float *wc_h, *wc_w, *bc_h, *bc_w;
   const float *gamma_h, *gamma_w, *alpha, *beta;
-  float *u, *part, *stat, *t, *ah, *aw;
+  float *u, *part, *stat, *t, *t0, *ah, *aw;          /* u, t, t0 [2][R][m] */
   int R, C, m, nblk, training;
   float eps, momentum;
 } DmCaGates;
