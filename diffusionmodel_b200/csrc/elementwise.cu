@@ -307,7 +307,6 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j] += o[j];
     }
-#pragma unroll
     float* row = db + (long long)blockIdx.x * 2 * C;          // db = partial workspace here: [blocks][2][C], second half unused
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -372,16 +371,6 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ 
     for (int j = 0; j < 8; ++j)
       if (c0 + j < C) { g[c0 + j] = s1[j]; g[ld + c0 + j] = s2[j]; }
   }
-}
-
-__global__ void zero_kernel(float* p, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = 0.f;
-}
-int zero_f32(float* p, long long n, cudaStream_t st) {
-  if (n <= 0) return DM_OK;
-  zero_kernel<<<ew_grid(n), kEwThreads, 0, st>>>(p, n);
-  DM_CHECK_LAUNCH();
-  return DM_OK;
 }
 
 // ---------------------------------------------------------------------------------- BatchNorm

@@ -331,7 +331,7 @@ def test_gemm_native_weight_storage(dev):
 
 
 @pytest.mark.parametrize("training", [True, False])
-@pytest.mark.parametrize("shape", [(4, 192, 16), (2, 64, 12), (3, 32, 7)])
+@pytest.mark.parametrize("shape", [(4, 192, 16), (2, 64, 12), (3, 32, 7), (2, 3072, 8)], ids=lambda s: "x".join(map(str, s)))
 def test_coordattn_fused_gates_match_torch_subgraph(dev, shape, training):
     """dm_ca_gates_fwd/bwd (the CoordAttn gate network as five kernels) against the same network run as a torch
     fp32 sub-graph with autograd: output, dx, every parameter gradient, BatchNorm running statistics + counters."""
