@@ -9,6 +9,7 @@ per backward pass.
 from __future__ import annotations
 
 import ctypes
+import os as _os
 import weakref
 
 import torch
@@ -646,7 +647,7 @@ class _BnAct(torch.autograd.Function):
 
 
 _counters_batched = False     # True while a model forward bumps all num_batches_tracked buffers in one launch
-FUSED_CONV_STATS = False      # True: BatchNorm statistics from the conv epilogue; False: a separate pass over y
+FUSED_CONV_STATS = _os.environ.get("DM_FUSED_CONV_STATS", "0") == "1"      # True: BatchNorm statistics from the conv epilogue; False: a separate pass over y
 
 
 class batched_counters:
@@ -937,7 +938,6 @@ class _CoordAttnFused(torch.autograd.Function):
         return (dx, None, None) + (None,) * len(pm)
 
 
-import os as _os
 FUSED_CA_GATES = _os.environ.get("DM_FUSED_CA", "1") != "0"         # False: the gate network as a torch sub-graph (the fallback for H != W)
 
 
