@@ -8,7 +8,8 @@ Flag names, defaults and the missing-checkpoint behaviour are the reference's.  
 caller contract of SURVEY.md 2.1 (train_model new_scripy.py:659-943, gen_samples :945-1108): accumulation
 over ACCUM_STEPS micro-batches, clip 1.0, AdamW(lr 1e-4, wd 1e-5), CosineAnnealingWarmRestarts(10, 2, 3e-5),
 checkpoints as ``{'epoch', 'model_state_dict', 'optimizer_state_dict', 'loss'}``.  The reference's dataset
-(./cropped_images, VOC XML) is not shipped with it, so batches are synthetic road-damage-shaped tensors
+(./cropped_images, VOC XML) is not shipped with it: ``--data DIR`` reads that layout through the device-side batch
+pipeline (data.py), otherwise batches are synthetic road-damage-shaped tensors
 (images in [-1,1], labels, attention map 0.5 / 1.0 lower half / 3.0 box, new_scripy.py:535-546); FID/SSIM
 evaluation (new_scripy.py:1111-1290) is out of scope, ``--no_eval`` is accepted and ignored.
 """
@@ -54,6 +55,11 @@ def train_model(args):
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     torch.manual_seed(0)
+    cache = None
+    if args.data:                      # the reference's ./cropped_images layout: decoded + resized once, cached on the device
+        from .data import CachedCrackBatches
+        cache = CachedCrackBatches.from_voc_dir(args.data, args.img, device)
+        args.n_classes = len(cache.classes)                      # new_scripy.py:692
     ddpm = build(args.n_classes, device, args.n_feat).train()
     optim = FusedAdamW(ddpm.parameters(), lr=Cfg.LR, weight_decay=Cfg.WD, max_grad_norm=1.0)
     sched = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(optim, T_0=10, T_mult=2, eta_min=3e-5)
@@ -65,7 +71,10 @@ def train_model(args):
     for ep in range(args.epochs):
         t0, ema, seen = time.time(), None, 0
         for step in range(args.steps_per_epoch):
-            x, c, m = (t.to(device, non_blocking=True) for t in synth_batch(gen, Cfg.BATCH_SIZE, args.img, args.n_classes))
+            if cache is not None:      # random batch of the cached set; flip / normalise / mask rasterisation in one kernel
+                x, c, m = cache.batch(torch.randint(0, len(cache), (Cfg.BATCH_SIZE,), generator=gen), generator=gen)
+            else:
+                x, c, m = (t.to(device, non_blocking=True) for t in synth_batch(gen, Cfg.BATCH_SIZE, args.img, args.n_classes))
             if step_fn is None and not args.no_graph:
                 step_fn = ddpm.capture_train_step(x, c, m, loss_scale=1.0 / Cfg.ACCUM_STEPS)
                 optim.zero_grad()
@@ -138,6 +147,8 @@ def main(argv=None):
     parser.add_argument("--n_feat", type=int, default=Cfg.N_FEAT)
     parser.add_argument("--img", type=int, default=Cfg.IMG_SIZE)
     parser.add_argument("--no_graph", action="store_true", help="eager launches instead of the CUDA-graphed micro-step")
+    parser.add_argument("--data", type=str, default=None,
+                        help="dataset root in the reference's layout (images/<class>/*.jpg + annotations/*.xml); synthetic batches if omitted")
     args = parser.parse_args(argv)
     if args.mode == "train":
         train_model(args)

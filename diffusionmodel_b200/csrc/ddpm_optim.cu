@@ -319,6 +319,30 @@ __global__ void __launch_bounds__(256) pack_transpose_kernel(const bf16* __restr
   }
 }
 
+// Input pipeline tail on the device (CrackDataset.__getitem__ + the torchvision transforms, new_scripy.py:516-551,683-688)
+// for a cached uint8 batch [B][H][W][3] already decoded and resized: RandomHorizontalFlip (decision per sample from
+// the host RNG), ToTensor (u8 / 255), Normalize ((v - mean) / std, separately rounded like the eager ops) -> x fp32
+// NCHW, and the attention mask: `low` everywhere, `mid` in the lower half, `high` inside the scaled bounding box
+// [ymin, ymax) x [xmin, xmax) (the reference does NOT flip the mask with the image).
+__global__ void __launch_bounds__(256) prep_batch_kernel(const unsigned char* __restrict__ img, const int* __restrict__ flip,
+                                                          const int* __restrict__ box, float* __restrict__ x,
+                                                          float* __restrict__ mask, int B, int H, int W, float mean, float stdv,
+                                                          float low, float mid, float high) {
+  const long long total = (long long)B * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W), h = (int)((i / W) % H), b = (int)(i / ((long long)W * H));
+    const int ws = flip[b] ? W - 1 - w : w;
+    const unsigned char* px = img + (((long long)b * H + h) * W + ws) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      x[(((long long)b * 3 + c) * H + h) * W + w] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)px[c], 255.0f), mean), stdv);
+    const int* bx = box + 4 * b;                       // xmin, ymin, xmax, ymax (scaled, clamped)
+    float m = h >= H / 2 ? mid : low;
+    if (h >= bx[1] && h < bx[3] && w >= bx[0] && w < bx[2]) m = high;
+    mask[i] = m;
+  }
+}
+
 }  // namespace
 
 static void fill_pack(PackArgs& A, int rows, int cols, int ntaps, const long long* tap_off, long long s_row, long long s_col,
@@ -453,6 +477,16 @@ extern "C" int dm_pack_transpose(const void* src, void* dst, int cout, int cin, 
   if (cin % 64) { dm_set_error("dm_pack_transpose: Cin must be a multiple of 64"); return DM_ERR_ARG; }
   dim3 grid(cin / 64, dm::cdiv(cout, 64), ntaps);
   pack_transpose_kernel<<<grid, 256, 0, ST>>>((const bf16*)src, (bf16*)dst, cout, cin, ntaps, dst_pitch, A);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
+/* cached uint8 batch -> normalised fp32 NCHW images + attention masks (new_scripy.py:516-551,683-688) */
+extern "C" int dm_prep_batch(const void* img_u8, const int* flip, const int* box, float* x, float* mask, int B, int H, int W,
+                             float mean, float stdv, float low, float mid, float high, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0) return DM_OK;
+  prep_batch_kernel<<<grid_for((long long)B * H * W), 256, 0, ST>>>((const unsigned char*)img_u8, flip, box, x, mask, B, H, W,
+                                                                    mean, stdv, low, mid, high);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }

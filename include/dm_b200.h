@@ -215,6 +215,13 @@ int dm_ca_gates_rows_per_block(void);
 int dm_ca_gates_fwd(const DmCaGates* p, void* stream);
 int dm_ca_gates_bwd(const DmCaGates* p, const DmCaGatesGrad* q, void* stream);
 
+/* ---- input pipeline tail (next-row 3 of SURVEY 8f; CrackDataset.__getitem__ new_scripy.py:516-551 + transforms :683-688)
+ * img_u8 [B][H][W][3] decoded + resized (cached on the device), flip[B] (0/1: RandomHorizontalFlip decisions), box[B][4] =
+ * (xmin, ymin, xmax, ymax) already scaled + clamped like :542-545 -> x fp32 [B][3][H][W] = ((u8/255) - mean)/std and
+ * mask fp32 [B][H][W] = low | mid (rows >= H/2) | high (rows [ymin,ymax), cols [xmin,xmax); not flipped, as in the reference) */
+int dm_prep_batch(const void* img_u8, const int* flip, const int* box, float* x, float* mask, int B, int H, int W,
+                  float mean, float stdv, float low, float mid, float high, void* stream);
+
 /* ---- optimizer side (new_scripy.py:797-803) --------------------------------------------------------- */
 int dm_sumsq(const float* g, long long n, float* out, void* stream);          /* *out += sum g^2 */
 int dm_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

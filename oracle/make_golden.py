@@ -200,12 +200,58 @@ def check_shipped_callsite(new_scripy):
     print("shipped call site (B=1,n_classes=1) == patched(zero map) == port: bit-exact")
 
 
+def crack_dataset_case(new_scripy):
+    """Pin oracle.ref_port.crack_item against the REAL CrackDataset (new_scripy.py:479-551) + the training transform
+    (:683-688) on a throw-away VOC-style directory, and write the fixture the data-pipeline tests replay."""
+    import tempfile
+    from PIL import Image
+    from torchvision import transforms
+    rng = np.random.RandomState(5)
+    size = new_scripy.Cfg.IMG_SIZE
+    items = []
+    with tempfile.TemporaryDirectory() as root:
+        specs = [("D00", "a", (200, 150), (31, 40, 123, 117)), ("D10", "b", (333, 257), (0, 10, 332, 256)),
+                 ("D10", "c", (64, 48), (5, 3, 6, 47))]
+        for cname, stem, (w, h), box in specs:
+            os.makedirs(os.path.join(root, "images", cname), exist_ok=True)
+            os.makedirs(os.path.join(root, "annotations"), exist_ok=True)
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = np.stack([(xx * 255 // max(w - 1, 1)), (yy * 255 // max(h - 1, 1)), ((xx + yy) * 7 % 256)], -1).astype(np.uint8)
+            img[rng.randint(0, h, 40), rng.randint(0, w, 40)] = 255
+            Image.fromarray(img).save(os.path.join(root, "images", cname, stem + ".png"))
+            with open(os.path.join(root, "annotations", stem + ".xml"), "w") as f:
+                f.write(f"<annotation><size><width>{w}</width><height>{h}</height></size><object><bndbox>"
+                        f"<xmin>{box[0]}</xmin><ymin>{box[1]}</ymin><xmax>{box[2]}</xmax><ymax>{box[3]}</ymax>"
+                        f"</bndbox></object></annotation>")
+        for flip in (0, 1):
+            tf = transforms.Compose([transforms.Resize((size, size)), transforms.RandomHorizontalFlip(float(flip)),
+                                     transforms.ToTensor(), transforms.Normalize(new_scripy.Cfg.NORM_MEAN, new_scripy.Cfg.NORM_STD)])
+            ds = new_scripy.CrackDataset(root, transform=tf)
+            for i in range(len(ds)):
+                x_ref, label, m_ref = ds[i]
+                img_path, xml_path, _ = ds.samples[i]
+                spec = [sp for sp in specs if sp[1] == os.path.basename(img_path)[:-4]][0]
+                u8 = torch.from_numpy(np.asarray(Image.open(img_path).convert("RGB").resize((size, size), Image.BILINEAR),
+                                                 dtype=np.uint8).copy())
+                x_o, m_o = P.crack_item(u8, spec[3], spec[2], bool(flip), size)
+                assert bit_equal(x_ref, x_o) and bit_equal(m_ref, m_o), (spec, flip)
+                items.append((u8.numpy(), np.array(spec[3] + spec[2], dtype=np.int64), flip, label, x_ref.numpy(), m_ref.numpy()))
+    np.savez_compressed(os.path.join(GOLD, "crack_items.npz"),
+                        u8=np.stack([it[0] for it in items]), box_wh=np.stack([it[1] for it in items]),
+                        flip=np.array([it[2] for it in items]), label=np.array([it[3] for it in items]),
+                        x=np.stack([it[4] for it in items]), mask=np.stack([it[5] for it in items]))
+    print(f"CrackDataset + transforms == oracle crack_item on {len(items)} items: bit-exact")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
     new_scripy, MNIST_script = import_reference()
     check_shipped_callsite(new_scripy)
     check_schedules(new_scripy, MNIST_script)
+    crack_dataset_case(new_scripy)
+    if "--only-data" in sys.argv:
+        return
     one_case(new_scripy, MNIST_script, "mnist", 16, 28, 8, 10, 11, 400, "mnist_f16_b8")
     one_case(new_scripy, MNIST_script, "rdd", 16, 128, 2, 5, 12, 700, "rdd_f16_s128_b2")
     one_case(new_scripy, MNIST_script, "rdd", 32, 128, 1, 5, 13, 700, "rdd_f32_s128_b1_nomap", use_attn_map=False)

@@ -382,3 +382,25 @@ def rel_l2(a, b):
     a = a.detach().double().flatten()
     b = b.detach().double().flatten()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+# --------------------------------------------------------------------------------------- input pipeline (8f rank 3)
+def crack_item(image_u8, box_xyxy, orig_wh, flip, img_size, low=0.5, mid=1.0, high=3.0, mean=0.5, std=0.5):
+    """CrackDataset.__getitem__ (new_scripy.py:516-551) after decode + Resize, with the transform tail of :683-688:
+    ``image_u8`` [H,W,3] uint8 (already resized) -> (x fp32 [3,H,W], attn_mask fp32 [H,W]).  ``flip``: the
+    RandomHorizontalFlip decision.  The mask is built before / independently of the transform (:535-549), i.e. it is not
+    flipped; box coordinates use Python round() and the clamp of :542-545."""
+    xmin, ymin, xmax, ymax = box_xyxy
+    ow, oh = orig_wh
+    attn = torch.ones((img_size, img_size)) * low                                   # :535
+    attn[img_size // 2:, :] = mid                                                   # :538-539
+    cl = lambda v: max(0, min(img_size - 1, v))
+    xs0, xs1 = cl(round(xmin * img_size / ow)), cl(round(xmax * img_size / ow))     # :542-543
+    ys0, ys1 = cl(round(ymin * img_size / oh)), cl(round(ymax * img_size / oh))     # :544-545
+    attn[ys0:ys1, xs0:xs1] = high                                                   # :546
+    img = image_u8
+    if flip:
+        img = img.flip(1)                                                           # RandomHorizontalFlip, :685
+    x = img.permute(2, 0, 1).to(torch.float32).div(255)                             # ToTensor, :686
+    x = (x - mean) / std                                                            # Normalize, :687
+    return x, attn

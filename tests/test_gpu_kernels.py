@@ -399,3 +399,33 @@ def test_fused_adamw_matches_torch(dev):
         o_ref.step(); o.step(); o.zero_grad()
     for a, b in zip(mine, ref):
         assert rel(a.detach().cpu(), b.detach()) < 1e-5
+
+
+def test_cached_batch_prep_bit_exact(dev):
+    """diffusionmodel_b200.data.CachedCrackBatches (dm_prep_batch) against the reference CrackDataset outputs in
+    tests/golden/crack_items.npz: normalised images and attention masks bit-exact, flip decisions honoured, labels."""
+    import os
+    import numpy as np
+    from diffusionmodel_b200 import data
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "crack_items.npz"))
+    size = g["u8"].shape[1]
+    boxes = torch.tensor([data.scale_box(*[int(v) for v in bw[:4]], int(bw[4]), int(bw[5]), size) for bw in g["box_wh"]],
+                         dtype=torch.int32)
+    cache = data.CachedCrackBatches(torch.from_numpy(g["u8"]), torch.from_numpy(g["label"]), boxes, dev)
+    idx = torch.arange(len(cache))
+    x, c, m = cache.batch(idx, flips=torch.from_numpy(g["flip"]))
+    assert torch.equal(x.cpu(), torch.from_numpy(g["x"])) and torch.equal(m.cpu(), torch.from_numpy(g["mask"]))
+    assert torch.equal(c.cpu(), torch.from_numpy(g["label"]).long())
+    # default flips: torch.rand(B) < 0.5 from the host generator (what torchvision's RandomHorizontalFlip draws per sample)
+    gen = torch.Generator().manual_seed(3)
+    expect = torch.rand(len(cache), generator=torch.Generator().manual_seed(3)) < 0.5
+    x2, _, m2 = cache.batch(idx, generator=gen)
+    for i in range(len(cache)):
+        ref = torch.from_numpy(g["x"][i]) if bool(expect[i]) == bool(g["flip"][i]) else torch.from_numpy(g["x"][i]).flip(2)
+        assert torch.equal(x2[i].cpu(), ref)
+    assert torch.equal(m2.cpu(), torch.from_numpy(g["mask"]))          # the reference never flips the mask
+    # ragged request: repeated / out-of-order indices, empty batch
+    x3, c3, _ = cache.batch([4, 0, 4], flips=[0, 1, 1])
+    assert x3.shape[0] == 3 and int(c3[1]) == int(g["label"][0])
+    x4, c4, m4 = cache.batch([], flips=[])
+    assert x4.shape[0] == 0 and m4.shape[0] == 0
