@@ -100,6 +100,7 @@ _SIGS = {
     "dm_ca_gates_fwd": "p p",
     "dm_ca_gates_bwd": "p p p",
     "dm_prep_batch": "ppp pp iii fffff p",
+    "dm_image_metrics": "ppp i l p",
     "dm_sumsq": "p l p p",
     "dm_pack_transpose": "pp iii p l p",
     "dm_adamw": "pppp l fffffff p f p",

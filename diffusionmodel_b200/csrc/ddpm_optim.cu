@@ -343,6 +343,50 @@ __global__ void __launch_bounds__(256) prep_batch_kernel(const unsigned char* __
   }
 }
 
+// Per-image-pair quality metrics of ImageMetrics.calc_ssim / calc_psnr (new_scripy.py:1189-1251): global-statistics SSIM
+// and PSNR on images mapped to [0,1] ("(x+1)/2 if x.min() < 0", decided per image).  One block per pair: pass 1 the two
+// minima, pass 2 six sums in double precision.  out[n] = (ssim, psnr); psnr = +inf for identical images.
+__global__ void __launch_bounds__(1024) image_metrics_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                              float* __restrict__ out, long long elems) {
+  __shared__ float smin[2][32];
+  __shared__ double ssum[6][32];
+  const float* pa = a + (long long)blockIdx.x * elems;
+  const float* pb = b + (long long)blockIdx.x * elems;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ma = 3.4e38f, mb = 3.4e38f;
+  for (long long i = threadIdx.x; i < elems; i += blockDim.x) { ma = fminf(ma, pa[i]); mb = fminf(mb, pb[i]); }
+  for (int o = 16; o > 0; o >>= 1) { ma = fminf(ma, __shfl_xor_sync(0xffffffffu, ma, o)); mb = fminf(mb, __shfl_xor_sync(0xffffffffu, mb, o)); }
+  if (lane == 0) { smin[0][warp] = ma; smin[1][warp] = mb; }
+  __syncthreads();
+  ma = smin[0][0]; mb = smin[1][0];
+  for (int w = 1; w < 32; ++w) { ma = fminf(ma, smin[0][w]); mb = fminf(mb, smin[1][w]); }
+  const bool ca = ma < 0.f, cb = mb < 0.f;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (long long i = threadIdx.x; i < elems; i += blockDim.x) {
+    float x = pa[i], y = pb[i];
+    if (ca) x = (x + 1.f) / 2.f;
+    if (cb) y = (y + 1.f) / 2.f;
+    const double dx = x, dy = y, df = (double)(x - y);
+    s[0] += dx; s[1] += dy; s[2] += dx * dx; s[3] += dy * dy; s[4] += dx * dy; s[5] += df * df;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double v = s[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) ssum[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[6];
+    for (int k = 0; k < 6; ++k) { t[k] = 0; for (int w = 0; w < 32; ++w) t[k] += ssum[k][w]; }
+    const double n = (double)elems, mu1 = t[0] / n, mu2 = t[1] / n;
+    const double v1 = t[2] / n - mu1 * mu1, v2 = t[3] / n - mu2 * mu2, c12 = t[4] / n - mu1 * mu2, mse = t[5] / n;
+    const double C1 = 0.01 * 0.01, C2 = 0.03 * 0.03;
+    out[2 * blockIdx.x] = (float)(((2 * mu1 * mu2 + C1) * (2 * c12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (v1 + v2 + C2)));
+    out[2 * blockIdx.x + 1] = mse == 0.0 ? __int_as_float(0x7f800000) : (float)(20.0 * log10(1.0 / sqrt(mse)));
+  }
+}
+
 }  // namespace
 
 static void fill_pack(PackArgs& A, int rows, int cols, int ntaps, const long long* tap_off, long long s_row, long long s_col,
@@ -487,6 +531,14 @@ extern "C" int dm_prep_batch(const void* img_u8, const int* flip, const int* box
   if (B <= 0 || H <= 0 || W <= 0) return DM_OK;
   prep_batch_kernel<<<grid_for((long long)B * H * W), 256, 0, ST>>>((const unsigned char*)img_u8, flip, box, x, mask, B, H, W,
                                                                     mean, stdv, low, mid, high);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+
+/* SSIM (global statistics) and PSNR of N image pairs, ImageMetrics.calc_ssim / calc_psnr (new_scripy.py:1189-1251) */
+extern "C" int dm_image_metrics(const float* a, const float* b, float* out, int N, long long elems, void* stream) {
+  if (N <= 0 || elems <= 0) return DM_OK;
+  image_metrics_kernel<<<N, 1024, 0, ST>>>(a, b, out, elems);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }

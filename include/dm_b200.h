@@ -222,6 +222,11 @@ int dm_ca_gates_bwd(const DmCaGates* p, const DmCaGatesGrad* q, void* stream);
 int dm_prep_batch(const void* img_u8, const int* flip, const int* box, float* x, float* mask, int B, int H, int W,
                   float mean, float stdv, float low, float mid, float high, void* stream);
 
+/* ---- sample quality (next-row 4 of SURVEY 8f): ImageMetrics.calc_ssim / calc_psnr (new_scripy.py:1189-1251) for N pairs of
+ * fp32 images [N][elems] (any range: mapped with (x+1)/2 when an image's minimum is negative, like the reference);
+ * out [N][2] = (ssim, psnr).  FID (:1146-1187) needs pretrained Inception weights and stays out of scope. */
+int dm_image_metrics(const float* a, const float* b, float* out, int N, long long elems, void* stream);
+
 /* ---- optimizer side (new_scripy.py:797-803) --------------------------------------------------------- */
 int dm_sumsq(const float* g, long long n, float* out, void* stream);          /* *out += sum g^2 */
 int dm_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,

@@ -243,6 +243,26 @@ def crack_dataset_case(new_scripy):
     print(f"CrackDataset + transforms == oracle crack_item on {len(items)} items: bit-exact")
 
 
+def image_metrics_case(new_scripy):
+    """Pin oracle calc_ssim / calc_psnr against ImageMetrics' static methods (new_scripy.py:1189-1251) and write a tiny
+    fixture (image pairs in [-1,1], in [0,1], one of each, identical pair) with the reference's values."""
+    g = torch.Generator().manual_seed(17)
+    a = torch.rand(6, 3, 24, 20, generator=g)
+    b = (a + 0.1 * torch.randn(a.shape, generator=g)).clamp(0, 1)
+    a[0], b[0] = a[0] * 2 - 1, b[0] * 2 - 1            # both in [-1,1]
+    a[1] = a[1] * 2 - 1                                # only the first converted
+    b[2] = b[2] * 2 - 1                                # only the second converted
+    b[3] = a[3].clone()                                # identical: psnr = inf
+    ssim, psnr = [], []
+    for i in range(a.shape[0]):
+        s_ref, p_ref = new_scripy.ImageMetrics.calc_ssim(a[i], b[i]), new_scripy.ImageMetrics.calc_psnr(a[i], b[i])
+        s_o, p_o = P.calc_ssim(a[i], b[i]), P.calc_psnr(a[i], b[i])
+        assert float(s_ref) == float(s_o) and (float(p_ref) == float(p_o)), i
+        ssim.append(float(s_ref)); psnr.append(float(p_ref))
+    np.savez(os.path.join(GOLD, "image_metrics.npz"), a=a.numpy(), b=b.numpy(), ssim=np.array(ssim), psnr=np.array(psnr))
+    print("ImageMetrics.calc_ssim / calc_psnr == oracle on 6 pairs: bit-exact")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -250,6 +270,7 @@ def main():
     check_shipped_callsite(new_scripy)
     check_schedules(new_scripy, MNIST_script)
     crack_dataset_case(new_scripy)
+    image_metrics_case(new_scripy)
     if "--only-data" in sys.argv:
         return
     one_case(new_scripy, MNIST_script, "mnist", 16, 28, 8, 10, 11, 400, "mnist_f16_b8")

@@ -404,3 +404,32 @@ def crack_item(image_u8, box_xyxy, orig_wh, flip, img_size, low=0.5, mid=1.0, hi
     x = img.permute(2, 0, 1).to(torch.float32).div(255)                             # ToTensor, :686
     x = (x - mean) / std                                                            # Normalize, :687
     return x, attn
+
+
+# --------------------------------------------------------------------------------------- sample quality (8f rank 4)
+def calc_ssim(img1, img2):
+    """ImageMetrics.calc_ssim (new_scripy.py:1189-1222): global-statistics SSIM in numpy float32."""
+    import numpy as np
+    if img1.min() < 0:
+        img1 = (img1 + 1) / 2
+    if img2.min() < 0:
+        img2 = (img2 + 1) / 2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    a, b = img1.cpu().numpy(), img2.cpu().numpy()
+    mu1, mu2 = np.mean(a), np.mean(b)
+    s1, s2 = np.std(a), np.std(b)
+    s12 = np.mean((a - mu1) * (b - mu2))
+    return ((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 ** 2 + mu2 ** 2 + C1) * (s1 ** 2 + s2 ** 2 + C2))
+
+
+def calc_psnr(img1, img2):
+    """ImageMetrics.calc_psnr (new_scripy.py:1224-1251)."""
+    import numpy as np
+    if img1.min() < 0:
+        img1 = (img1 + 1) / 2
+    if img2.min() < 0:
+        img2 = (img2 + 1) / 2
+    mse = torch.mean((img1 - img2) ** 2).item()
+    if mse == 0:
+        return float("inf")
+    return 20 * np.log10(1.0 / np.sqrt(mse))

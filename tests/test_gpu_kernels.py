@@ -429,3 +429,32 @@ def test_cached_batch_prep_bit_exact(dev):
     assert x3.shape[0] == 3 and int(c3[1]) == int(g["label"][0])
     x4, c4, m4 = cache.batch([], flips=[])
     assert x4.shape[0] == 0 and m4.shape[0] == 0
+
+
+def test_image_metrics_ssim_psnr(dev):
+    """dm_image_metrics against the reference's ImageMetrics values (golden) and the oracle on larger random pairs:
+    per-image [-1,1] -> [0,1] mapping, identical pair -> +inf PSNR, evaluate_batch means."""
+    import math
+    import os
+    import numpy as np
+    from diffusionmodel_b200 import metrics
+    from oracle import ref_port as P
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "image_metrics.npz"))
+    a, b = torch.from_numpy(g["a"]), torch.from_numpy(g["b"])
+    out = metrics.ssim_psnr(a.to(dev), b.to(dev)).cpu()
+    for i in range(a.shape[0]):
+        assert abs(float(out[i, 0]) - float(g["ssim"][i])) < 2e-5 * max(1.0, abs(float(g["ssim"][i]))), i
+        if math.isinf(float(g["psnr"][i])):
+            assert math.isinf(float(out[i, 1])) and float(out[i, 1]) > 0
+        else:
+            assert abs(float(out[i, 1]) - float(g["psnr"][i])) < 1e-4 * abs(float(g["psnr"][i])), i
+    gen = torch.Generator().manual_seed(2)
+    x = torch.rand(3, 3, 256, 256, generator=gen) * 2 - 1
+    y = (x + 0.05 * torch.randn(x.shape, generator=gen)).clamp(-1, 1)
+    out = metrics.ssim_psnr(x.to(dev), y.to(dev)).cpu()
+    for i in range(3):
+        assert abs(float(out[i, 0]) - float(P.calc_ssim(x[i], y[i]))) < 2e-5
+        assert abs(float(out[i, 1]) - float(P.calc_psnr(x[i], y[i]))) < 1e-3
+    m = metrics.evaluate_batch(x.to(dev), y.to(dev))
+    assert abs(m["ssim"] - float(out[:, 0].double().mean())) < 1e-6 and abs(m["psnr"] - float(out[:, 1].double().mean())) < 1e-4
+    assert metrics.evaluate_batch(x[:2].to(dev), y.to(dev)) == {}
