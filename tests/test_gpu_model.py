@@ -369,3 +369,49 @@ def test_coordattn_fused_gates_match_torch_subgraph(dev, shape, training):
         assert noise or P.rel_l2(g1[k], g0[k]) < 2e-4, (k, g0[k].flatten()[:4], g1[k].flatten()[:4])
     for k in b0:
         assert torch.equal(b0[k], b1[k]) if "tracked" in k else P.rel_l2(b1[k], b0[k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("variant", ["mnist", "rdd"])
+def test_loss_curve_tracks_fp32_reference_training(dev, variant):
+    """A dozen optimizer steps (train-mode BatchNorm, clip 1.0, AdamW) from identical weights, data and per-step
+    random draws: the bf16 B200 path's loss curve against the fp32 oracle trained with torch.optim.AdamW on the CPU
+    (the reference loop, new_scripy.py:784-803 / MNIST_script.py:339-349)."""
+    import diffusionmodel_b200 as D
+    n_feat, size, batch, n_classes, n_T, in_ch = (16, 28, 16, 10, 400, 1) if variant == "mnist" else (16, 128, 2, 5, 700, 3)
+    steps, lr, wd = 12, 1e-3, 1e-5
+    ddpm, sd = build(variant, n_feat, n_classes, n_T, 21, dev, **({"enhance_with_attn_map": True} if variant == "rdd" else {}))
+    ddpm.train()
+    inp = make_inputs(variant, batch, in_ch, size, n_classes, n_T, 21)
+    g = torch.Generator().manual_seed(77)
+    draws = [(torch.randint(1, n_T + 1, (batch,), generator=g), torch.randn(batch, in_ch, size, size, generator=g),
+              torch.bernoulli(torch.full((batch,), 0.9 if variant == "rdd" else 0.1), generator=g)) for _ in range(steps)]
+    # ---- fp32 oracle + torch AdamW
+    sd_o = {k: v.clone() for k, v in sd.items()}
+    params = [v.requires_grad_(True) for k, v in sd_o.items()
+              if v.is_floating_point() and k.startswith("nn_model.") and "running" not in k]
+    opt_o = torch.optim.AdamW(params, lr=lr, weight_decay=wd)
+    sched = P.ddpm_schedules(1e-4, 0.02, n_T)
+    ref = []
+    for ts, noise, ctx in draws:
+        opt_o.zero_grad()
+        lo = P.ddpm_loss(sd_o, sched, inp["x"], inp["c"], inp["attn_mask"], ts, noise, ctx, variant=variant, n_T=n_T,
+                         training=True, attn_map=inp["attn_mask"] if variant == "rdd" else None)
+        lo.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt_o.step()
+        ref.append(float(lo))
+    # ---- ours
+    opt = D.FusedAdamW(ddpm.parameters(), lr=lr, weight_decay=wd, max_grad_norm=1.0)
+    x, c, attn = inp["x"].to(dev), inp["c"].to(dev), inp["attn_mask"].to(dev)
+    ours = []
+    for ts, noise, ctx in draws:
+        lo = ddpm(x, c, attn if variant == "rdd" else None, randoms=(ts.to(dev), noise.to(dev), ctx.to(dev)))
+        lo.backward()
+        opt.step()
+        opt.zero_grad()
+        ours.append(float(lo))
+    dev_rel = [abs(a - b) / abs(b) for a, b in zip(ours, ref)]
+    print(f"{variant}: fp32 reference losses {['%.4f' % v for v in ref]}")
+    print(f"{variant}: B200 bf16 losses      {['%.4f' % v for v in ours]}  max rel dev {max(dev_rel):.3e}")
+    assert max(dev_rel) < 0.05 and sum(dev_rel) / steps < 0.02
+    assert sum(ours[-3:]) < sum(ours[:3])              # and it trains
