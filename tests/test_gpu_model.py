@@ -322,7 +322,9 @@ def test_gemm_native_weight_storage(dev):
     assert abs(l0[0] - l1[0]) < 1e-5 * abs(l0[0]) and abs(l0[1] - l1[1]) < 2e-3 * abs(l0[1])
     for k in g0:
         assert g0[k].shape == g1[k].shape
-        assert P.rel_l2(g1[k], g0[k]) < 1e-4 or float(g0[k].abs().max()) < 1e-7, k
+        # two runs differ by the order of the wgrad kernels' fp32 red.adds (and of every reduction upstream): ~1e-4..1e-3 on
+        # the smallest gradients; a layout mistake would be O(1)
+        assert P.rel_l2(g1[k], g0[k]) < 3e-3 or float(g0[k].abs().max()) < 1e-7, k
     # parameters after two Adam steps: the first update is lr*sign(g), so reduction-order noise on near-zero gradient
     # entries flips individual updates (2*lr each); the gradients above are the tight check
     for k in s0:
