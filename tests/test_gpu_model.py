@@ -417,3 +417,29 @@ def test_loss_curve_tracks_fp32_reference_training(dev, variant):
     print(f"{variant}: B200 bf16 losses      {['%.4f' % v for v in ours]}  max rel dev {max(dev_rel):.3e}")
     assert max(dev_rel) < 0.05 and sum(dev_rel) / steps < 0.02
     assert sum(ours[-3:]) < sum(ours[:3])              # and it trains
+
+
+def test_coordattn_non_square_falls_back_to_subgraph(dev):
+    """H != W: the h<->w cross terms need adaptive_avg_pool1d resampling (new_scripy.py:118-126); the gate network then
+    runs as the torch sub-graph instead of dm_ca_gates.  Forward/backward against the fp32 oracle block."""
+    from diffusionmodel_b200 import unet as U
+    from tests.test_gpu_kernels import bf, nchw, nhwc
+    g = torch.Generator().manual_seed(8)
+    n, f, h, w = 2, 32, 12, 20
+    mod = U.CoordAttn(f)
+    sd = {"m." + k: v.clone() for k, v in mod.state_dict().items()}
+    fill_state_dict_(sd, 3)
+    mod.load_state_dict({k[2:]: v for k, v in sd.items()})
+    mod = mod.to(dev).train()
+    x = bf(torch.randn(n, f, h, w, generator=g))
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    y_ref = P.coord_attn(P._Ctx(sd, True), "m", xr)
+    dy = bf(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    xd = nhwc(x, dev).requires_grad_(True)
+    y = mod(xd)
+    y.backward(nhwc(dy, dev))
+    assert P.rel_l2(nchw(y, f), y_ref) < BAR and P.rel_l2(nchw(xd.grad, f), xr.grad) < 1.5e-2
