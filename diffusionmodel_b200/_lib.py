@@ -77,6 +77,10 @@ _SIGS = {
     "dm_pool_prod_nhw": "pi pi p iii f p",
     "dm_se_apply_fwd": "pi p pi pi iii f p",
     "dm_se_apply_bwd": "pi p p pi pi iii f p",
+    "dm_linear_act_fwd": "ppp pp iii i p",
+    "dm_linear_bwd_parts": "i",
+    "dm_linear_act_bwd": "pi pi pp pp p iii p",
+    "dm_sum_parts": "pi p l p",
     "dm_ca_pool": "pi pi pp iiii ff p",
     "dm_ca_gate_fwd": "pi pp pi iiii p",
     "dm_ca_gate_bwd": "pi pp pp pi iiii p",

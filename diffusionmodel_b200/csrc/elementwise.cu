@@ -1123,6 +1123,124 @@ struct UpcatBwd {
   }
 };
 
+// Quad forms of the two passes above (same arithmetic, same accumulation order -> bit-identical results).
+// With align_corners=True and an exact x2 factor, output rows 2k-1 and 2k both interpolate between source
+// rows k-1 and k (lerp_src: (int)(o*(h-1)/(2h-1)) = k-1 for both), so a thread that owns the 2x2 output quad
+// (rows 2ky-1..2ky, cols 2kx-1..2kx) needs exactly one 2x2 source block: one 16-byte load per 16-byte store
+// instead of four.  Quads on the border have one valid row and/or column.
+__global__ void __launch_bounds__(kEwThreads) upcat_fwd_quad_kernel(UpcatFwd f, unsigned total, unsigned Cv) {
+  const int h = f.h, w = f.w, W2 = 2 * w, H2 = 2 * h;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned q = i / Cv;
+    const int c0 = (int)(i - q * Cv) * 8;
+    const int kx = q % (unsigned)(w + 1); q /= (unsigned)(w + 1);
+    const int ky = q % (unsigned)(h + 1);
+    const int n = q / (unsigned)(h + 1);
+    const bool vy[2] = {ky >= 1, ky <= h - 1}, vx[2] = {kx >= 1, kx <= w - 1};
+    const int oy[2] = {vy[0] ? 2 * ky - 1 : 2 * ky, vy[1] ? 2 * ky : 2 * ky - 1};
+    const int ox[2] = {vx[0] ? 2 * kx - 1 : 2 * kx, vx[1] ? 2 * kx : 2 * kx - 1};
+    const Lerp Y[2] = {lerp_src(oy[0], h, f.sy), lerp_src(oy[1], h, f.sy)};
+    const Lerp X[2] = {lerp_src(ox[0], w, f.sx), lerp_src(ox[1], w, f.sx)};
+    const bf16* src; int ld, c, C;
+    if (c0 < f.Ca) { src = f.a; ld = f.lda; c = c0; C = f.Ca; } else { src = f.b; ld = f.ldb; c = c0 - f.Ca; C = f.Cb; }
+    const long long base = (long long)n * h * w;
+    float v00[8], v01[8], v10[8], v11[8], o[8];
+    load8(src + (base + (long long)Y[0].i0 * w + X[0].i0) * ld + c, v00);
+    load8(src + (base + (long long)Y[0].i0 * w + X[0].i1) * ld + c, v01);
+    load8(src + (base + (long long)Y[0].i1 * w + X[0].i0) * ld + c, v10);
+    load8(src + (base + (long long)Y[0].i1 * w + X[0].i1) * ld + c, v11);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      if (!vy[a]) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (!vx[b]) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = (c + j < C) ? Y[a].l0 * (X[b].l0 * v00[j] + X[b].l1 * v01[j]) + Y[a].l1 * (X[b].l0 * v10[j] + X[b].l1 * v11[j]) : 0.f;
+        store8(f.out + (((long long)n * H2 + oy[a]) * W2 + ox[b]) * f.ldo + c0, o);
+      }
+    }
+  }
+}
+// Backward: a thread owns a 2x2 block of input pixels and walks the 6x6 output window that touches it (rows
+// 2*iy0-1 .. 2*iy0+4): 9 loads per input vector instead of 16, all of one window row in flight together, no
+// data-dependent control flow.  Per input pixel the products are added in the same (row, column) order as UpcatBwd.
+__global__ void __launch_bounds__(kEwThreads) upcat_bwd_quad_kernel(UpcatBwd f, unsigned total, unsigned Cv) {
+  const int h = f.h, w = f.w, W2 = 2 * w, H2 = 2 * h, hb = (h + 1) / 2, wb = (w + 1) / 2;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned q = i / Cv;
+    const int c0 = (int)(i - q * Cv) * 8;
+    const int ix0 = 2 * (int)(q % (unsigned)wb); q /= (unsigned)wb;
+    const int iy0 = 2 * (int)(q % (unsigned)hb);
+    const int n = q / (unsigned)hb;
+    float wy[2][6], wx[2][6];
+    int ry[6], rx[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const int oy = 2 * iy0 - 1 + r, ox = 2 * ix0 - 1 + r;
+      const bool vy = oy >= 0 && oy < H2, vx = ox >= 0 && ox < W2;
+      ry[r] = vy ? oy : 0; rx[r] = vx ? ox : 0;
+      const Lerp Y = lerp_src(ry[r], h, f.sy), X = lerp_src(rx[r], w, f.sx);
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        wy[a][r] = vy ? (Y.i0 == iy0 + a ? Y.l0 : 0.f) + (Y.i1 == iy0 + a ? Y.l1 : 0.f) : 0.f;
+        wx[a][r] = vx ? (X.i0 == ix0 + a ? X.l0 : 0.f) + (X.i1 == ix0 + a ? X.l1 : 0.f) : 0.f;
+      }
+    }
+    float acc[2][2][8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[a][b][j] = 0.f;
+    const bf16* gbase = f.dout + (long long)n * H2 * W2 * f.lddo + c0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      uint4 raw[6];
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) raw[cc] = dm::ldg16(gbase + ((long long)ry[r] * W2 + rx[cc]) * f.lddo);
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) {
+        float g[8];
+        g[0] = dm::bf_lo(raw[cc].x); g[1] = dm::bf_hi(raw[cc].x); g[2] = dm::bf_lo(raw[cc].y); g[3] = dm::bf_hi(raw[cc].y);
+        g[4] = dm::bf_lo(raw[cc].z); g[5] = dm::bf_hi(raw[cc].z); g[6] = dm::bf_lo(raw[cc].w); g[7] = dm::bf_hi(raw[cc].w);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (r < 2 * a || r >= 2 * a + 4) continue;      // rows outside 2*iy-1 .. 2*iy+2 never sample input row iy
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            if (cc < 2 * b || cc >= 2 * b + 4) continue;
+            const float wt = wy[a][r] * wx[b][cc];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[a][b][j] += wt * g[j];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      if (iy0 + a >= h) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (ix0 + b >= w) continue;
+        const long long p = ((long long)n * h + iy0 + a) * w + ix0 + b;
+        if (c0 < f.Ca) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (c0 + j >= f.Ca) acc[a][b][j] = 0.f;
+          store8(f.da + p * f.ldda + c0, acc[a][b]);
+        } else {
+          const int c = c0 - f.Ca;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (c + j >= f.Cb) acc[a][b][j] = 0.f;
+          store8(f.db + p * f.lddb + c, acc[a][b]);
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------- pooling
 struct AvgPoolFwd {
   const bf16* x; int ldx; bf16* out; int ldo; int H, W, C, k, act;
@@ -1594,14 +1712,26 @@ extern "C" int dm_upcat_fwd(const void* a, int lda, int Ca, const void* b, int l
   REQ8(lda, "dm_upcat_fwd"); REQ8(ldb, "dm_upcat_fwd"); REQ8(ldo, "dm_upcat_fwd"); REQ8(Ca, "dm_upcat_fwd(Ca)");
   UpcatFwd f{(const bf16*)a, lda, Ca, (const bf16*)b, ldb, Cb, (bf16*)out, ldo, h, w,
              h > 1 ? (float)(h - 1) / (float)(2 * h - 1) : 0.f, w > 1 ? (float)(w - 1) / (float)(2 * w - 1) : 0.f};
-  return ew_launch((long long)N * 4 * h * w, Ca + Cb, f, ST);
+  if (dm_debug_value(9) == 1) return ew_launch((long long)N * 4 * h * w, Ca + Cb, f, ST);   // dev: one thread per output pixel
+  const long long Cv = (Ca + Cb + 7) / 8, total = (long long)N * (h + 1) * (w + 1) * Cv;
+  if (total <= 0) return DM_OK;
+  if (total >= (1ll << 32) || (long long)N * 4 * h * w * Cv >= (1ll << 32)) { dm_set_error("dm_upcat_fwd: tensor too large"); return DM_ERR_ARG; }
+  upcat_fwd_quad_kernel<<<ew_grid(total), kEwThreads, 0, ST>>>(f, (unsigned)total, (unsigned)Cv);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
 }
 extern "C" int dm_upcat_bwd(const void* dout, int lddo, void* da, int ldda, int Ca, void* db, int lddb, int Cb, int N,
                             int h, int w, void* stream) {
   REQ8(lddo, "dm_upcat_bwd"); REQ8(ldda, "dm_upcat_bwd"); REQ8(lddb, "dm_upcat_bwd"); REQ8(Ca, "dm_upcat_bwd(Ca)");
   UpcatBwd f{(const bf16*)dout, lddo, (bf16*)da, ldda, Ca, (bf16*)db, lddb, Cb, h, w,
              h > 1 ? (float)(h - 1) / (float)(2 * h - 1) : 0.f, w > 1 ? (float)(w - 1) / (float)(2 * w - 1) : 0.f};
-  return ew_launch((long long)N * h * w, Ca + Cb, f, ST);
+  if (dm_debug_value(9) == 1) return ew_launch((long long)N * h * w, Ca + Cb, f, ST);      // dev: one thread per input pixel
+  const long long Cv = (Ca + Cb + 7) / 8, total = (long long)N * ((h + 1) / 2) * ((w + 1) / 2) * Cv;
+  if (total <= 0) return DM_OK;
+  if ((long long)N * 4 * h * w * Cv >= (1ll << 32)) { dm_set_error("dm_upcat_bwd: tensor too large"); return DM_ERR_ARG; }
+  upcat_bwd_quad_kernel<<<ew_grid(total), kEwThreads, 0, ST>>>(f, (unsigned)total, (unsigned)Cv);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
 }
 extern "C" int dm_film_fwd(const void* x, int ldx, const float* ce, const float* te, void* out, int ldo, int N, int HW,
                            int C, void* stream) {

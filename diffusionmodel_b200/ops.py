@@ -751,33 +751,112 @@ def _small_backward(ins, outs, grads, params):
     return res[:len(ins)]
 
 
-class _SeResidual(torch.autograd.Function):
-    """out = (res + x2 * gate(x2)) * scale, gate = SEBlock MLP on the global average pool
-    (new_scripy.py:154-158,196-205).  mlp=None: plain (res + x2) * scale (MNIST_script.py:57-61)."""
+ACT_SIGMOID = 3      # dm_linear_act_* only
+
+
+def _param_grad_ptr(p):
+    return _p(grad_buf(p)) if p is not None and p.requires_grad else None
+
+
+def mlp2_fwd(x, w1, b1, w2, b2, act1, act2):
+    """act2(act1(x W1^T + b1) W2^T + b2) on fp32 rows [N, Cin] through dm_linear_act_fwd (two launches).
+    Returns (y, saved) with saved = what mlp2_bwd needs."""
+    n, cin = x.shape
+    hid, cout = w1.shape[0], w2.shape[0]
+    st = _stream()
+    pre1 = torch.empty((n, hid), device=x.device, dtype=torch.float32)
+    h = torch.empty_like(pre1)
+    y = torch.empty((n, cout), device=x.device, dtype=torch.float32)
+    pre2 = torch.empty_like(y) if act2 in (ACT_GELU, ACT_RELU) else None
+    call("dm_linear_act_fwd", _p(x), _p(w1), _p(b1), _p(pre1), _p(h), n, cin, hid, act1, st)
+    call("dm_linear_act_fwd", _p(h), _p(w2), _p(b2), _p(pre2), _p(y), n, hid, cout, act2, st)
+    return y, (x, pre1, h, y if act2 == ACT_SIGMOID else pre2)
+
+
+def mlp2_bwd(saved, dy, w1, b1, w2, b2, act1, act2, need_dx):
+    """Backward of mlp2_fwd: parameter gradients are added straight into the parameters' .grad memory; returns the
+    input gradient (or None).  Three launches (two without an input gradient), no atomics."""
+    x, pre1, h, aux2 = saved
+    n, cin = x.shape
+    hid, cout = w1.shape[0], w2.shape[0]
+    st = _stream()
+    np2 = _lib.fn("dm_linear_bwd_parts")(cout)
+    parts2 = torch.empty((np2, n, hid), device=x.device, dtype=torch.float32)
+    call("dm_linear_act_bwd", _p(dy), 1, _p(aux2), act2, _p(h), _p(w2), _param_grad_ptr(w2), _param_grad_ptr(b2),
+         _p(parts2), n, hid, cout, st)
+    np1 = _lib.fn("dm_linear_bwd_parts")(hid)
+    parts1 = torch.empty((np1, n, cin), device=x.device, dtype=torch.float32) if need_dx else None
+    call("dm_linear_act_bwd", _p(parts2), np2, _p(pre1), act1, _p(x), _p(w1), _param_grad_ptr(w1), _param_grad_ptr(b1),
+         _p(parts1), n, cin, hid, st)
+    if not need_dx:
+        return None
+    if np1 == 1:
+        return parts1[0]
+    dx = torch.empty((n, cin), device=x.device, dtype=torch.float32)
+    call("dm_sum_parts", _p(parts1), np1, _p(dx), n * cin, st)
+    return dx
+
+
+def _lin_param(p):
+    if p is None:
+        return None
+    if p.dtype != torch.float32 or not p.is_contiguous():
+        raise _lib.DmB200Error("linear parameters must be contiguous fp32")
+    return p
+
+
+class _Mlp2(torch.autograd.Function):
+    """EmbedFC.model = Linear - GELU - Linear (new_scripy.py:259-263; MNIST_script.py:107-111) on [N, input_dim] rows."""
 
     @staticmethod
-    def forward(ctx, x2, res, c, scale, mlp, *params):
+    def forward(ctx, x, act1, act2, w1, b1, w2, b2):
+        x = x.detach().to(torch.float32).contiguous()
+        if not x.is_cuda:
+            raise _lib.DmB200Error("mlp2: CUDA tensors only (no CPU fallback)")
+        y, saved = mlp2_fwd(x, w1.detach(), b1.detach() if b1 is not None else None, w2.detach(),
+                            b2.detach() if b2 is not None else None, act1, act2)
+        ctx.saved = saved
+        ctx.cfg = (act1, act2, w1, b1, w2, b2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        act1, act2, w1, b1, w2, b2 = ctx.cfg
+        dx = mlp2_bwd(ctx.saved, dy.to(torch.float32).contiguous(), w1, b1, w2, b2, act1, act2, ctx.needs_input_grad[0])
+        return dx, None, None, None, None, None, None
+
+
+def embed_fc(x, lin1, lin2):
+    """EmbedFC forward on [N, input_dim] rows (new_scripy.py:265-268)."""
+    return _Mlp2.apply(x, ACT_GELU, ACT_NONE, _lin_param(lin1.weight), _lin_param(lin1.bias), _lin_param(lin2.weight),
+                       _lin_param(lin2.bias))
+
+
+class _SeResidual(torch.autograd.Function):
+    """out = (res + x2 * gate(x2)) * scale, gate = SEBlock MLP on the global average pool
+    (new_scripy.py:154-158,196-205).  w1 None: plain (res + x2) * scale (MNIST_script.py:57-61)."""
+
+    @staticmethod
+    def forward(ctx, x2, res, c, scale, w1, w2):
         ld2, ldr = _chk(x2, "se x2"), _chk(res, "se residual")
         n, h, w, _ = x2.shape
         st = _stream()
         gate = None
         ctx.small = None
-        if mlp is not None:
+        if w1 is not None:
             pooled = torch.empty((n, c), device=x2.device, dtype=torch.float32)
             call("dm_pool_nhw", _p(x2), ld2, _p(pooled), n, h * w, c, 1.0 / (h * w), st)
-            ins, gate_g = _run_small(mlp, [pooled], params)
-            gate = gate_g.detach().contiguous()
-            ctx.small = (ins, gate_g)
+            gate, ctx.small = mlp2_fwd(pooled, w1.detach(), None, w2.detach(), None, ACT_GELU, ACT_SIGMOID)
         out = torch.empty_like(x2)
         call("dm_se_apply_fwd", _p(x2), ld2, _p(gate), _p(res), ldr, _p(out), out.stride(2), n, h * w, c, scale, st)
         ctx.save_for_backward(x2, gate)
-        ctx.cfg = (c, scale, params)
+        ctx.cfg = (c, scale, w1, w2)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x2, gate = ctx.saved_tensors
-        c, scale, params = ctx.cfg
+        c, scale, w1, w2 = ctx.cfg
         lddo = _chk(dout, "se grad")
         n, h, w, _ = x2.shape
         st = _stream()
@@ -785,25 +864,18 @@ class _SeResidual(torch.autograd.Function):
         if ctx.small is not None:
             dgate = torch.empty((n, c), device=x2.device, dtype=torch.float32)
             call("dm_pool_prod_nhw", _p(dout), lddo, _p(x2), x2.stride(2), _p(dgate), n, h * w, c, scale, st)
-            ins, gate_g = ctx.small
-            (dpool,) = _small_backward(ins, [gate_g], [dgate], list(params))
-            dpool = dpool.contiguous()
+            dpool = mlp2_bwd(ctx.small, dgate, w1, None, w2, None, ACT_GELU, ACT_SIGMOID, True)
         dx2 = torch.empty_like(x2)
         dres = torch.empty_like(x2)
         call("dm_se_apply_bwd", _p(dout), lddo, _p(gate), _p(dpool), _p(dx2), dx2.stride(2), _p(dres), dres.stride(2), n,
              h * w, c, scale, st)
-        return (dx2, dres, None, None, None) + (None,) * len(params)
+        return dx2, dres, None, None, None, None
 
 
 def se_residual(x2, res, c, scale, se_fc=None):
     if se_fc is None:
-        return _SeResidual.apply(x2, res, c, scale, None)
-    w1, w2 = se_fc[0].weight, se_fc[2].weight
-
-    def mlp(y):
-        return torch.sigmoid(torch.nn.functional.linear(
-            torch.nn.functional.gelu(torch.nn.functional.linear(y, w1)), w2))
-    return _SeResidual.apply(x2, res, c, scale, mlp, w1, w2)
+        return _SeResidual.apply(x2, res, c, scale, None, None)
+    return _SeResidual.apply(x2, res, c, scale, _lin_param(se_fc[0].weight), _lin_param(se_fc[2].weight))
 
 
 class _CoordAttn(torch.autograd.Function):

@@ -242,8 +242,8 @@ class UnetUp(nn.Module):
 
 
 class EmbedFC(nn.Module):
-    """Linear-GELU-Linear on a scalar / one-hot input (new_scripy.py:255-268): [N, <=n_classes] sized,
-    runs as plain fp32 library GEMMs."""
+    """Linear-GELU-Linear on a scalar / one-hot input (new_scripy.py:255-268): [N, <=n_classes] fp32 rows through
+    the weight-stationary dm_linear_act_fwd/bwd kernels (2 launches forward, 2 backward)."""
 
     def __init__(self, input_dim, emb_dim):
         super().__init__()
@@ -251,7 +251,7 @@ class EmbedFC(nn.Module):
         self.model = nn.Sequential(nn.Linear(input_dim, emb_dim), nn.GELU(), nn.Linear(emb_dim, emb_dim))
 
     def forward(self, x):
-        return self.model(x.view(-1, self.input_dim))
+        return ops.embed_fc(x.view(-1, self.input_dim), self.model[0], self.model[2])
 
 
 def _head(x, x0, seq, c_each):

@@ -125,6 +125,20 @@ int dm_se_apply_fwd(const void* x2, int ld2, const float* gate, const void* res,
 int dm_se_apply_bwd(const void* dout, int lddo, const float* gate, const float* dpool, void* dx2, int lddx2,
                     void* dres, int lddr, int N, int HW, int C, float scale, void* stream);
 
+/* ---- [N, C]-sized fp32 linear layers: SEBlock.fc (new_scripy.py:148-152), EmbedFC.model (new_scripy.py:259-263) ---
+ * act: 0 none, 1 GELU (erf), 2 ReLU, 3 sigmoid.  W is the nn.Linear weight [Cout][Cin]; b nullable.
+ * fwd: y = act(x W^T + b); pre (nullable) receives the pre-activation (what the GELU/ReLU backward needs).
+ * bwd: g = (sum of the nparts rows-blocks dy[p][N][Cout]) * act'(aux), aux = pre (GELU/ReLU) or y (sigmoid);
+ *      dW += g^T x, db += column sums of g (both nullable), dx_parts[s][N][Cin] = g[:, slice s] W[slice s, :] for the
+ *      dm_linear_bwd_parts(Cout) output-feature slices (nullable).  The next dm_linear_act_bwd in the chain consumes
+ *      the partial rows directly (its dy/nparts); dm_sum_parts folds them when a plain tensor is needed. */
+int dm_linear_act_fwd(const float* x, const float* W, const float* b, float* pre, float* y, int N, int Cin, int Cout,
+                      int act, void* stream);
+int dm_linear_bwd_parts(int Cout);
+int dm_linear_act_bwd(const float* dy, int nparts, const float* aux, int act, const float* x, const float* W, float* dW,
+                      float* db, float* dx_parts, int N, int Cin, int Cout, void* stream);
+int dm_sum_parts(const float* parts, int nparts, float* out, long long n, void* stream);
+
 /* ---- CoordAttn directional pooling and gating (new_scripy.py:97-140) ------------------------------- */
 int dm_ca_pool(const void* a, int lda, const void* b, int ldb, float* oh, float* ow, int N, int H, int W, int C,
                float scale_h, float scale_w, void* stream);   /* oh[n,h,c]=scale_h*sum_w a*b ; b NULL -> a */

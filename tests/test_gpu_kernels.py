@@ -304,6 +304,81 @@ def test_upcat_film_pool(dev):
     assert torch.equal(nchw(xd.grad, 16), xr.grad)
 
 
+@pytest.mark.parametrize("shape", [(2, 8, 8, 16, 24), (1, 5, 7, 8, 3), (3, 1, 1, 8, 8), (2, 16, 16, 192, 192), (1, 6, 4, 40, 20)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_upcat_quad_kernels_bit_identical_to_per_pixel_form(dev, shape):
+    """The 2x2-quad upsample+cat kernels (one source block per output quad / 6x6 window per input block) must
+    reproduce the one-thread-per-pixel kernels bit for bit, forward and backward, incl. odd sizes and ragged channels."""
+    from diffusionmodel_b200 import ops, _lib
+    n, h, w, ca, cb = shape
+    g = torch.Generator().manual_seed(23)
+    a = nhwc(torch.randn(n, ca, h, w, generator=g), dev)
+    b = nhwc(torch.randn(n, cb, h, w, generator=g), dev)
+    dy = None
+    res = {}
+    for mode in (1, 0):
+        _lib.debug_set(9, mode)
+        try:
+            ad, bd = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            up = ops.upcat(ad, bd, ca, cb)
+            if dy is None:
+                dy = torch.randn(up.shape, generator=g).to(torch.bfloat16).to(dev)
+            up.backward(dy)
+            torch.cuda.synchronize()
+            res[mode] = (up.detach().clone(), ad.grad.clone(), bd.grad.clone())
+        finally:
+            _lib.debug_set(9, 0)
+    for x, y in zip(res[0], res[1]):
+        assert torch.equal(x, y)
+    ref = F.interpolate(torch.cat((nchw(a, ca), nchw(b, cb)), 1), scale_factor=2, mode="bilinear", align_corners=True)
+    assert rel(nchw(res[0][0], ca + cb), ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("case", [(4, 1, 1536, 1536, 1, 0, True), (4, 5, 768, 768, 1, 0, True), (30, 192, 12, 192, 1, 3, False),
+                                  (4, 1536, 96, 1536, 1, 3, False), (130, 10, 256, 256, 1, 0, True), (3, 40, 7, 33, 2, 2, True)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_linear_mlp_kernels(dev, case):
+    """dm_linear_act_fwd/bwd (SEBlock.fc, EmbedFC.model) against the same two-layer MLP in fp32 torch on the CPU:
+    outputs, input gradient, and parameter gradients accumulated (+=) into pre-filled buffers."""
+    from diffusionmodel_b200 import ops
+    n, cin, hid, cout, act1, act2, bias = case
+    g = torch.Generator().manual_seed(29)
+    acts = {0: lambda v: v, 1: F.gelu, 2: F.relu, 3: torch.sigmoid}
+    x = torch.randn(n, cin, generator=g)
+    w1 = torch.randn(hid, cin, generator=g) / math.sqrt(cin)
+    w2 = torch.randn(cout, hid, generator=g) / math.sqrt(hid)
+    b1 = torch.randn(hid, generator=g) if bias else None
+    b2 = torch.randn(cout, generator=g) if bias else None
+    dy = torch.randn(n, cout, generator=g)
+    ps = [t.clone().requires_grad_(True) for t in (x, w1, w2)] + [t.clone().requires_grad_(True) if t is not None else None for t in (b1, b2)]
+    xr, w1r, w2r, b1r, b2r = ps
+    yr = acts[act2](F.linear(acts[act1](F.linear(xr, w1r, b1r)), w2r, b2r))
+    yr.backward(dy)
+    d = [t.to(dev) if t is not None else None for t in (x, w1, b1, w2, b2)]
+    xd, w1d, b1d, w2d, b2d = d
+    pre = {}
+    for name, t in (("w1", w1d), ("b1", b1d), ("w2", w2d), ("b2", b2d)):
+        if t is not None:
+            t.requires_grad_(True)
+            t.grad = torch.randn(t.shape, generator=g).to(dev)
+            pre[name] = t.grad.clone()
+    y, saved = ops.mlp2_fwd(xd, w1d.detach(), None if b1d is None else b1d.detach(), w2d.detach(),
+                            None if b2d is None else b2d.detach(), act1, act2)
+    assert rel(y.cpu(), yr.detach()) < F32_TOL
+    dx = ops.mlp2_bwd(saved, dy.to(dev), w1d, b1d, w2d, b2d, act1, act2, True)
+    assert rel(dx.cpu(), xr.grad) < F32_TOL
+    for name, t, r in (("w1", w1d, w1r), ("b1", b1d, b1r), ("w2", w2d, w2r), ("b2", b2d, b2r)):
+        if t is not None:
+            assert rel((t.grad - pre[name]).cpu(), r.grad) < F32_TOL, name
+    # autograd wrapper without an input gradient (EmbedFC: t and the one-hot class need none)
+    for t in (w1d, b1d, w2d, b2d):
+        if t is not None:
+            t.grad = None
+    out = ops._Mlp2.apply(xd, act1, act2, w1d, b1d, w2d, b2d)
+    out.backward(dy.to(dev))
+    assert rel(w1d.grad.cpu(), w1r.grad) < F32_TOL and rel(w2d.grad.cpu(), w2r.grad) < F32_TOL
+
+
 def test_local_enhancer_mask_bit_exact(dev):
     """(mask > 1.2) index set must be bit-exact incl. the threshold itself, its neighbours and NaN."""
     from diffusionmodel_b200 import ops
