@@ -41,6 +41,9 @@ def lib() -> ctypes.CDLL:
         _lib.dm_debug_set.argtypes = [ctypes.c_int, ctypes.c_longlong]
         _lib.dm_debug_set.restype = None
         _lib.dm_launch_count.restype = ctypes.c_longlong
+        for kv in filter(None, os.environ.get("DM_DEBUG", "").split(",")):      # dev switches, e.g. DM_DEBUG=10=3,9=1
+            k, v = kv.split("=")
+            _lib.dm_debug_set(int(k), int(v))
     return _lib
 
 
@@ -81,6 +84,8 @@ _SIGS = {
     "dm_linear_bwd_parts": "i",
     "dm_linear_act_bwd": "pi pi pp pp p iii p",
     "dm_sum_parts": "pi p l p",
+    "dm_skinny_gemm_scratch": "ii",
+    "dm_skinny_gemm": "pl pl pi p iii p",
     "dm_ca_pool": "pi pi pp iiii ff p",
     "dm_ca_gate_fwd": "pi pp pi iiii p",
     "dm_ca_gate_bwd": "pi pp pp pi iiii p",
@@ -110,7 +115,7 @@ _SIGS = {
     "dm_adamw": "pppp l fffffff p f p",
     "dm_adamw_bf16": "ppppp l fffffff p f p",
 }
-_RET_LL = {"dm_bn_act_bwd_scratch", "dm_gn_scratch"}          # size queries return long long, not a status
+_RET_LL = {"dm_bn_act_bwd_scratch", "dm_gn_scratch", "dm_skinny_gemm_scratch"}          # size queries return long long, not a status
 _CT = {"p": _P, "i": _I, "l": _L, "f": _F, "d": _D}
 _bound = {}
 

@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libdm_b200.so")
-SOURCES = ["conv_gemm.cu", "elementwise.cu", "ddpm_optim.cu", "coordattn.cu", "mlp.cu"]
+SOURCES = ["conv_gemm.cu", "elementwise.cu", "ddpm_optim.cu", "coordattn.cu", "mlp.cu", "skinny.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]

@@ -1292,7 +1292,7 @@ wgrad4_pair2_kernel(const __grid_constant__ Wgrad2Params p) {
 
 // ------------------------------------------------------------------------------------------ host side
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
-long long g_debug[16] = {0};   // 8..15: elementwise.cu experiments (dm_debug_value); 0 stages 1 grid 2 splits 3 block_n 4 wgrad kernel 5 no-halo 6 base-offset 7 ablation
+long long g_debug[16] = {0};   // 8..15: elementwise.cu experiments (dm_debug_value); 0 stages 1 grid 2 splits 3 block_n 4 wgrad kernel 5 no-halo 6 base-offset 7 ablation 9 upcat per-pixel 10 wgrad stages
 
 int ensure_encode() {
   if (g_encode) return DM_OK;
@@ -1763,6 +1763,7 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
     int stages = (kSmemBudget - 1024 - 512) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (g_debug[0] > 0 && g_debug[0] < stages) stages = (int)g_debug[0];
+    if (g_debug[10] > 0 && g_debug[10] < stages) stages = (int)g_debug[10];   // dev: wgrad-only ring depth (leaves shared memory for co-resident kernels)
     P.stages = stages;
     const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
     static bool attr_f = false;
@@ -1803,6 +1804,7 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
     int stages = (kSmemBudget - 1024 - 512) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (g_debug[0] > 0 && g_debug[0] < stages) stages = (int)g_debug[0];
+    if (g_debug[10] > 0 && g_debug[10] < stages) stages = (int)g_debug[10];   // dev: wgrad-only ring depth (leaves shared memory for co-resident kernels)
     P.stages = stages;
     const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
     static bool attr_g = false;
@@ -1841,6 +1843,7 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
     int stages = (kSmemBudget - 1024 - 512) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (g_debug[0] > 0 && g_debug[0] < stages) stages = (int)g_debug[0];
+    if (g_debug[10] > 0 && g_debug[10] < stages) stages = (int)g_debug[10];   // dev: wgrad-only ring depth (leaves shared memory for co-resident kernels)
     P.stages = stages;
     const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
     if (!g_attr_c) {
@@ -1882,6 +1885,7 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
   int stages = (kSmemBudget - 1024 - kAuxBytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (g_debug[0] > 0 && g_debug[0] < stages) stages = (int)g_debug[0];
+    if (g_debug[10] > 0 && g_debug[10] < stages) stages = (int)g_debug[10];   // dev: wgrad-only ring depth (leaves shared memory for co-resident kernels)
   P.stages = stages;
   size_t smem = 1024 + (size_t)stages * stage_bytes + kAuxBytes;
   if (!g_attr_b) {

@@ -36,6 +36,45 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# --------------------------------------------------------------------------------------- weight gradients on a side stream
+# Nothing in the backward pass consumes a weight gradient, so the wgrad GEMMs (tensor-pipe bound) can run on a second
+# stream next to the bandwidth-bound normalisation / pooling kernels of the layers below.  Fork: the side stream waits
+# for an event recorded on the launching stream (dy and x are ready there); join: the launching stream waits for the
+# side stream when the backward pass ends (autograd engine callback).  The operands are kept alive until the join so
+# the caching allocator cannot hand their memory to a later main-stream kernel.  Works inside CUDA-graph capture
+# (the fork/join become graph edges).
+WGRAD_SIDE_STREAM = _os.environ.get("DM_WGRAD_STREAM", "0") == "1"
+_side = {}
+
+
+def _fork_wgrad(*keep):
+    """Order the side stream after the current stream and return its handle for one wgrad launch."""
+    dev = torch.cuda.current_device()
+    s = _side.get(dev)
+    if s is None:
+        s = _side[dev] = dict(stream=torch.cuda.Stream(device=dev), hold=[], main=None)
+    main = torch.cuda.current_stream()
+    if s["main"] is not None and s["main"] != main:
+        join_side_stream()
+    if s["main"] is None:
+        s["main"] = main
+        torch.autograd.Variable._execution_engine.queue_callback(join_side_stream)
+    ev = torch.cuda.Event()
+    ev.record(main)
+    s["stream"].wait_event(ev)
+    s["hold"].append(keep)
+    return ctypes.c_void_p(s["stream"].cuda_stream)
+
+
+def join_side_stream():
+    """The launching stream waits for every forked wgrad; releases the operands held for them."""
+    for s in _side.values():
+        if s["main"] is not None:
+            s["main"].wait_stream(s["stream"])
+            s["main"] = None
+            s["hold"].clear()
+
+
 # --------------------------------------------------------------------------------------- GEMM-native weight storage
 # The fused optimizer may store a Conv2d weight [Cout, Cin, kh, kw] in the implicit GEMM's own order
 # [Cout][kh][kw][Cin] (the parameter becomes a permuted view: same shape, same values, same state_dict).  Then
@@ -437,12 +476,13 @@ class _Conv2d(torch.autograd.Function):
         # weight gradient: packed fp32 [Cout][taps][Cin_k], scattered (+=) into the NCHW parameter grad
         ck = _cols_k(cin, c0 if x1 is not None else 0)
 
-        def run_wgrad(dwp):
+        def run_wgrad(dwp, stream=st):
             call("dm_conv2d_wgrad", _p(x0), c0, x0.stride(2), _p(x1), c1, x1.stride(2) if x1 is not None else 0, _p(dy),
-                 lddy, _p(dwp), n, hin, win, cout, kh, kw, stride, pad, st)
+                 lddy, _p(dwp), n, hin, win, cout, kh, kw, stride, pad, stream)
         gw = grad_buf(weight)
         if ck == cin and _native_of(weight) is not None and tuple(gw.stride()) == native_strides(weight.shape):
-            run_wgrad(gw)                 # GEMM-native storage: param.grad's memory is the packed accumulator
+            # GEMM-native storage: param.grad's memory is the packed accumulator
+            run_wgrad(gw, _fork_wgrad(x0, x1, dy, gw) if WGRAD_SIDE_STREAM else st)
         else:
             s0, s1, s2, s3 = gw.stride()
             offs = [r * s2 + s * s3 for r in range(kh) for s in range(kw)]
@@ -598,8 +638,18 @@ class _ConvT(torch.autograd.Function):
             s2d = new_act(n, hin, win, kc, dy.device)
             call("dm_space_to_depth", _p(dy), lddy, _p(s2d), s2d.stride(2), n, hin, win, cout, k, 0, st)
             dx = new_act(n, hin, win, cin, dy.device)
-            call("dm_conv2d_fwd", _p(s2d), kc, s2d.stride(2), None, 0, 0, _p(wd), None, None, 0, _p(dx), dx.stride(2), 0, None, 0,
-                 n, hin, win, cin, 1, 1, 1, 0, st)
+            m = n * hin * win
+            if m <= 16 and kc % 32 == 0 and kc >= 4096:
+                # a handful of pixels against a huge K (up0 on the 2x2 bottleneck: 16 x 98304 x 1536): as a conv this is
+                # 9 output tiles; the skinny kernel splits K over the grid and streams the weight pack once at HBM rate
+                if dx.shape[3] != cin:
+                    dx.zero_()
+                scratch = torch.empty(_lib.fn("dm_skinny_gemm_scratch")(cin, kc), device=dy.device, dtype=torch.float32)
+                call("dm_skinny_gemm", _p(s2d), s2d.stride(2), _p(wd), wd.stride(0), _p(dx), dx.stride(2), _p(scratch), m, cin,
+                     kc, st)
+            else:
+                call("dm_conv2d_fwd", _p(s2d), kc, s2d.stride(2), None, 0, 0, _p(wd), None, None, 0, _p(dx), dx.stride(2), 0,
+                     None, 0, n, hin, win, cin, 1, 1, 1, 0, st)
         return dx, None, None, None, None
 
 

@@ -125,6 +125,14 @@ int dm_se_apply_fwd(const void* x2, int ld2, const float* gate, const void* res,
 int dm_se_apply_bwd(const void* dout, int lddo, const float* gate, const float* dpool, void* dx2, int lddx2,
                     void* dres, int lddr, int N, int HW, int C, float scale, void* stream);
 
+/* ---- skinny GEMM: out[m][n] = sum_k A[m][k] * W[n][k], bf16 operands, M <= 16 rows, K a multiple of 32 -----------
+ * The data gradient of up0 = ConvTranspose2d(8F, 8F, 8, 8) on the 2x2 bottleneck (new_scripy.py:297-301): 16 pixels x
+ * K = 98304 x N = 1536.  K is split over the grid (2048 per block); scratch = dm_skinny_gemm_scratch(N, K) floats of
+ * per-slice partial sums, folded in a fixed order and rounded to bf16 into out (row pitch ldo). */
+long long dm_skinny_gemm_scratch(int N, int K);
+int dm_skinny_gemm(const void* A, long long lda, const void* W, long long ldw, void* out, int ldo, float* scratch, int M,
+                   int N, int K, void* stream);
+
 /* ---- [N, C]-sized fp32 linear layers: SEBlock.fc (new_scripy.py:148-152), EmbedFC.model (new_scripy.py:259-263) ---
  * act: 0 none, 1 GELU (erf), 2 ReLU, 3 sigmoid.  W is the nn.Linear weight [Cout][Cin]; b nullable.
  * fwd: y = act(x W^T + b); pre (nullable) receives the pre-activation (what the GELU/ReLU backward needs).

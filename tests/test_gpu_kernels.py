@@ -176,7 +176,7 @@ def test_wgrad_both_kernels(dev, case, version):
     assert rel(wd.grad.cpu(), wr.grad) < F32_TOL
 
 
-@pytest.mark.parametrize("case", [(4, 2, 2, 128, 128, 8), (3, 1, 1, 32, 32, 7), (2, 7, 7, 64, 16, 2)],
+@pytest.mark.parametrize("case", [(4, 2, 2, 128, 128, 8), (3, 1, 1, 32, 32, 7), (2, 7, 7, 64, 16, 2), (2, 2, 2, 72, 96, 8)],
                          ids=lambda c: "x".join(map(str, c)))
 def test_conv_transpose(dev, case):
     from diffusionmodel_b200 import ops
@@ -199,6 +199,26 @@ def test_conv_transpose(dev, case):
     assert rel(nchw(xd.grad, cin), xr.grad) < BF16_TOL
     assert rel(wd.grad.cpu(), wr.grad) < F32_TOL
     assert rel(bd.grad.cpu(), br.grad) < F32_TOL
+
+
+@pytest.mark.parametrize("case", [(16, 1536, 8192), (5, 100, 2144), (1, 8, 32), (16, 72, 6144)], ids=lambda c: "x".join(map(str, c)))
+def test_skinny_gemm(dev, case):
+    """dm_skinny_gemm (split-K mma.sync GEMM for <= 16 rows, the up0 data gradient) against an fp32 matmul of the
+    bf16 operands; ragged M / N, a partial last K slice, and pad lanes of the output left untouched."""
+    from diffusionmodel_b200 import ops, _lib
+    m, n, k = case
+    g = torch.Generator().manual_seed(31)
+    a = bf(torch.randn(m, k, generator=g))
+    w = bf(torch.randn(n, k, generator=g)) / math.sqrt(k)
+    w = bf(w)
+    ref = a @ w.t()
+    ad, wd = a.to(torch.bfloat16).to(dev), w.to(torch.bfloat16).to(dev)
+    ldo = (n + 7) // 8 * 8 + 8
+    out = torch.full((m, ldo), 7.0, dtype=torch.bfloat16, device=dev)
+    scratch = torch.empty(_lib.fn("dm_skinny_gemm_scratch")(n, k), device=dev, dtype=torch.float32)
+    ops.call("dm_skinny_gemm", ops._p(ad), k, ops._p(wd), k, ops._p(out), ldo, ops._p(scratch), m, n, k, ops._stream())
+    assert rel(out[:, :n].float().cpu(), ref) < BF16_TOL
+    assert float((out[:, n:].float() - 7.0).abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("training", [True, False])
