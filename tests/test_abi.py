@@ -63,4 +63,11 @@ def test_sass_is_blackwell_native():
         return
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
-    assert " HMMA" not in sass
+    # the only warp-level MMA in the library is the 16-row split-K product of the up0 data gradient (skinny.cu: one
+    # m16n8k16 fragment IS the whole M extent, the kernel is bound by the 302 MB weight stream, not by the tensor pipe)
+    for fn in sass.split("Function : ")[1:]:
+        name = fn.split("\n", 1)[0]
+        if " HMMA" in fn:
+            assert "skinny_gemm_kernel" in name, name
+        if "conv_gemm_cu" in name:                       # every GEMM kernel of conv_gemm.cu issues tcgen05.mma
+            assert "UTCHMMA" in fn, name
