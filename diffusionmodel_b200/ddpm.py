@@ -131,7 +131,10 @@ class DDPM(nn.Module):
                 dst.copy_(src, non_blocking=True)
             graph.replay()
             for e in touched:
-                e.dirty = True
+                if hasattr(e, "after_replay"):
+                    e.after_replay()              # queued wgrad operands: staging buffers -> this pass's queue slot
+                else:
+                    e.dirty = True
             ops.bump_bn_stats_epoch()         # the replay updated BatchNorm running statistics in place
             return loss
         step.graph, step.kernels_per_replay = graph, kernels

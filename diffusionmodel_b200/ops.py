@@ -44,6 +44,7 @@ def _stream():
 # the caching allocator cannot hand their memory to a later main-stream kernel.  Works inside CUDA-graph capture
 # (the fork/join become graph edges).
 WGRAD_SIDE_STREAM = _os.environ.get("DM_WGRAD_STREAM", "0") == "1"
+RANK_DEFER = _os.environ.get("DM_RANK_DEFER", "1") != "0"      # queue the up0 wgrad operands, one GEMM per optimizer step
 _side = {}
 
 
@@ -350,6 +351,75 @@ class _PackedGrad:
             self.dirty = False
 
 
+class _RankGrad:
+    """Deferred weight gradient of a ConvTranspose2d(k, stride=k) that sees only a handful of input pixels per
+    backward pass (up0 on the 2x2 bottleneck: 16 pixels against a 151 M-element weight, new_scripy.py:297-301).
+    Its wgrad GEMM has K = 16 and is bound by the read-modify-write of the 604 MB fp32 gradient, so instead of one such
+    pass per micro-batch the operands (the space-to-depth'd output gradient and the input) of up to CAP backward passes
+    are queued -- 3 MB each -- and contracted by ONE GEMM with K = 16 * passes when the optimizer flushes.
+    Inside a CUDA-graph capture the operands go to fixed staging buffers; ``after_replay`` moves them into the queue."""
+
+    CAP = 8
+    __slots__ = ("weight", "geom", "ss", "xs", "stage_s", "stage_x", "count", "dirty")
+
+    def __init__(self, weight, n, hin, win, cin, ldx, kc):
+        dev = weight.device
+        self.weight, self.geom = weight, (n, hin, win, cin, ldx, kc)
+        self.ss = torch.empty((self.CAP * n, hin, win, kc), device=dev, dtype=torch.bfloat16)
+        self.xs = torch.empty((self.CAP * n, hin, win, ldx), device=dev, dtype=torch.bfloat16)
+        self.stage_s = self.stage_x = None
+        self.count, self.dirty = 0, False
+
+    def _slot(self):
+        if self.count == self.CAP:
+            self.flush()
+        n, k = self.geom[0], self.count
+        self.count += 1
+        self.dirty = True
+        return self.ss[k * n:(k + 1) * n], self.xs[k * n:(k + 1) * n]
+
+    def targets(self):
+        """(space-to-depth destination, input destination) for the backward pass being recorded."""
+        if _capture_log is not None:
+            if self.stage_s is None:
+                n = self.geom[0]
+                self.stage_s, self.stage_x = torch.empty_like(self.ss[:n]), torch.empty_like(self.xs[:n])
+            _capture_log.append(self)
+            return self.stage_s, self.stage_x
+        return self._slot()
+
+    def after_replay(self):
+        s, x = self._slot()
+        s.copy_(self.stage_s)
+        x.copy_(self.stage_x)
+
+    def flush(self):
+        if self.count:
+            n, hin, win, cin, ldx, kc = self.geom
+            call("dm_conv2d_wgrad", _p(self.ss), kc, kc, None, 0, 0, _p(self.xs), ldx, _p(grad_buf(self.weight)),
+                 n * self.count, hin, win, cin, 1, 1, 1, 0, _stream())
+        self.count, self.dirty = 0, False
+
+    def discard(self):
+        self.count, self.dirty = 0, False
+
+
+def _rank_grad_entry(weight, n, hin, win, cin, ldx, kc):
+    """The queue for ``weight`` if the optimizer registered it for deferred gradients (defer_weight_grads), else None."""
+    slot = _deferred.get(weight.data_ptr())
+    if slot is None:
+        return None
+    p = slot[0]()
+    if p is None or p.shape != weight.shape:
+        return None
+    e = slot[1]
+    if not isinstance(e, _RankGrad) or e.geom != (n, hin, win, cin, ldx, kc):
+        if e is not None:
+            e.flush()
+        e = slot[1] = _RankGrad(weight, n, hin, win, cin, ldx, kc)
+    return e
+
+
 _deferred = {}          # weight.data_ptr() -> [weakref(param), _PackedGrad | None]
 _capture_log = None     # while a train step is being captured: the _PackedGrad entries it accumulates into
 
@@ -394,7 +464,9 @@ def flush_weight_grads():
 def discard_weight_grads():
     """zero_grad(): drop packed gradients that were never flushed."""
     for e in _live_entries():
-        if e.dirty:
+        if isinstance(e, _RankGrad):
+            e.discard()
+        elif e.dirty:
             e.dwp.zero_()
             e.dirty = False
 
@@ -619,17 +691,26 @@ class _ConvT(torch.autograd.Function):
         # (co*k*k + tap) and the GEMM roles swapped (rows = ci, columns = (co, tap)), the product
         # dW[ci][(co, tap)] = sum_pixels x[ci] * dy[(co, tap)] lands in the [Cin, Cout, k, k] gradient itself:
         # the wgrad kernel red.adds straight into p.grad -- no packed detour for the 151 M-parameter up0.
-        s2c = new_act(n, hin, win, kc, dy.device)
-        call("dm_space_to_depth", _p(dy), lddy, _p(s2c), s2c.stride(2), n, hin, win, cout, k, 1, st)
-        if kc % 64 == 0:
-            call("dm_conv2d_wgrad", _p(s2c), kc, s2c.stride(2), None, 0, 0, _p(x), x.stride(2), _p(grad_buf(weight)),
-                 n, hin, win, cin, 1, 1, 1, 0, st)
-        else:                       # K columns not a multiple of 64 (e.g. 7x7x16): padded staging buffer
-            ckc = r64(kc)
-            unpack = (cin, kc, 1, _taps([0]), kc, 1, 0, ckc, ckc, 0)
-            _wgrad_into(weight, (cin, ckc), unpack, lambda dwp: call(
-                "dm_conv2d_wgrad", _p(s2c), kc, s2c.stride(2), None, 0, 0, _p(x), x.stride(2), _p(dwp), n, hin, win, cin,
-                1, 1, 1, 0, st))
+        rank = None
+        if RANK_DEFER and kc % 64 == 0 and n * hin * win <= 64:
+            rank = _rank_grad_entry(weight, n, hin, win, cin, x.stride(2), kc)
+        if rank is not None:
+            # few pixels against a huge weight: queue the operands, one GEMM per optimizer step (see _RankGrad)
+            s2c, xq = rank.targets()
+            call("dm_space_to_depth", _p(dy), lddy, _p(s2c), s2c.stride(2), n, hin, win, cout, k, 1, st)
+            xq.copy_(x)
+        else:
+            s2c = new_act(n, hin, win, kc, dy.device)
+            call("dm_space_to_depth", _p(dy), lddy, _p(s2c), s2c.stride(2), n, hin, win, cout, k, 1, st)
+            if kc % 64 == 0:
+                call("dm_conv2d_wgrad", _p(s2c), kc, s2c.stride(2), None, 0, 0, _p(x), x.stride(2), _p(grad_buf(weight)),
+                     n, hin, win, cin, 1, 1, 1, 0, st)
+            else:                       # K columns not a multiple of 64 (e.g. 7x7x16): padded staging buffer
+                ckc = r64(kc)
+                unpack = (cin, kc, 1, _taps([0]), kc, 1, 0, ckc, ckc, 0)
+                _wgrad_into(weight, (cin, ckc), unpack, lambda dwp: call(
+                    "dm_conv2d_wgrad", _p(s2c), kc, s2c.stride(2), None, 0, 0, _p(x), x.stride(2), _p(dwp), n, hin, win,
+                    cin, 1, 1, 1, 0, st))
         del s2c
         dx = None
         if ctx.needs_input_grad[0]:

@@ -201,6 +201,37 @@ def test_conv_transpose(dev, case):
     assert rel(bd.grad.cpu(), br.grad) < F32_TOL
 
 
+@pytest.mark.parametrize("passes", [1, 4, 11])
+def test_conv_transpose_queued_weight_gradient(dev, passes):
+    """ConvTranspose weights owned by FusedAdamW that see <= 64 pixels per backward queue their wgrad operands
+    (ops._RankGrad) and contract them with one GEMM at flush: the gradient after `passes` backward passes (11 > the
+    queue depth of 8 forces an intermediate flush) must equal the sum of the per-pass gradients."""
+    from diffusionmodel_b200 import ops, FusedAdamW
+    n, h, w, cin, cout, k = 2, 2, 2, 64, 32, 8
+    g = torch.Generator().manual_seed(37)
+    wt = torch.randn(cin, cout, k, k, generator=g) / math.sqrt(cin)
+    wr = bf(wt).requires_grad_(True)
+    wd = torch.nn.Parameter(wt.to(dev))
+    opt = FusedAdamW([wd], lr=1e-3)
+    pack = ops.WeightPack()
+    dx_ref = []
+    for i in range(passes):
+        x = bf(torch.randn(n, cin, h, w, generator=g))
+        dy = bf(torch.randn(n, cout, h * k, w * k, generator=g))
+        xr = x.clone().requires_grad_(True)
+        F.conv_transpose2d(xr, wr, None, k).backward(dy)
+        xd = nhwc(x, dev).requires_grad_(True)
+        ops.conv_transpose(xd, wd, None, pack, k).backward(nhwc(dy, dev))
+        assert rel(nchw(xd.grad, cin), xr.grad) < BF16_TOL
+    entry = ops._rank_grad_entry(wd, n, h, w, cin, cin, k * k * cout)
+    assert isinstance(entry, ops._RankGrad) and entry.count == (passes if passes <= 8 else passes - 8)
+    opt.flush()
+    assert entry.count == 0
+    assert rel(wd.grad.cpu(), wr.grad) < F32_TOL
+    opt.zero_grad()
+    assert float(wd.grad.abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("case", [(16, 1536, 8192), (5, 100, 2144), (1, 8, 32), (16, 72, 6144)], ids=lambda c: "x".join(map(str, c)))
 def test_skinny_gemm(dev, case):
     """dm_skinny_gemm (split-K mma.sync GEMM for <= 16 rows, the up0 data gradient) against an fp32 matmul of the
