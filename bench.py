@@ -177,6 +177,73 @@ def cpu_baseline_sample():
             "sample": "1 image fwd+bwd (F=192, 3x256x256, fp32) through oracle/ref_port.py, single cold run"}
 
 
+def hbm_kernel_table(dev, hbm_peak):
+    """Achieved algorithmic GB/s of the bandwidth-bound kernel classes on the dominant activation shape of the step
+    (4 x 256 x 256 x 192 bf16 = 100.7 MB per tensor).  Each kernel is launched 9 times back to back on the current
+    stream, rotating over 3 operand sets (>= 600 MB in total, far above the 126 MB L2, so every launch reads cold
+    data), between one pair of CUDA events; bytes = the DESIGN.md per-element figures x elements."""
+    from diffusionmodel_b200 import _lib, ops
+    P_, st = ops._p, ops._stream()
+    n, h, c = CFG["batch"], CFG["img"], CFG["n_feat"]
+    P = n * h * h
+    E = P * c
+    g = torch.Generator(device=dev).manual_seed(5)
+    sets = []
+    for _ in range(3):
+        d = dict(y=torch.randn(n, h, h, c, device=dev, generator=g).to(torch.bfloat16),
+                 dz=torch.randn(n, h, h, c, device=dev, generator=g).to(torch.bfloat16))
+        d["z"] = torch.empty_like(d["y"])
+        d["a"] = torch.randn(n, h // 2, h // 2, c, device=dev, generator=g).to(torch.bfloat16)
+        d["b"] = torch.randn(n, h // 2, h // 2, c, device=dev, generator=g).to(torch.bfloat16)
+        d["up"] = torch.empty((n, h, h, 2 * c), device=dev, dtype=torch.bfloat16)
+        d["da"], d["db"] = torch.empty_like(d["a"]), torch.empty_like(d["b"])
+        sets.append(d)
+    mean, inv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+    ga, be = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+    dga, dbe = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+    scr = torch.empty(_lib.fn("dm_bn_act_bwd_scratch")(P, c), device=dev)
+    part = torch.empty((_lib.fn("dm_bn_stats_rows")(P, c), 2, c), device=dev)
+    gate = torch.rand(n, c, device=dev)
+    ns = 15
+    eps = torch.randn(2 * ns, h, h, 4, device=dev)
+    xs, zs = torch.randn(ns, 3, h, h, device=dev), torch.randn(ns, 3, h, h, device=dev)
+    xo, xt = torch.empty_like(xs), torch.empty((2 * ns, h, h, 8), device=dev, dtype=torch.bfloat16)
+    kernels = [
+        ("bn_stats_kernel", "dm_bn_stats", 2 * E,
+         lambda d: ops.call("dm_bn_stats", P_(d["y"]), c, P_(part), c, P, c, st)),
+        ("bn_fwd_kernel (BatchNorm + GELU)", "dm_bn_act_fwd", 4 * E,
+         lambda d: ops.call("dm_bn_act_fwd", P_(d["y"]), c, P_(mean), P_(inv), P_(ga), P_(be), P_(d["z"]), c, P, c, 1, st)),
+        ("bn_bwd_reduce + finalize + apply", "dm_bn_act_bwd", 10 * E,
+         lambda d: ops.call("dm_bn_act_bwd", P_(d["dz"]), c, P_(d["y"]), c, P_(mean), P_(inv), P_(ga), P_(be), P_(d["z"]), c,
+                            P_(dga), P_(dbe), None, P_(scr), P, c, 1, 1, st)),
+        ("ew_kernel<SeFwd> (SE gate + residual)", "dm_se_apply_fwd", 6 * E,
+         lambda d: ops.call("dm_se_apply_fwd", P_(d["y"]), c, P_(gate), P_(d["dz"]), c, P_(d["z"]), c, n, h * h, c, 0.7072, st)),
+        ("upcat_fwd_quad_kernel (cat + bilinear x2)", "dm_upcat_fwd", (E // 4 * 2 + 2 * E) * 2,
+         lambda d: ops.call("dm_upcat_fwd", P_(d["a"]), c, c, P_(d["b"]), c, c, P_(d["up"]), 2 * c, n, h // 2, h // 2, st)),
+        ("upcat_bwd_quad_kernel", "dm_upcat_bwd", (E // 4 * 2 + 2 * E) * 2,
+         lambda d: ops.call("dm_upcat_bwd", P_(d["up"]), 2 * c, P_(d["da"]), c, c, P_(d["db"]), c, c, n, h // 2, h // 2, st)),
+        ("cfg_reverse_step_kernel (n=15)", "dm_cfg_reverse_step", ns * 3 * h * h * 20 + 2 * ns * h * h * 16,
+         lambda d: ops.call("dm_cfg_reverse_step", P_(eps), 4, P_(xs), P_(zs), P_(xo), P_(xt), 8, 2.0, 1.01, 0.02, 0.1, ns, 3,
+                            h, h, st)),
+    ]
+    rows = []
+    for kname, entry, nbytes, fn in kernels:
+        for d in sets:
+            fn(d)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(9):
+            fn(sets[i % 3])
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 9 * 1e3
+        gbs = nbytes / us / 1e3
+        rows.append({"kernel": kname, "entry": entry, "us": round(us, 1), "algorithmic_MB": round(nbytes / 1e6, 1),
+                     "GBps": round(gbs, 1), "frac": round(gbs / hbm_peak, 3)})
+    return rows
+
+
 def run_ours(args):
     import diffusionmodel_b200 as D
     from diffusionmodel_b200 import _lib, ops, parallel
@@ -314,6 +381,17 @@ def run_ours(args):
                 "other_kernels_ms_per_step": sum(v["ms"] for k, v in agg.items() if k not in ("conv_gemm", "wgrad_gemm")),
                 "step_tflops": GFLOP_PER_IMG_TRAIN * accum * batch / 1e3 / (ms / args.steps * 1e-3) / 1e0 / 1e0}
         roof["step_frac_of_peak"] = roof["step_tflops"] / peak
+        # the bandwidth-bound kernel classes against the measured HBM copy peak (cfg_reverse_step works on 23.6 MB: L2-sized)
+        roof["hbm_kernels"] = {"peak": pk["hbm_gbs"], "peak_source": f"{src} hbm_gbs", "unit": "GB/s",
+                               "shape": "4x256x256x192 bf16 NHWC (100.7 MB per tensor), cold operands",
+                               "rows": hbm_kernel_table(dev, pk["hbm_gbs"])}
+        ad = agg.get("dm_adamw_bf16") or agg.get("dm_adamw")
+        if ad and ad["ms"] > 0:
+            nb = 30.0 * opt._n
+            roof["hbm_kernels"]["rows"].append({"kernel": "adamw_bf16_kernel (clip + AdamW + bf16 weight copy, whole model)",
+                                                "entry": "dm_adamw_bf16", "us": round(ad["ms"] * 1e3 / ad["n"], 1),
+                                                "algorithmic_MB": round(nb / 1e6, 1), "GBps": round(nb / (ad["ms"] / ad["n"]) / 1e6, 1),
+                                                "frac": round(nb / (ad["ms"] / ad["n"]) / 1e6 / pk["hbm_gbs"], 3)})
         cpu = cpu_baseline_sample() if (world == 1 and not fast) else None
         line = {"metric": "ddpm_train_imgs_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
