@@ -160,29 +160,49 @@ __device__ __forceinline__ void gate_front(const DmCaGates& p, const GateSmem& g
   }
   __syncthreads();
   // P_d[r][j] = bp_d[j] + sum_k T0_d[r][k] * wp_d[j][k]: a warp per (d, j), lanes over k (coalesced weight rows; one
-  // lane per row of wp_d would turn every load into 32 separate sectors)
+  // lane per row of wp_d would turn every load into 32 separate sectors).  A warp takes kProjRows rows at a time and
+  // requests all of their weights before the first use: one round trip to L2/DRAM per four rows (a rolled k loop
+  // inside a rolled row loop paid m/32 dependent round trips per row -- 72 in a row for m = 96, most of the kernel).
   {
+    constexpr int kProjRows = 4, kKU = kThreads / 32;         // m <= kThreads: at most kKU weights per lane and row
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int dj = warp; dj < 2 * m; dj += kThreads / 32) {
-      const int d = dj / m, j = dj - d * m;
-      const float* wp = (d ? p.wp_w2h : p.wp_h2w) + (long long)j * m;
-      const float* t0 = g.t0 + d * kRows * m;
-      float acc[kRows];
+    for (int dj0 = warp * kProjRows; dj0 < 2 * m; dj0 += (kThreads / 32) * kProjRows) {
+      float wv[kProjRows][kKU];
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) acc[r] = 0.0f;
-      for (int k = lane; k < m; k += 32) {
-        const float wv = __ldg(wp + k);
+      for (int q = 0; q < kProjRows; ++q) {
+        const int dj = dj0 + q, d = dj >= m, j = dj - d * m;
+        const float* wp = (d ? p.wp_w2h : p.wp_h2w) + (long long)j * m;
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) acc[r] = fmaf(t0[r * m + k], wv, acc[r]);
+        for (int u = 0; u < kKU; ++u) {
+          const int k = lane + 32 * u;
+          wv[q][u] = (dj < 2 * m && k < m) ? __ldg(wp + k) : 0.0f;
+        }
       }
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) acc[r] = dm::warp_sum(acc[r]);
-      const float b = (d ? p.bp_w2h : p.bp_h2w)[j];
-      float mine = 0.0f;
+      for (int q = 0; q < kProjRows; ++q) {
+        const int dj = dj0 + q, d = dj >= m, j = dj - d * m;
+        if (dj >= 2 * m) continue;                             // warp-uniform
+        const float* t0 = g.t0 + d * kRows * m;
+        float acc[kRows];
 #pragma unroll
-      for (int r = 0; r < kRows; ++r)
-        if (lane == r) mine = acc[r];
-      if (lane < kRows) g.pp[(d * kRows + lane) * m + j] = mine + b;      // pp[0] = h2w_proj(T0_h) feeds T_w, pp[1] feeds T_h
+        for (int r = 0; r < kRows; ++r) acc[r] = 0.0f;
+#pragma unroll
+        for (int u = 0; u < kKU; ++u) {
+          const int k = lane + 32 * u;
+          if (k < m) {
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) acc[r] = fmaf(t0[r * m + k], wv[q][u], acc[r]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) acc[r] = dm::warp_sum(acc[r]);
+        const float b = (d ? p.bp_w2h : p.bp_h2w)[j];
+        float mine = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+          if (lane == r) mine = acc[r];
+        if (lane < kRows) g.pp[(d * kRows + lane) * m + j] = mine + b;      // pp[0] = h2w_proj(T0_h) feeds T_w, pp[1] feeds T_h
+      }
     }
   }
   __syncthreads();
@@ -191,7 +211,7 @@ __device__ __forceinline__ void gate_front(const DmCaGates& p, const GateSmem& g
 // ---- forward 2: statistics, gelu, cross interaction, output gates.  grid (nblk, ceil(C/256)): the small front part
 // is recomputed per channel chunk, each block reads only its 256 rows of the output weights
 __global__ void __launch_bounds__(kThreads) ca_gate_fwd_kernel(const DmCaGates p, const int use_slab) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int m = p.m, C = p.C, R = p.R, r0 = blockIdx.x * kRows;
   const GateSmem g = carve_gate(sm, m);
   float* ts = g.pp + 2 * kRows * m;            // T[2][kRows][m]
@@ -228,11 +248,33 @@ __global__ void __launch_bounds__(kThreads) ca_gate_fwd_kernel(const DmCaGates p
 #pragma unroll
       for (int r = 0; r < kRows; ++r) acc[r] = b;
       const float* ws = slab + lane * (m + 1);
-#pragma unroll 4
-      for (int j = 0; j < m; ++j) {
-        const float wv = use_slab ? ws[j] : __ldg(w + j);
+      if (!use_slab && (m & 3) == 0 && (reinterpret_cast<uintptr_t>(wc) & 15) == 0) {
+        // the thread's own weight row, eight 16-byte loads requested at a time (same j order as the scalar loop)
+        const float4* w4 = reinterpret_cast<const float4*>(w);
+        for (int j0 = 0; j0 < m; j0 += 32) {
+          float4 wv[8];
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) acc[r] = fmaf(t[r * m + j], wv, acc[r]);
+          for (int u = 0; u < 8; ++u)
+            wv[u] = j0 + 4 * u < m ? __ldg(w4 + (j0 >> 2) + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int j = j0 + 4 * u;
+            if (j >= m) continue;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+              const float4 tv = *reinterpret_cast<const float4*>(t + r * m + j);
+              acc[r] = fmaf(tv.x, wv[u].x, acc[r]); acc[r] = fmaf(tv.y, wv[u].y, acc[r]);
+              acc[r] = fmaf(tv.z, wv[u].z, acc[r]); acc[r] = fmaf(tv.w, wv[u].w, acc[r]);
+            }
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int j = 0; j < m; ++j) {
+          const float wv = use_slab ? ws[j] : __ldg(w + j);
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) acc[r] = fmaf(t[r * m + j], wv, acc[r]);
+        }
       }
 #pragma unroll
       for (int r = 0; r < kRows; ++r)
@@ -245,7 +287,7 @@ __global__ void __launch_bounds__(kThreads) ca_gate_fwd_kernel(const DmCaGates p
 // ---- backward 1a: dZ = dA * k * a(1-a) (stored for the weight-gradient kernel), the scale sums, and this channel
 // chunk's share of dT_d = dZ_d Wc_d (atomics into the zeroed q.dt).  grid (nblk, ceil(C/256), 2)
 __global__ void __launch_bounds__(kThreads) ca_gate_bwd_a_kernel(const DmCaGates p, const DmCaGatesGrad q) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int m = p.m, C = p.C, R = p.R, r0 = blockIdx.x * kRows, c0 = blockIdx.y * kThreads, d = blockIdx.z;
   float* dzs = sm;                       // [kRows][kThreads]
   float* dts = dzs + kRows * kThreads;   // [kRows][m]
@@ -306,7 +348,7 @@ __global__ void __launch_bounds__(kThreads) ca_gate_bwd_a_kernel(const DmCaGates
 // ---- backward 1b: the cross interaction and the gelu, per row tile: dT -> dHhat, projection / gamma gradients, and
 // the BatchNorm-backward partial sums.  grid (nblk).  sm: gate arrays, dT[2][kRows][m], dT0[2][kRows][m]
 __global__ void __launch_bounds__(kThreads) ca_gate_bwd_b_kernel(const DmCaGates p, const DmCaGatesGrad q) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int m = p.m, R = p.R, r0 = blockIdx.x * kRows, km = kRows * m;
   const GateSmem g = carve_gate(sm, m);
   float* dts = g.pp + 2 * km;
@@ -373,7 +415,7 @@ __global__ void __launch_bounds__(kThreads) ca_gate_bwd_b_kernel(const DmCaGates
 
 // ---- backward 2: BatchNorm backward, then through the first 1x1 convolution.  grid (nblk, ceil(C/256), 2)
 __global__ void __launch_bounds__(kThreads) ca_lin1_bwd_kernel(const DmCaGates p, const DmCaGatesGrad q) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int d = blockIdx.z, r0 = blockIdx.x * kRows, C = p.C, m = p.m, R = p.R;
   const bool first = blockIdx.y == 0;  // the channel chunk that also owns the per-row-tile side outputs
   float* du = sm;                      // [kRows][m]
@@ -441,8 +483,16 @@ __global__ void __launch_bounds__(1024) ca_wgrad_kernel(const WgArgs a) {
   float acc[8], sb = 0.0f;
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.0f;
+  // the accumulate-into-.grad reads go first (one DRAM round trip hidden behind the sums) instead of eight serial
+  // load-add-store round trips at the end
+  const bool owner = sl == 0 && c < a.C;
+  float old[8], oldb = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj)
+    old[jj] = (owner && jj < nj) ? __ldcg(a.out[d] + (long long)c * a.so_c + (long long)(j0 + jj) * a.so_j) : 0.0f;
+  if (owner && a.bias[d] != nullptr && blockIdx.y == 0) oldb = __ldcg(a.bias[d] + c);
   if (c < a.C)
-#pragma unroll 4
+#pragma unroll 8
     for (int r = sl; r < a.R; r += 32) {
       const float av = __ldg(A + (long long)r * a.C + c);
       const float* b = B + (long long)r * a.m + j0;
@@ -462,18 +512,20 @@ __global__ void __launch_bounds__(1024) ca_wgrad_kernel(const WgArgs a) {
   red[sl][cl][8] = sb;
   __syncthreads();
   const float scale = a.gate[d] != nullptr ? sigmoidf_(a.gate[d][0]) : 1.0f;
-  if (sl == 0 && c < a.C) {
-    for (int jj = 0; jj < nj; ++jj) {
+  if (owner) {
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      if (jj >= nj) continue;
       float tot = 0.0f;
 #pragma unroll
       for (int s2 = 0; s2 < 32; ++s2) tot += red[s2][cl][jj];
-      a.out[d][(long long)c * a.so_c + (long long)(j0 + jj) * a.so_j] += scale * tot;
+      a.out[d][(long long)c * a.so_c + (long long)(j0 + jj) * a.so_j] = old[jj] + scale * tot;
     }
     if (a.bias[d] != nullptr && blockIdx.y == 0) {
       float tot = 0.0f;
 #pragma unroll
       for (int s2 = 0; s2 < 32; ++s2) tot += red[s2][cl][8];
-      a.bias[d][c] += scale * tot;
+      a.bias[d][c] = oldb + scale * tot;
     }
   }
 }

@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(1024) reduce_finalize_kernel(const float* __re
   const int cl = threadIdx.x & 15, sl = threadIdx.x >> 4;          // 16 outputs x 64 row slices
   const long long total = (long long)groups * C;
   const long long i = (long long)blockIdx.x * 16 + cl;
-  float a = 0.f, b = 0.f;
+  float a = 0.f, b = 0.f, o1 = 0.f, o2 = 0.f;
+  if (accumulate && sl == 0 && i < total) { o1 = __ldcg(out1 + i); if (out2) o2 = __ldcg(out2 + i); }   // old values first
   if (i < total) {
     const long long g = i / C; const int c = (int)(i - g * C);
     const float* base = part + g * 2 * C + c;
@@ -200,8 +201,8 @@ __global__ void __launch_bounds__(1024) reduce_finalize_kernel(const float* __re
   __syncthreads();
   if (sl == 0 && i < total) {
     for (int k = 1; k < 64; ++k) { a += sa[k][cl]; b += sb[k][cl]; }
-    if (accumulate) { out1[i] += a * scale; if (out2) out2[i] += b * scale; }
-    else { out1[i] = a * scale; if (out2) out2[i] = b * scale; }
+    out1[i] = o1 + a * scale;
+    if (out2) out2[i] = o2 + b * scale;
   }
 }
 static inline int finalize_grid(long long total) { return (int)((total + 15) / 16); }
@@ -383,6 +384,8 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* partials
   const int cl = threadIdx.x & 15, rr = threadIdx.x >> 4;
   const int c = blockIdx.x * 16 + cl;
   double a = 0.0, b = 0.0;
+  float o_rm = 0.f, o_rv = 0.f, cb = 0.f;         // the closing thread's operands, requested before the partial rows
+  if (rr == 0 && c < C && rmean) { o_rm = __ldcg(rmean + c); o_rv = __ldcg(rvar + c); cb = conv_bias ? __ldg(conv_bias + c) : 0.f; }
   if (c < C)
     for (int t = rr; t < m_tiles; t += 512) {
       float x[8], y[8];
@@ -416,12 +419,12 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* partials
       if (rmean) {
         const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
         // conv_bias: the producing conv left its bias out of y (the batch norm cancels it); the tracked mean is of conv + bias
-        rmean[c] = (1.f - momentum) * rmean[c] + momentum * ((float)mu + (conv_bias ? conv_bias[c] : 0.f));
-        rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+        rmean[c] = (1.f - momentum) * o_rm + momentum * ((float)mu + cb);
+        rvar[c] = (1.f - momentum) * o_rv + momentum * (float)unb;
       }
     } else {
-      mean[c] = rmean[c];
-      invstd[c] = 1.0f / sqrtf(rvar[c] + eps);
+      mean[c] = o_rm;
+      invstd[c] = 1.0f / sqrtf(o_rv + eps);
     }
   }
 }
@@ -601,6 +604,15 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
   const int cl = threadIdx.x & 15, rr = threadIdx.x >> 4;          // 16 channels x 64 row slices, see bn_finalize_kernel
   const int c = blockIdx.x * 16 + cl;
   float f0 = 0.f, f1 = 0.f;
+  // the closing thread's operands (and the old values of the accumulate-into-.grad outputs) are requested up front:
+  // read at the end they are three more dependent round trips behind the partial-row loads
+  const bool closer = rr == 0 && c < C;
+  float p_inv = 0.f, p_mean = 0.f, p_gamma = 0.f, o_beta = 0.f, o_gamma = 0.f, o_bias = 0.f;
+  if (closer) {
+    p_inv = __ldg(invstd + c); p_mean = __ldg(mean + c); p_gamma = __ldg(gamma + c);
+    o_beta = __ldcg(dbeta + c); o_gamma = __ldcg(dgamma + c);
+    if (dbias && !training) o_bias = __ldcg(dbias + c);
+  }
   if (c < C) {
     for (int t = rr; t < nblk; t += 512) {
       float x0[8], x1[8];
@@ -617,19 +629,19 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
   }
   sh[0][rr][cl] = f0; sh[1][rr][cl] = f1;
   __syncthreads();
-  if (rr == 0 && c < C) {
+  if (closer) {
     double sg = 0.0, sgy = 0.0;
     for (int k = 0; k < 64; ++k) { sg += (double)sh[0][k][cl]; sgy += (double)sh[1][k][cl]; }
-    const double a = (double)invstd[c], b = -(double)mean[c] * a, ga = (double)gamma[c];
+    const double a = (double)p_inv, b = -(double)p_mean * a, ga = (double)p_gamma;
     const double sgx = a * sgy + b * sg;          // sum g*xhat
     const double k0 = ga * a;
     const double m1 = training ? sg / P : 0.0, m2 = training ? sgx / P : 0.0;
     coef[c] = (float)k0;
     coef[C + c] = (float)(-k0 * (m1 + m2 * b));   // -K1
     coef[2 * C + c] = (float)(-k0 * m2 * a);      // -K2
-    dbeta[c] += (float)sg;
-    dgamma[c] += (float)sgx;
-    if (dbias && !training) dbias[c] += (float)(k0 * sg);
+    dbeta[c] = o_beta + (float)sg;
+    dgamma[c] = o_gamma + (float)sgx;
+    if (dbias && !training) dbias[c] = o_bias + (float)(k0 * sg);
   }
 }
 

@@ -31,6 +31,9 @@ __device__ __forceinline__ float lin_act_grad(float aux, int act) {
 }
 
 // y[n,o] = act(b[o] + sum_i W[o,i] x[n,i]).  One warp per output feature, lanes stride the input features.
+// The weight row is the only cold stream (DRAM latency ~0.8 us): a lane issues kFwdU 16-byte weight loads before it
+// consumes the first one (a rolled loop of dependent 4-byte loads ran at one DRAM round trip per 32 input features).
+constexpr int kFwdU = 6;
 __global__ void __launch_bounds__(256) linear_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                              const float* __restrict__ b, float* __restrict__ pre,
                                                              float* __restrict__ y, int N, int Cin, int Cout, int act) {
@@ -38,15 +41,54 @@ __global__ void __launch_bounds__(256) linear_act_fwd_kernel(const float* __rest
   if (o >= Cout) return;
   const float* w = W + (long long)o * Cin;
   const float bias = b ? __ldg(b + o) : 0.0f;
+  const bool vec = (Cin & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
   for (int n0 = 0; n0 < N; n0 += kRows) {
     float acc[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) acc[r] = 0.0f;
-    for (int i = lane; i < Cin; i += 32) {
-      const float wv = __ldg(w + i);
+    if (vec) {
+      const int C4 = Cin >> 2;
+      const float4* w4 = reinterpret_cast<const float4*>(w);
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+      for (int base = 0; base < C4; base += 32 * kFwdU) {
+        float4 wv[kFwdU];
 #pragma unroll
-      for (int r = 0; r < kRows; ++r)
-        if (n0 + r < N) acc[r] = fmaf(wv, __ldg(x + (long long)(n0 + r) * Cin + i), acc[r]);
+        for (int u = 0; u < kFwdU; ++u) {
+          const int i4 = base + u * 32 + lane;
+          wv[u] = i4 < C4 ? __ldg(w4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kFwdU; ++u) {
+          const int i4 = base + u * 32 + lane;
+          if (i4 >= C4) continue;
+#pragma unroll
+          for (int r = 0; r < kRows; ++r)
+            if (n0 + r < N) {
+              const float4 xv = __ldg(x4 + (long long)(n0 + r) * C4 + i4);
+              acc[r] = fmaf(wv[u].x, xv.x, acc[r]);
+              acc[r] = fmaf(wv[u].y, xv.y, acc[r]);
+              acc[r] = fmaf(wv[u].z, xv.z, acc[r]);
+              acc[r] = fmaf(wv[u].w, xv.w, acc[r]);
+            }
+        }
+      }
+    } else {
+      for (int base = 0; base < Cin; base += 32 * kFwdU) {
+        float wv[kFwdU];
+#pragma unroll
+        for (int u = 0; u < kFwdU; ++u) {
+          const int i = base + u * 32 + lane;
+          wv[u] = i < Cin ? __ldg(w + i) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < kFwdU; ++u) {
+          const int i = base + u * 32 + lane;
+          if (i >= Cin) continue;
+#pragma unroll
+          for (int r = 0; r < kRows; ++r)
+            if (n0 + r < N) acc[r] = fmaf(wv[u], __ldg(x + (long long)(n0 + r) * Cin + i), acc[r]);
+        }
+      }
     }
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
@@ -82,6 +124,12 @@ __global__ void __launch_bounds__(kBwdThreads) linear_act_bwd_kernel(const float
   for (int o = 0; o < kSlice; ++o) dwacc[o] = 0.0f;
   float dbacc = 0.0f;
   const long long part_stride = (long long)N * Cout;
+  // The accumulate-into-.grad reads are issued first, before anything depends on them, so their DRAM round trip hides
+  // behind the two phases below.  (Written as `dW[..] += ..` at the end, the compiler has to keep every load behind the
+  // previous store -- it cannot prove the rows distinct -- which cost 32 serial DRAM round trips per thread.)
+  float old[kSlice];
+#pragma unroll
+  for (int o = 0; o < kSlice; ++o) old[o] = (live && dW && o < no) ? __ldcg(dW + (long long)(o0 + o) * Cin + i) : 0.0f;
   for (int n0 = 0; n0 < N; n0 += kRows) {
     __syncthreads();
     for (int e = threadIdx.x; e < kRows * kSlice; e += kBwdThreads) {
@@ -89,7 +137,13 @@ __global__ void __launch_bounds__(kBwdThreads) linear_act_bwd_kernel(const float
       float v = 0.0f;
       if (n0 + r < N && o < no) {
         const long long at = (long long)(n0 + r) * Cout + o0 + o;
-        for (int p = 0; p < nparts; ++p) v += __ldg(dy + p * part_stride + at);
+        for (int p0 = 0; p0 < nparts; p0 += 8) {       // eight partial rows in flight, folded in row order
+          float t[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) t[k] = p0 + k < nparts ? __ldg(dy + (p0 + k) * part_stride + at) : 0.0f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v += t[k];
+        }
         v *= lin_act_grad(act ? __ldg(aux + at) : 0.0f, act);
       }
       g[r][o] = v;
@@ -126,7 +180,7 @@ __global__ void __launch_bounds__(kBwdThreads) linear_act_bwd_kernel(const float
   if (live && dW) {
 #pragma unroll
     for (int o = 0; o < kSlice; ++o)
-      if (o < no) dW[(long long)(o0 + o) * Cin + i] += dwacc[o];
+      if (o < no) dW[(long long)(o0 + o) * Cin + i] = old[o] + dwacc[o];
   }
 }
 
@@ -135,7 +189,13 @@ __global__ void __launch_bounds__(256) sum_parts_kernel(const float* __restrict_
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = 0.0f;
-  for (int p = 0; p < nparts; ++p) v += __ldg(parts + p * n + i);
+  for (int p0 = 0; p0 < nparts; p0 += 8) {
+    float t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] = p0 + k < nparts ? __ldg(parts + (p0 + k) * n + i) : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += t[k];
+  }
   out[i] = v;
 }
 
