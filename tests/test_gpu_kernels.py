@@ -584,3 +584,63 @@ def test_image_metrics_ssim_psnr(dev):
     m = metrics.evaluate_batch(x.to(dev), y.to(dev))
     assert abs(m["ssim"] - float(out[:, 0].double().mean())) < 1e-6 and abs(m["psnr"] - float(out[:, 1].double().mean())) < 1e-4
     assert metrics.evaluate_batch(x[:2].to(dev), y.to(dev)) == {}
+
+
+def test_abi_empty_inputs_and_argument_errors(dev):
+    """C-ABI edge behaviour: empty batches are a no-op that returns DM_OK and touches nothing; malformed arguments come
+    back as a negative status with a message (raised as DmB200Error by the ctypes mirror), never as a launch."""
+    from diffusionmodel_b200 import _lib, ops
+    from diffusionmodel_b200._lib import DmB200Error
+    P_, st = ops._p, ops._stream()
+    c = 24
+    y = torch.randn(2, 4, 4, c, device=dev).to(torch.bfloat16)
+    z = torch.full_like(y, 7.0)
+    ones, zeros = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+    n0 = _lib.launch_count()
+    assert ops.call("dm_bn_act_fwd", P_(y), c, P_(zeros), P_(ones), P_(ones), P_(zeros), P_(z), c, 0, c, 1, st) == 0
+    assert ops.call("dm_upcat_fwd", P_(y), c, c, P_(y), c, c, P_(z), 2 * c, 0, 4, 4, st) == 0
+    x = torch.randn(4, 8, device=dev)
+    w = torch.randn(16, 8, device=dev)
+    out = torch.full((4, 16), 7.0, device=dev)
+    assert ops.call("dm_linear_act_fwd", P_(x), P_(w), None, None, P_(out), 0, 8, 16, 0, st) == 0
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == n0                                     # nothing was launched
+    assert float(z.float().min()) == 7.0 and float(out.min()) == 7.0      # and nothing written
+    with pytest.raises(DmB200Error, match="dm_bn_act_fwd"):
+        ops.call("dm_bn_act_fwd", P_(y), 12, P_(zeros), P_(ones), P_(ones), P_(zeros), P_(z), c, 32, c, 1, st)   # pitch % 8
+    with pytest.raises(DmB200Error, match="dm_bn_stats"):
+        ops.call("dm_bn_stats", P_(y), c, P_(zeros), c, 0, c, st)
+    with pytest.raises(DmB200Error, match="act must be"):
+        ops.call("dm_linear_act_fwd", P_(x), P_(w), None, None, P_(out), 4, 8, 16, 7, st)
+    a = torch.zeros(17, 64, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(DmB200Error, match="M must be"):
+        ops.call("dm_skinny_gemm", P_(a), 64, P_(a), 64, P_(a), 64, P_(x), 17, 17, 64, st)
+    with pytest.raises(DmB200Error, match="divisible"):
+        ops.call("dm_gn_act_fwd", P_(y), c, P_(ones), P_(zeros), P_(z), c, P_(zeros), P_(zeros), P_(zeros), 2, 16, c, 7, 1e-5, 1, st)
+    assert _lib.launch_count() == n0
+
+
+def test_linear_fwd_scalar_and_vector_paths_agree(dev):
+    """dm_linear_act_fwd takes 16-byte weight loads when Cin % 4 == 0 and both operands are 16-byte aligned, scalar loads
+    otherwise: the same matrix at an aligned and at a 4-byte-offset address must give the same rows (fp32 tolerance:
+    the two paths add in a different order), and both must match torch."""
+    from diffusionmodel_b200 import ops
+    P_, st = ops._p, ops._stream()
+    g = torch.Generator().manual_seed(31)
+    for n, cin, cout in ((4, 1536, 96), (30, 200, 40), (9, 772, 17)):
+        x = torch.randn(n, cin, generator=g)
+        w = torch.randn(cout, cin, generator=g) / math.sqrt(cin)
+        b = torch.randn(cout, generator=g)
+        ref = F.gelu(F.linear(x, w, b))
+        xd, bd = x.to(dev), b.to(dev)
+        buf = torch.zeros(cout * cin + 1, device=dev)
+        outs = []
+        for off in (0, 1):
+            wd = buf[off:off + cout * cin].view(cout, cin)
+            wd.copy_(w)
+            assert (wd.data_ptr() % 16 == 0) == (off == 0)
+            pre, yv = torch.empty(n, cout, device=dev), torch.empty(n, cout, device=dev)
+            ops.call("dm_linear_act_fwd", P_(xd), P_(wd), P_(bd), P_(pre), P_(yv), n, cin, cout, 1, st)
+            outs.append(yv.cpu())
+            assert rel(yv.cpu(), ref) < F32_TOL
+        assert rel(outs[0], outs[1]) < 1e-5
