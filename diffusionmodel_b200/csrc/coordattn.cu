@@ -476,6 +476,7 @@ struct WgArgs {
 };
 __global__ void __launch_bounds__(1024) ca_wgrad_kernel(const WgArgs a) {
   __shared__ float red[32][32][9];
+  const int nsl = blockDim.x >> 5;        // row slices: 32 for long reductions, fewer (smaller blocks) for R < 256
   const int d = blockIdx.z, cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl, j0 = blockIdx.y * 8;
   const int nj = min(8, a.m - j0);
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(1024) ca_wgrad_kernel(const WgArgs a) {
   if (owner && a.bias[d] != nullptr && blockIdx.y == 0) oldb = __ldcg(a.bias[d] + c);
   if (c < a.C)
 #pragma unroll 8
-    for (int r = sl; r < a.R; r += 32) {
+    for (int r = sl; r < a.R; r += nsl) {
       const float av = __ldg(A + (long long)r * a.C + c);
       const float* b = B + (long long)r * a.m + j0;
       sb += av;
@@ -518,13 +519,13 @@ __global__ void __launch_bounds__(1024) ca_wgrad_kernel(const WgArgs a) {
       if (jj >= nj) continue;
       float tot = 0.0f;
 #pragma unroll
-      for (int s2 = 0; s2 < 32; ++s2) tot += red[s2][cl][jj];
+      for (int s2 = 0; s2 < nsl; ++s2) tot += red[s2][cl][jj];
       a.out[d][(long long)c * a.so_c + (long long)(j0 + jj) * a.so_j] = old[jj] + scale * tot;
     }
     if (a.bias[d] != nullptr && blockIdx.y == 0) {
       float tot = 0.0f;
 #pragma unroll
-      for (int s2 = 0; s2 < 32; ++s2) tot += red[s2][cl][8];
+      for (int s2 = 0; s2 < nsl; ++s2) tot += red[s2][cl][8];
       a.bias[d][c] = oldb + scale * tot;
     }
   }
@@ -601,21 +602,26 @@ extern "C" int dm_ca_gates_bwd(const DmCaGates* p, const DmCaGatesGrad* q, void*
   ca_gate_bwd_b_kernel<<<p->nblk, kThreads, sb, st>>>(*p, *q);
   DM_CHECK_LAUNCH();
   const dim3 wg_grid(dm::cdiv(p->C, 32), dm::cdiv(p->m, 8), 2);
+  // row slices per block: about eight rows per thread, so the C = 1536 instance (R = 64 rows, 1152 blocks) runs as one
+  // wave of 256-thread blocks instead of four waves of 1024-thread blocks that each add two rows
+  int wg_slices = 32;
+  while (wg_slices > 1 && wg_slices * 8 > p->R) wg_slices >>= 1;
+  const int wg_threads = 32 * wg_slices;
   WgArgs wc = {{q->dz, q->dz + RC}, {p->t, p->t + Rm}, {q->g_wc_h, q->g_wc_w}, {q->g_bc_h, q->g_bc_w}, {nullptr, nullptr},
                p->R, p->C, p->m, (long long)p->m, 1};
-  ca_wgrad_kernel<<<wg_grid, 1024, 0, st>>>(wc);
+  ca_wgrad_kernel<<<wg_grid, wg_threads, 0, st>>>(wc);
   DM_CHECK_LAUNCH();
   // projection gradients: d wp_e[k][j] = sg[1-e] * sum_r dT_{1-e}[r][k] * T0_e[r][j]  (wp_0 = h2w, wp_1 = w2h)
   WgArgs wpj = {{q->dt + Rm, q->dt}, {p->t0, p->t0 + Rm}, {q->g_wp_h2w, q->g_wp_w2h}, {q->g_bp_h2w, q->g_bp_w2h},
                 {p->gamma_w, p->gamma_h}, p->R, p->m, p->m, (long long)p->m, 1};
-  ca_wgrad_kernel<<<dim3(dm::cdiv(p->m, 32), dm::cdiv(p->m, 8), 2), 1024, 0, st>>>(wpj);
+  ca_wgrad_kernel<<<dim3(dm::cdiv(p->m, 32), dm::cdiv(p->m, 8), 2), wg_threads, 0, st>>>(wpj);
   DM_CHECK_LAUNCH();
   const size_t s2 = ((size_t)kRows * p->m + 2 * p->m) * sizeof(float);
   ca_lin1_bwd_kernel<<<dim3(p->nblk, csplit, 2), kThreads, s2, st>>>(*p, *q);
   DM_CHECK_LAUNCH();
   WgArgs w1 = {{p->xh, p->xw}, {q->du, q->du + Rm}, {q->g_w1_h, q->g_w1_w}, {nullptr, nullptr}, {nullptr, nullptr},
                p->R, p->C, p->m, 1, (long long)p->C};
-  ca_wgrad_kernel<<<wg_grid, 1024, 0, st>>>(w1);
+  ca_wgrad_kernel<<<wg_grid, wg_threads, 0, st>>>(w1);
   DM_CHECK_LAUNCH();
   ca_scalars_bwd_kernel<<<1, 32, 0, st>>>(*p, *q);
   DM_CHECK_LAUNCH();

@@ -31,71 +31,92 @@ __device__ __forceinline__ float lin_act_grad(float aux, int act) {
 }
 
 // y[n,o] = act(b[o] + sum_i W[o,i] x[n,i]).  One warp per output feature, lanes stride the input features.
-// The weight row is the only cold stream (DRAM latency ~0.8 us): a lane issues kFwdU 16-byte weight loads before it
-// consumes the first one (a rolled loop of dependent 4-byte loads ran at one DRAM round trip per 32 input features).
-constexpr int kFwdU = 6;
+// Two streams, both requested in one batch: the warp's weight row (cold, DRAM latency ~0.8 us) as kFwdB 16-byte loads per
+// lane issued before anything else, and the kRows activation rows staged once per block in shared memory while those
+// loads fly (read per use from L1/L2 they came back in groups of two behind each other, 15 us for a 9.4 MB matrix; a
+// rolled loop of dependent 4-byte weight loads before that ran at one DRAM round trip per 32 input features, 33 us).
+constexpr int kFwdB = 12;                  // weight loads in flight per lane
+constexpr int kChunk = 32 * kFwdB * 4;     // input features per staged chunk (1536: 48 KB of rows)
+
+template <bool VEC>
+__device__ __forceinline__ void lin_fwd_rows(const float* __restrict__ x, const float* __restrict__ w, float* xs,
+                                             float (&acc)[kRows], int n0, int N, int Cin, bool live, int lane) {
+  constexpr int VW = VEC ? 4 : 1, kSpan = 32 * kFwdB * VW;
+  for (int c0 = 0; c0 < Cin; c0 += kChunk) {
+    const int cn = min(kChunk, Cin - c0);
+    float wv[kFwdB][VW];
+    auto load_batch = [&](int b0) {
+#pragma unroll
+      for (int u = 0; u < kFwdB; ++u) {
+        const int j = b0 + (u * 32 + lane) * VW;
+        const bool ok = live && j < cn;
+        if (VEC) {
+          const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(w + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          wv[u][0] = t.x; wv[u][VW > 1 ? 1 : 0] = t.y; wv[u][VW > 2 ? 2 : 0] = t.z; wv[u][VW > 3 ? 3 : 0] = t.w;
+        } else {
+          wv[u][0] = ok ? __ldg(w + c0 + j) : 0.0f;
+        }
+      }
+    };
+    load_batch(0);
+    __syncthreads();                                   // the previous chunk's readers are done
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {                  // rows past N are staged as zeros: no row test in the FMA loop
+      const bool row = n0 + r < N;
+      const float* xr = x + (long long)(n0 + r) * Cin + c0;
+      if (VEC) {
+        for (int j4 = threadIdx.x; j4 < (cn >> 2); j4 += blockDim.x)
+          *reinterpret_cast<float4*>(xs + r * kChunk + 4 * j4) =
+              row ? __ldg(reinterpret_cast<const float4*>(xr) + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        for (int j = threadIdx.x; j < cn; j += blockDim.x) xs[r * kChunk + j] = row ? __ldg(xr + j) : 0.0f;
+      }
+    }
+    __syncthreads();
+    for (int b0 = 0; b0 < cn; b0 += kSpan) {
+      if (b0) load_batch(b0);
+#pragma unroll
+      for (int u = 0; u < kFwdB; ++u) {
+        const int j = b0 + (u * 32 + lane) * VW;
+        if (j >= cn) continue;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          if (VEC) {
+            const float4 xv = *reinterpret_cast<const float4*>(xs + r * kChunk + j);
+            acc[r] = fmaf(wv[u][0], xv.x, acc[r]);
+            acc[r] = fmaf(wv[u][VW > 1 ? 1 : 0], xv.y, acc[r]);
+            acc[r] = fmaf(wv[u][VW > 2 ? 2 : 0], xv.z, acc[r]);
+            acc[r] = fmaf(wv[u][VW > 3 ? 3 : 0], xv.w, acc[r]);
+          } else {
+            acc[r] = fmaf(wv[u][0], xs[r * kChunk + j], acc[r]);
+          }
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) linear_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                              const float* __restrict__ b, float* __restrict__ pre,
                                                              float* __restrict__ y, int N, int Cin, int Cout, int act) {
+  extern __shared__ __align__(16) float xs[];          // [kRows][kChunk]
   const int lane = threadIdx.x & 31, o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (o >= Cout) return;
-  const float* w = W + (long long)o * Cin;
-  const float bias = b ? __ldg(b + o) : 0.0f;
+  const bool live = o < Cout;                          // dead warps still help staging and hit the barriers
+  const float* w = W + (long long)(live ? o : 0) * Cin;
+  const float bias = (b && live) ? __ldg(b + o) : 0.0f;
   const bool vec = (Cin & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
   for (int n0 = 0; n0 < N; n0 += kRows) {
     float acc[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) acc[r] = 0.0f;
-    if (vec) {
-      const int C4 = Cin >> 2;
-      const float4* w4 = reinterpret_cast<const float4*>(w);
-      const float4* x4 = reinterpret_cast<const float4*>(x);
-      for (int base = 0; base < C4; base += 32 * kFwdU) {
-        float4 wv[kFwdU];
-#pragma unroll
-        for (int u = 0; u < kFwdU; ++u) {
-          const int i4 = base + u * 32 + lane;
-          wv[u] = i4 < C4 ? __ldg(w4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < kFwdU; ++u) {
-          const int i4 = base + u * 32 + lane;
-          if (i4 >= C4) continue;
-#pragma unroll
-          for (int r = 0; r < kRows; ++r)
-            if (n0 + r < N) {
-              const float4 xv = __ldg(x4 + (long long)(n0 + r) * C4 + i4);
-              acc[r] = fmaf(wv[u].x, xv.x, acc[r]);
-              acc[r] = fmaf(wv[u].y, xv.y, acc[r]);
-              acc[r] = fmaf(wv[u].z, xv.z, acc[r]);
-              acc[r] = fmaf(wv[u].w, xv.w, acc[r]);
-            }
-        }
-      }
-    } else {
-      for (int base = 0; base < Cin; base += 32 * kFwdU) {
-        float wv[kFwdU];
-#pragma unroll
-        for (int u = 0; u < kFwdU; ++u) {
-          const int i = base + u * 32 + lane;
-          wv[u] = i < Cin ? __ldg(w + i) : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < kFwdU; ++u) {
-          const int i = base + u * 32 + lane;
-          if (i >= Cin) continue;
-#pragma unroll
-          for (int r = 0; r < kRows; ++r)
-            if (n0 + r < N) acc[r] = fmaf(wv[u], __ldg(x + (long long)(n0 + r) * Cin + i), acc[r]);
-        }
-      }
-    }
+    if (vec) lin_fwd_rows<true>(x, w, xs, acc, n0, N, Cin, live, lane);
+    else lin_fwd_rows<false>(x, w, xs, acc, n0, N, Cin, live, lane);
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], s);
     }
-    if (lane == 0) {
+    if (lane == 0 && live) {
 #pragma unroll
       for (int r = 0; r < kRows; ++r)
         if (n0 + r < N) {
@@ -208,7 +229,7 @@ extern "C" int dm_linear_act_fwd(const float* x, const float* W, const float* b,
   if (act < 0 || act > 3) { dm_set_error("dm_linear_act_fwd: act must be 0 (none), 1 (gelu), 2 (relu) or 3 (sigmoid)"); return DM_ERR_ARG; }
   if (N <= 0 || Cout <= 0) return DM_OK;
   if (Cin <= 0) { dm_set_error("dm_linear_act_fwd: Cin must be positive"); return DM_ERR_ARG; }
-  linear_act_fwd_kernel<<<(Cout + 7) / 8, 256, 0, ST>>>(x, W, b, pre, y, N, Cin, Cout, act);
+  linear_act_fwd_kernel<<<(Cout + 7) / 8, 256, (size_t)kRows * kChunk * sizeof(float), ST>>>(x, W, b, pre, y, N, Cin, Cout, act);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
