@@ -1074,6 +1074,26 @@ __device__ __forceinline__ Lerp lerp_src(int o, int in, float scale) {
   Lerp L; L.i0 = (int)s; L.i1 = L.i0 + (L.i0 < in - 1 ? 1 : 0); L.l1 = s - (float)L.i0; L.l0 = 1.0f - L.l1;
   return L;
 }
+// Bilinear blend of one bf16x2 word from each of the four source pixels on packed fp32 pairs (FMUL2 / FFMA2: half the
+// issue slots of the scalar form -- the upsample kernels are issue-bound, not HBM-bound).  One fixed rounding sequence,
+// shared by the per-pixel and the quad kernel, so the two stay bit-identical:
+//   top = fma(x1, v01, x0*v00), bot = fma(x1, v11, x0*v10), out = fma(y1, bot, y0*top)
+__device__ __forceinline__ f32x2 xlerp2(uint32_t v0, uint32_t v1, f32x2 x0, f32x2 x1) {
+  return fma2(x1, bf2_to_f2(v1), mul2(x0, bf2_to_f2(v0)));
+}
+__device__ __forceinline__ uint32_t ylerp2_bf(f32x2 top, f32x2 bot, f32x2 y0, f32x2 y1) {
+  return f2_to_bf2(fma2(y1, bot, mul2(y0, top)));
+}
+// zero the lanes of a stored 8-channel vector that lie past the tensor's channel count (ragged last vector only)
+__device__ __forceinline__ void mask_tail(uint4& o, int valid) {
+  if (valid >= 8) return;
+  uint32_t* w = &o.x;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (2 * q >= valid) w[q] = 0u;
+    else if (2 * q + 1 >= valid) w[q] &= 0x0000ffffu;
+  }
+}
 struct UpcatFwd {
   const bf16* a; int lda, Ca; const bf16* b; int ldb, Cb; bf16* out; int ldo; int h, w; float sy, sx;
   __device__ void operator()(unsigned p, int c0) const {
@@ -1083,15 +1103,19 @@ struct UpcatFwd {
     const bf16* src; int ld, c, C;
     if (c0 < Ca) { src = a; ld = lda; c = c0; C = Ca; } else { src = b; ld = ldb; c = c0 - Ca; C = Cb; }
     const long long base = (long long)n * h * w;
-    float v00[8], v01[8], v10[8], v11[8], o[8];
-    load8(src + (base + (long long)Y.i0 * w + X.i0) * ld + c, v00);
-    load8(src + (base + (long long)Y.i0 * w + X.i1) * ld + c, v01);
-    load8(src + (base + (long long)Y.i1 * w + X.i0) * ld + c, v10);
-    load8(src + (base + (long long)Y.i1 * w + X.i1) * ld + c, v11);
+    const uint4 r00 = dm::ldg16(src + (base + (long long)Y.i0 * w + X.i0) * ld + c);
+    const uint4 r01 = dm::ldg16(src + (base + (long long)Y.i0 * w + X.i1) * ld + c);
+    const uint4 r10 = dm::ldg16(src + (base + (long long)Y.i1 * w + X.i0) * ld + c);
+    const uint4 r11 = dm::ldg16(src + (base + (long long)Y.i1 * w + X.i1) * ld + c);
+    const f32x2 x0 = bc2(X.l0), x1 = bc2(X.l1), y0 = bc2(Y.l0), y1 = bc2(Y.l1);
+    const uint32_t *p00 = &r00.x, *p01 = &r01.x, *p10 = &r10.x, *p11 = &r11.x;
+    uint4 o;
+    uint32_t* po = &o.x;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      o[j] = (c + j < C) ? Y.l0 * (X.l0 * v00[j] + X.l1 * v01[j]) + Y.l1 * (X.l0 * v10[j] + X.l1 * v11[j]) : 0.f;
-    store8(out + (long long)p * ldo + c0, o);
+    for (int q = 0; q < 4; ++q)
+      po[q] = ylerp2_bf(xlerp2(p00[q], p01[q], x0, x1), xlerp2(p10[q], p11[q], x0, x1), y0, y1);
+    mask_tail(o, C - c);
+    *reinterpret_cast<uint4*>(out + (long long)p * ldo + c0) = o;
   }
 };
 // gather-form backward: every input pixel sums the output pixels that sampled it (deterministic)
@@ -1140,14 +1164,16 @@ struct UpcatBwd {
 // rows k-1 and k (lerp_src: (int)(o*(h-1)/(2h-1)) = k-1 for both), so a thread that owns the 2x2 output quad
 // (rows 2ky-1..2ky, cols 2kx-1..2kx) needs exactly one 2x2 source block: one 16-byte load per 16-byte store
 // instead of four.  Quads on the border have one valid row and/or column.
-__global__ void __launch_bounds__(kEwThreads) upcat_fwd_quad_kernel(UpcatFwd f, unsigned total, unsigned Cv) {
+// grid: x over the (w + 1) * Cv (quad column, channel vector) pairs of one quad row, y = n * (h + 1) + ky -- one integer
+// division per thread instead of three, and every address is one 64-bit base plus small steps.
+__global__ void __launch_bounds__(kEwThreads) upcat_fwd_quad_kernel(UpcatFwd f, unsigned Cv) {
   const int h = f.h, w = f.w, W2 = 2 * w, H2 = 2 * h;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    unsigned q = i / Cv;
-    const int c0 = (int)(i - q * Cv) * 8;
-    const int kx = q % (unsigned)(w + 1); q /= (unsigned)(w + 1);
-    const int ky = q % (unsigned)(h + 1);
-    const int n = q / (unsigned)(h + 1);
+  const int n = blockIdx.y / (unsigned)(h + 1), ky = blockIdx.y - n * (h + 1);
+  {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kx = i / Cv;
+    if (kx > w) return;
+    const int c0 = (int)(i - kx * Cv) * 8;
     const bool vy[2] = {ky >= 1, ky <= h - 1}, vx[2] = {kx >= 1, kx <= w - 1};
     const int oy[2] = {vy[0] ? 2 * ky - 1 : 2 * ky, vy[1] ? 2 * ky : 2 * ky - 1};
     const int ox[2] = {vx[0] ? 2 * kx - 1 : 2 * kx, vx[1] ? 2 * kx : 2 * kx - 1};
@@ -1155,22 +1181,38 @@ __global__ void __launch_bounds__(kEwThreads) upcat_fwd_quad_kernel(UpcatFwd f, 
     const Lerp X[2] = {lerp_src(ox[0], w, f.sx), lerp_src(ox[1], w, f.sx)};
     const bf16* src; int ld, c, C;
     if (c0 < f.Ca) { src = f.a; ld = f.lda; c = c0; C = f.Ca; } else { src = f.b; ld = f.ldb; c = c0 - f.Ca; C = f.Cb; }
-    const long long base = (long long)n * h * w;
-    float v00[8], v01[8], v10[8], v11[8], o[8];
-    load8(src + (base + (long long)Y[0].i0 * w + X[0].i0) * ld + c, v00);
-    load8(src + (base + (long long)Y[0].i0 * w + X[0].i1) * ld + c, v01);
-    load8(src + (base + (long long)Y[0].i1 * w + X[0].i0) * ld + c, v10);
-    load8(src + (base + (long long)Y[0].i1 * w + X[0].i1) * ld + c, v11);
+    const bf16* s00 = src + (((long long)n * h + Y[0].i0) * w + X[0].i0) * ld + c;
+    const int sdx = (X[0].i1 - X[0].i0) * ld;                       // 0 on the right border
+    const long long sdy = (long long)(Y[0].i1 - Y[0].i0) * w * ld;  // 0 on the bottom border
+    const uint4 r00 = dm::ldg16(s00);
+    const uint4 r01 = dm::ldg16(s00 + sdx);
+    const uint4 r10 = dm::ldg16(s00 + sdy);
+    const uint4 r11 = dm::ldg16(s00 + sdy + sdx);
+    bf16* o00 = f.out + (((long long)n * H2 + oy[0]) * W2 + ox[0]) * f.ldo + c0;
+    const int odx = (ox[1] - ox[0]) * f.ldo;
+    const long long ody = (long long)(oy[1] - oy[0]) * W2 * f.ldo;
+    const uint32_t *p00 = &r00.x, *p01 = &r01.x, *p10 = &r10.x, *p11 = &r11.x;
+    // horizontal blends of the two source rows for both output columns, shared by the two output rows
+    f32x2 top[2][4], bot[2][4];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const f32x2 x0 = bc2(X[b].l0), x1 = bc2(X[b].l1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { top[b][q] = xlerp2(p00[q], p01[q], x0, x1); bot[b][q] = xlerp2(p10[q], p11[q], x0, x1); }
+    }
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       if (!vy[a]) continue;
+      const f32x2 y0 = bc2(Y[a].l0), y1 = bc2(Y[a].l1);
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
         if (!vx[b]) continue;
+        uint4 o;
+        uint32_t* po = &o.x;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = (c + j < C) ? Y[a].l0 * (X[b].l0 * v00[j] + X[b].l1 * v01[j]) + Y[a].l1 * (X[b].l0 * v10[j] + X[b].l1 * v11[j]) : 0.f;
-        store8(f.out + (((long long)n * H2 + oy[a]) * W2 + ox[b]) * f.ldo + c0, o);
+        for (int q = 0; q < 4; ++q) po[q] = ylerp2_bf(top[b][q], bot[b][q], y0, y1);
+        mask_tail(o, C - c);
+        *reinterpret_cast<uint4*>(o00 + (a ? ody : 0) + (b ? odx : 0)) = o;
       }
     }
   }
@@ -1200,36 +1242,49 @@ __global__ void __launch_bounds__(kEwThreads) upcat_bwd_quad_kernel(UpcatBwd f, 
         wx[a][r] = vx ? (X.i0 == ix0 + a ? X.l0 : 0.f) + (X.i1 == ix0 + a ? X.l1 : 0.f) : 0.f;
       }
     }
-    float acc[2][2][8];
+    // accumulators on packed fp32 pairs (FFMA2: the same fma per element as the scalar form, half the issue slots)
+    f32x2 acc[2][2][4];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < 2; ++b)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[a][b][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[a][b][j] = bc2(0.f);
     const bf16* gbase = f.dout + (long long)n * H2 * W2 * f.lddo + c0;
+    int coff[6];
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) coff[cc] = rx[cc] * f.lddo;
+    // window rows are double-buffered: the next row's six loads are requested before this row's arithmetic
+    uint4 raw[6], nxt[6];
+    {
+      const bf16* rowp = gbase + (long long)ry[0] * W2 * f.lddo;
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) raw[cc] = dm::ldg16(rowp + coff[cc]);
+    }
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      uint4 raw[6];
+      if (r + 1 < 6) {
+        const bf16* rowp = gbase + (long long)ry[r + 1] * W2 * f.lddo;
 #pragma unroll
-      for (int cc = 0; cc < 6; ++cc) raw[cc] = dm::ldg16(gbase + ((long long)ry[r] * W2 + rx[cc]) * f.lddo);
+        for (int cc = 0; cc < 6; ++cc) nxt[cc] = dm::ldg16(rowp + coff[cc]);
+      }
 #pragma unroll
       for (int cc = 0; cc < 6; ++cc) {
-        float g[8];
-        g[0] = dm::bf_lo(raw[cc].x); g[1] = dm::bf_hi(raw[cc].x); g[2] = dm::bf_lo(raw[cc].y); g[3] = dm::bf_hi(raw[cc].y);
-        g[4] = dm::bf_lo(raw[cc].z); g[5] = dm::bf_hi(raw[cc].z); g[6] = dm::bf_lo(raw[cc].w); g[7] = dm::bf_hi(raw[cc].w);
+        const f32x2 g[4] = {bf2_to_f2(raw[cc].x), bf2_to_f2(raw[cc].y), bf2_to_f2(raw[cc].z), bf2_to_f2(raw[cc].w)};
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
           if (r < 2 * a || r >= 2 * a + 4) continue;      // rows outside 2*iy-1 .. 2*iy+2 never sample input row iy
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
             if (cc < 2 * b || cc >= 2 * b + 4) continue;
-            const float wt = wy[a][r] * wx[b][cc];
+            const f32x2 wt = bc2(wy[a][r] * wx[b][cc]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[a][b][j] += wt * g[j];
+            for (int j = 0; j < 4; ++j) acc[a][b][j] = fma2(wt, g[j], acc[a][b][j]);
           }
         }
       }
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) raw[cc] = nxt[cc];
     }
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
@@ -1238,15 +1293,15 @@ __global__ void __launch_bounds__(kEwThreads) upcat_bwd_quad_kernel(UpcatBwd f, 
       for (int b = 0; b < 2; ++b) {
         if (ix0 + b >= w) continue;
         const long long p = ((long long)n * h + iy0 + a) * w + ix0 + b;
+        uint4 o;
+        o.x = f2_to_bf2(acc[a][b][0]); o.y = f2_to_bf2(acc[a][b][1]); o.z = f2_to_bf2(acc[a][b][2]); o.w = f2_to_bf2(acc[a][b][3]);
         if (c0 < f.Ca) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) if (c0 + j >= f.Ca) acc[a][b][j] = 0.f;
-          store8(f.da + p * f.ldda + c0, acc[a][b]);
+          mask_tail(o, f.Ca - c0);
+          *reinterpret_cast<uint4*>(f.da + p * f.ldda + c0) = o;
         } else {
           const int c = c0 - f.Ca;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) if (c + j >= f.Cb) acc[a][b][j] = 0.f;
-          store8(f.db + p * f.lddb + c, acc[a][b]);
+          mask_tail(o, f.Cb - c);
+          *reinterpret_cast<uint4*>(f.db + p * f.lddb + c) = o;
         }
       }
     }
@@ -1728,7 +1783,9 @@ extern "C" int dm_upcat_fwd(const void* a, int lda, int Ca, const void* b, int l
   const long long Cv = (Ca + Cb + 7) / 8, total = (long long)N * (h + 1) * (w + 1) * Cv;
   if (total <= 0) return DM_OK;
   if (total >= (1ll << 32) || (long long)N * 4 * h * w * Cv >= (1ll << 32)) { dm_set_error("dm_upcat_fwd: tensor too large"); return DM_ERR_ARG; }
-  upcat_fwd_quad_kernel<<<ew_grid(total), kEwThreads, 0, ST>>>(f, (unsigned)total, (unsigned)Cv);
+  if ((long long)N * (h + 1) > 65535) { dm_set_error("dm_upcat_fwd: N * (h + 1) must fit the grid's y extent (65535)"); return DM_ERR_ARG; }
+  const dim3 grid((unsigned)(((w + 1) * Cv + kEwThreads - 1) / kEwThreads), (unsigned)(N * (h + 1)));
+  upcat_fwd_quad_kernel<<<grid, kEwThreads, 0, ST>>>(f, (unsigned)Cv);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
