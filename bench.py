@@ -188,11 +188,12 @@ def cpu_baseline_sample():
 
 def hbm_kernel_table(dev, hbm_peak):
     """Achieved algorithmic GB/s of the bandwidth-bound kernel classes on the dominant activation shape of the step
-    (4 x 256 x 256 x 192 bf16 = 100.7 MB per tensor).  Each kernel is launched 9 times back to back on the current
-    stream, rotating over 3 operand sets (>= 600 MB in total, far above the 126 MB L2, so every launch reads cold
-    data), between one pair of CUDA events; bytes = the DESIGN.md per-element figures x elements."""
+    (4 x 256 x 256 x 192 bf16 = 100.7 MB per tensor).  Each kernel is launched 9 times back to back, rotating over 3
+    operand sets (>= 600 MB in total, far above the 126 MB L2, so every launch reads cold data), between one pair of
+    CUDA events; the nine launches are replayed as one CUDA graph so that the figure does not depend on how fast this
+    box's host can issue 20 us kernels through ctypes; bytes = the DESIGN.md per-element figures x elements."""
     from diffusionmodel_b200 import _lib, ops
-    P_, st = ops._p, ops._stream()
+    P_ = ops._p
     n, h, c = CFG["batch"], CFG["img"], CFG["n_feat"]
     P = n * h * h
     E = P * c
@@ -219,31 +220,36 @@ def hbm_kernel_table(dev, hbm_peak):
     xo, xt = torch.empty_like(xs), torch.empty((2 * ns, h, h, 8), device=dev, dtype=torch.bfloat16)
     kernels = [
         ("bn_stats_kernel", "dm_bn_stats", 2 * E,
-         lambda d: ops.call("dm_bn_stats", P_(d["y"]), c, P_(part), c, P, c, st)),
+         lambda d: ops.call("dm_bn_stats", P_(d["y"]), c, P_(part), c, P, c, ops._stream())),
         ("bn_fwd_kernel (BatchNorm + GELU)", "dm_bn_act_fwd", 4 * E,
-         lambda d: ops.call("dm_bn_act_fwd", P_(d["y"]), c, P_(mean), P_(inv), P_(ga), P_(be), P_(d["z"]), c, P, c, 1, st)),
+         lambda d: ops.call("dm_bn_act_fwd", P_(d["y"]), c, P_(mean), P_(inv), P_(ga), P_(be), P_(d["z"]), c, P, c, 1, ops._stream())),
         ("bn_bwd_reduce + finalize + apply", "dm_bn_act_bwd", 10 * E,
          lambda d: ops.call("dm_bn_act_bwd", P_(d["dz"]), c, P_(d["y"]), c, P_(mean), P_(inv), P_(ga), P_(be), P_(d["z"]), c,
-                            P_(dga), P_(dbe), None, P_(scr), P, c, 1, 1, st)),
+                            P_(dga), P_(dbe), None, P_(scr), P, c, 1, 1, ops._stream())),
         ("ew_kernel<SeFwd> (SE gate + residual)", "dm_se_apply_fwd", 6 * E,
-         lambda d: ops.call("dm_se_apply_fwd", P_(d["y"]), c, P_(gate), P_(d["dz"]), c, P_(d["z"]), c, n, h * h, c, 0.7072, st)),
+         lambda d: ops.call("dm_se_apply_fwd", P_(d["y"]), c, P_(gate), P_(d["dz"]), c, P_(d["z"]), c, n, h * h, c, 0.7072, ops._stream())),
         ("upcat_fwd_quad_kernel (cat + bilinear x2)", "dm_upcat_fwd", (E // 4 * 2 + 2 * E) * 2,
-         lambda d: ops.call("dm_upcat_fwd", P_(d["a"]), c, c, P_(d["b"]), c, c, P_(d["up"]), 2 * c, n, h // 2, h // 2, st)),
+         lambda d: ops.call("dm_upcat_fwd", P_(d["a"]), c, c, P_(d["b"]), c, c, P_(d["up"]), 2 * c, n, h // 2, h // 2, ops._stream())),
         ("upcat_bwd_quad_kernel", "dm_upcat_bwd", (E // 4 * 2 + 2 * E) * 2,
-         lambda d: ops.call("dm_upcat_bwd", P_(d["up"]), 2 * c, P_(d["da"]), c, c, P_(d["db"]), c, c, n, h // 2, h // 2, st)),
+         lambda d: ops.call("dm_upcat_bwd", P_(d["up"]), 2 * c, P_(d["da"]), c, c, P_(d["db"]), c, c, n, h // 2, h // 2, ops._stream())),
         ("cfg_reverse_step_kernel (n=15)", "dm_cfg_reverse_step", ns * 3 * h * h * 20 + 2 * ns * h * h * 16,
          lambda d: ops.call("dm_cfg_reverse_step", P_(eps), 4, P_(xs), P_(zs), P_(xo), P_(xt), 8, 2.0, 1.01, 0.02, 0.1, ns, 3,
-                            h, h, st)),
+                            h, h, ops._stream())),
     ]
     rows = []
     for kname, entry, nbytes, fn in kernels:
         for d in sets:
             fn(d)
         torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(9):
+                fn(sets[i % 3])
+        graph.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(9):
-            fn(sets[i % 3])
+        graph.replay()
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 9 * 1e3
