@@ -191,7 +191,7 @@ def hbm_kernel_table(dev, hbm_peak):
     (4 x 256 x 256 x 192 bf16 = 100.7 MB per tensor).  Each kernel is launched 9 times back to back, rotating over 3
     operand sets (>= 600 MB in total, far above the 126 MB L2, so every launch reads cold data), between one pair of
     CUDA events; the nine launches are replayed as one CUDA graph so that the figure does not depend on how fast this
-    box's host can issue 20 us kernels through ctypes; bytes = the DESIGN.md per-element figures x elements."""
+    box's host can issue 20 us kernels through ctypes (median of five replays); bytes = the DESIGN.md per-element figures x elements."""
     from diffusionmodel_b200 import _lib, ops
     P_ = ops._p
     n, h, c = CFG["batch"], CFG["img"], CFG["n_feat"]
@@ -247,12 +247,15 @@ def hbm_kernel_table(dev, hbm_peak):
                 fn(sets[i % 3])
         graph.replay()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        graph.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / 9 * 1e3
+        reps = []
+        for _ in range(5):                      # median of five replays (clocks move under the power cap)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            reps.append(e0.elapsed_time(e1))
+        us = sorted(reps)[2] / 9 * 1e3
         gbs = nbytes / us / 1e3
         rows.append({"kernel": kname, "entry": entry, "us": round(us, 1), "algorithmic_MB": round(nbytes / 1e6, 1),
                      "GBps": round(gbs, 1), "frac": round(gbs / hbm_peak, 3)})

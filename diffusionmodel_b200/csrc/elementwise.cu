@@ -1220,7 +1220,7 @@ __global__ void __launch_bounds__(kEwThreads) upcat_fwd_quad_kernel(UpcatFwd f, 
 // Backward: a thread owns a 2x2 block of input pixels and walks the 6x6 output window that touches it (rows
 // 2*iy0-1 .. 2*iy0+4): 9 loads per input vector instead of 16, all of one window row in flight together, no
 // data-dependent control flow.  Per input pixel the products are added in the same (row, column) order as UpcatBwd.
-__global__ void __launch_bounds__(kEwThreads) upcat_bwd_quad_kernel(UpcatBwd f, unsigned total, unsigned Cv) {
+__global__ void __launch_bounds__(128) upcat_bwd_quad_kernel(UpcatBwd f, unsigned total, unsigned Cv) {
   const int h = f.h, w = f.w, W2 = 2 * w, H2 = 2 * h, hb = (h + 1) / 2, wb = (w + 1) / 2;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     unsigned q = i / Cv;
@@ -1798,7 +1798,9 @@ extern "C" int dm_upcat_bwd(const void* dout, int lddo, void* da, int ldda, int 
   const long long Cv = (Ca + Cb + 7) / 8, total = (long long)N * ((h + 1) / 2) * ((w + 1) / 2) * Cv;
   if (total <= 0) return DM_OK;
   if ((long long)N * 4 * h * w * Cv >= (1ll << 32)) { dm_set_error("dm_upcat_bwd: tensor too large"); return DM_ERR_ARG; }
-  upcat_bwd_quad_kernel<<<ew_grid(total), kEwThreads, 0, ST>>>(f, (unsigned)total, (unsigned)Cv);
+  // one work item per thread in 128-thread blocks: at ~100 registers that is 5 resident blocks (20 warps) per SM instead
+  // of 2 x 256 threads, and no capped grid-stride loop (786 K items on 606 K threads ran as one full round + a 30 % one)
+  upcat_bwd_quad_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ST>>>(f, (unsigned)total, (unsigned)Cv);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
