@@ -41,9 +41,6 @@ def lib() -> ctypes.CDLL:
         _lib.dm_debug_set.argtypes = [ctypes.c_int, ctypes.c_longlong]
         _lib.dm_debug_set.restype = None
         _lib.dm_launch_count.restype = ctypes.c_longlong
-        for kv in filter(None, os.environ.get("DM_DEBUG", "").split(",")):      # dev switches, e.g. DM_DEBUG=10=3,9=1
-            k, v = kv.split("=")
-            _lib.dm_debug_set(int(k), int(v))
     return _lib
 
 
@@ -81,6 +78,7 @@ _SIGS = {
     "dm_se_apply_fwd": "pi p pi pi iii f p",
     "dm_se_apply_bwd": "pi p p pi pi iii f p",
     "dm_linear_act_fwd": "ppp pp iii i p",
+    "dm_ctx_onehot": "pp i p iii p",
     "dm_linear_bwd_parts": "i",
     "dm_linear_act_bwd": "pi pi pp pp p iii p",
     "dm_sum_parts": "pi p l p",
@@ -105,6 +103,7 @@ _SIGS = {
     "dm_ddpm_loss_bwd": "pi p p p pi iiii ffffff p",
     "dm_cfg_reverse_step": "pi p p p pi ffff iiii p",
     "dm_cfg_reverse_step_dev": "pi p p p pi p iiii p",
+    "dm_cfg_reverse_step_w": "pi p p p pi p p iiii p",
     "dm_ca_gates_rows_per_block": "",
     "dm_ca_gates_fwd": "p p",
     "dm_ca_gates_bwd": "p p p",
@@ -156,6 +155,37 @@ def call(name, *args):
 
 def launch_count() -> int:
     return int(lib().dm_launch_count())
+
+
+def kernel_count(name: str) -> int:
+    """Launches so far of the kernel variant ``name`` (dm_kernel_count)."""
+    f = lib().dm_kernel_count
+    f.argtypes, f.restype = [ctypes.c_char_p], ctypes.c_longlong
+    return int(f(name.encode()))
+
+
+def last_kernel():
+    """(name, parameter) of the most recent conv / weight-gradient / skinny launch (dm_last_kernel)."""
+    f = lib().dm_last_kernel
+    f.argtypes, f.restype = [ctypes.POINTER(ctypes.c_int)], ctypes.c_char_p
+    v = ctypes.c_int(0)
+    return f(ctypes.byref(v)).decode(), int(v.value)
+
+
+class kernel_counts:
+    """Context manager: ``with kernel_counts() as k: ...; k["conv3x3_halo2"]`` = launches of that variant inside."""
+    NAMES = ("conv_gemm", "conv3x3_halo", "conv3x3_halo2", "wgrad_gemm", "wgrad2_gemm", "wgrad3_pair", "skinny_gemm")
+
+    def __enter__(self):
+        self._before = {n: kernel_count(n) for n in self.NAMES}
+        self.delta = {}
+        return self
+
+    def __exit__(self, *exc):
+        self.delta = {n: kernel_count(n) - self._before[n] for n in self.NAMES}
+
+    def __getitem__(self, name):
+        return self.delta[name]
 
 
 def debug_set(key: int, value: int) -> None:

@@ -7,7 +7,8 @@
 Flag names, defaults and the missing-checkpoint behaviour are the reference's.  The drivers are the thin
 caller contract of SURVEY.md 2.1 (train_model new_scripy.py:659-943, gen_samples :945-1108): accumulation
 over ACCUM_STEPS micro-batches, clip 1.0, AdamW(lr 1e-4, wd 1e-5), CosineAnnealingWarmRestarts(10, 2, 3e-5),
-checkpoints as ``{'epoch', 'model_state_dict', 'optimizer_state_dict', 'loss'}``.  The reference's dataset
+checkpoints as ``{'epoch', 'model_state_dict', 'optimizer_state_dict', 'scheduler_state_dict', 'loss', 'metrics'}``
+(:736-743; ``--resume CKPT`` continues from one, optimizer moments and scheduler position included).  The reference's dataset
 (./cropped_images, VOC XML) is not shipped with it: ``--data DIR`` reads that layout through the device-side batch
 pipeline (data.py), otherwise batches are synthetic road-damage-shaped tensors
 (images in [-1,1], labels, attention map 0.5 / 1.0 lower half / 3.0 box, new_scripy.py:535-546); FID/SSIM
@@ -44,10 +45,19 @@ def synth_batch(gen, batch, img, n_classes):
     return x, c, m
 
 
-def build(n_classes, device, n_feat=Cfg.N_FEAT):
+def build(n_classes, device, n_feat=Cfg.N_FEAT, enhance_with_attn_map=False):
+    """Default = the shipped semantics (LocalEnhancer contributes +0 in training AND in sampling, new_scripy.py:353).
+    ``enhance_with_attn_map=True`` feeds the attention map to LocalEnhancer during training; ``DDPM.sample`` has no
+    attention map to give it, so a model trained that way is sampled without the enhancer term."""
     net = ContextUnet(in_ch=Cfg.IN_CH, n_feat=n_feat, n_classes=n_classes)
     return DDPM(nn_model=net, betas=Cfg.BETAS, n_T=Cfg.N_T, device=device, drop_prob=Cfg.DROP_PROB,
-                enhance_with_attn_map=True).to(device)
+                enhance_with_attn_map=enhance_with_attn_map).to(device)
+
+
+def save_ckpt(path, ddpm, optim, sched, epoch, loss, metrics_log=None):
+    """The reference's checkpoint dict (new_scripy.py:730-744)."""
+    torch.save({"epoch": epoch, "model_state_dict": ddpm.state_dict(), "optimizer_state_dict": optim.state_dict(),
+                "scheduler_state_dict": sched.state_dict(), "loss": loss, "metrics": metrics_log or {}}, path)
 
 
 def train_model(args):
@@ -60,15 +70,25 @@ def train_model(args):
         from .data import CachedCrackBatches
         cache = CachedCrackBatches.from_voc_dir(args.data, args.img, device)
         args.n_classes = len(cache.classes)                      # new_scripy.py:692
-    ddpm = build(args.n_classes, device, args.n_feat).train()
+    ddpm = build(args.n_classes, device, args.n_feat, args.enhance_attn_map).train()
     optim = FusedAdamW(ddpm.parameters(), lr=Cfg.LR, weight_decay=Cfg.WD, max_grad_norm=1.0)
     sched = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(optim, T_0=10, T_mult=2, eta_min=3e-5)
+    first_epoch = 0
+    if args.resume:
+        ck = torch.load(args.resume, map_location="cpu")
+        ddpm.load_state_dict(ck["model_state_dict"])
+        if "optimizer_state_dict" in ck:
+            optim.load_state_dict(ck["optimizer_state_dict"])
+        if "scheduler_state_dict" in ck:
+            sched.load_state_dict(ck["scheduler_state_dict"])
+        first_epoch = int(ck.get("epoch", -1)) + 1
     parallel.broadcast_parameters(optim.flat_param, list(ddpm.buffers()))
     gen = torch.Generator().manual_seed(100 + rank)
     torch.manual_seed(1234 + rank)
     step_fn = None
     os.makedirs(Cfg.SAVE_DIR, exist_ok=True)
-    for ep in range(args.epochs):
+    ema = None
+    for ep in range(first_epoch, args.epochs):
         t0, ema, seen = time.time(), None, 0
         for step in range(args.steps_per_epoch):
             if cache is not None:      # random batch of the cached set; flip / normalise / mask rasterisation in one kernel
@@ -97,13 +117,13 @@ def train_model(args):
             print(f"epoch {ep}: loss(ema) {ema:.4f}  lr {optim.param_groups[0]['lr']:.2e}  {seen / dt:.1f} img/s", flush=True)
     if rank == 0:
         path = os.path.join(Cfg.SAVE_DIR, "best_model.pt")
-        torch.save({"epoch": args.epochs, "model_state_dict": ddpm.state_dict(), "loss": ema}, path)   # :730-744
+        save_ckpt(path, ddpm, optim, sched, args.epochs - 1, ema)                       # :730-744, final save :926
         print(f"saved {path}")
     return ddpm
 
 
 def gen_samples(ckpt, n_samples_per_class=3, guide_scales=(2.0, 4.0), eval_quality=True, n_classes=5, n_feat=Cfg.N_FEAT,
-                img=Cfg.IMG_SIZE):
+                img=Cfg.IMG_SIZE, sequential_scales=False):
     rank, local, world = parallel.init_from_env()
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
@@ -119,16 +139,19 @@ def gen_samples(ckpt, n_samples_per_class=3, guide_scales=(2.0, 4.0), eval_quali
     ddpm.eval()
     os.makedirs(Cfg.SAMPLE_DIR, exist_ok=True)
     out = {}
-    for w in guide_scales:                                         # :1036
-        n_sample = parallel.shard_samples(n_samples_per_class * n_classes, n_classes, rank, world)
+    n_sample = parallel.shard_samples(n_samples_per_class * n_classes, n_classes, rank, world)
+    # the reference loops over the guidance scales (:1036-1041); here all scales run as ONE trajectory batch unless
+    # --sequential_scales asks for the reference's loop (same trajectories, S times the kernel launches)
+    groups = [[w] for w in guide_scales] if sequential_scales else [list(guide_scales)]
+    for ws in groups:
         t0 = time.time()
-        x_gen = ddpm.sample(n_sample, (3, img, img), device, guide_w=w) if n_sample else None
+        xs = ddpm.sample(n_sample, (3, img, img), device, guide_w=ws) if n_sample else []
         torch.cuda.synchronize()
-        if x_gen is not None:
+        for w, x_gen in zip(ws, xs):
             torch.save(x_gen.cpu(), os.path.join(Cfg.SAMPLE_DIR, f"samples_w{w}_rank{rank}.pt"))
             out[w] = x_gen
         if rank == 0:
-            print(f"guide_w={w}: {n_sample} samples/rank in {time.time() - t0:.1f}s", flush=True)
+            print(f"guide_w={ws}: {n_sample} samples/rank per scale in {time.time() - t0:.1f}s", flush=True)
     return out
 
 
@@ -146,6 +169,11 @@ def main(argv=None):
     parser.add_argument("--n_classes", type=int, default=5)
     parser.add_argument("--n_feat", type=int, default=Cfg.N_FEAT)
     parser.add_argument("--img", type=int, default=Cfg.IMG_SIZE)
+    parser.add_argument("--sequential_scales", action="store_true",
+                        help="generate: one sampling run per guidance scale like the reference, instead of one batch of all scales")
+    parser.add_argument("--resume", type=str, default=None, help="checkpoint to continue training from")
+    parser.add_argument("--enhance_attn_map", action="store_true",
+                        help="feed the attention map to LocalEnhancer while training (the shipped call site passes ctx_mask: +0)")
     parser.add_argument("--no_graph", action="store_true", help="eager launches instead of the CUDA-graphed micro-step")
     parser.add_argument("--data", type=str, default=None,
                         help="dataset root in the reference's layout (images/<class>/*.jpg + annotations/*.xml); synthetic batches if omitted")
@@ -158,7 +186,8 @@ def main(argv=None):
             parser.print_help()
             sys.exit(1)
         gen_samples(args.ckpt, n_samples_per_class=args.samples, guide_scales=args.guide_scales,
-                    eval_quality=not args.no_eval, n_classes=args.n_classes, n_feat=args.n_feat, img=args.img)
+                    eval_quality=not args.no_eval, n_classes=args.n_classes, n_feat=args.n_feat, img=args.img,
+                    sequential_scales=args.sequential_scales)
 
 
 if __name__ == "__main__":

@@ -18,6 +18,7 @@
 
 void dm_set_error(const char* msg);
 void dm_count_launch();
+void dm_note_kernel(const char* name, int param);   // which kernel variant a dispatcher chose (dm_kernel_count / dm_last_kernel)
 long long dm_debug_value(int key);      // dev switches set through dm_debug_set (conv_gemm.cu)
 
 #define DM_NUM_SMS 148

@@ -1142,157 +1142,9 @@ wgrad3_pair_kernel(const __grid_constant__ Wgrad2Params p) {
   if (warp == 1) { tc_fence_after(); tc_dealloc2(tmem_base, 512); }
 }
 
-// ------------------------------------------------------------------------------------------ kernel G
-// CTA-pair weight gradient with TWO accumulators per CTA (M = 512 im2col rows per pair and K step): rank r
-// stages boxes 4r..4r+3 of an 8-box M tile plus half of the dY tile's channels; eight M=256 instructions per
-// 64 pixels.  Against kernel C (same 256 rows per CTA, M=128 instructions) the MN-major M=256 instruction
-// costs ~250 cycles instead of 2 x 170, and each CTA stages half of dY.  Accumulators single-buffered.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-wgrad4_pair2_kernel(const __grid_constant__ Wgrad2Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int nbh = p.nb;                                  // dY boxes per CTA (its half of the tile's channels)
-  const int a_bytes = 4 * 8192, stage_bytes = a_bytes + nbh * 8192;
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + (uint32_t)p.stages * (uint32_t)stage_bytes;
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * kMaxStages, bar_tfull = bar_empty + 8 * kMaxStages,
-                 bar_tempty = bar_tfull + 16, tmem_slot = bar_tempty + 16;
-  const int chunks = p.chunks0 + p.chunks1;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
-  const int t_first = blockIdx.x >> 1, t_step = gridDim.x >> 1;
-  const int half_n = p.block_n >> 1;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    mbar_init(bar_tfull, 1); mbar_init(bar_tempty, 8);                                         // 4 epilogue warps x 2 CTAs
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmX[0]); tma_prefetch_desc(&p.tmDY); }
-  if (warp == 1) tc_alloc2(tmem_slot, 512);
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t l_full = mapa_shared(bar_full, 0), l_tempty = mapa_shared(bar_tempty, 0);
-
-  auto decode = [&](int tile, int& mt, int& nt, int& sp) {
-    mt = tile % p.m_tiles; tile /= p.m_tiles;
-    nt = tile % p.n_tiles; sp = tile / p.n_tiles;
-  };
-
-  if (warp == 0) {
-    int stage = 0; uint32_t phase = 0;
-    for (int tile = t_first; tile < total_tiles; tile += t_step) {
-      int mt, nt, sp; decode(tile, mt, nt, sp);
-      const int nA_all = min(8, p.total_boxes - mt * 8);              // live boxes of the 8-box tile
-      const int nA = max(0, min(4, nA_all - 4 * (int)rank));          // ... of which this CTA stages
-      const int p0 = sp * p.patches_per_split;
-      const int p1 = min(p.patches, p0 + p.patches_per_split);
-      int bmap[4], bc0[4], bdx[4], bdy[4];
-      for (int j = 0; j < 4; ++j) {
-        const int box = min(mt * 8 + 4 * (int)rank + j, p.total_boxes - 1);
-        const int tap = box / chunks, ch = box - tap * chunks;
-        const TapInfo t = p.taps[tap];
-        bmap[j] = t.map; bc0[j] = ch * 64; bdx[j] = t.dx; bdy[j] = t.dy;
-        if (p.dual && ch >= p.chunks0) { bmap[j] = 1; bc0[j] = (ch - p.chunks0) * 64; }
-      }
-      const int co0 = nt * p.block_n + (int)rank * half_n;
-      for (int pp = p0; pp < p1; ++pp) {
-        const int tw = pp % p.tiles_w, th = (pp / p.tiles_w) % p.tiles_h, tb = pp / (p.tiles_w * p.tiles_h);
-        const int w0 = tw << p.log_bw, h0 = th << p.log_bh, n0 = tb << p.log_bn;
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
-        const uint32_t fb = l_full + 8 * stage;
-        if (elect_one()) {
-          if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, (nA_all + 2 * nbh) * 8192);
-          for (int j = 0; j < nbh; ++j) tma_load_4d_2sm(sb + j * 8192, &p.tmDY, co0 + j * 64, w0, h0, n0, fb);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j < nA) tma_load_4d_2sm(sa + j * 8192, &p.tmX[bmap[j]], bc0[j], w0 + bdx[j], h0 + bdy[j], n0, fb);
-        }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (rank == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int tile = t_first; tile < total_tiles; tile += t_step, ++it) {
-        int mt, nt, sp; decode(tile, mt, nt, sp);
-        const int nh = min(8, p.total_boxes - mt * 8) > 2 ? 2 : 1;     // second accumulator: boxes 2,3 (6,7 in the peer)
-        const int p0 = sp * p.patches_per_split;
-        const int p1 = min(p.patches, p0 + p.patches_per_split);
-        mbar_wait(bar_tempty, (uint32_t)((it & 1) ^ 1));
-        tc_fence_after();
-        for (int pp = p0; pp < p1; ++pp) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
-          const uint64_t adesc = p.desc_hi | ((uint64_t)p.lbo << 16) | (uint64_t)((sa & 0x3FFFFu) >> 4);
-          const uint64_t bdesc = p.desc_hi | ((uint64_t)p.lbo << 16) | (uint64_t)((sb & 0x3FFFFu) >> 4);
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {    // 16 pixels per MMA = two 8-row swizzle groups = 2048 B
-              tc_mma2_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), p.idesc, (pp != p0) | (k != 0));
-              if (nh == 2)                   // boxes 2,3 of each CTA: 16 KB further = 1024 descriptor units
-                tc_mma2_bf16(tmem_base + 256u, adesc + (uint64_t)(1024 + k * 128), bdesc + (uint64_t)(k * 128), p.idesc,
-                             (pp != p0) | (k != 0));
-            }
-            tc_commit2(bar_empty + 8 * stage);
-            if (pp == p1 - 1) tc_commit2(bar_tfull);
-          }
-          __syncwarp();
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    int it = 0;
-    for (int tile = t_first; tile < total_tiles; tile += t_step, ++it) {
-      int mt, nt, sp; decode(tile, mt, nt, sp);
-      const int nh = min(8, p.total_boxes - mt * 8) > 2 ? 2 : 1;
-      mbar_wait(bar_tfull, (uint32_t)(it & 1));
-      tc_fence_after();
-      for (int h = 0; h < nh; ++h) {
-      const int box = mt * 8 + 4 * (int)rank + 2 * h + (r >> 6);
-      const int tap = box / chunks, ch = box - tap * chunks;
-      const int cil = r & 63;
-      const bool first = !(p.dual && ch >= p.chunks0);
-      const int creal = first ? ch * 64 + cil : (ch - p.chunks0) * 64 + cil;
-      const bool live = box < p.total_boxes && creal < (first ? p.C0 : p.C1);
-      float* dst = p.dwp + (long long)tap * p.cin_k + ch * 64 + cil;
-      const long long co_stride = (long long)p.num_taps * p.cin_k;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256);
-      for (int cc = 0; cc < p.block_n; cc += 32) {
-        float v[32];
-        tc_ld32(t_row + (uint32_t)cc, v);
-        if (live) {
-          const int co0 = nt * p.block_n + cc;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (co0 + j < p.Cout && cc + j < p.block_n)
-              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)(co0 + j) * co_stride), "f"(v[j]) : "memory");
-        }
-      }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(l_tempty);
-    }
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 1) { tc_fence_after(); tc_dealloc2(tmem_base, 512); }
-}
-
 // ------------------------------------------------------------------------------------------ host side
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
-long long g_debug[16] = {0};   // 8..15: elementwise.cu experiments (dm_debug_value); 0 stages 1 grid 2 splits 3 block_n 4 wgrad kernel 5 no-halo 6 base-offset 7 ablation 9 upcat per-pixel 10 wgrad stages
+long long g_debug[16] = {0};   // 8..15: elementwise.cu experiments (dm_debug_value); 0 stages 1 grid 2 splits 3 block_n 4 wgrad kernel (1 B, 2 C, 3 F) 5 no-halo 6 base-offset 7 ablation 9 upcat per-pixel 10 wgrad stages
 
 int ensure_encode() {
   if (g_encode) return DM_OK;
@@ -1425,6 +1277,7 @@ static int launch_conv(ConvParams& P, cudaStream_t st) {
   }
   int grid = conv_grid(P.m_tiles * P.n_tiles);
   if (!P.stats && g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
+  dm_note_kernel("conv_gemm", P.block_n);
   conv_gemm_kernel<<<grid, kConvThreads, smem, st>>>(P);
   DM_CHECK_LAUNCH();
   return DM_OK;
@@ -1454,6 +1307,7 @@ static int launch_conv_halo(ConvParams& P, cudaStream_t st) {
     g_attr_d = true;
   }
   const int grid = conv_grid(P.m_tiles * P.n_tiles);
+  dm_note_kernel("conv3x3_halo", P.block_n);
   conv3x3_halo_kernel<<<grid, kConvThreads, smem, st>>>(P);
   DM_CHECK_LAUNCH();
   return DM_OK;
@@ -1483,6 +1337,7 @@ static int launch_conv_halo2(ConvParams& P, const void* wpk, long long w_rows, l
     g_attr_e = true;
   }
   const int clusters = P.pair_tiles < DM_NUM_SMS / 2 ? P.pair_tiles : DM_NUM_SMS / 2;
+  dm_note_kernel("conv3x3_halo2", P.block_n);
   conv3x3_halo2_kernel<<<2 * clusters, kConvThreads, smem, st>>>(P);
   DM_CHECK_LAUNCH();
   return DM_OK;
@@ -1774,48 +1629,8 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
     }
     const int tiles = P.m_tiles * P.n_tiles * P.splits;
     const int clusters = tiles < DM_NUM_SMS / 2 ? tiles : DM_NUM_SMS / 2;
+    dm_note_kernel("wgrad3_pair", P.splits);
     wgrad3_pair_kernel<<<2 * clusters, kThreads, smem, (cudaStream_t)stream>>>(P);
-    DM_CHECK_LAUNCH();
-    return DM_OK;
-  }
-  if (g_debug[4] == 4) {
-    // kernel G (ablation only: measured equal to or slower than kernel C on every layer): CTA pairs, 8 boxes per M tile,
-    // N tile = Cout up to 256
-    Wgrad2Params P;
-    memset(&P, 0, sizeof P);
-    memcpy(P.tmX, tmX, sizeof tmX); P.tmDY = tmDY; memcpy(P.taps, taps, sizeof taps);
-    P.num_taps = num_taps; P.chunks0 = chunks0; P.chunks1 = chunks1; P.dual = x1 ? 1 : 0;
-    P.log_bw = log_bw; P.log_bh = log_bh; P.log_bn = log_bn;
-    P.tiles_w = tiles_w; P.tiles_h = tiles_h; P.tiles_b = tiles_b; P.patches = patches;
-    P.total_boxes = num_taps * chunks;
-    P.m_tiles = dm::cdiv(P.total_boxes, 8);
-    P.n_tiles = dm::cdiv(Cout, 256);
-    P.block_n = (dm::cdiv(Cout, P.n_tiles) + 31) / 32 * 32;
-    P.nb = dm::cdiv(P.block_n / 2, 64);
-    P.Cout = Cout; P.cin_k = chunks * 64; P.C0 = C0; P.C1 = C1;
-    int splits = pick_splits(P.m_tiles * P.n_tiles, patches, 8, DM_NUM_SMS / 2);
-    if (g_debug[2] > 0) splits = (int)g_debug[2];
-    P.patches_per_split = dm::cdiv(patches, splits);
-    P.splits = dm::cdiv(patches, P.patches_per_split);
-    P.dwp = dwp;
-    P.idesc = (make_idesc(P.block_n, true, true) & ~(0x1Fu << 24)) | ((256u >> 4) << 24);
-    P.desc_hi = kDescHiMN; P.lbo = 8192 >> 4;
-    const int stage_bytes = (4 + P.nb) * 8192;
-    int stages = (kSmemBudget - 1024 - 512) / stage_bytes;
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (g_debug[0] > 0 && g_debug[0] < stages) stages = (int)g_debug[0];
-    if (g_debug[10] > 0 && g_debug[10] < stages) stages = (int)g_debug[10];   // dev: wgrad-only ring depth (leaves shared memory for co-resident kernels)
-    P.stages = stages;
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
-    static bool attr_g = false;
-    if (!attr_g) {
-      cudaError_t e = cudaFuncSetAttribute(wgrad4_pair2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-      if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
-      attr_g = true;
-    }
-    const int tiles = P.m_tiles * P.n_tiles * P.splits;
-    const int clusters = tiles < DM_NUM_SMS / 2 ? tiles : DM_NUM_SMS / 2;
-    wgrad4_pair2_kernel<<<2 * clusters, kThreads, smem, (cudaStream_t)stream>>>(P);
     DM_CHECK_LAUNCH();
     return DM_OK;
   }
@@ -1854,6 +1669,7 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
     const int tiles = P.m_tiles * P.n_tiles * P.splits;
     int grid = tiles < DM_NUM_SMS ? tiles : DM_NUM_SMS;
     if (g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
+    dm_note_kernel("wgrad2_gemm", P.splits);
     wgrad2_gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
     DM_CHECK_LAUNCH();
     return DM_OK;
@@ -1896,6 +1712,7 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
   int tiles = base_tiles * P.splits;
   int grid = tiles < DM_NUM_SMS ? tiles : DM_NUM_SMS;
   if (g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
+  dm_note_kernel("wgrad_gemm", P.splits);
   wgrad_gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
   DM_CHECK_LAUNCH();
   return DM_OK;

@@ -16,6 +16,20 @@ extern "C" int dm_version(void) { return 100; }
 static long long g_launches = 0;
 void dm_count_launch() { ++g_launches; }
 extern "C" long long dm_launch_count(void) { return g_launches; }
+// Which kernel variant the dispatchers chose: per-name launch counters and the most recent (name, parameter) pair
+// (parameter = tile width for the conv kernels, split-K count for the weight-gradient kernels).  Host-side only.
+namespace { struct KernelNote { const char* name; long long count; }; KernelNote g_notes[32]; int g_num_notes = 0;
+            const char* g_last_name = ""; int g_last_param = 0; }
+void dm_note_kernel(const char* name, int param) {
+  g_last_name = name; g_last_param = param;
+  for (int i = 0; i < g_num_notes; ++i) if (!strcmp(g_notes[i].name, name)) { ++g_notes[i].count; return; }
+  if (g_num_notes < 32) { g_notes[g_num_notes].name = name; g_notes[g_num_notes].count = 1; ++g_num_notes; }
+}
+extern "C" long long dm_kernel_count(const char* name) {
+  for (int i = 0; i < g_num_notes; ++i) if (!strcmp(g_notes[i].name, name)) return g_notes[i].count;
+  return 0;
+}
+extern "C" const char* dm_last_kernel(int* param) { if (param) *param = g_last_param; return g_last_name; }
 
 #define ST ((cudaStream_t)stream)
 
@@ -199,11 +213,13 @@ __global__ void loss_bwd_kernel(const float* pred, int ldp, const float* noise, 
 }
 
 __global__ void cfg_reverse_kernel(const float* eps, int ldp, const float* x, const float* z, float* x_out, bf16* xt_next,
-                                   int ldo, float gw, float a, float b, float s, const float* coef, int n, int C, int HW) {
+                                   int ldo, float gw, float a, float b, float s, const float* coef, const float* wvec, int n,
+                                   int C, int HW) {
   if (coef != nullptr) { gw = coef[0]; a = coef[1]; b = coef[2]; s = coef[3]; }     // graph-replayable: scalars from device memory
   const long long P = (long long)n * HW;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
     const long long i = p / HW, hw = p % HW;
+    if (wvec != nullptr) gw = wvec[i];               // one guidance scale per trajectory (several scales in one batch)
     for (int c0 = 0; c0 < ldo; c0 += 8) {
       float v[8];
 #pragma unroll
@@ -474,7 +490,7 @@ extern "C" int dm_cfg_reverse_step(const float* eps, int ldp, const float* x, co
                                    int n, int C, int H, int W, void* stream) {
   if (ldo & 7) { dm_set_error("dm_cfg_reverse_step: pitch must be a multiple of 8"); return DM_ERR_ARG; }
   cfg_reverse_kernel<<<grid_for((long long)n * H * W), 256, 0, ST>>>(eps, ldp, x, z, x_out, (bf16*)xt_next, ldo, guide_w,
-                                                                    oneover_sqrta, mab_over_sqrtmab, sqrt_beta, nullptr, n, C, H * W);
+                                                                    oneover_sqrta, mab_over_sqrtmab, sqrt_beta, nullptr, nullptr, n, C, H * W);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
@@ -483,7 +499,17 @@ extern "C" int dm_cfg_reverse_step_dev(const float* eps, int ldp, const float* x
   if (ldo & 7) { dm_set_error("dm_cfg_reverse_step_dev: pitch must be a multiple of 8"); return DM_ERR_ARG; }
   if (coef4 == nullptr) { dm_set_error("dm_cfg_reverse_step_dev: coefficient buffer required"); return DM_ERR_ARG; }
   cfg_reverse_kernel<<<grid_for((long long)n * H * W), 256, 0, ST>>>(eps, ldp, x, z, x_out, (bf16*)xt_next, ldo, 0.f, 0.f, 0.f, 0.f,
-                                                                    coef4, n, C, H * W);
+                                                                    coef4, nullptr, n, C, H * W);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}
+/* same with one guidance scale per trajectory: w[n] replaces coef4[0] (several --guide_scales as ONE trajectory batch) */
+extern "C" int dm_cfg_reverse_step_w(const float* eps, int ldp, const float* x, const float* z, float* x_out, void* xt_next,
+                                     int ldo, const float* coef4, const float* w, int n, int C, int H, int W, void* stream) {
+  if (ldo & 7) { dm_set_error("dm_cfg_reverse_step_w: pitch must be a multiple of 8"); return DM_ERR_ARG; }
+  if (coef4 == nullptr || w == nullptr) { dm_set_error("dm_cfg_reverse_step_w: coefficient and scale buffers required"); return DM_ERR_ARG; }
+  cfg_reverse_kernel<<<grid_for((long long)n * H * W), 256, 0, ST>>>(eps, ldp, x, z, x_out, (bf16*)xt_next, ldo, 0.f, 0.f, 0.f, 0.f,
+                                                                    coef4, w, n, C, H * W);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }

@@ -255,3 +255,27 @@ extern "C" int dm_sum_parts(const float* parts, int nparts, float* out, long lon
   DM_CHECK_LAUNCH();
   return DM_OK;
 }
+
+// Masked one-hot class rows, the input of the context EmbedFCs (new_scripy.py:337-340: one_hot(c) * ctx_mask, no flip;
+// MNIST_script.py:165-171: one_hot(c) * -(1 - context_mask)).  mask_i64 != 0: the mask holds int64 (DDPM.sample builds it
+// with zeros_like(c_i)), else fp32.  One launch instead of one_hot + type + repeat + mul (+ the flip).
+namespace {
+__global__ void ctx_onehot_kernel(const long long* __restrict__ c, const void* __restrict__ mask, int mask_i64, float* out,
+                                  int N, int ncls, int flip) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * ncls) return;
+  const int n = i / ncls, k = i - n * ncls;
+  float m = mask_i64 ? (float)reinterpret_cast<const long long*>(mask)[n] : reinterpret_cast<const float*>(mask)[n];
+  if (flip) m = -1.0f * (1.0f - m);
+  out[i] = (c[n] == k ? 1.0f : 0.0f) * m;
+}
+}  // namespace
+
+extern "C" int dm_ctx_onehot(const long long* c, const void* mask, int mask_i64, float* out, int N, int ncls, int flip,
+                             void* stream) {
+  if (N <= 0 || ncls <= 0) { dm_set_error("dm_ctx_onehot: bad sizes"); return DM_ERR_ARG; }
+  const int total = N * ncls;
+  ctx_onehot_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c, mask, mask_i64, out, N, ncls, flip);
+  DM_CHECK_LAUNCH();
+  return DM_OK;
+}

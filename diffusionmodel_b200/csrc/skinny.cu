@@ -111,6 +111,7 @@ extern "C" int dm_skinny_gemm(const void* A, long long lda, const void* W, long 
   }
   const int slices = (K + kKc - 1) / kKc;
   dim3 grid((N + kRowsPerBlock - 1) / kRowsPerBlock, slices);
+  dm_note_kernel("skinny_gemm", (int)grid.x);
   skinny_gemm_kernel<<<grid, 256, smem, ST>>>((const dm::bf16*)A, lda, (const dm::bf16*)W, ldw, scratch, M, N, K);
   DM_CHECK_LAUNCH();
   skinny_fold_kernel<<<(M * N + 255) / 256, 256, 0, ST>>>(scratch, slices, (dm::bf16*)out, ldo, M, N);

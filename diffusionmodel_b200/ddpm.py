@@ -100,10 +100,15 @@ class DDPM(nn.Module):
         next call) that copies the batch into the graph's static inputs, draws the step's randoms exactly
         like ``forward`` (new_scripy.py:405-413) and replays ~500 kernel launches with one graph launch.
         Gradients accumulate into the parameters' ``.grad`` (the optimizer's flat buffer) as in eager mode.
-        The warm-up/capture passes accumulate gradients too: call ``optimizer.zero_grad()`` afterwards.
+        The warm-up passes accumulate gradients: call ``optimizer.zero_grad()`` afterwards.  BatchNorm running
+        statistics, ``num_batches_tracked`` and the CPU / CUDA RNG streams are restored to their state at entry.
         Shapes are fixed to those of the example batch; parameters must not be re-allocated afterwards."""
         sx, sc = x.detach().clone().float().contiguous(), c.detach().clone()
         sm = attn_mask.detach().clone().to(self.device) if attn_mask is not None else None
+        # the warm-up passes must leave no trace but gradients: BatchNorm running statistics / counters and both RNG
+        # streams are put back afterwards, so graphed training starts from the same state as eager training
+        cpu_rng, cuda_rng = torch.get_rng_state(), torch.cuda.get_rng_state(sx.device)
+        saved_bufs = [(b, b.detach().clone()) for b in self.nn_model.buffers()]
         r = self.draw_randoms(sx, sc)
         st = [t.detach().clone() for t in r]
         side = torch.cuda.Stream()
@@ -120,6 +125,12 @@ class DDPM(nn.Module):
             loss.backward()
         touched = list(touched)
         kernels = _lib.launch_count() - k0          # library kernels recorded in the graph (run on every replay)
+        with torch.no_grad():
+            for b, v in saved_bufs:
+                b.copy_(v)
+        ops.bump_bn_stats_epoch()
+        torch.set_rng_state(cpu_rng)
+        torch.cuda.set_rng_state(cuda_rng, sx.device)
 
         def step(x, c, attn_mask=None, randoms=None):
             rr = randoms if randoms is not None else self.draw_randoms(x, c)
@@ -129,6 +140,7 @@ class DDPM(nn.Module):
                 sm.copy_(attn_mask, non_blocking=True)
             for dst, src in zip(st, rr):
                 dst.copy_(src, non_blocking=True)
+            ops.refresh_weight_packs()        # no-op after FusedAdamW.step; re-packs in place after any other weight change
             graph.replay()
             for e in touched:
                 if hasattr(e, "after_replay"):
@@ -149,7 +161,8 @@ class DDPM(nn.Module):
         if g is not None:
             return g
         st = dict(x=torch.zeros((n_sample, *size), device=dev), z=torch.zeros((n_sample, *size), device=dev),
-                  t=torch.zeros(2 * n_sample, device=dev), coef=torch.zeros(4, device=dev), c=c_i.clone(), m=ctx_mask.clone())
+                  t=torch.zeros(2 * n_sample, device=dev), coef=torch.zeros(4, device=dev), c=c_i.clone(), m=ctx_mask.clone(),
+                  w=torch.zeros(n_sample, device=dev))
         st["xt"] = ops.new_act(2 * n_sample, size[1], size[2], size[0], dev).zero_()
         st["x_out"], st["xt_out"] = torch.empty_like(st["x"]), torch.empty_like(st["xt"])
 
@@ -160,7 +173,7 @@ class DDPM(nn.Module):
                 eps = self.nn_model.decode(enc, st["c"], st["t"], st["m"])
             else:
                 eps = self.nn_model.forward_nhwc(st["xt"], st["c"], st["t"], st["m"])
-            ops.cfg_reverse_step_dev(eps, st["x"], st["z"], st["coef"], st["x_out"], st["xt_out"])
+            ops.cfg_reverse_step_w(eps, st["x"], st["z"], st["coef"], st["w"], st["x_out"], st["xt_out"])
             st["x"].copy_(st["x_out"])
             st["xt"].copy_(st["xt_out"])
         side = torch.cuda.Stream()
@@ -176,12 +189,13 @@ class DDPM(nn.Module):
         self._sample_graphs[key] = st
         return st
 
-    def _sample_graphed(self, x_i, xt, c_i, ctx_mask, n_sample, size, guide_w, steps, noise, shared):
+    def _sample_graphed(self, x_i, xt, c_i, ctx_mask, n_sample, size, wvec, steps, noise, shared):
         st = self._reverse_step_graph(n_sample, size, c_i, ctx_mask, shared)
         from . import unet
         unet.refresh_folded_norms()          # weights / running statistics may have changed since the capture
-        st["x"].copy_(x_i); st["xt"].copy_(xt); st["c"].copy_(c_i); st["m"].copy_(ctx_mask)
-        st["coef"][0] = float(guide_w)
+        ops.refresh_weight_packs()           # ... and the bf16 weight packs the captured kernels read (load_state_dict,
+                                             # a torch optimizer, manual edits): stamp compare, re-packed in place
+        st["x"].copy_(x_i); st["xt"].copy_(xt); st["c"].copy_(c_i); st["m"].copy_(ctx_mask); st["w"].copy_(wvec)
         store, done, n_T = [], 0, self.n_T
         for i in range(n_T, 0, -1):
             st["t"].fill_(i / n_T)
@@ -201,10 +215,7 @@ class DDPM(nn.Module):
             done += 1
             if steps is not None and done >= steps:
                 break
-        x_fin = st["x"].clone()
-        if self.variant == "mnist":
-            return x_fin, np.array(store)
-        return x_fin
+        return st["x"].clone(), store
 
     def _sched(self):
         if self._host_sched is None:
@@ -220,27 +231,45 @@ class DDPM(nn.Module):
     @torch.no_grad()
     def sample(self, n_sample, size, device, guide_w=0.0, refine_steps=2, steps=None, noise=None):
         """Classifier-free-guided reverse loop (new_scripy.py:441-477; MNIST_script.py:254-300).
-        ``steps`` truncates the loop and ``noise=(x_T, {i: z_i})`` injects the noise (tests)."""
+        ``steps`` truncates the loop and ``noise=(x_T, {i: z_i})`` injects the noise (tests).
+
+        ``guide_w`` may be a list of S guidance scales: the S x ``n_sample`` trajectories then run as ONE batch (the
+        reference loops over the scales, new_scripy.py:1036-1041; at samples_per_class=1 a 5-trajectory batch leaves more
+        than half of the machine idle) and a list of S tensors comes back.  Every trajectory is the computation the
+        sequential call would do; with ``sample_noise="reference"`` the CPU noise stream is drawn for the whole batch per
+        step, i.e. it is not the stream the S sequential calls would consume (inject ``noise`` to compare)."""
         sched = self._sched()
         n_T = self.n_T
+        scales = [float(w) for w in guide_w] if isinstance(guide_w, (list, tuple)) else None
+        n_each = n_sample
+        ws = scales if scales is not None else [float(guide_w)]
+        n_sample = n_each * len(ws)
         x_i = (noise[0].to(device) if noise is not None else self._randn((n_sample, *size), device)).float().contiguous()
+        if x_i.shape[0] != n_sample:
+            raise RuntimeError(f"DDPM.sample: injected x_T holds {x_i.shape[0]} trajectories, expected {n_sample}")
         ncls = 10 if self.variant == "mnist" else self.n_classes        # MNIST_script.py:262 hard-codes 10
-        c_i = torch.arange(0, ncls, device=device).repeat(int(n_sample / ncls)).repeat(2)
+        c_i = torch.arange(0, ncls, device=device).repeat(int(n_each / ncls)).repeat(len(ws)).repeat(2)
         ctx_mask = torch.zeros_like(c_i)
         ctx_mask[n_sample:] = 1.0
+        wvec = torch.tensor(ws, dtype=torch.float32).repeat_interleave(n_each).to(device)
         xt = ops.to_nhwc(torch.cat([x_i, x_i], 0))
         shared = self.shared_encoder_cfg and not self.nn_model.training
+
+        def result(x_fin, store):
+            out = list(x_fin.view(len(ws), n_each, *x_fin.shape[1:]).unbind(0)) if scales is not None else x_fin
+            return (out, np.array(store)) if self.variant == "mnist" else out
+        if self.graph_sampling and not self.nn_model.training and x_i.is_cuda:
+            return result(*self._sample_graphed(x_i, xt, c_i, ctx_mask, n_sample, size, wvec, steps, noise, shared))
         store = []
         done = 0
-        if self.graph_sampling and not self.nn_model.training and x_i.is_cuda:
-            return self._sample_graphed(x_i, xt, c_i, ctx_mask, n_sample, size, guide_w, steps, noise, shared)
+        coef = torch.zeros(4, device=device)
         for i in range(n_T, 0, -1):
             t_is = torch.full((2 * n_sample,), i / n_T, device=device, dtype=torch.float32)
             if i > 1:
                 z = (noise[1][i].to(device) if noise is not None else self._randn((n_sample, *size), device))
                 z = z.float().contiguous()
             else:
-                z = None
+                z = torch.zeros_like(x_i)
             if shared:
                 # eval mode: the encoder sees neither c nor ctx_mask and t is the same for both halves, so the
                 # two halves of the reference's doubled batch are identical up to up0 -- run it once
@@ -249,13 +278,13 @@ class DDPM(nn.Module):
                 eps = self.nn_model.decode(enc, c_i, t_is, ctx_mask)
             else:
                 eps = self.nn_model.forward_nhwc(xt, c_i, t_is, ctx_mask)
-            x_i, xt = ops.cfg_reverse_step(eps, x_i, z, guide_w, sched["oneover_sqrta"][i],
-                                           sched["mab_over_sqrtmab"][i], sched["sqrt_beta_t"][i])
+            coef[1:] = torch.tensor([sched["oneover_sqrta"][i], sched["mab_over_sqrtmab"][i], sched["sqrt_beta_t"][i]])
+            x_out, xt = torch.empty_like(x_i), torch.empty_like(xt)
+            ops.cfg_reverse_step_w(eps, x_i, z, coef, wvec, x_out, xt)
+            x_i = x_out
             if self.variant == "mnist" and (i % 20 == 0 or i == n_T or i < 8):
                 store.append(x_i.detach().cpu().numpy())
             done += 1
             if steps is not None and done >= steps:
                 break
-        if self.variant == "mnist":
-            return x_i, np.array(store)
-        return x_i
+        return result(x_i, store)

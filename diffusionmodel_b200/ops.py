@@ -9,7 +9,6 @@ per backward pass.
 from __future__ import annotations
 
 import ctypes
-import os as _os
 import weakref
 
 import torch
@@ -34,46 +33,6 @@ def bump_bn_stats_epoch():
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-
-# --------------------------------------------------------------------------------------- weight gradients on a side stream
-# Nothing in the backward pass consumes a weight gradient, so the wgrad GEMMs (tensor-pipe bound) can run on a second
-# stream next to the bandwidth-bound normalisation / pooling kernels of the layers below.  Fork: the side stream waits
-# for an event recorded on the launching stream (dy and x are ready there); join: the launching stream waits for the
-# side stream when the backward pass ends (autograd engine callback).  The operands are kept alive until the join so
-# the caching allocator cannot hand their memory to a later main-stream kernel.  Works inside CUDA-graph capture
-# (the fork/join become graph edges).
-WGRAD_SIDE_STREAM = _os.environ.get("DM_WGRAD_STREAM", "0") == "1"
-RANK_DEFER = _os.environ.get("DM_RANK_DEFER", "1") != "0"      # queue the up0 wgrad operands, one GEMM per optimizer step
-_side = {}
-
-
-def _fork_wgrad(*keep):
-    """Order the side stream after the current stream and return its handle for one wgrad launch."""
-    dev = torch.cuda.current_device()
-    s = _side.get(dev)
-    if s is None:
-        s = _side[dev] = dict(stream=torch.cuda.Stream(device=dev), hold=[], main=None)
-    main = torch.cuda.current_stream()
-    if s["main"] is not None and s["main"] != main:
-        join_side_stream()
-    if s["main"] is None:
-        s["main"] = main
-        torch.autograd.Variable._execution_engine.queue_callback(join_side_stream)
-    ev = torch.cuda.Event()
-    ev.record(main)
-    s["stream"].wait_event(ev)
-    s["hold"].append(keep)
-    return ctypes.c_void_p(s["stream"].cuda_stream)
-
-
-def join_side_stream():
-    """The launching stream waits for every forked wgrad; releases the operands held for them."""
-    for s in _side.values():
-        if s["main"] is not None:
-            s["main"].wait_stream(s["stream"])
-            s["main"] = None
-            s["hold"].clear()
 
 
 # --------------------------------------------------------------------------------------- GEMM-native weight storage
@@ -114,6 +73,14 @@ def wants_native(p):
 
 def register_native(param, shadow2d):
     _native[param.data_ptr()] = _NativeWeight(param, shadow2d)
+
+
+def release_registries():
+    """Forget every parameter registered by an optimizer (GEMM-native shadows, deferred packed gradients): lets a model
+    and its optimizer be garbage-collected before another one is built in the same process."""
+    _native.clear()
+    _deferred.clear()
+    _conv2d_weights.clear()
 
 
 def _native_of(w):
@@ -554,7 +521,7 @@ class _Conv2d(torch.autograd.Function):
         gw = grad_buf(weight)
         if ck == cin and _native_of(weight) is not None and tuple(gw.stride()) == native_strides(weight.shape):
             # GEMM-native storage: param.grad's memory is the packed accumulator
-            run_wgrad(gw, _fork_wgrad(x0, x1, dy, gw) if WGRAD_SIDE_STREAM else st)
+            run_wgrad(gw)
         else:
             s0, s1, s2, s3 = gw.stride()
             offs = [r * s2 + s * s3 for r in range(kh) for s in range(kw)]
@@ -692,7 +659,7 @@ class _ConvT(torch.autograd.Function):
         # dW[ci][(co, tap)] = sum_pixels x[ci] * dy[(co, tap)] lands in the [Cin, Cout, k, k] gradient itself:
         # the wgrad kernel red.adds straight into p.grad -- no packed detour for the 151 M-parameter up0.
         rank = None
-        if RANK_DEFER and kc % 64 == 0 and n * hin * win <= 64:
+        if kc % 64 == 0 and n * hin * win <= 64:
             rank = _rank_grad_entry(weight, n, hin, win, cin, x.stride(2), kc)
         if rank is not None:
             # few pixels against a huge weight: queue the operands, one GEMM per optimizer step (see _RankGrad)
@@ -778,7 +745,8 @@ class _BnAct(torch.autograd.Function):
 
 
 _counters_batched = False     # True while a model forward bumps all num_batches_tracked buffers in one launch
-FUSED_CONV_STATS = _os.environ.get("DM_FUSED_CONV_STATS", "0") == "1"      # True: BatchNorm statistics from the conv epilogue; False: a separate pass over y
+FUSED_CONV_STATS = False      # True: BatchNorm statistics from the conv epilogue (measured slower: the per-column shuffle
+                              # reduction sits on the epilogue warps' critical path); False: a separate pass over y
 
 
 class batched_counters:
@@ -860,28 +828,7 @@ def gn_act(x, gn, act):
     return _GnAct.apply(x, gn.weight, gn.bias, gn.num_channels, gn.num_groups, float(gn.eps), act)
 
 
-# --------------------------------------------------------------------------------------- tiny sub-graphs
-def _run_small(fn_small, inputs, params):
-    """Run a tiny fp32 torch sub-graph (a few [N,C]-sized linears) under its own autograd tape so the
-    enclosing Function can back-propagate through it with torch.autograd.grad."""
-    with torch.enable_grad():
-        ins = [t.detach().requires_grad_(True) for t in inputs]
-        outs = fn_small(*ins)
-    return ins, outs
-
-
-def _small_backward(ins, outs, grads, params):
-    live = [p for p in params if p.requires_grad]
-    res = torch.autograd.grad(outs, ins + live, grads, allow_unused=True)
-    bufs, gs = [], []
-    for p, g in zip(live, res[len(ins):]):
-        if g is not None:
-            bufs.append(grad_buf(p)); gs.append(g)
-    if bufs:
-        torch._foreach_add_(bufs, gs)            # one multi-tensor launch instead of one add per parameter
-    return res[:len(ins)]
-
-
+# --------------------------------------------------------------------------------------- small MLPs
 ACT_SIGMOID = 3      # dm_linear_act_* only
 
 
@@ -957,6 +904,21 @@ class _Mlp2(torch.autograd.Function):
         return dx, None, None, None, None, None, None
 
 
+def ctx_onehot(c, ctx_mask, n_classes, flip):
+    """one_hot(c) * ctx_mask (new_scripy.py:337-340) or one_hot(c) * -(1 - ctx_mask) (``flip``, MNIST_script.py:165-171)
+    as fp32 rows [N, n_classes]; no gradient (both inputs are data)."""
+    if not c.is_cuda:
+        raise _lib.DmB200Error("ctx_onehot: CUDA tensors only (no CPU fallback)")
+    c = c.long().contiguous()
+    if ctx_mask.dtype not in (torch.float32, torch.int64):
+        ctx_mask = ctx_mask.to(torch.float32)
+    ctx_mask = ctx_mask.contiguous()
+    out = torch.empty((c.shape[0], n_classes), device=c.device, dtype=torch.float32)
+    call("dm_ctx_onehot", _p(c), _p(ctx_mask), int(ctx_mask.dtype == torch.int64), _p(out), c.shape[0], n_classes,
+         int(flip), _stream())
+    return out
+
+
 def embed_fc(x, lin1, lin2):
     """EmbedFC forward on [N, input_dim] rows (new_scripy.py:265-268)."""
     return _Mlp2.apply(x, ACT_GELU, ACT_NONE, _lin_param(lin1.weight), _lin_param(lin1.bias), _lin_param(lin2.weight),
@@ -1009,45 +971,6 @@ def se_residual(x2, res, c, scale, se_fc=None):
     return _SeResidual.apply(x2, res, c, scale, _lin_param(se_fc[0].weight), _lin_param(se_fc[2].weight))
 
 
-class _CoordAttn(torch.autograd.Function):
-    """x * (alpha' * a_h + beta' * a_w) with the directional pooling and the gating pass as kernels and
-    the C/16-wide gate MLP as a tiny fp32 sub-graph (new_scripy.py:97-140)."""
-
-    @staticmethod
-    def forward(ctx, x, c, gates, *params):
-        ldx = _chk(x, "coordattn input")
-        n, h, w, _ = x.shape
-        st = _stream()
-        xh = torch.empty((n, h, c), device=x.device, dtype=torch.float32)
-        xw = torch.empty((n, w, c), device=x.device, dtype=torch.float32)
-        call("dm_ca_pool", _p(x), ldx, None, 0, _p(xh), _p(xw), n, h, w, c, 1.0 / w, 1.0 / h, st)
-        ins, (ah_g, aw_g) = _run_small(gates, [xh, xw], params)
-        ah, aw = ah_g.detach().contiguous(), aw_g.detach().contiguous()
-        out = torch.empty_like(x)
-        call("dm_ca_gate_fwd", _p(x), ldx, _p(ah), _p(aw), _p(out), out.stride(2), n, h, w, c, st)
-        ctx.save_for_backward(x, ah, aw)
-        ctx.small = (ins, (ah_g, aw_g))
-        ctx.cfg = (c, params)
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        x, ah, aw = ctx.saved_tensors
-        c, params = ctx.cfg
-        lddo = _chk(dout, "coordattn grad")
-        n, h, w, _ = x.shape
-        st = _stream()
-        dah = torch.empty((n, h, c), device=x.device, dtype=torch.float32)
-        daw = torch.empty((n, w, c), device=x.device, dtype=torch.float32)
-        call("dm_ca_pool", _p(dout), lddo, _p(x), x.stride(2), _p(dah), _p(daw), n, h, w, c, 1.0, 1.0, st)
-        ins, outs = ctx.small
-        dxh, dxw = _small_backward(ins, list(outs), [dah, daw], list(params))
-        dx = torch.empty_like(x)
-        call("dm_ca_gate_bwd", _p(dout), lddo, _p(ah), _p(aw), _p(dxh.contiguous()), _p(dxw.contiguous()), _p(dx),
-             dx.stride(2), n, h, w, c, st)
-        return (dx, None, None) + (None,) * len(params)
-
-
 class _CaGatesC(ctypes.Structure):
     """DmCaGates (include/dm_b200.h)."""
     _PTRS = ("xh xw w1_h w1_w b1_h b1_w bn_g_h bn_g_w bn_b_h bn_b_w bn_rm_h bn_rm_w bn_rv_h bn_rv_w wp_h2w wp_w2h "
@@ -1073,8 +996,8 @@ def _ca_param_map(mod):
 
 
 class _CoordAttnFused(torch.autograd.Function):
-    """Same operator with the gate network on the dm_ca_gates kernels (H == W): 2 + 7 launches per call instead of
-    ~90 tiny library kernels."""
+    """x * (alpha' * a_h + beta' * a_w) (new_scripy.py:97-140): directional pooling (dm_ca_pool), the C/16-wide gate
+    network (dm_ca_gates_fwd/bwd, fp32) and the gating pass (dm_ca_gate_fwd/bwd); H == W."""
 
     @staticmethod
     def forward(ctx, x, c, mod, *params):
@@ -1141,14 +1064,14 @@ class _CoordAttnFused(torch.autograd.Function):
         return (dx, None, None) + (None,) * len(pm)
 
 
-FUSED_CA_GATES = _os.environ.get("DM_FUSED_CA", "1") != "0"         # False: the gate network as a torch sub-graph (the fallback for H != W)
-
-
-def coord_attn(x, c, gates, params, mod=None):
-    if FUSED_CA_GATES and mod is not None and x.shape[1] == x.shape[2]:
-        pm = _ca_param_map(mod)
-        return _CoordAttnFused.apply(x, c, mod, *pm.values())
-    return _CoordAttn.apply(x, c, gates, *params)
+def coord_attn(x, c, mod):
+    """CoordAttn.forward (new_scripy.py:97-140) on a square feature map.  H != W would need the adaptive_avg_pool1d
+    resampling of the h<->w cross terms (:118-126), which the gate kernels do not implement: fail loudly."""
+    if x.shape[1] != x.shape[2]:
+        raise _lib.DmB200Error(f"CoordAttn: square feature maps only (got {x.shape[1]}x{x.shape[2]}); the U-Net's inputs are "
+                               "square (Cfg.IMG_SIZE, new_scripy.py:25)")
+    pm = _ca_param_map(mod)
+    return _CoordAttnFused.apply(x, c, mod, *pm.values())
 
 
 # --------------------------------------------------------------------------------------- resampling / glue
@@ -1432,6 +1355,14 @@ def cfg_reverse_step_dev(eps_nhwc_f32, x, z, coef4, x_out, xt_out):
          xt_out.stride(2), _p(coef4), n, c, h, w, _stream())
 
 
+def cfg_reverse_step_w(eps_nhwc_f32, x, z, coef4, wvec, x_out, xt_out):
+    """Graph-capturable reverse step with one guidance scale per trajectory: ``wvec`` [n] fp32 on the device,
+    ``coef4[1:]`` = (oneover_sqrta, mab_over_sqrtmab, sqrt_beta)."""
+    n, c, h, w = x.shape
+    call("dm_cfg_reverse_step_w", _p(eps_nhwc_f32), eps_nhwc_f32.stride(2), _p(x), _p(z), _p(x_out), _p(xt_out),
+         xt_out.stride(2), _p(coef4), _p(wvec), n, c, h, w, _stream())
+
+
 # --------------------------------------------------------------------------------------- profiling hook
 class _Profile:
     """CUDA-event timing of every C-ABI call on the launching stream (bench.py's roofline numbers)."""
@@ -1454,25 +1385,129 @@ class _Profile:
             return 2.0 * a[7] * a[8] * a[9] * a[1] * a[10] * a[11] * a[11]
         return 0.0
 
+    @staticmethod
+    def _bytes(name, a):
+        """Algorithmic HBM bytes of one call of a bandwidth-bound entry point (DESIGN.md section 3 per-element figures:
+        every operand read once, every result written once, bf16 activations), 0 for the GEMM entries."""
+        E = lambda *idx: float(_prod(a[i] for i in idx))
+        if name == "dm_bn_stats":
+            return 2 * E(4, 5)
+        if name == "dm_bn_act_fwd":
+            return 4 * E(8, 9)
+        if name == "dm_bn_act_bwd":
+            return 10 * E(14, 15)
+        if name == "dm_gn_act_fwd":
+            return 6 * E(9, 10, 11)
+        if name == "dm_gn_act_bwd":
+            return 10 * E(13, 14, 15)
+        if name == "dm_pool_nhw":
+            return 2 * E(3, 4, 5)
+        if name == "dm_pool_prod_nhw":
+            return 4 * E(5, 6, 7)
+        if name == "dm_se_apply_fwd":
+            return 6 * E(7, 8, 9)
+        if name == "dm_se_apply_bwd":
+            return 6 * E(8, 9, 10)
+        if name == "dm_ca_pool":
+            return (2 if a[2] is None else 4) * E(6, 7, 8, 9)
+        if name == "dm_ca_gate_fwd":
+            return 4 * E(6, 7, 8, 9)
+        if name == "dm_ca_gate_bwd":
+            return 4 * E(8, 9, 10, 11)
+        if name == "dm_upcat_fwd":
+            return 10 * E(8, 9, 10) * (a[2] + a[5])
+        if name == "dm_upcat_bwd":
+            return 10 * E(8, 9, 10) * (a[4] + a[7])
+        if name == "dm_film_fwd":
+            return 4 * E(6, 7, 8)
+        if name == "dm_film_bwd":
+            return 6 * E(9, 10, 11)
+        if name == "dm_avgpool_act_fwd":
+            return 2 * E(4, 5, 6, 7) * (1 + 1.0 / (a[8] * a[8]))
+        if name == "dm_avgpool_act_bwd":
+            return 2 * E(6, 7, 8, 9) * (2 + 1.0 / (a[10] * a[10]))
+        if name == "dm_maxpool2_fwd":
+            return 2 * E(4, 5, 6, 7) * 1.25
+        if name == "dm_maxpool2_bwd":
+            return 2 * E(6, 7, 8, 9) * 2.25
+        if name == "dm_mask_fma":
+            return (4 if a[0] is None else 6) * E(8, 9)
+        if name == "dm_axpby":
+            return (4 if a[2] is None else 6) * E(6, 7)
+        if name == "dm_colsum":
+            return 2 * E(3, 4)
+        if name == "dm_q_sample":
+            return 10 * E(7, 8, 9, 10)
+        if name == "dm_ddpm_loss_fwd":
+            return (8 + 4.0 / a[7]) * E(6, 7, 8, 9)
+        if name == "dm_ddpm_loss_bwd":
+            return (12 + 4.0 / a[8]) * E(7, 8, 9, 10)
+        if name == "dm_cfg_reverse_step":
+            return 20 * E(11, 12, 13, 14) + 4 * a[6] * E(11, 13, 14)
+        if name == "dm_cfg_reverse_step_dev":
+            return 20 * E(8, 9, 10, 11) + 4 * a[6] * E(8, 10, 11)
+        if name == "dm_cfg_reverse_step_w":
+            return 20 * E(9, 10, 11, 12) + 4 * a[6] * E(9, 11, 12)
+        if name == "dm_im2col3x3":
+            return (2 * a[1] + 64) * E(3, 4, 5)
+        if name == "dm_space_to_depth":
+            return 4 * E(4, 5, 6, 7, 8, 8)
+        if name in ("dm_nchw_to_nhwc", "dm_nhwc_to_nchw"):
+            return 6 * E(4, 5, 6, 7) if name == "dm_nchw_to_nhwc" else 6 * E(4, 5, 6, 7)
+        if name == "dm_cast_nhwc":
+            return 6 * E(4, 5)
+        if name == "dm_linear_act_fwd":
+            return 4 * E(6, 7)
+        if name == "dm_linear_act_bwd":
+            return 12 * E(10, 11)
+        if name == "dm_skinny_gemm":
+            return 2 * E(8, 9)
+        if name == "dm_sumsq":
+            return 4 * E(1)
+        if name == "dm_adamw":
+            return 28 * E(4)
+        if name == "dm_adamw_bf16":
+            return 30 * E(5)
+        if name == "dm_pack_transpose":
+            return 4 * E(2, 3, 4)
+        if name == "dm_pack_weight":
+            return 6 * E(2, 3, 4)
+        if name == "dm_unpack_wgrad":
+            return 12 * E(2, 3, 4)
+        if name in ("dm_ca_gates_fwd", "dm_ca_gates_bwd"):
+            g = _CaGatesC.from_address(a[0])
+            once = 16.0 * g.C * g.m + 16.0 * g.R * g.C          # both directions: two C x m weights, rows in, rows out (fp32)
+            return once if name == "dm_ca_gates_fwd" else 3 * once
+        return 0.0
+
     def call(self, name, *args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = _lib.call(name, *args)
         e1.record()
-        self.records.append((name, self._flops(name, args), e0, e1))
+        fl = self._flops(name, args)
+        self.records.append((name, fl, 0.0 if fl else self._bytes(name, args), e0, e1))
         return rc
 
     def summary(self):
         groups = {"dm_conv2d_fwd": "conv_gemm", "dm_conv2d_s2_dgrad": "conv_gemm", "dm_convt_fwd": "conv_gemm",
                   "dm_conv2d_wgrad": "wgrad_gemm"}
         out = {}
-        for name, fl, e0, e1 in self.records:
+        for name, fl, nb, e0, e1 in self.records:
             g = groups.get(name, name)
-            d = out.setdefault(g, {"ms": 0.0, "flops": 0.0, "n": 0})
+            d = out.setdefault(g, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
             d["ms"] += e0.elapsed_time(e1)
             d["flops"] += fl
+            d["bytes"] += nb
             d["n"] += 1
         return out
+
+
+def _prod(it):
+    r = 1
+    for v in it:
+        r *= v
+    return r
 
 
 def enable_profile():

@@ -68,6 +68,50 @@ class FusedAdamW(torch.optim.Optimizer):
             return flat[o:o + p.numel()].view(cout, kh, kw, cin).permute(0, 3, 1, 2)
         return flat[o:o + p.numel()].view_as(p)
 
+    # ------------------------------------------------------------------ checkpointing (new_scripy.py:736-741)
+    def state_dict(self):
+        """``torch.optim.AdamW`` layout: ``{'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]}`` with
+        per-parameter moments in the parameter's own (reference, NCHW-contiguous) shape -- GEMM-native moments are
+        permuted back -- so a checkpoint written here resumes under ``torch.optim.AdamW`` and vice versa."""
+        state = {}
+        if self._step > 0:
+            for i, (p, o, nat) in enumerate(zip(self._params, self._offsets, self._native)):
+                state[i] = {"step": torch.tensor(float(self._step)),
+                            "exp_avg": self._view(self.exp_avg, o, p, nat).contiguous().clone(),
+                            "exp_avg_sq": self._view(self.exp_avg_sq, o, p, nat).contiguous().clone()}
+        groups = [{**{k: v for k, v in g.items() if k != "params"}, "params": list(range(len(self._params)))}
+                  for g in self.param_groups]
+        return {"state": state, "param_groups": groups, "max_grad_norm": self.max_grad_norm}
+
+    @torch.no_grad()
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self._params):
+            raise ValueError("FusedAdamW.load_state_dict: expected one parameter group with "
+                             f"{len(self._params)} parameters, got {[len(g['params']) for g in groups]}")
+        state = sd["state"]
+        steps = set()
+        for i, (p, o, nat) in enumerate(zip(self._params, self._offsets, self._native)):
+            st = state.get(groups[0]["params"][i], state.get(i))
+            if st is None:
+                self._view(self.exp_avg, o, p, nat).zero_()
+                self._view(self.exp_avg_sq, o, p, nat).zero_()
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"FusedAdamW.load_state_dict: moment {i} has shape {tuple(st['exp_avg'].shape)}, "
+                                 f"parameter has {tuple(p.shape)}")
+            self._view(self.exp_avg, o, p, nat).copy_(st["exp_avg"])
+            self._view(self.exp_avg_sq, o, p, nat).copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"FusedAdamW.load_state_dict: parameters disagree on the step count: {sorted(steps)}")
+        self._step = steps.pop() if steps else 0
+        for k, v in groups[0].items():
+            if k != "params":
+                self.param_groups[0][k] = v
+        if "max_grad_norm" in sd:
+            self.max_grad_norm = float(sd["max_grad_norm"])
+
     def flush(self):
         """Make ``p.grad`` (the flat gradient buffer) complete: scatter any packed weight gradients."""
         self._attach_grads()

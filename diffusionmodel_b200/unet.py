@@ -15,7 +15,6 @@ import weakref
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 from .ops import ACT_GELU, ACT_NONE, ACT_RELU
@@ -126,8 +125,9 @@ class ResConvBlock(nn.Module):
 
 
 class CoordAttn(nn.Module):
-    """Coordinate attention (new_scripy.py:70-140): row/column mean pooling and the final gating pass
-    are bandwidth kernels; the C/16-wide gate network runs as a tiny fp32 sub-graph."""
+    """Coordinate attention (new_scripy.py:70-140): row/column mean pooling and the final gating pass are bandwidth
+    kernels; the C/16-wide gate network (two 1x1 convs + BatchNorm + GELU, the h<->w cross projections, two 1x1 convs +
+    sigmoid) runs in fp32 on the dm_ca_gates kernels.  Square feature maps only."""
 
     def __init__(self, channel, reduction=16):
         super().__init__()
@@ -150,39 +150,8 @@ class CoordAttn(nn.Module):
         self.alpha = nn.Parameter(torch.zeros(1))
         self.beta = nn.Parameter(torch.zeros(1))
 
-    def _lin(self, m, v):
-        return F.linear(v, m.weight.flatten(1), m.bias)
-
-    def _bn(self, bn, v):
-        # BatchNorm2d over [N, mid, L, 1] == batch statistics over the N*L rows (new_scripy.py:105-111)
-        shp = v.shape
-        out = F.batch_norm(v.reshape(-1, shp[-1]), bn.running_mean, bn.running_var, bn.weight, bn.bias,
-                           bn.training, bn.momentum, bn.eps)
-        if bn.training and not ops._counters_batched:
-            bn.num_batches_tracked.add_(1)
-        return out.reshape(shp)
-
-    def _gates(self, xh, xw):
-        """xh [N,H,C], xw [N,W,C] (directional means) -> alpha'*a_h [N,H,C], beta'*a_w [N,W,C]."""
-        h, w = xh.shape[1], xw.shape[1]
-        th = F.gelu(self._bn(self.bn1_h, self._lin(self.conv1_h, xh)))
-        tw = F.gelu(self._bn(self.bn1_w, self._lin(self.conv1_w, xw)))
-        h2w = self._lin(self.h2w_proj, th)          # [N,H,mid] -> resampled along W
-        w2h = self._lin(self.w2h_proj, tw)
-        if h != w:
-            h2w = F.adaptive_avg_pool1d(h2w.transpose(1, 2), w).transpose(1, 2)
-            w2h = F.adaptive_avg_pool1d(w2h.transpose(1, 2), h).transpose(1, 2)
-        th = th + torch.sigmoid(self.gamma_h) * w2h
-        tw = tw + torch.sigmoid(self.gamma_w) * h2w
-        a_h = torch.sigmoid(self._lin(self.conv_h, th))
-        a_w = torch.sigmoid(self._lin(self.conv_w, tw))
-        alpha, beta = torch.sigmoid(self.alpha), torch.sigmoid(self.beta)
-        wsum = alpha + beta + 1e-8
-        return (alpha / wsum) * a_h, (beta / wsum) * a_w
-
     def forward(self, x):
-        params = [p for p in self.parameters()]
-        return ops.coord_attn(x, self.channel, self._gates, params, mod=self)
+        return ops.coord_attn(x, self.channel, self)
 
 
 class LocalEnhancer(nn.Module):
@@ -318,8 +287,7 @@ class ContextUnet(nn.Module):
     def decode(self, enc, c, t, ctx_mask, attn_map=None):
         """Embeddings, FiLM, up1..up4, LocalEnhancer, head (new_scripy.py:334-355) -> eps as fp32 NHWC."""
         f = self.n_feat
-        c1h = F.one_hot(c.long(), num_classes=self.n_classes).type(torch.float)
-        c1h = c1h * ctx_mask[:, None].repeat(1, self.n_classes).to(c1h.dtype)     # no flip (new_scripy.py:337-340)
+        c1h = ops.ctx_onehot(c, ctx_mask, self.n_classes, flip=False)             # no flip (new_scripy.py:337-340)
         t = t.to(torch.float32)
         cemb1, temb1 = self.ctx_emb1(c1h), self.time_emb1(t)
         cemb2, temb2 = self.ctx_emb2(c1h), self.time_emb2(t)
@@ -436,9 +404,7 @@ class MnistContextUnet(nn.Module):
 
     def decode(self, enc, c, t, context_mask, attn_map=None):
         f = self.n_feat
-        c1h = F.one_hot(c.long(), num_classes=self.n_classes).type(torch.float)
-        m = context_mask[:, None].repeat(1, self.n_classes).to(c1h.dtype)
-        c1h = c1h * (-1 * (1 - m))                                     # flip and negate (MNIST_script.py:170)
+        c1h = ops.ctx_onehot(c, context_mask, self.n_classes, flip=True)          # flip and negate (MNIST_script.py:170)
         t = t.to(torch.float32)
         cemb1, temb1 = self.contextembed1(c1h), self.timeembed1(t)
         cemb2, temb2 = self.contextembed2(c1h), self.timeembed2(t)

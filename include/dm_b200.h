@@ -25,6 +25,12 @@ const char* dm_last_error(void);
 int dm_version(void);
 void dm_debug_set(int key, long long value);
 long long dm_launch_count(void);   /* kernels launched by this library so far (bench.py's gpu_launches) */
+/* Which kernel variant the conv / weight-gradient dispatchers chose (tests assert the selection at the benchmarked
+ * shapes): launches so far under a kernel name ("conv_gemm", "conv3x3_halo", "conv3x3_halo2", "wgrad_gemm",
+ * "wgrad2_gemm", "wgrad3_pair", "skinny_gemm"), and the most recent launch with its parameter (conv: tile width in
+ * output channels; wgrad: split-K count). */
+long long dm_kernel_count(const char* name);
+const char* dm_last_kernel(int* param);
 /* Device scratch (>= 16 MiB recommended) for the partial sums of the reduction kernels (pooling, colsum, FiLM
  * gradients): used in stream order by every call, so one buffer per stream; must outlive captured graphs. */
 int dm_set_workspace(void* ptr, long long bytes);
@@ -142,6 +148,9 @@ int dm_skinny_gemm(const void* A, long long lda, const void* W, long long ldw, v
  *      the partial rows directly (its dy/nparts); dm_sum_parts folds them when a plain tensor is needed. */
 int dm_linear_act_fwd(const float* x, const float* W, const float* b, float* pre, float* y, int N, int Cin, int Cout,
                       int act, void* stream);
+/* masked one-hot class rows out[N][ncls] (fp32) feeding the context EmbedFCs: one_hot(c) * mask (new_scripy.py:337-340),
+ * flip != 0: one_hot(c) * -(1 - mask) (MNIST_script.py:165-171).  c int64 [N]; mask fp32 [N], or int64 when mask_i64 != 0. */
+int dm_ctx_onehot(const long long* c, const void* mask, int mask_i64, float* out, int N, int ncls, int flip, void* stream);
 int dm_linear_bwd_parts(int Cout);
 int dm_linear_act_bwd(const float* dy, int nparts, const float* aux, int act, const float* x, const float* W, float* dW,
                       float* db, float* dx_parts, int N, int Cin, int Cout, void* stream);
@@ -203,6 +212,10 @@ int dm_cfg_reverse_step(const float* eps, int ldp, const float* x, const float* 
  * captured CUDA graph of the reverse step serves all n_T iterations (z must be a valid buffer: zeros at i == 1) */
 int dm_cfg_reverse_step_dev(const float* eps, int ldp, const float* x, const float* z, float* x_out, void* xt_next,
                             int ldo, const float* coef4, int n, int C, int H, int W, void* stream);
+/* same with ONE GUIDANCE SCALE PER TRAJECTORY: w[n] (device) replaces coef4[0], so the reference's sequential loop over
+ * --guide_scales (new_scripy.py:1036-1041) runs as one trajectory batch */
+int dm_cfg_reverse_step_w(const float* eps, int ldp, const float* x, const float* z, float* x_out, void* xt_next,
+                          int ldo, const float* coef4, const float* w, int n, int C, int H, int W, void* stream);
 
 /* ---- CoordAttn gate network (new_scripy.py:97-140): everything between the directional pooling and the gating pass,
  * forward in two launches and backward in six (+ one memset).  R = N*L rows per direction (H == W == L), C channels, m = C/16.

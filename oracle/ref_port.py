@@ -28,6 +28,15 @@ contributes exactly +0).  ``attn_map=None`` reproduces the shipped behaviour
 ``operand_dtype=torch.bfloat16`` rounds the inputs and weights of every
 conv / conv-transpose / linear to bf16 (fp32 accumulate, everything else fp32):
 the precision-matched oracle of SURVEY.md Appendix D.
+
+``store_dtype=torch.bfloat16`` (with ``operand_dtype=torch.bfloat16``) is the KERNEL-MATCHED oracle: the same
+algorithm with a rounding wherever the B200 path keeps a tensor in bf16 between two kernels -- the output of every
+tensor-core convolution, of every norm+activation pass, of the SE / CoordAttn / FiLM / upsample / mask passes, x_t --
+in the forward pass and, at the same tensors, on the gradient in the backward pass; the [N, C]-sized layers the
+kernels run in fp32 (SE and EmbedFC linears, the CoordAttn gate network) keep fp32 operands; a convolution feeding a
+batch-statistics BatchNorm is stored WITHOUT its bias (the norm cancels it).  Train-mode
+BatchNorm amplifies every rounding difference with depth (Appendix D), so only an oracle that rounds where the kernels
+round can be compared tightly at full depth; with it the remaining differences are fp32 summation order.
 """
 from __future__ import annotations
 
@@ -62,17 +71,52 @@ def ddpm_schedules(beta1: float, beta2: float, T: int) -> dict:
 
 
 # --------------------------------------------------------------------------- primitives
-class _Ctx:
-    """Carries the state dict, train/eval flag and operand rounding through the port."""
+class _StoreRound(torch.autograd.Function):
+    """A tensor kept in a narrow dtype between two kernels: rounded going forward, its gradient rounded going back."""
 
-    def __init__(self, sd, training, operand_dtype=None, tap=None):
+    @staticmethod
+    def forward(ctx, t, dt):
+        ctx.dt = dt
+        return t.to(dt).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dt).to(torch.float32), None
+
+
+class _GradRound(torch.autograd.Function):
+    """Identity forward; the gradient is rounded (the fp32 head output whose gradient the GEMMs take in bf16)."""
+
+    @staticmethod
+    def forward(ctx, t, dt):
+        ctx.dt = dt
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dt).to(torch.float32), None
+
+
+class _Ctx:
+    """Carries the state dict, train/eval flag and operand / storage rounding through the port."""
+
+    def __init__(self, sd, training, operand_dtype=None, tap=None, store_dtype=None):
         self.sd = sd
         self.training = training
         self.od = operand_dtype
         self.tap = tap  # optional dict: name -> intermediate tensor
+        self.sdt = store_dtype
 
     def rnd(self, t):
         return t if self.od is None else t.to(self.od).to(torch.float32)
+
+    def rnd_small(self, t):
+        """Operands of the [N, C]-sized fp32 layers (linears, CoordAttn gate network): fp32 in the kernel-matched mode."""
+        return t if (self.od is None or self.sdt is not None) else t.to(self.od).to(torch.float32)
+
+    def st(self, t):
+        """A tensor the B200 path stores in ``store_dtype`` between kernels (identity in the plain modes)."""
+        return t if self.sdt is None else _StoreRound.apply(t, self.sdt)
 
     def p(self, name):
         return self.sd[name]
@@ -83,16 +127,25 @@ class _Ctx:
         return t
 
 
-def _conv(cx, pre, x, stride=1, padding=0):
-    return F.conv2d(cx.rnd(x), cx.rnd(cx.p(pre + ".weight")), cx.p(pre + ".bias"), stride, padding)
+def _conv(cx, pre, x, stride=1, padding=0, before_batch_stats=False):
+    """``before_batch_stats``: this conv feeds a BatchNorm.  Kernel-matched train mode stores it without the bias."""
+    if cx.sdt is not None and before_batch_stats and cx.training:
+        y = cx.st(F.conv2d(cx.rnd(x), cx.rnd(cx.p(pre + ".weight")), None, stride, padding))
+        return y + cx.p(pre + ".bias").view(1, -1, 1, 1)
+    return cx.st(F.conv2d(cx.rnd(x), cx.rnd(cx.p(pre + ".weight")), cx.p(pre + ".bias"), stride, padding))
+
+
+def _conv_small(cx, pre, x):
+    """1x1 convs of the CoordAttn gate network on the pooled [N, C, L, 1] rows (fp32 kernels on the B200 path)."""
+    return F.conv2d(cx.rnd_small(x), cx.rnd_small(cx.p(pre + ".weight")), cx.p(pre + ".bias"))
 
 
 def _convT(cx, pre, x, stride):
-    return F.conv_transpose2d(cx.rnd(x), cx.rnd(cx.p(pre + ".weight")), cx.p(pre + ".bias"), stride)
+    return cx.st(F.conv_transpose2d(cx.rnd(x), cx.rnd(cx.p(pre + ".weight")), cx.p(pre + ".bias"), stride))
 
 
 def _linear(cx, pre, x, bias=True):
-    return F.linear(cx.rnd(x), cx.rnd(cx.p(pre + ".weight")), cx.p(pre + ".bias") if bias else None)
+    return F.linear(cx.rnd_small(x), cx.rnd_small(cx.p(pre + ".weight")), cx.p(pre + ".bias") if bias else None)
 
 
 def _bn(cx, pre, x):
@@ -110,7 +163,7 @@ def _gn(cx, pre, x, groups=8):
 
 def _conv_bn_gelu(cx, pre, x):
     """Sequential(Conv2d 3x3 p1, BatchNorm2d, GELU): new_scripy.py:183-187."""
-    return F.gelu(_bn(cx, pre + ".1", _conv(cx, pre + ".0", x, 1, 1)))
+    return cx.st(F.gelu(_bn(cx, pre + ".1", _conv(cx, pre + ".0", x, 1, 1, before_batch_stats=True))))
 
 
 # --------------------------------------------------------------------------- blocks
@@ -119,7 +172,7 @@ def se_block(cx, pre, x):
     b, c = x.shape[:2]
     y = F.adaptive_avg_pool2d(x, 1).squeeze(-1).squeeze(-1)
     y = torch.sigmoid(_linear(cx, pre + ".fc.2", F.gelu(_linear(cx, pre + ".fc.0", y, False)), False))
-    return x * y.view(b, c, 1, 1)
+    return x * y.view(b, c, 1, 1)          # stored only after the residual add (res_conv_block)
 
 
 def res_conv_block(cx, pre, x, is_res, has_se):
@@ -132,7 +185,7 @@ def res_conv_block(cx, pre, x, is_res, has_se):
         x2 = se_block(cx, pre + ".se", x2)
     same = cx.p(pre + ".conv1.0.weight").shape[0] == cx.p(pre + ".conv1.0.weight").shape[1]
     out = (x + x2) if same else (x1 + x2)
-    return out / 1.414
+    return cx.st(out / 1.414)
 
 
 def coord_attn(cx, pre, x):
@@ -140,36 +193,36 @@ def coord_attn(cx, pre, x):
     n, c, h, w = x.shape
     x_h = F.adaptive_avg_pool2d(x, (None, 1))
     x_w = F.adaptive_avg_pool2d(x, (1, None))
-    x_h = F.gelu(_bn(cx, pre + ".bn1_h", _conv(cx, pre + ".conv1_h", x_h)))
-    x_w = F.gelu(_bn(cx, pre + ".bn1_w", _conv(cx, pre + ".conv1_w", x_w)))
-    h2w = _conv(cx, pre + ".h2w_proj", x_h).permute(0, 1, 3, 2)
-    w2h = _conv(cx, pre + ".w2h_proj", x_w).permute(0, 1, 3, 2)
+    x_h = F.gelu(_bn(cx, pre + ".bn1_h", _conv_small(cx, pre + ".conv1_h", x_h)))
+    x_w = F.gelu(_bn(cx, pre + ".bn1_w", _conv_small(cx, pre + ".conv1_w", x_w)))
+    h2w = _conv_small(cx, pre + ".h2w_proj", x_h).permute(0, 1, 3, 2)
+    w2h = _conv_small(cx, pre + ".w2h_proj", x_w).permute(0, 1, 3, 2)
     h2w = F.adaptive_avg_pool2d(h2w, (1, w))
     w2h = F.adaptive_avg_pool2d(w2h, (h, 1))
     x_h = x_h + torch.sigmoid(cx.p(pre + ".gamma_h")) * w2h
     x_w = x_w + torch.sigmoid(cx.p(pre + ".gamma_w")) * h2w
-    a_h = torch.sigmoid(_conv(cx, pre + ".conv_h", x_h))
-    a_w = torch.sigmoid(_conv(cx, pre + ".conv_w", x_w))
+    a_h = torch.sigmoid(_conv_small(cx, pre + ".conv_h", x_h))
+    a_w = torch.sigmoid(_conv_small(cx, pre + ".conv_w", x_w))
     alpha = torch.sigmoid(cx.p(pre + ".alpha"))
     beta = torch.sigmoid(cx.p(pre + ".beta"))
     wsum = alpha + beta + 1e-8
-    return x * ((alpha / wsum) * a_h + (beta / wsum) * a_w)
+    return cx.st(x * ((alpha / wsum) * a_h + (beta / wsum) * a_w))
 
 
 def local_enhancer(cx, pre, x, mask, high_thresh=HIGH_THRESH):
     """new_scripy.py:161-174 with a [B,H,W] attention map."""
     high = (mask > high_thresh).float().unsqueeze(1)
     y = _conv(cx, pre + ".conv.0", x, 1, 1)
-    y = F.gelu(_gn(cx, pre + ".conv.1", y))
+    y = cx.st(F.gelu(_gn(cx, pre + ".conv.1", y)))
     y = _conv(cx, pre + ".conv.3", y, 1, 1)
-    return x + y * high
+    return cx.st(x + y * high)
 
 
 def unet_down_rdd(cx, pre, x):
     """new_scripy.py:211-235."""
-    x = F.gelu(_bn(cx, pre + ".channel_compress.1", _conv(cx, pre + ".channel_compress.0", x)))
+    x = cx.st(F.gelu(_bn(cx, pre + ".channel_compress.1", _conv(cx, pre + ".channel_compress.0", x, before_batch_stats=True))))
     x = _conv(cx, pre + ".ch_adjust", x)
-    x = F.gelu(_bn(cx, pre + ".down.1", _conv(cx, pre + ".down.0", x, 1, 1)))
+    x = cx.st(F.gelu(_bn(cx, pre + ".down.1", _conv(cx, pre + ".down.0", x, 1, 1, before_batch_stats=True))))
     x = res_conv_block(cx, pre + ".down.3", x, True, True)
     return _conv(cx, pre + ".down.4", x, 2, 1)
 
@@ -177,7 +230,7 @@ def unet_down_rdd(cx, pre, x):
 def unet_up_rdd(cx, pre, x, skip):
     """new_scripy.py:237-253."""
     x = torch.cat((x, skip), 1)
-    x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+    x = cx.st(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True))
     x = _conv(cx, pre + ".model.0.1", x, 1, 1)
     x = res_conv_block(cx, pre + ".model.1", x, False, False)
     return res_conv_block(cx, pre + ".model.2", x, False, False)
@@ -185,7 +238,7 @@ def unet_up_rdd(cx, pre, x, skip):
 
 def unet_down_mnist(cx, pre, x):
     """MNIST_script.py:68-78."""
-    return F.max_pool2d(res_conv_block(cx, pre + ".model.0", x, False, False), 2)
+    return cx.st(F.max_pool2d(res_conv_block(cx, pre + ".model.0", x, False, False), 2))
 
 
 def unet_up_mnist(cx, pre, x, skip):
@@ -203,24 +256,27 @@ def embed_fc(cx, pre, x, input_dim):
 
 def up0(cx, pre, hidden, k):
     """ConvTranspose2d(k, k) + GroupNorm(8) + ReLU: new_scripy.py:297-301 / MNIST_script.py:139-144."""
-    return F.relu(_gn(cx, pre + ".1", _convT(cx, pre + ".0", hidden, k)))
+    return cx.st(F.relu(_gn(cx, pre + ".1", _convT(cx, pre + ".0", hidden, k))))
 
 
 def out_head(cx, pre, x):
     """conv3x3 + GroupNorm(8) + ReLU + conv3x3: new_scripy.py:310-315."""
-    y = F.relu(_gn(cx, pre + ".1", _conv(cx, pre + ".0", x, 1, 1)))
-    return _conv(cx, pre + ".3", y, 1, 1)
+    y = cx.st(F.relu(_gn(cx, pre + ".1", _conv(cx, pre + ".0", x, 1, 1))))
+    w, b = cx.rnd(cx.p(pre + ".3.weight")), cx.p(pre + ".3.bias")
+    y = F.conv2d(cx.rnd(y), w, b, 1, 1)                          # the head's output stays fp32 ...
+    return y if cx.sdt is None else _GradRound.apply(y, cx.sdt)  # ... its gradient reaches the GEMMs in bf16
 
 
 # --------------------------------------------------------------------------- denoisers
 def unet_forward(sd, x, c, t, ctx_mask, *, variant, training, attn_map=None,
-                 operand_dtype=None, prefix="", tap=None):
+                 operand_dtype=None, prefix="", tap=None, store_dtype=None):
     """ContextUnet.forward.  ``sd`` uses the reference's parameter names (optionally under
     ``prefix``, e.g. "nn_model.").  In train mode the BatchNorm running buffers in ``sd`` are
     updated in place exactly as the reference's modules would."""
     if prefix:
         sd = _PrefixView(sd, prefix)
-    cx = _Ctx(sd, training, operand_dtype, tap)
+    cx = _Ctx(sd, training, operand_dtype, tap, store_dtype)
+    x = cx.st(x)                            # x_t reaches the first conv in the storage dtype
     if variant == "rdd":
         return _unet_rdd(cx, x, c, t, ctx_mask, attn_map)
     if variant == "mnist":
@@ -252,7 +308,7 @@ def _unet_rdd(cx, x, c, t, ctx_mask, attn_map):
     d2 = cx.record("down2", coord_attn(cx, "ca2", unet_down_rdd(cx, "down2", d1)))
     d3 = cx.record("down3", coord_attn(cx, "ca3", unet_down_rdd(cx, "down3", d2)))
     d4 = cx.record("down4", coord_attn(cx, "ca4", unet_down_rdd(cx, "down4", d3)))
-    hidden = F.gelu(F.avg_pool2d(d4, 8))
+    hidden = cx.st(F.gelu(F.avg_pool2d(d4, 8)))
     c1h = F.one_hot(c.long(), num_classes=n_classes).type(torch.float)
     c1h = c1h * ctx_mask[:, None].repeat(1, n_classes)          # :337-340, no flip
     cemb1 = embed_fc(cx, "ctx_emb1", c1h, n_classes).view(-1, n_feat * 8, 1, 1)
@@ -260,8 +316,8 @@ def _unet_rdd(cx, x, c, t, ctx_mask, attn_map):
     cemb2 = embed_fc(cx, "ctx_emb2", c1h, n_classes).view(-1, n_feat * 4, 1, 1)
     temb2 = embed_fc(cx, "time_emb2", t, 1).view(-1, n_feat * 4, 1, 1)
     u1 = cx.record("up0", up0(cx, "up0", hidden, 8))
-    u2 = cx.record("up1", unet_up_rdd(cx, "up1", cemb1 * u1 + temb1, d4))
-    u3 = cx.record("up2", unet_up_rdd(cx, "up2", cemb2 * u2 + temb2, d3))
+    u2 = cx.record("up1", unet_up_rdd(cx, "up1", cx.st(cemb1 * u1 + temb1), d4))
+    u3 = cx.record("up2", unet_up_rdd(cx, "up2", cx.st(cemb2 * u2 + temb2), d3))
     u4 = cx.record("up3", unet_up_rdd(cx, "up3", u3, d2))
     u5 = cx.record("up4", unet_up_rdd(cx, "up4", u4, d1))
     if attn_map is None:
@@ -278,7 +334,7 @@ def _unet_mnist(cx, x, c, t, context_mask):
     x0 = cx.record("init_conv", res_conv_block(cx, "init_conv", x, True, False))
     d1 = cx.record("down1", unet_down_mnist(cx, "down1", x0))
     d2 = cx.record("down2", unet_down_mnist(cx, "down2", d1))
-    hidden = F.gelu(F.avg_pool2d(d2, 7))
+    hidden = cx.st(F.gelu(F.avg_pool2d(d2, 7)))
     c1h = F.one_hot(c, num_classes=n_classes).type(torch.float)
     m = context_mask[:, None].repeat(1, n_classes)
     m = (-1 * (1 - m))                                          # :170 flip and negate
@@ -288,8 +344,8 @@ def _unet_mnist(cx, x, c, t, context_mask):
     cemb2 = embed_fc(cx, "contextembed2", c1h, n_classes).view(-1, n_feat, 1, 1)
     temb2 = embed_fc(cx, "timeembed2", t, 1).view(-1, n_feat, 1, 1)
     u1 = cx.record("up0", up0(cx, "up0", hidden, 7))
-    u2 = cx.record("up1", unet_up_mnist(cx, "up1", cemb1 * u1 + temb1, d2))
-    u3 = cx.record("up2", unet_up_mnist(cx, "up2", cemb2 * u2 + temb2, d1))
+    u2 = cx.record("up1", unet_up_mnist(cx, "up1", cx.st(cemb1 * u1 + temb1), d2))
+    u3 = cx.record("up2", unet_up_mnist(cx, "up2", cx.st(cemb2 * u2 + temb2), d1))
     return out_head(cx, "out", torch.cat((u3, x0), 1))
 
 
@@ -323,11 +379,11 @@ def weighted_loss(noise, pred, attn_mask):
 
 
 def ddpm_loss(sd, sched, x, c, attn_mask, ts, noise, ctx_mask, *, variant, n_T, training=True,
-              attn_map=None, operand_dtype=None, prefix="nn_model."):
+              attn_map=None, operand_dtype=None, prefix="nn_model.", store_dtype=None):
     """DDPM.forward with the random draws passed in (see draw_train_randoms)."""
     x_t = q_sample(sched, x, ts, noise)
     pred = unet_forward(sd, x_t, c, ts / n_T, ctx_mask, variant=variant, training=training,
-                        attn_map=attn_map, operand_dtype=operand_dtype, prefix=prefix)
+                        attn_map=attn_map, operand_dtype=operand_dtype, prefix=prefix, store_dtype=store_dtype)
     if variant == "rdd":
         return weighted_loss(noise, pred, attn_mask)
     return F.mse_loss(noise, pred)                               # MNIST_script.py:252 (arg order kept)
@@ -340,10 +396,10 @@ def reverse_step(sched, x_i, eps1, eps2, z, i, guide_w):
 
 
 def ddpm_sample(sd, sched, x_T, zs, guide_w, *, variant, n_T, n_classes, steps=None,
-                operand_dtype=None, prefix="nn_model.", store=None):
+                operand_dtype=None, prefix="nn_model.", store=None, trace=None):
     """CFG reverse loop (new_scripy.py:441-477 / MNIST_script.py:254-300) with x_T and the
     per-step noises ``zs[i]`` (i = n_T .. 2) supplied by the caller.  ``steps`` truncates the
-    loop to the first ``steps`` iterations (for tests)."""
+    loop to the first ``steps`` iterations (for tests); ``trace`` (a list) receives x_i after every step."""
     n = x_T.shape[0]
     ncls = 10 if variant == "mnist" else n_classes              # MNIST_script.py:262 hard-codes 10
     c_i = torch.arange(0, ncls).repeat(int(n / ncls)).repeat(2)
@@ -359,6 +415,8 @@ def ddpm_sample(sd, sched, x_T, zs, guide_w, *, variant, n_T, n_classes, steps=N
         x_i = reverse_step(sched, x_i, eps[:n], eps[n:], z, i, guide_w)
         if store is not None and (i % 20 == 0 or i == n_T or i < 8):
             store.append(x_i.detach().clone())
+        if trace is not None:
+            trace.append(x_i.detach().clone())
         done += 1
         if steps is not None and done >= steps:
             break

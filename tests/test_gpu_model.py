@@ -333,44 +333,47 @@ def test_gemm_native_weight_storage(dev):
 
 
 @pytest.mark.parametrize("training", [True, False])
-@pytest.mark.parametrize("shape", [(4, 192, 16), (2, 64, 12), (3, 32, 7), (2, 3072, 8)], ids=lambda s: "x".join(map(str, s)))
-def test_coordattn_fused_gates_match_torch_subgraph(dev, shape, training):
-    """dm_ca_gates_fwd/bwd (the CoordAttn gate network as five kernels) against the same network run as a torch
-    fp32 sub-graph with autograd: output, dx, every parameter gradient, BatchNorm running statistics + counters."""
-    import copy
-    from diffusionmodel_b200 import ops, unet as U
-    from tests.test_gpu_kernels import bf, nhwc
+@pytest.mark.parametrize("shape", [(4, 192, 16), (2, 64, 12), (3, 32, 7), (2, 3072, 8), (4, 1536, 16)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_coordattn_gate_kernels_vs_oracle(dev, shape, training):
+    """CoordAttn (new_scripy.py:97-140) with the gate network on dm_ca_gates_fwd/bwd against the fp32 oracle block on
+    the CPU (same bf16-rounded input; everything inside the block is fp32 on both sides): output, dx, every parameter
+    gradient, BatchNorm running statistics + counters.  (4, 1536, 16) is ca4 at the benchmarked configuration."""
+    from diffusionmodel_b200 import unet as U
+    from tests.test_gpu_kernels import bf, nchw, nhwc
     n, c, s = shape
     g = torch.Generator().manual_seed(5)
-    base = U.CoordAttn(c)
-    sd = {k: v.clone() for k, v in base.state_dict().items()}
+    mod = U.CoordAttn(c)
+    sd = {"m." + k: v.clone() for k, v in mod.state_dict().items()}
     fill_state_dict_(sd, 9)
     for k in ("gamma_h", "gamma_w", "alpha", "beta"):
-        sd[k] = torch.randn(1, generator=g) * 0.7
-    base.load_state_dict(sd)
+        sd["m." + k] = torch.randn(1, generator=g) * 0.7
+    mod.load_state_dict({k[2:]: v for k, v in sd.items()})
+    mod = mod.to(dev).train(training)
     x = bf(torch.randn(n, c, s, s, generator=g))
     dy = bf(torch.randn(n, c, s, s, generator=g))
-    res = []
-    for fused in (False, True):
-        mod = copy.deepcopy(base).to(dev).train(training)
-        ops.FUSED_CA_GATES = fused
-        try:
-            xd = nhwc(x, dev).requires_grad_(True)
-            y = mod(xd)
-            y.backward(nhwc(dy, dev))
-        finally:
-            ops.FUSED_CA_GATES = True
-        torch.cuda.synchronize()
-        res.append((y.detach().float().cpu(), xd.grad.float().cpu(), {k: p.grad.cpu() for k, p in mod.named_parameters()},
-                    {k: v.cpu().clone() for k, v in mod.state_dict().items() if "running" in k or "tracked" in k}))
-    (y0, dx0, g0, b0), (y1, dx1, g1, b1) = res
-    assert P.rel_l2(y1, y0) < 3e-4 and P.rel_l2(dx1, dx0) < 5e-4          # bf16 outputs: isolated one-ulp flips
-    scale = max(float(v.abs().max()) for v in g0.values())
-    for k in g0:      # (a bias in front of a batch-statistics BatchNorm has zero gradient: rounding noise on both sides)
-        noise = float(g0[k].abs().max()) < 1e-4 * scale and float(g1[k].abs().max()) < 1e-4 * scale
-        assert noise or P.rel_l2(g1[k], g0[k]) < 2e-4, (k, g0[k].flatten()[:4], g1[k].flatten()[:4])
-    for k in b0:
-        assert torch.equal(b0[k], b1[k]) if "tracked" in k else P.rel_l2(b1[k], b0[k]) < 1e-5, k
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    y_ref = P.coord_attn(P._Ctx(sd, training), "m", xr)
+    y_ref.backward(dy)
+    xd = nhwc(x, dev).requires_grad_(True)
+    y = mod(xd)
+    y.backward(nhwc(dy, dev))
+    torch.cuda.synchronize()
+    assert P.rel_l2(nchw(y, c), y_ref) < 4e-3 and P.rel_l2(nchw(xd.grad, c), xr.grad) < 4e-3      # one bf16 rounding
+    g_ref = {k[2:]: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
+    scale = max(float(v.abs().max()) for v in g_ref.values())
+    for k, p in mod.named_parameters():      # (a bias in front of a batch-statistics BatchNorm has zero gradient: noise on both sides)
+        go = g_ref[k]
+        noise = float(go.abs().max()) < 1e-4 * scale and float(p.grad.abs().max()) < 1e-4 * scale
+        assert noise or P.rel_l2(p.grad.cpu(), go) < 1e-3, (k, go.flatten()[:4], p.grad.flatten()[:4])
+    for k, v in mod.state_dict().items():
+        if "tracked" in k:
+            assert int(v) == int(sd["m." + k])
+        elif "running" in k:
+            assert P.rel_l2(v.cpu(), sd["m." + k]) < 1e-5, k
 
 
 @pytest.mark.parametrize("variant", ["mnist", "rdd"])
@@ -419,27 +422,11 @@ def test_loss_curve_tracks_fp32_reference_training(dev, variant):
     assert sum(ours[-3:]) < sum(ours[:3])              # and it trains
 
 
-def test_coordattn_non_square_falls_back_to_subgraph(dev):
-    """H != W: the h<->w cross terms need adaptive_avg_pool1d resampling (new_scripy.py:118-126); the gate network then
-    runs as the torch sub-graph instead of dm_ca_gates.  Forward/backward against the fp32 oracle block."""
+def test_coordattn_non_square_fails_loudly(dev):
+    """H != W needs the adaptive_avg_pool1d resampling of the h<->w cross terms (new_scripy.py:118-126), which the gate
+    kernels do not implement; the U-Net only ever sees square maps.  No torch fallback: the call raises."""
     from diffusionmodel_b200 import unet as U
-    from tests.test_gpu_kernels import bf, nchw, nhwc
-    g = torch.Generator().manual_seed(8)
-    n, f, h, w = 2, 32, 12, 20
-    mod = U.CoordAttn(f)
-    sd = {"m." + k: v.clone() for k, v in mod.state_dict().items()}
-    fill_state_dict_(sd, 3)
-    mod.load_state_dict({k[2:]: v for k, v in sd.items()})
-    mod = mod.to(dev).train()
-    x = bf(torch.randn(n, f, h, w, generator=g))
-    for k, v in sd.items():
-        if v.is_floating_point() and "running" not in k:
-            v.requires_grad_(True)
-    xr = x.clone().requires_grad_(True)
-    y_ref = P.coord_attn(P._Ctx(sd, True), "m", xr)
-    dy = bf(torch.randn(y_ref.shape, generator=g))
-    y_ref.backward(dy)
-    xd = nhwc(x, dev).requires_grad_(True)
-    y = mod(xd)
-    y.backward(nhwc(dy, dev))
-    assert P.rel_l2(nchw(y, f), y_ref) < BAR and P.rel_l2(nchw(xd.grad, f), xr.grad) < 1.5e-2
+    from diffusionmodel_b200._lib import DmB200Error
+    mod = U.CoordAttn(32).to(dev)
+    with pytest.raises(DmB200Error):
+        mod(torch.zeros((2, 12, 20, 32), device=dev, dtype=torch.bfloat16))
