@@ -580,13 +580,11 @@ def run_ours(args):
     # roofline of the dominant kernel class (conv_gemm_kernel: fwd + dgrad implicit GEMMs), CUDA events
     # around every launch of one extra instrumented step on the launching stream
     micro = micro_eager                                   # CUDA events cannot be recorded inside a graph replay
-    side_stream, ops.WGRAD_SIDE_STREAM = ops.WGRAD_SIDE_STREAM, False      # per-launch events need one stream
     step_resident()
     prof = ops.enable_profile()
     step_resident()
     torch.cuda.synchronize()
     ops.disable_profile()
-    ops.WGRAD_SIDE_STREAM = side_stream
     agg = prof.summary()
     if rank == 0 and os.environ.get("DM_BENCH_BREAKDOWN"):
         with open(os.environ["DM_BENCH_BREAKDOWN"], "w") as f:

@@ -33,7 +33,7 @@ def timed_call(name, *args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); rc = real(name, *args); e1.record()
     ints = tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool))
-    recs.append((name, ints, e0, e1))
+    recs.append((name, ints, e0, e1, ops._Profile._flops(name, args), ops._Profile._bytes(name, args)))
     return rc
 
 
@@ -44,13 +44,14 @@ for _ in range(REPS):
 torch.cuda.synchronize()
 ops.call = real
 groups = {}
-for name, ints, e0, e1 in recs:
-    g = groups.setdefault((name, ints), [0.0, 0])
-    g[0] += e0.elapsed_time(e1) / REPS; g[1] += 1
-rows = sorted(([k[0], list(k[1]), round(v[0], 4), v[1] // REPS] for k, v in groups.items()), key=lambda r: -r[2])
+for name, ints, e0, e1, fl, nb in recs:
+    g = groups.setdefault((name, ints), [0.0, 0, 0.0, 0.0])
+    g[0] += e0.elapsed_time(e1) / REPS; g[1] += 1; g[2] += fl / REPS; g[3] += (0.0 if fl else nb) / REPS
+rows = sorted(([k[0], list(k[1]), round(v[0], 4), v[1] // REPS, v[2], v[3]] for k, v in groups.items()), key=lambda r: -r[2])
 tot = sum(r[2] for r in rows)
 print(f"total {tot:.2f} ms per micro-step over {sum(r[3] for r in rows)} launches")
-for r in rows[:70]:
-    print(f"{r[2]:8.3f} ms  x{r[3]:<3d} {r[0]:22s} {r[1]}")
+for r in rows[:90]:
+    rate = f"{r[4] / r[2] / 1e9:7.0f} TF/s" if r[4] else (f"{r[5] / r[2] / 1e6:7.0f} GB/s" if r[5] else " " * 12)
+    print(f"{r[2]:8.3f} ms  x{r[3]:<3d} {rate} {r[0]:22s} {r[1]}")
 if len(sys.argv) > 1:
     json.dump({"total_ms": tot, "rows": rows}, open(sys.argv[1], "w"))
