@@ -168,7 +168,10 @@ def workload_config(n):
             "global_batch": CFG["batch"] * CFG["accum"] * n, "micro_batch": CFG["batch"], "accum_steps": CFG["accum"],
             "parallelism": f"dp{n}",
             "reference_arm": "--impl reference = CPU oracle port, 1 image fwd+bwd per step, no optimizer, normalised per image",
-            "cuda_graph": os.environ.get("DM_BENCH_GRAPH", "1") != "0", "l2": "per-step working set (>5 GB of activations) is far larger than the 126 MB L2"}
+            "cuda_graph": os.environ.get("DM_BENCH_GRAPH", "1") != "0",
+            "allreduce": ("last micro-step's backward in 3 graphs: decoder-side gradients (62 % of the bytes) all-reduced under the "
+                          "trunk's backward, down4's (29 %) under init_conv..down3's, the rest after it" if n > 1 and os.environ.get("DM_BENCH_OVERLAP", "1") != "0" else
+                          ("one NCCL all-reduce of the flat fp32 gradient after the last micro-step" if n > 1 else "none (1 GPU)")), "l2": "per-step working set (>5 GB of activations) is far larger than the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -519,31 +522,47 @@ def run_ours(args):
     # the public fast path: one CUDA graph per micro-step (forward + backward), see DDPM.capture_train_step
     use_graph = os.environ.get("DM_BENCH_GRAPH", "1") != "0"
     micro = micro_eager
+    last, red = None, None
     if use_graph:
         micro = ddpm.capture_train_step(*resident[0], loss_scale=1.0 / accum)
+        if world > 1 and os.environ.get("DM_BENCH_OVERLAP", "1") != "0":
+            # N > 1: the last micro-step of the window as two graphs, the all-reduce of the decoder-side gradients (62 % of
+            # the bytes) issued between them and hidden behind the trunk's backward (parallel.OverlappedGradReduce)
+            last = ddpm.capture_train_step(*resident[0], loss_scale=1.0 / accum, split_backward=True,
+                                           trunk_sm_limit=148 - parallel.NCCL_CTAS)
+            red = parallel.OverlappedGradReduce(opt, net.grad_ready_regions())
+        opt.zero_grad()
+
+    def reduce_and_update():
+        if red is not None:
+            red.finish()
+        else:
+            opt.flush()
+            parallel.allreduce_mean_(opt.flat_grad)
+        opt.step()
         opt.zero_grad()
 
     def step_resident():
-        for x, c, m in resident:
-            micro(x, c, m)
-        opt.flush()
-        parallel.allreduce_mean_(opt.flat_grad)
-        opt.step()
-        opt.zero_grad()
+        for i, (x, c, m) in enumerate(resident):
+            if last is not None and i == accum - 1:
+                last(x, c, m, between=red.reduce_ready)
+            else:
+                micro(x, c, m)
+        reduce_and_update()
 
     def step_e2e():
         # pinned host batches -> device every micro-step; the running loss (new_scripy.py:789 reads it per micro-batch
         # for the progress bar) is accumulated on the device and read back once per optimizer step, so the host never
         # stalls the launch queue inside the accumulation window
         tot = None
-        for hx, hc, hm in host:
+        for i, (hx, hc, hm) in enumerate(host):
             x, c, m = hx.to(dev, non_blocking=True), hc.to(dev, non_blocking=True), hm.to(dev, non_blocking=True)
-            l = micro(x, c, m).detach()
+            if last is not None and i == accum - 1:
+                l = last(x, c, m, between=red.reduce_ready).detach()
+            else:
+                l = micro(x, c, m).detach()
             tot = l.clone() if tot is None else tot + l
-        opt.flush()
-        parallel.allreduce_mean_(opt.flat_grad)
-        opt.step()
-        opt.zero_grad()
+        reduce_and_update()
         return float(tot)                                 # device->host read of the step's loss
 
     def timed(fn, steps):
@@ -579,7 +598,7 @@ def run_ours(args):
 
     # roofline of the dominant kernel class (conv_gemm_kernel: fwd + dgrad implicit GEMMs), CUDA events
     # around every launch of one extra instrumented step on the launching stream
-    micro = micro_eager                                   # CUDA events cannot be recorded inside a graph replay
+    micro, last, red = micro_eager, None, None            # CUDA events cannot be recorded inside a graph replay
     step_resident()
     prof = ops.enable_profile()
     step_resident()

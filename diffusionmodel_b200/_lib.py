@@ -188,5 +188,20 @@ class kernel_counts:
         return self.delta[name]
 
 
+class sm_limit:
+    """``with sm_limit(132): ...``: the persistent GEMM grids launched (or graph-captured) inside leave SMs free for a
+    kernel running concurrently on another stream (dm_set_sm_limit)."""
+
+    def __init__(self, sms):
+        self.sms = int(sms)
+
+    def __enter__(self):
+        if lib().dm_set_sm_limit(self.sms) != 0:
+            raise DmB200Error(lib().dm_last_error().decode())
+
+    def __exit__(self, *exc):
+        lib().dm_set_sm_limit(148)
+
+
 def debug_set(key: int, value: int) -> None:
     lib().dm_debug_set(key, value)

@@ -85,7 +85,7 @@ def train_model(args):
     parallel.broadcast_parameters(optim.flat_param, list(ddpm.buffers()))
     gen = torch.Generator().manual_seed(100 + rank)
     torch.manual_seed(1234 + rank)
-    step_fn = None
+    step_fn = last_fn = red = None
     os.makedirs(Cfg.SAVE_DIR, exist_ok=True)
     ema = None
     for ep in range(first_epoch, args.epochs):
@@ -95,20 +95,28 @@ def train_model(args):
                 x, c, m = cache.batch(torch.randint(0, len(cache), (Cfg.BATCH_SIZE,), generator=gen), generator=gen)
             else:
                 x, c, m = (t.to(device, non_blocking=True) for t in synth_batch(gen, Cfg.BATCH_SIZE, args.img, args.n_classes))
+            closes = (step + 1) % Cfg.ACCUM_STEPS == 0 or step + 1 == args.steps_per_epoch      # :795
             if step_fn is None and not args.no_graph:
                 step_fn = ddpm.capture_train_step(x, c, m, loss_scale=1.0 / Cfg.ACCUM_STEPS)
+                if world > 1:      # last micro-step of a window: staged backward, gradient all-reduce hidden behind it
+                    last_fn = ddpm.capture_train_step(x, c, m, loss_scale=1.0 / Cfg.ACCUM_STEPS, split_backward=True,
+                                                      trunk_sm_limit=148 - parallel.NCCL_CTAS)
+                    red = parallel.OverlappedGradReduce(optim, ddpm.nn_model.grad_ready_regions())
                 optim.zero_grad()
             if step_fn is not None:
-                loss = step_fn(x, c, m)
+                loss = last_fn(x, c, m, between=red.reduce_ready) if (closes and last_fn is not None) else step_fn(x, c, m)
             else:
                 loss = ddpm(x, c, m) / Cfg.ACCUM_STEPS              # new_scripy.py:785-786
                 ddpm.scaler.scale(loss).backward()                 # :792 (disabled scaler: bf16)
             li = loss.item() * Cfg.ACCUM_STEPS
             ema = li if ema is None else 0.95 * ema + 0.05 * li    # :806-809
             seen += Cfg.BATCH_SIZE * world
-            if (step + 1) % Cfg.ACCUM_STEPS == 0 or step + 1 == args.steps_per_epoch:     # :795
-                optim.flush()
-                parallel.allreduce_mean_(optim.flat_grad)
+            if closes:
+                if red is not None:
+                    red.finish()
+                else:
+                    optim.flush()
+                    parallel.allreduce_mean_(optim.flat_grad)
                 optim.step()                                       # unscale / clip 1.0 / AdamW, :797-801
                 optim.zero_grad()
         sched.step()                                               # :848

@@ -1144,6 +1144,7 @@ wgrad3_pair_kernel(const __grid_constant__ Wgrad2Params p) {
 
 // ------------------------------------------------------------------------------------------ host side
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+int g_sm_limit = DM_NUM_SMS;   // SMs the persistent GEMM grids may occupy (dm_set_sm_limit)
 long long g_debug[16] = {0};   // 8..15: elementwise.cu experiments (dm_debug_value); 0 stages 1 grid 2 splits 3 block_n 4 wgrad kernel (1 B, 2 C, 3 F) 5 no-halo 6 base-offset 7 ablation 9 upcat per-pixel 10 wgrad stages
 
 int ensure_encode() {
@@ -1224,7 +1225,7 @@ int pick_block_n_tiles(int cout, int m_tiles) {
   for (int bn = 256; bn >= 96; bn -= 16) {
     const int nt = (cout + bn - 1) / bn;
     const long long tiles = (long long)m_tiles * nt;
-    const long long rounds = (tiles + DM_NUM_SMS - 1) / DM_NUM_SMS;
+    const long long rounds = (tiles + g_sm_limit - 1) / g_sm_limit;
     const double cost = (double)rounds * (bn + 48);      // 48 ~ the per-tile share that does not shrink with N
     if (cost < best_cost * 0.98) { best_cost = cost; best = bn; }
   }
@@ -1252,11 +1253,18 @@ struct ConvGeom {
 }  // namespace
 
 extern "C" int dm_conv2d_fwd_stat_rows(int N, int Ho, int Wo, int Cout);
+// Leave SMs free for a concurrent kernel on another stream (an NCCL all-reduce overlapped with the backward pass): the
+// GEMM kernels hold a whole SM's shared memory per CTA, so a full-width grid would queue behind such a kernel's CTAs.
+extern "C" int dm_set_sm_limit(int sms) {
+  if (sms < 2 || sms > DM_NUM_SMS) { dm_set_error("dm_set_sm_limit: 2..148"); return DM_ERR_ARG; }
+  g_sm_limit = sms & ~1;          // CTA pairs
+  return DM_OK;
+}
 extern "C" void dm_debug_set(int key, long long value) { if (key >= 0 && key < 16) g_debug[key] = value; }
 long long dm_debug_value(int key) { return (key >= 0 && key < 16) ? g_debug[key] : 0; }
 
 // Generic launcher for kernel A.  All geometry is resolved by the typed entry points below.
-static int conv_grid(int tiles) { return tiles < DM_NUM_SMS ? tiles : DM_NUM_SMS; }
+static int conv_grid(int tiles) { return tiles < g_sm_limit ? tiles : g_sm_limit; }
 
 static int launch_conv(ConvParams& P, cudaStream_t st) {
   int stage_bytes = kAStage + P.b_stage_bytes;
@@ -1336,7 +1344,7 @@ static int launch_conv_halo2(ConvParams& P, const void* wpk, long long w_rows, l
     if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
     g_attr_e = true;
   }
-  const int clusters = P.pair_tiles < DM_NUM_SMS / 2 ? P.pair_tiles : DM_NUM_SMS / 2;
+  const int clusters = P.pair_tiles < g_sm_limit / 2 ? P.pair_tiles : g_sm_limit / 2;
   dm_note_kernel("conv3x3_halo2", P.block_n);
   conv3x3_halo2_kernel<<<2 * clusters, kConvThreads, smem, st>>>(P);
   DM_CHECK_LAUNCH();
@@ -1511,7 +1519,8 @@ extern "C" int dm_convt_fwd(const void* x, int Cin, int ldx, const void* wpk, co
 // Split-K choice for the weight-gradient GEMMs: `base` output tiles, `patches` 64-pixel K-steps.
 // Static round-robin tile schedule => time ~ waves * (K-steps per split + per-tile overhead); pick the
 // split count that minimises it (i.e. fills the last wave) instead of a fixed "two waves" rule.
-static int pick_splits(int base, int patches, int tile_overhead_steps, int slots = DM_NUM_SMS) {
+static int pick_splits(int base, int patches, int tile_overhead_steps, int slots = 0) {
+  if (slots <= 0) slots = g_sm_limit;
   int max_splits = patches / 8; if (max_splits < 1) max_splits = 1;
   if (max_splits > 1024) max_splits = 1024;
   int best = 1; double best_cost = 1e30;
@@ -1607,7 +1616,7 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
     P.block_n = (dm::cdiv(Cout, P.n_tiles) + 31) / 32 * 32;      // both halves multiples of 16 columns
     P.nb = dm::cdiv(P.block_n / 2, 64);                         // boxes per CTA
     P.Cout = Cout; P.cin_k = chunks * 64; P.C0 = C0; P.C1 = C1;
-    int splits = pick_splits(P.m_tiles * P.n_tiles, patches, 3, DM_NUM_SMS / 2);
+    int splits = pick_splits(P.m_tiles * P.n_tiles, patches, 3, g_sm_limit / 2);
     if (g_debug[2] > 0) splits = (int)g_debug[2];
     P.patches_per_split = dm::cdiv(patches, splits);
     P.splits = dm::cdiv(patches, P.patches_per_split);
@@ -1628,7 +1637,7 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
       attr_f = true;
     }
     const int tiles = P.m_tiles * P.n_tiles * P.splits;
-    const int clusters = tiles < DM_NUM_SMS / 2 ? tiles : DM_NUM_SMS / 2;
+    const int clusters = tiles < g_sm_limit / 2 ? tiles : g_sm_limit / 2;
     dm_note_kernel("wgrad3_pair", P.splits);
     wgrad3_pair_kernel<<<2 * clusters, kThreads, smem, (cudaStream_t)stream>>>(P);
     DM_CHECK_LAUNCH();
@@ -1667,7 +1676,7 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
       g_attr_c = true;
     }
     const int tiles = P.m_tiles * P.n_tiles * P.splits;
-    int grid = tiles < DM_NUM_SMS ? tiles : DM_NUM_SMS;
+    int grid = tiles < g_sm_limit ? tiles : g_sm_limit;
     if (g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
     dm_note_kernel("wgrad2_gemm", P.splits);
     wgrad2_gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);
@@ -1710,7 +1719,7 @@ extern "C" int dm_conv2d_wgrad(const void* x0, int C0, int ld0, const void* x1, 
     g_attr_b = true;
   }
   int tiles = base_tiles * P.splits;
-  int grid = tiles < DM_NUM_SMS ? tiles : DM_NUM_SMS;
+  int grid = tiles < g_sm_limit ? tiles : g_sm_limit;
   if (g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
   dm_note_kernel("wgrad_gemm", P.splits);
   wgrad_gemm_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(P);

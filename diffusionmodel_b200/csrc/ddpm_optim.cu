@@ -246,8 +246,13 @@ __global__ void cfg_reverse_kernel(const float* eps, int ldp, const float* x, co
 }
 
 // ------------------------------------------------------------------------------------------ optimizer
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* g, long long n, float* out) {
+// Deterministic: per-block partial sums, combined in a fixed order (double precision) by the last block to arrive.  The
+// clip coefficient derived from this norm scales the whole update, so under data parallelism it must come out BIT-IDENTICAL
+// on every rank from bit-identical all-reduced gradients (an atomicAdd per block did not: the ranks' parameters drifted
+// apart in the last bits step by step).  out[0] is overwritten (no zero-fill needed); ws = [gridDim.x partials][counter].
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* g, long long n, float* out, float* ws) {
   __shared__ float sm[32];
+  __shared__ bool last;
   float s = 0.f;
   const long long n4 = n / 4;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -257,7 +262,25 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* g, long long n,
   }
   for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += g[i] * g[i];
   s = dm::block_sum(s, sm);
-  if (threadIdx.x == 0) atomicAdd(out, s);
+  unsigned* counter = reinterpret_cast<unsigned*>(ws + gridDim.x);
+  if (threadIdx.x == 0) {
+    ws[blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  __shared__ double sd[256];
+  double a = 0.0;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) a += (double)__ldcg(ws + i);
+  sd[threadIdx.x] = a;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if ((int)threadIdx.x < k) sd[threadIdx.x] += sd[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = (float)sd[0]; *counter = 0u; }
 }
 
 // torch.optim.AdamW semantics (decoupled decay, bias-corrected), gradient pre-scaled by the
@@ -515,7 +538,16 @@ extern "C" int dm_cfg_reverse_step_w(const float* eps, int ldp, const float* x, 
 }
 
 extern "C" int dm_sumsq(const float* g, long long n, float* out, void* stream) {
-  sumsq_kernel<<<grid_for(n / 4 + 1), 256, 0, ST>>>(g, n, out);
+  static float* ws = nullptr;          // partial sums + arrival counter (one device per process, like the reduction workspace)
+  const int grid = grid_for(n / 4 + 1);
+  if (ws == nullptr) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(ST, &cap);
+    if (cap != cudaStreamCaptureStatusNone) { dm_set_error("dm_sumsq: first call inside a stream capture (scratch not allocated yet)"); return DM_ERR_ARG; }
+    const size_t bytes = ((size_t)DM_NUM_SMS * 16 + 1) * sizeof(float);
+    if (cudaMalloc(&ws, bytes) != cudaSuccess || cudaMemset(ws, 0, bytes) != cudaSuccess) { dm_set_error("dm_sumsq: scratch allocation failed"); return DM_ERR_CUDA; }
+  }
+  sumsq_kernel<<<grid, 256, 0, ST>>>(g, n, out, ws);
   DM_CHECK_LAUNCH();
   return DM_OK;
 }

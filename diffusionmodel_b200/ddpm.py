@@ -93,7 +93,46 @@ class DDPM(nn.Module):
         pred = self.nn_model.forward_nhwc(xt, c, ts / self.n_T, ctx_mask, **kw)
         return ops.ddpm_loss(pred, noise, attn_mask if self.variant == "rdd" else None)
 
-    def capture_train_step(self, x, c, attn_mask=None, loss_scale=1.0, warmup=2):
+    def _forward_cut(self, x, c, attn_mask, randoms):
+        """``forward`` with the autograd tape cut between the trunk and the decoder side (up0, embeddings, up1.., head):
+        returns (loss, stages) with stages = [(outputs, detached stand-ins), ...] in forward order.  ``loss.backward()`` then
+        runs the decoder side's backward only (parameter gradients of everything from ``time_emb1`` on, in ``parameters()``
+        order) and leaves the gradients of the last stage's outputs in ``stand_in.grad``;
+        ``torch.autograd.backward(outputs, [stand_in.grad ...])``, last stage first, runs the rest (new_scripy: down4 +
+        CoordAttn, then init_conv ... down3)."""
+        ts, noise, ctx_mask = randoms
+        x = x.contiguous().float()
+        noise = noise.contiguous().float()
+        xt = ops.q_sample(x, noise, self.sqrtab, self.sqrtmab, ts.long())
+        kw = {}
+        if self.variant == "rdd":
+            if attn_mask is None:
+                raise RuntimeError("DDPM.forward: attn_mask is required (new_scripy.py:401)")
+            if self.enhance_with_attn_map:
+                kw["attn_map"] = attn_mask
+        net = self.nn_model
+
+        def cut(tensors):
+            names = list(tensors)
+            outs = [tensors[k] for k in names]
+            leaves = [o.detach().requires_grad_(True) for o in outs]
+            return dict(zip(names, leaves)), (outs, leaves)
+        stages = []                                      # [(outputs, detached stand-ins)], in forward order
+        with ops.batched_counters(net):
+            if hasattr(net, "trunk_back"):               # trunk in two pieces: a third backward stage
+                enc, st0 = cut(net.trunk_front(xt))      # skip tensors: their gradients come from the decoder side,
+                stages.append(st0)                       # d3_in's from the trunk_back stage
+                back, st1 = cut(net.trunk_back(enc.pop("d3_in")))
+                stages.append(st1)
+                enc.update(back)
+            else:
+                enc, st0 = cut(net.trunk(xt))
+                stages.append(st0)
+            enc["u1"] = net.up0_of(enc.pop("hidden"))
+            pred = net.decode(enc, c, ts / self.n_T, ctx_mask, **kw)
+        return ops.ddpm_loss(pred, noise, attn_mask if self.variant == "rdd" else None), stages
+
+    def capture_train_step(self, x, c, attn_mask=None, loss_scale=1.0, warmup=2, split_backward=False, trunk_sm_limit=0):
         """CUDA-graph one training micro-step: ``loss = self(x, c, attn_mask) * loss_scale; loss.backward()``.
 
         Returns ``step(x, c, attn_mask=None, randoms=None) -> loss`` (a static device scalar, valid until the
@@ -102,7 +141,16 @@ class DDPM(nn.Module):
         Gradients accumulate into the parameters' ``.grad`` (the optimizer's flat buffer) as in eager mode.
         The warm-up passes accumulate gradients: call ``optimizer.zero_grad()`` afterwards.  BatchNorm running
         statistics, ``num_batches_tracked`` and the CPU / CUDA RNG streams are restored to their state at entry.
-        Shapes are fixed to those of the example batch; parameters must not be re-allocated afterwards."""
+        Shapes are fixed to those of the example batch; parameters must not be re-allocated afterwards.
+
+        ``split_backward=True`` captures the step as SEVERAL graphs -- forward + the decoder side's backward, then the
+        trunk's backward in one (MNIST) or two (new_scripy: down4 + CoordAttn, then init_conv ... down3) more -- and
+        ``step(..., between=fn)`` calls ``fn(k)`` after graph k (except the last): when it runs, the gradients of
+        ``nn_model.grad_ready_regions()[k]`` are final (k = 0: every parameter from ``time_emb1`` on, 62 % of the flat
+        gradient buffer; k = 1: down4, 29 %), so a data-parallel all-reduce of that region overlaps the rest of the
+        backward pass (parallel.OverlappedGradReduce).  ``trunk_sm_limit`` caps the GEMM grids of the later graphs so the
+        collective's CTAs find free SMs."""
+        from . import _lib
         sx, sc = x.detach().clone().float().contiguous(), c.detach().clone()
         sm = attn_mask.detach().clone().to(self.device) if attn_mask is not None else None
         # the warm-up passes must leave no trace but gradients: BatchNorm running statistics / counters and both RNG
@@ -111,20 +159,45 @@ class DDPM(nn.Module):
         saved_bufs = [(b, b.detach().clone()) for b in self.nn_model.buffers()]
         r = self.draw_randoms(sx, sc)
         st = [t.detach().clone() for t in r]
+
+        def first_stage():
+            if not split_backward:
+                loss = self.forward(sx, sc, sm, randoms=tuple(st)) * loss_scale
+                loss.backward()
+                return loss, []
+            loss, stages = self._forward_cut(sx, sc, sm, tuple(st))
+            loss = loss * loss_scale
+            loss.backward()
+            return loss, stages[::-1]                 # backward order
+
+        def later_stage(stage):
+            outs, leaves = stage
+            live = [(o, l.grad) for o, l in zip(outs, leaves) if l.grad is not None]
+            with _lib.sm_limit(trunk_sm_limit or 148):
+                torch.autograd.backward([o for o, _ in live], [g for _, g in live])
+        def warm():
+            # in a function so that no local keeps an autograd graph alive afterwards: a live graph pins the parameters'
+            # grad accumulators to the warm-up stream, and the captured backward must not wait on an uncaptured stream
+            for stg in first_stage()[1]:
+                later_stage(stg)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                (self.forward(sx, sc, sm, randoms=tuple(st)) * loss_scale).backward()
+                warm()
         torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        from . import _lib
+        graphs, touched_by = [torch.cuda.CUDAGraph()], []
         k0 = _lib.launch_count()
-        with ops.capture_log() as touched, torch.cuda.graph(graph):
-            loss = self.forward(sx, sc, sm, randoms=tuple(st)) * loss_scale
-            loss.backward()
-        touched = list(touched)
-        kernels = _lib.launch_count() - k0          # library kernels recorded in the graph (run on every replay)
+        with ops.capture_log() as touched, torch.cuda.graph(graphs[0]):
+            loss, stages = first_stage()
+        touched_by.append(list(touched))
+        for stg in stages:
+            g = torch.cuda.CUDAGraph()
+            with ops.capture_log() as touched, torch.cuda.graph(g, pool=graphs[0].pool()):
+                later_stage(stg)
+            graphs.append(g)
+            touched_by.append(list(touched))
+        kernels = _lib.launch_count() - k0          # library kernels recorded in the graph(s) (run on every replay)
         with torch.no_grad():
             for b, v in saved_bufs:
                 b.copy_(v)
@@ -132,7 +205,14 @@ class DDPM(nn.Module):
         torch.set_rng_state(cpu_rng)
         torch.cuda.set_rng_state(cuda_rng, sx.device)
 
-        def step(x, c, attn_mask=None, randoms=None):
+        def mark(entries):
+            for e in entries:
+                if hasattr(e, "after_replay"):
+                    e.after_replay()              # queued wgrad operands: staging buffers -> this pass's queue slot
+                else:
+                    e.dirty = True
+
+        def step(x, c, attn_mask=None, randoms=None, between=None):
             rr = randoms if randoms is not None else self.draw_randoms(x, c)
             sx.copy_(x, non_blocking=True)
             sc.copy_(c, non_blocking=True)
@@ -141,15 +221,14 @@ class DDPM(nn.Module):
             for dst, src in zip(st, rr):
                 dst.copy_(src, non_blocking=True)
             ops.refresh_weight_packs()        # no-op after FusedAdamW.step; re-packs in place after any other weight change
-            graph.replay()
-            for e in touched:
-                if hasattr(e, "after_replay"):
-                    e.after_replay()              # queued wgrad operands: staging buffers -> this pass's queue slot
-                else:
-                    e.dirty = True
+            for k, g in enumerate(graphs):
+                g.replay()
+                mark(touched_by[k])
+                if between is not None and k + 1 < len(graphs):
+                    between(k)                # the gradients of nn_model.grad_ready_regions()[k] are final
             ops.bump_bn_stats_epoch()         # the replay updated BatchNorm running statistics in place
             return loss
-        step.graph, step.kernels_per_replay = graph, kernels
+        step.graph, step.graphs, step.kernels_per_replay = graphs[0], graphs, kernels
         return step
 
     # ------------------------------------------------------------------ sampling

@@ -269,20 +269,50 @@ class ContextUnet(nn.Module):
                                  nn.Conv2d(f, self.in_ch, 3, 1, 1))
         ops.mark_conv2d_weights(self)
 
-    def encode(self, x):
-        """Everything that does not depend on (c, t, ctx_mask): init_conv ... down4, CoordAttn, to_vec, up0
-        (new_scripy.py:318-332,347).  x: bf16 NHWC."""
+    def trunk_front(self, x):
+        """init_conv ... down3 with CoordAttn (new_scripy.py:318-326): the first three skip tensors and ``d3_in``, the
+        tensor that enters down4.  x: bf16 NHWC."""
         f = self.n_feat
         x0, x0_skip = ops.fork(self.init_conv(x), f)
         d1, d1s = ops.fork(self.ca1(self.down1(x0)), f)
         d2, d2s = ops.fork(self.ca2(self.down2(d1)), 2 * f)
         d3, d3s = ops.fork(self.ca3(self.down3(d2)), 4 * f)
-        d4 = self.ca4(self.down4(d3))
-        d4, d4s = ops.fork(d4, 8 * f)
-        hidden = ops.avgpool_act(d4, 8 * f, 8, ACT_GELU)
+        return dict(x0=x0_skip, d1=d1s, d2=d2s, d3=d3s, d3_in=d3)
+
+    def trunk_back(self, d3_in):
+        """down4 + CoordAttn + to_vec (new_scripy.py:327-332): 101 M of the trunk's 135 M parameters."""
+        f = self.n_feat
+        d4, d4s = ops.fork(self.ca4(self.down4(d3_in)), 8 * f)
+        return dict(d4=d4s, hidden=ops.avgpool_act(d4, 8 * f, 8, ACT_GELU))
+
+    def trunk(self, x):
+        """Everything up to the pooled bottleneck: the skip tensors and ``hidden``.  Every parameter used here precedes
+        ``time_emb1`` in ``parameters()`` order."""
+        t = self.trunk_front(x)
+        t.update(self.trunk_back(t.pop("d3_in")))
+        return t
+
+    def grad_ready_regions(self):
+        """For a backward pass run in three stages (decoder side; trunk_back; trunk_front): after stage k the gradients of
+        the parameters in ``[first, end)`` -- given as (first parameter, first parameter after the region or None) -- are
+        final.  Stage 0: time_emb1 ... out (62 % of the bytes); stage 1: down4 (29 %)."""
+        return [(next(self.time_emb1.parameters()), None), (next(self.down4.parameters()), next(self.ca1.parameters()))]
+
+    def first_decoder_param(self):
+        """First parameter (in ``parameters()`` order) that ``trunk`` does not use: everything from here on belongs to the
+        decoder side (embeddings, up0, up blocks, LocalEnhancer, head)."""
+        return next(self.time_emb1.parameters())
+
+    def up0_of(self, hidden):
+        """up0 = ConvTranspose2d(8f, 8f, 8, 8) + GroupNorm + ReLU (new_scripy.py:297-301,347)."""
         u1 = ops.conv_transpose(hidden, self.up0[0].weight, self.up0[0].bias, _pack_of(self.up0[0]), 8)
-        u1 = ops.gn_act(u1, self.up0[1], ACT_RELU)
-        return dict(x0=x0_skip, d1=d1s, d2=d2s, d3=d3s, d4=d4s, u1=u1)
+        return ops.gn_act(u1, self.up0[1], ACT_RELU)
+
+    def encode(self, x):
+        """Everything that does not depend on (c, t, ctx_mask): trunk + up0 (new_scripy.py:318-332,347).  x: bf16 NHWC."""
+        enc = self.trunk(x)
+        enc["u1"] = self.up0_of(enc.pop("hidden"))
+        return enc
 
     def decode(self, enc, c, t, ctx_mask, attn_map=None):
         """Embeddings, FiLM, up1..up4, LocalEnhancer, head (new_scripy.py:334-355) -> eps as fp32 NHWC."""
@@ -391,16 +421,30 @@ class MnistContextUnet(nn.Module):
     def in_ch(self):
         return self.in_channels
 
-    def encode(self, x):
-        """init_conv, down1, down2, to_vec, up0 (MNIST_script.py:157-161,176): independent of (c, t, mask)."""
+    def trunk(self, x):
+        """init_conv, down1, down2, to_vec (MNIST_script.py:157-161): independent of (c, t, mask)."""
         f = self.n_feat
         x0, x0s = ops.fork(self.init_conv(x), f)
         d1, d1s = ops.fork(self.down1(x0), f)
         d2, d2s = ops.fork(self.down2(d1), 2 * f)
         hidden = ops.avgpool_act(d2, 2 * f, 7, ACT_GELU)
+        return dict(x0=x0s, d1=d1s, d2=d2s, hidden=hidden)
+
+    def first_decoder_param(self):
+        return next(self.timeembed1.parameters())
+
+    def grad_ready_regions(self):
+        return [(next(self.timeembed1.parameters()), None)]
+
+    def up0_of(self, hidden):
+        """up0 = ConvTranspose2d(2f, 2f, 7, 7) + GroupNorm + ReLU (MNIST_script.py:139-144,176)."""
         u1 = ops.conv_transpose(hidden, self.up0[0].weight, self.up0[0].bias, _pack_of(self.up0[0]), 7)
-        u1 = ops.gn_act(u1, self.up0[1], ACT_RELU)
-        return dict(x0=x0s, d1=d1s, d2=d2s, u1=u1)
+        return ops.gn_act(u1, self.up0[1], ACT_RELU)
+
+    def encode(self, x):
+        enc = self.trunk(x)
+        enc["u1"] = self.up0_of(enc.pop("hidden"))
+        return enc
 
     def decode(self, enc, c, t, context_mask, attn_map=None):
         f = self.n_feat

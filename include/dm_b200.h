@@ -29,6 +29,11 @@ long long dm_launch_count(void);   /* kernels launched by this library so far (b
  * shapes): launches so far under a kernel name ("conv_gemm", "conv3x3_halo", "conv3x3_halo2", "wgrad_gemm",
  * "wgrad2_gemm", "wgrad3_pair", "skinny_gemm"), and the most recent launch with its parameter (conv: tile width in
  * output channels; wgrad: split-K count). */
+/* SMs the persistent convolution / weight-gradient grids may occupy (default and maximum 148; rounded down to even).
+ * Lower it while another stream runs a long kernel that also needs SM residency (the data-parallel gradient all-reduce
+ * overlapped with the encoder's backward pass): a GEMM CTA owns a whole SM's shared memory and cannot share one.  The value
+ * is read at launch time, so a CUDA graph captured under a limit keeps it. */
+int dm_set_sm_limit(int sms);
 long long dm_kernel_count(const char* name);
 const char* dm_last_kernel(int* param);
 /* Device scratch (>= 16 MiB recommended) for the partial sums of the reduction kernels (pooling, colsum, FiLM
@@ -263,7 +268,7 @@ int dm_prep_batch(const void* img_u8, const int* flip, const int* box, float* x,
 int dm_image_metrics(const float* a, const float* b, float* out, int N, long long elems, void* stream);
 
 /* ---- optimizer side (new_scripy.py:797-803) --------------------------------------------------------- */
-int dm_sumsq(const float* g, long long n, float* out, void* stream);          /* *out += sum g^2 */
+int dm_sumsq(const float* g, long long n, float* out, void* stream);          /* *out = sum g^2, deterministic (fixed-order combine: bit-identical on every data-parallel rank) */
 int dm_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
              float eps, float wd, float bc1, float bc2, const float* gnorm_sq, float max_norm, void* stream);
 /* dm_adamw that also writes a bf16 copy of the updated parameters (the forward weight pack of convolution weights

@@ -50,7 +50,7 @@ def test_ctypes_signatures_match_header():
     for name, sig in _lib._SIGS.items():
         assert name in protos, name
         assert sig.replace(" ", "") == protos[name], f"{name}: binding {sig.replace(' ', '')} != header {protos[name]}"
-    unbound = set(protos) - set(_lib._SIGS) - {"dm_last_error", "dm_version", "dm_debug_set", "dm_launch_count", "dm_kernel_count", "dm_last_kernel",
+    unbound = set(protos) - set(_lib._SIGS) - {"dm_last_error", "dm_version", "dm_debug_set", "dm_launch_count", "dm_kernel_count", "dm_last_kernel", "dm_set_sm_limit",
                                                      "dm_set_workspace"}
     assert not unbound, f"header entry points without a Python binding: {sorted(unbound)}"
 

@@ -261,6 +261,46 @@ def test_graphed_train_step_matches_eager(dev, training):
         assert e < 1e-3
 
 
+@pytest.mark.parametrize("variant", ["rdd", "mnist"])
+def test_split_backward_graphs_match_single_graph(dev, variant):
+    """capture_train_step(split_backward=True) -- forward + decoder-side backward as one graph, the trunk's backward as a
+    second (under an SM limit), a callback in between -- accumulates the same gradients as the single graph, and when the
+    callback runs every gradient from ``first_decoder_param()`` on is already final."""
+    import diffusionmodel_b200 as D
+    from diffusionmodel_b200 import parallel
+    n_feat, size, in_ch, ncls, n_T = (64, 128, 3, 5, 700) if variant == "rdd" else (32, 28, 1, 10, 400)
+    inp = make_inputs(variant, 2, in_ch, size, ncls, n_T, 3)
+    x, c, attn, ts, noise, ctx = (inp[k].to(dev) for k in ("x", "c", "attn_mask", "ts", "noise", "ctx_mask"))
+    attn = attn if variant == "rdd" else None
+    grads, tails = [], []
+    for split in (False, True):
+        ddpm, _ = build(variant, n_feat, ncls, n_T, 3, dev, **({"enhance_with_attn_map": True} if variant == "rdd" else {}))
+        ddpm.eval()
+        opt = D.FusedAdamW(ddpm.parameters(), lr=1e-4, weight_decay=1e-5, max_grad_norm=1.0)
+        step = ddpm.capture_train_step(x, c, attn, loss_scale=0.5, split_backward=split, trunk_sm_limit=132 if split else 0)
+        opt.zero_grad()
+        red = parallel.OverlappedGradReduce(opt, ddpm.nn_model.grad_ready_regions())
+        seen = {}
+
+        def between(k):
+            red.reduce_ready(k)                # world size 1: flushes the packed / queued gradients, no collective
+            lo, hi = red.spans[k]
+            seen[k] = opt.flat_grad[lo:hi].clone()
+        for _ in range(2):
+            step(x, c, attn, randoms=(ts, noise, ctx), **({"between": between} if split else {}))
+        red.finish()
+        torch.cuda.synchronize()
+        grads.append(opt.flat_grad.detach().cpu().clone())
+        if split:
+            assert len(seen) == (2 if variant == "rdd" else 1)
+            for k, g in seen.items():                                              # final when the callback ran
+                lo, hi = red.spans[k]
+                assert torch.equal(g.cpu(), grads[-1][lo:hi]) and 0 < lo < hi <= opt.flat_grad.numel()
+    e = P.rel_l2(grads[1], grads[0])
+    print(f"{variant}: split-backward vs single-graph gradient rel-L2 {e:.3e}")
+    assert e < 1e-3 and float(grads[0].norm()) > 0
+
+
 def test_state_dict_roundtrip_and_fail_loudly(dev):
     import diffusionmodel_b200 as D
     from diffusionmodel_b200._lib import DmB200Error
