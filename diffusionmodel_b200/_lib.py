@@ -133,7 +133,9 @@ _workspace = None
 
 
 def _ensure_workspace():
-    """One 32 MiB device scratch buffer for the reduction kernels' partial sums (dm_set_workspace)."""
+    """One 32 MiB device scratch buffer for the reduction kernels' partial sums (dm_set_workspace).  It lives on the
+    device that is current at the first call and is used in stream order: the library serves ONE device and ONE compute
+    stream per process (the data-parallel layout is one process per GPU); ops._chk rejects tensors of another device."""
     global _workspace
     if _workspace is None:
         import torch

@@ -249,7 +249,8 @@ __global__ void cfg_reverse_kernel(const float* eps, int ldp, const float* x, co
 // Deterministic: per-block partial sums, combined in a fixed order (double precision) by the last block to arrive.  The
 // clip coefficient derived from this norm scales the whole update, so under data parallelism it must come out BIT-IDENTICAL
 // on every rank from bit-identical all-reduced gradients (an atomicAdd per block did not: the ranks' parameters drifted
-// apart in the last bits step by step).  out[0] is overwritten (no zero-fill needed); ws = [gridDim.x partials][counter].
+// apart in the last bits step by step).  out[0] is overwritten (no zero-fill needed); ws = [kSumsqSlots partials][counter].
+constexpr int kSumsqSlots = DM_NUM_SMS * 16;          // = the grid cap of grid_for()
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* g, long long n, float* out, float* ws) {
   __shared__ float sm[32];
   __shared__ bool last;
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* g, long long n,
   }
   for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += g[i] * g[i];
   s = dm::block_sum(s, sm);
-  unsigned* counter = reinterpret_cast<unsigned*>(ws + gridDim.x);
+  unsigned* counter = reinterpret_cast<unsigned*>(ws + kSumsqSlots);          // fixed slot: grids of different sizes share ws
   if (threadIdx.x == 0) {
     ws[blockIdx.x] = s;
     __threadfence();
@@ -544,7 +545,7 @@ extern "C" int dm_sumsq(const float* g, long long n, float* out, void* stream) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(ST, &cap);
     if (cap != cudaStreamCaptureStatusNone) { dm_set_error("dm_sumsq: first call inside a stream capture (scratch not allocated yet)"); return DM_ERR_ARG; }
-    const size_t bytes = ((size_t)DM_NUM_SMS * 16 + 1) * sizeof(float);
+    const size_t bytes = ((size_t)kSumsqSlots + 1) * sizeof(float);
     if (cudaMalloc(&ws, bytes) != cudaSuccess || cudaMemset(ws, 0, bytes) != cudaSuccess) { dm_set_error("dm_sumsq: scratch allocation failed"); return DM_ERR_CUDA; }
   }
   sumsq_kernel<<<grid, 256, 0, ST>>>(g, n, out, ws);

@@ -120,6 +120,10 @@ def r64(c):
 def _chk(t, name="tensor"):
     if t.device.type != "cuda":
         raise _lib.DmB200Error(f"{name}: the hot path runs on CUDA only (got {t.device}); there is no CPU fallback")
+    if t.device.index != torch.cuda.current_device():
+        # raw pointers, the reduction workspace and the launching stream all belong to the CURRENT device (one process per GPU)
+        raise _lib.DmB200Error(f"{name}: tensor lives on {t.device} but the current device is cuda:{torch.cuda.current_device()}; "
+                               "call torch.cuda.set_device() first (one process per GPU)")
     if t.dtype != torch.bfloat16 or t.dim() != 4 or t.stride(3) != 1:
         raise _lib.DmB200Error(f"{name}: expected a bf16 NHWC activation, got {t.dtype} {tuple(t.shape)} {t.stride()}")
     n, h, w, _ = t.shape
