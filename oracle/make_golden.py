@@ -263,6 +263,41 @@ def image_metrics_case(new_scripy):
     print("ImageMetrics.calc_ssim / calc_psnr == oracle on 6 pairs: bit-exact")
 
 
+def fid_case(new_scripy):
+    """Pin the oracle's FID arithmetic against ImageMetrics.calc_fid (new_scripy.py:1146-1187).  The pretrained Inception-v3
+    the reference downloads (:1123) is not available offline, so the Inception call is replaced -- on the reference object
+    itself -- by a fixed random projection of the preprocessed 299 x 299 batch; everything around it (batching, the
+    batch-level [-1,1] -> [0,1] decision, the resize, mean / covariance / sqrtm / trace) is the reference's own code."""
+    g = torch.Generator().manual_seed(23)
+    real = torch.rand(24, 3, 32, 32, generator=g) * 2 - 1
+    gen = (real * 0.8 + 0.3 * torch.randn(real.shape, generator=g)).clamp(-1, 1)
+    gen[8:16] = (gen[8:16] + 1) / 2                    # one batch of 8 already in [0,1]: no remap for that batch only
+    proj = P.fid_stub_projection(29)                   # regenerated from its seed by the tests (17 MB otherwise)
+    feat = lambda x: x.flatten(1) @ proj
+
+    class Stub(torch.nn.Module):
+        def forward(self, x):
+            return feat(x)
+    m = new_scripy.ImageMetrics(device="cpu")
+    m.inception_model, m.inception_loaded = Stub(), True
+    # the reference calls scipy.linalg.sqrtm(A, disp=False) -> (value, error estimate); this image's SciPy dropped the
+    # argument (the call raises TypeError and the reference reports fid = nan): give it the old signature back
+    real_sqrtm = new_scripy.linalg.sqrtm
+    shim = types.SimpleNamespace(sqrtm=lambda a, disp=True: (real_sqrtm(a), 0.0) if not disp else real_sqrtm(a))
+    saved, new_scripy.linalg = new_scripy.linalg, shim
+    try:
+        fid_ref = float(m.calc_fid(real, gen, batch_size=8))
+    finally:
+        new_scripy.linalg = saved
+    fr = torch.cat([feat(P.fid_preprocess(real[i:i + 8])) for i in range(0, 24, 8)]).numpy()
+    fg = torch.cat([feat(P.fid_preprocess(gen[i:i + 8])) for i in range(0, 24, 8)]).numpy()
+    fid_o = float(P.fid_from_features(fr, fg))
+    assert fid_ref == fid_o, (fid_ref, fid_o)
+    np.savez(os.path.join(GOLD, "fid.npz"), real=real.numpy(), gen=gen.numpy(), proj_seed=np.array(29), feats_real=fr,
+             feats_gen=fg, fid=np.array(fid_ref))
+    print(f"ImageMetrics.calc_fid (Inception call stubbed by a fixed projection) == oracle: bit-exact, fid = {fid_ref:.6f}")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
@@ -271,6 +306,7 @@ def main():
     check_schedules(new_scripy, MNIST_script)
     crack_dataset_case(new_scripy)
     image_metrics_case(new_scripy)
+    fid_case(new_scripy)
     if "--only-data" in sys.argv:
         return
     one_case(new_scripy, MNIST_script, "mnist", 16, 28, 8, 10, 11, 400, "mnist_f16_b8")

@@ -491,3 +491,33 @@ def calc_psnr(img1, img2):
     if mse == 0:
         return float("inf")
     return 20 * np.log10(1.0 / np.sqrt(mse))
+
+
+def fid_preprocess(images):
+    """ImageMetrics._extract_features up to the Inception call (new_scripy.py:1133-1142): map the BATCH to [0,1] when its
+    minimum is negative, resize to 299 x 299 (bilinear, align_corners=False)."""
+    if images.min() < 0:
+        images = (images + 1) / 2
+    if images.shape[2] != 299 or images.shape[3] != 299:
+        images = F.interpolate(images, size=(299, 299), mode="bilinear", align_corners=False)
+    return images
+
+
+def fid_from_features(real_feats, gen_feats):
+    """The Frechet half of ImageMetrics.calc_fid (new_scripy.py:1168-1187) on two [N, D] numpy feature matrices."""
+    import numpy as np
+    from scipy import linalg
+    mu_real = np.mean(real_feats, axis=0)
+    sigma_real = np.cov(real_feats, rowvar=False)
+    mu_gen = np.mean(gen_feats, axis=0)
+    sigma_gen = np.cov(gen_feats, rowvar=False)
+    diff = mu_real - mu_gen
+    covmean = linalg.sqrtm(sigma_real.dot(sigma_gen))      # the reference passes disp=False (SciPy < 1.16 signature: value, error)
+    if np.iscomplexobj(covmean):
+        covmean = covmean.real
+    return diff.dot(diff) + np.trace(sigma_real + sigma_gen - 2 * covmean)
+
+
+def fid_stub_projection(seed, dim=16):
+    """The fixed [3*299*299, dim] projection that stands in for Inception-v3 in the FID fixture (tests/golden/fid.npz)."""
+    return torch.randn(3 * 299 * 299, dim, generator=torch.Generator().manual_seed(int(seed))) / 300.0

@@ -645,3 +645,24 @@ def test_linear_fwd_scalar_and_vector_paths_agree(dev):
             outs.append(yv.cpu())
             assert rel(yv.cpu(), ref) < F32_TOL
         assert rel(outs[0], outs[1]) < 1e-5
+
+
+def test_fid_matches_reference_value(dev):
+    """metrics.calc_fid / evaluate_batch (ImageMetrics.calc_fid, new_scripy.py:1146-1187) with the golden's stub feature
+    network: batching, batch-level range decision, resize and the Frechet distance against the reference's value."""
+    import os
+    import numpy as np
+    from diffusionmodel_b200 import metrics
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fid.npz"))
+    proj = P.fid_stub_projection(int(g["proj_seed"])).to(dev)
+    real, gen = torch.from_numpy(g["real"]).to(dev), torch.from_numpy(g["gen"]).to(dev)
+    feature_fn = lambda x: x.flatten(1) @ proj
+    fid = metrics.calc_fid(real, gen, feature_fn, batch_size=8)
+    assert fid == pytest.approx(float(g["fid"]), rel=1e-4, abs=1e-5)
+    fd = metrics.frechet_distance(torch.from_numpy(g["feats_real"]).to(dev), torch.from_numpy(g["feats_gen"]).to(dev))
+    assert fd == pytest.approx(float(g["fid"]), rel=1e-8, abs=1e-9)
+    m = metrics.evaluate_batch(real, gen, feature_fn=feature_fn)
+    assert set(m) == {"fid", "ssim", "psnr"} and m["fid"] == pytest.approx(fid)
+    m = metrics.evaluate_batch(real, gen)                     # no feature network: the reference's failure value
+    assert math.isnan(m["fid"]) and "ssim" in m
+    assert "fid" not in metrics.evaluate_batch(real[:4], gen[:4])         # fewer than 10 samples: no FID (:1266)
