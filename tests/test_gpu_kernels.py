@@ -660,7 +660,7 @@ def test_fid_matches_reference_value(dev):
     fid = metrics.calc_fid(real, gen, feature_fn, batch_size=8)
     assert fid == pytest.approx(float(g["fid"]), rel=1e-4, abs=1e-5)
     fd = metrics.frechet_distance(torch.from_numpy(g["feats_real"]).to(dev), torch.from_numpy(g["feats_gen"]).to(dev))
-    assert fd == pytest.approx(float(g["fid"]), rel=1e-8, abs=1e-9)
+    assert fd == pytest.approx(float(g["fid"]), rel=1e-6, abs=1e-8)          # eigenvalue route vs scipy sqrtm: 4e-8
     m = metrics.evaluate_batch(real, gen, feature_fn=feature_fn)
     assert set(m) == {"fid", "ssim", "psnr"} and m["fid"] == pytest.approx(fid)
     m = metrics.evaluate_batch(real, gen)                     # no feature network: the reference's failure value
