@@ -641,8 +641,8 @@ def run_ours(args):
                 "achieved": ach, "peak": peak, "peak_source": f"{src} bf16_tflops_sustained", "unit": "TFLOP/s",
                 "frac": ach / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch on the dominant layer (3x3, 192->192,
-                # 4x256x256: 100.7 MB in, 100.7 MB out algorithmic), profiles/r01_gemm_kernels_ncu_full.txt
-                "traffic": 154.7e6, "traffic_unit": "B/launch (ncu --set full, dominant layer: dram read 101.4 MB + write 53.3 MB, the rest of the 100.7 MB output still in L2)",
+                # 4x256x256: 100.7 MB in, 100.7 MB out algorithmic), profiles/r02_dominant_layer_ncu_full.txt
+                "traffic": 152.1e6, "traffic_unit": "B/launch (ncu --set full, dominant layer, profiles/r02_dominant_layer_ncu_full.txt: dram read 101.5 MB + write 50.7 MB, the rest of the 100.7 MB output still in L2 at kernel end; algorithmic 201.3 MB)",
                 "launches": conv["n"], "ms_per_step": conv["ms"],
                 "wgrad": {"achieved": wg["flops"] / (wg["ms"] * 1e-3) / 1e12 if wg["ms"] > 0 else 0.0,
                           "ms_per_step": wg["ms"], "launches": wg["n"]},
@@ -662,9 +662,17 @@ def run_ours(args):
                                                 "algorithmic_MB": round(nb / 1e6, 1), "GBps": round(nb / (ad["ms"] / ad["n"]) / 1e6, 1),
                                                 "frac": round(nb / (ad["ms"] / ad["n"]) / 1e6 / pk["hbm_gbs"], 3)})
         cpu = cpu_baseline_sample() if (world == 1 and not fast) else None
+        eager = extra = None
         if world == 1 and not fast:
+            # the legs below are reported beside the headline; a failure in one of them must not lose the line
+            def guarded(fn, *a):
+                try:
+                    return fn(*a)
+                except Exception as e:          # noqa: BLE001
+                    torch.cuda.empty_cache()
+                    return {"error": f"{type(e).__name__}: {e}"[:300]}
             ddpm.eval()
-            sampling["sweep"] = sampling_sweep(ddpm, dev, world)
+            sampling["sweep"] = guarded(sampling_sweep, ddpm, dev, world)
             ddpm.train()
             # drop the cfg2 model before the baselines allocate theirs (closures above share these cells)
             del micro, opt, ddpm, net, resident
@@ -672,8 +680,8 @@ def run_ours(args):
             import gc
             gc.collect()
             torch.cuda.empty_cache()
-            eager = gpu_eager_baseline(dev)
-            extra = extra_configs(dev, 5)
+            eager = guarded(gpu_eager_baseline, dev)
+            extra = guarded(extra_configs, dev, 5)
         line = {"metric": "ddpm_train_imgs_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
