@@ -88,6 +88,7 @@ _SIGS = {
     "dm_ca_gate_fwd": "pi pp pi iiii p",
     "dm_ca_gate_bwd": "pi pp pp pi iiii p",
     "dm_upcat_fwd": "pii pii pi iii p",
+    "dm_upcat_fwd_shared": "pii pii i pi iii p",
     "dm_upcat_bwd": "pi pii pii iii p",
     "dm_film_fwd": "pi pp pi iii p",
     "dm_film_bwd": "pi pi p pi pp iii p",

@@ -1096,13 +1096,14 @@ __device__ __forceinline__ void mask_tail(uint4& o, int valid) {
 }
 struct UpcatFwd {
   const bf16* a; int lda, Ca; const bf16* b; int ldb, Cb; bf16* out; int ldo; int h, w; float sy, sx;
+  int nb;          // samples held by b: sample n of the batch reads b[n % nb] (a skip tensor shared by the CFG halves); 0 = N
   __device__ void operator()(unsigned p, int c0) const {
     const int W2 = 2 * w, H2 = 2 * h;
     const int ox = p % W2, oy = (p / W2) % H2, n = p / (W2 * H2);
     const Lerp Y = lerp_src(oy, h, sy), X = lerp_src(ox, w, sx);
-    const bf16* src; int ld, c, C;
-    if (c0 < Ca) { src = a; ld = lda; c = c0; C = Ca; } else { src = b; ld = ldb; c = c0 - Ca; C = Cb; }
-    const long long base = (long long)n * h * w;
+    const bf16* src; int ld, c, C, ns = n;
+    if (c0 < Ca) { src = a; ld = lda; c = c0; C = Ca; } else { src = b; ld = ldb; c = c0 - Ca; C = Cb; if (nb > 0) ns = n % nb; }
+    const long long base = (long long)ns * h * w;
     const uint4 r00 = dm::ldg16(src + (base + (long long)Y.i0 * w + X.i0) * ld + c);
     const uint4 r01 = dm::ldg16(src + (base + (long long)Y.i0 * w + X.i1) * ld + c);
     const uint4 r10 = dm::ldg16(src + (base + (long long)Y.i1 * w + X.i0) * ld + c);
@@ -1179,9 +1180,10 @@ __global__ void __launch_bounds__(kEwThreads) upcat_fwd_quad_kernel(UpcatFwd f, 
     const int ox[2] = {vx[0] ? 2 * kx - 1 : 2 * kx, vx[1] ? 2 * kx : 2 * kx - 1};
     const Lerp Y[2] = {lerp_src(oy[0], h, f.sy), lerp_src(oy[1], h, f.sy)};
     const Lerp X[2] = {lerp_src(ox[0], w, f.sx), lerp_src(ox[1], w, f.sx)};
-    const bf16* src; int ld, c, C;
-    if (c0 < f.Ca) { src = f.a; ld = f.lda; c = c0; C = f.Ca; } else { src = f.b; ld = f.ldb; c = c0 - f.Ca; C = f.Cb; }
-    const bf16* s00 = src + (((long long)n * h + Y[0].i0) * w + X[0].i0) * ld + c;
+    const bf16* src; int ld, c, C, ns = n;
+    if (c0 < f.Ca) { src = f.a; ld = f.lda; c = c0; C = f.Ca; }
+    else { src = f.b; ld = f.ldb; c = c0 - f.Ca; C = f.Cb; if (f.nb > 0) ns = n % f.nb; }
+    const bf16* s00 = src + (((long long)ns * h + Y[0].i0) * w + X[0].i0) * ld + c;
     const int sdx = (X[0].i1 - X[0].i0) * ld;                       // 0 on the right border
     const long long sdy = (long long)(Y[0].i1 - Y[0].i0) * w * ld;  // 0 on the bottom border
     const uint4 r00 = dm::ldg16(s00);
@@ -1774,11 +1776,19 @@ extern "C" int dm_ca_gate_bwd(const void* dout, int lddo, const float* ah, const
   return ew_launch((long long)N * H * W, C, f, ST);
 }
 
+extern "C" int dm_upcat_fwd_shared(const void* a, int lda, int Ca, const void* b, int ldb, int Cb, int Nb, void* out, int ldo,
+                                   int N, int h, int w, void* stream);
 extern "C" int dm_upcat_fwd(const void* a, int lda, int Ca, const void* b, int ldb, int Cb, void* out, int ldo, int N,
                             int h, int w, void* stream) {
+  return dm_upcat_fwd_shared(a, lda, Ca, b, ldb, Cb, 0, out, ldo, N, h, w, stream);
+}
+/* b holds Nb samples that the N = k * Nb samples of a share cyclically (sample n reads b[n % Nb]); Nb = 0: b holds N */
+extern "C" int dm_upcat_fwd_shared(const void* a, int lda, int Ca, const void* b, int ldb, int Cb, int Nb, void* out, int ldo,
+                                   int N, int h, int w, void* stream) {
   REQ8(lda, "dm_upcat_fwd"); REQ8(ldb, "dm_upcat_fwd"); REQ8(ldo, "dm_upcat_fwd"); REQ8(Ca, "dm_upcat_fwd(Ca)");
+  if (Nb < 0 || (Nb > 0 && N % Nb)) { dm_set_error("dm_upcat_fwd_shared: N must be a multiple of Nb"); return DM_ERR_ARG; }
   UpcatFwd f{(const bf16*)a, lda, Ca, (const bf16*)b, ldb, Cb, (bf16*)out, ldo, h, w,
-             h > 1 ? (float)(h - 1) / (float)(2 * h - 1) : 0.f, w > 1 ? (float)(w - 1) / (float)(2 * w - 1) : 0.f};
+             h > 1 ? (float)(h - 1) / (float)(2 * h - 1) : 0.f, w > 1 ? (float)(w - 1) / (float)(2 * w - 1) : 0.f, Nb == N ? 0 : Nb};
   if (dm_debug_value(9) == 1) return ew_launch((long long)N * 4 * h * w, Ca + Cb, f, ST);   // dev: one thread per output pixel
   const long long Cv = (Ca + Cb + 7) / 8, total = (long long)N * (h + 1) * (w + 1) * Cv;
   if (total <= 0) return DM_OK;

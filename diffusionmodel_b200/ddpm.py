@@ -247,8 +247,7 @@ class DDPM(nn.Module):
 
         def body():
             if shared:
-                enc = self.nn_model.encode(st["xt"][:n_sample])
-                enc = {k: torch.cat([v, v], 0) for k, v in enc.items()}
+                enc = self._shared_encoding(st["xt"][:n_sample])
                 eps = self.nn_model.decode(enc, st["c"], st["t"], st["m"])
             else:
                 eps = self.nn_model.forward_nhwc(st["xt"], st["c"], st["t"], st["m"])
@@ -295,6 +294,17 @@ class DDPM(nn.Module):
             if steps is not None and done >= steps:
                 break
         return st["x"].clone(), store
+
+    def _shared_encoding(self, xt_half):
+        """Encoder once for the n trajectories (it sees neither c nor ctx_mask, and t is the same for both CFG halves).  The
+        decoder runs on the doubled batch; the skip tensors are NOT duplicated: the upsample+cat kernel and the head's
+        dual-source conv read them cyclically (sample n reads skip[n % len(skip)]).  Only u1 (the 16x16 up0 output that
+        FiLM scales per sample) is repeated."""
+        enc = self.nn_model.encode(xt_half)
+        if self.variant == "mnist":          # 28x28 tensors through a materialised concat: repeated like the reference does
+            return {k: torch.cat([v, v], 0) for k, v in enc.items()}
+        enc["u1"] = torch.cat([enc["u1"], enc["u1"]], 0)
+        return enc
 
     def _sched(self):
         if self._host_sched is None:
@@ -352,8 +362,7 @@ class DDPM(nn.Module):
             if shared:
                 # eval mode: the encoder sees neither c nor ctx_mask and t is the same for both halves, so the
                 # two halves of the reference's doubled batch are identical up to up0 -- run it once
-                enc = self.nn_model.encode(xt[:n_sample])
-                enc = {k: torch.cat([v, v], 0) for k, v in enc.items()}
+                enc = self._shared_encoding(xt[:n_sample])
                 eps = self.nn_model.decode(enc, c_i, t_is, ctx_mask)
             else:
                 eps = self.nn_model.forward_nhwc(xt, c_i, t_is, ctx_mask)

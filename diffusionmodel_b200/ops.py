@@ -621,6 +621,29 @@ def conv2d_fused_eval(x0, weight, pack, shift, scale, act, *, x1=None, c1=0, str
     return y
 
 
+def _conv2d_shared_x1(x0, x1, weight, bias, pack, c0, c1, stride, pad, add_bias):
+    """Forward-only dual-source conv whose second source holds fewer samples than the first and is shared cyclically by
+    the batch (the CFG halves of a sampling batch share the encoder's x0, new_scripy.py:355): one launch per group of
+    len(x1) samples, no duplicated copy of x1."""
+    if torch.is_grad_enabled() and (x0.requires_grad or x1.requires_grad or weight.requires_grad):
+        raise _lib.DmB200Error("conv2d: a shared second source (fewer samples than the batch) is forward-only")
+    ld0, ld1 = _chk(x0, "conv input"), _chk(x1, "conv input 2")
+    n, hin, win, _ = x0.shape
+    nb = x1.shape[0]
+    if n % nb or x1.shape[1:3] != x0.shape[1:3]:
+        raise _lib.DmB200Error(f"conv2d: second source {tuple(x1.shape)} does not tile the batch {tuple(x0.shape)}")
+    cout, cin, kh, kw = weight.shape
+    ho = (hin + 2 * pad - kh) // stride + 1
+    wo = (win + 2 * pad - kw) // stride + 1
+    wpk = pack.get(weight, "fwd", c_split=c0)
+    y = new_act(n, ho, wo, cout, x0.device)
+    for g in range(n // nb):
+        xg, yg = x0[g * nb:(g + 1) * nb], y[g * nb:(g + 1) * nb]
+        call("dm_conv2d_fwd", _p(xg), c0, ld0, _p(x1), c1, ld1, _p(wpk), _p(bias) if add_bias else None, None, ACT_NONE, _p(yg),
+             y.stride(2), 0, None, cout, nb, hin, win, cout, kh, kw, stride, pad, _stream())
+    return y
+
+
 def conv2d(x0, weight, bias, pack, *, x1=None, c0=None, c1=0, stride=1, pad=0, want_stats=False, out_f32=False,
            bias_grad_by_norm=False, add_bias=True):
     c0 = weight.shape[1] - c1 if c0 is None else c0
@@ -629,6 +652,8 @@ def conv2d(x0, weight, bias, pack, *, x1=None, c0=None, c1=0, stride=1, pad=0, w
         return _Im2colConv3x3.apply(x0, weight, bias, pack, want_stats, bias_grad_by_norm, add_bias)
     if x1 is not None and (c0 % 8 or x0.shape[3] != c0):
         raise _lib.DmB200Error("dual-source conv needs a tight first source with a multiple-of-8 channel count")
+    if x1 is not None and x1.shape[0] != x0.shape[0]:
+        return _conv2d_shared_x1(x0, x1, weight, bias, pack, c0, c1, stride, pad, add_bias), None
     return _Conv2d.apply(x0, x1, weight, bias, pack, c0, c1, stride, pad, want_stats, out_f32, bias_grad_by_norm, add_bias)
 
 
@@ -1101,7 +1126,23 @@ class _Upcat(torch.autograd.Function):
         return da, db, None, None
 
 
+def _upcat_shared(a, b, ca, cb):
+    """Forward-only upcat with a skip tensor ``b`` of fewer samples than ``a``, shared cyclically (sample n reads
+    b[n % len(b)]): the CFG halves of a sampling batch share the encoder's skip tensors without duplicating them."""
+    if torch.is_grad_enabled() and (a.requires_grad or b.requires_grad):
+        raise _lib.DmB200Error("upcat: a shared skip tensor (fewer samples than the batch) is forward-only")
+    lda, ldb = _chk(a, "upcat a"), _chk(b, "upcat b")
+    n, h, w, _ = a.shape
+    if n % b.shape[0] or b.shape[1:3] != a.shape[1:3]:
+        raise _lib.DmB200Error(f"upcat: skip batch {tuple(b.shape)} does not tile the batch {tuple(a.shape)}")
+    out = new_act(n, 2 * h, 2 * w, ca + cb, a.device)
+    call("dm_upcat_fwd_shared", _p(a), lda, ca, _p(b), ldb, cb, b.shape[0], _p(out), out.stride(2), n, h, w, _stream())
+    return out
+
+
 def upcat(a, b, ca, cb):
+    if b.shape[0] != a.shape[0]:
+        return _upcat_shared(a, b, ca, cb)
     return _Upcat.apply(a, b, ca, cb)
 
 

@@ -172,6 +172,11 @@ int dm_ca_gate_bwd(const void* dout, int lddo, const float* ah, const float* aw,
 /* ---- cat + bilinear x2 (align_corners=True) + FiLM (new_scripy.py:242,251,348-349) ----------------- */
 int dm_upcat_fwd(const void* a, int lda, int Ca, const void* b, int ldb, int Cb, void* out, int ldo, int N, int h,
                  int w, void* stream);
+/* same with a skip tensor b of Nb samples shared cyclically by the N = k * Nb samples of a (sample n reads b[n % Nb]): the
+ * classifier-free-guidance halves of the sampling batch share the encoder's skip tensors (new_scripy.py:463-467 repeats
+ * the batch; the encoder sees neither c nor the context mask), so they are never duplicated in memory.  Forward only. */
+int dm_upcat_fwd_shared(const void* a, int lda, int Ca, const void* b, int ldb, int Cb, int Nb, void* out, int ldo, int N,
+                        int h, int w, void* stream);
 int dm_upcat_bwd(const void* dout, int lddo, void* da, int ldda, int Ca, void* db, int lddb, int Cb, int N, int h,
                  int w, void* stream);
 int dm_film_fwd(const void* x, int ldx, const float* ce, const float* te, void* out, int ldo, int N, int HW, int C,

@@ -666,3 +666,31 @@ def test_fid_matches_reference_value(dev):
     m = metrics.evaluate_batch(real, gen)                     # no feature network: the reference's failure value
     assert math.isnan(m["fid"]) and "ssim" in m
     assert "fid" not in metrics.evaluate_batch(real[:4], gen[:4])         # fewer than 10 samples: no FID (:1266)
+
+
+def test_shared_skip_upcat_and_shared_second_source_conv(dev):
+    """The sampling loop's CFG halves share the encoder's skip tensors: dm_upcat_fwd_shared and the dual-source conv with a
+    second source of fewer samples must equal the same ops on an explicitly repeated tensor, bit for bit."""
+    from diffusionmodel_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    n, nb, h, w, ca, cb = 6, 3, 8, 8, 16, 24
+    a = nhwc(bf(torch.randn(n, ca, h, w, generator=g)), dev)
+    b = nhwc(bf(torch.randn(nb, cb, h, w, generator=g)), dev)
+    with torch.no_grad():
+        shared = ops.upcat(a, b, ca, cb)
+        full = ops.upcat(a, torch.cat([b, b], 0), ca, cb)
+    assert shared.shape == full.shape and torch.equal(shared, full)
+    cout, c0, c1 = 16, 16, 24
+    x0 = nhwc(bf(torch.randn(n, c0, h, w, generator=g)), dev)
+    wt = torch.nn.Parameter((torch.randn(cout, c0 + c1, 3, 3, generator=g) / 19).to(dev))
+    bias = torch.nn.Parameter(torch.randn(cout, generator=g).to(dev) * 0.1)
+    with torch.no_grad():
+        ys, _ = ops.conv2d(x0, wt, bias, ops.WeightPack(), x1=b, c1=c1, stride=1, pad=1)
+        yf, _ = ops.conv2d(x0, wt, bias, ops.WeightPack(), x1=torch.cat([b, b], 0), c1=c1, stride=1, pad=1)
+    assert torch.equal(ys, yf)
+    from diffusionmodel_b200._lib import DmB200Error
+    with pytest.raises(DmB200Error):                       # forward-only
+        ops.upcat(a.clone().requires_grad_(True), b, ca, cb)
+    with pytest.raises(DmB200Error):                       # the skip batch must tile the batch
+        with torch.no_grad():
+            ops.upcat(a, b[:2].contiguous()[:, :, :, :].repeat(2, 1, 1, 1)[:4], ca, cb)
