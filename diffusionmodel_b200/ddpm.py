@@ -337,6 +337,10 @@ class DDPM(nn.Module):
         if x_i.shape[0] != n_sample:
             raise RuntimeError(f"DDPM.sample: injected x_T holds {x_i.shape[0]} trajectories, expected {n_sample}")
         ncls = 10 if self.variant == "mnist" else self.n_classes        # MNIST_script.py:262 hard-codes 10
+        if n_each <= 0 or n_each % ncls:
+            # the reference builds c_i = arange(ncls).repeat(n_sample // ncls) (new_scripy.py:447-448) and fails later with a
+            # shape mismatch when that is shorter than the batch; fail here, before any kernel sees mismatched rows
+            raise RuntimeError(f"DDPM.sample: n_sample ({n_each}) must be a positive multiple of the {ncls} classes")
         c_i = torch.arange(0, ncls, device=device).repeat(int(n_each / ncls)).repeat(len(ws)).repeat(2)
         ctx_mask = torch.zeros_like(c_i)
         ctx_mask[n_sample:] = 1.0

@@ -939,6 +939,8 @@ def ctx_onehot(c, ctx_mask, n_classes, flip):
     if not c.is_cuda:
         raise _lib.DmB200Error("ctx_onehot: CUDA tensors only (no CPU fallback)")
     c = c.long().contiguous()
+    if c.dim() != 1 or ctx_mask.shape != c.shape:
+        raise RuntimeError(f"ctx_onehot: labels {tuple(c.shape)} and context mask {tuple(ctx_mask.shape)} must be equal-length vectors")
     if ctx_mask.dtype not in (torch.float32, torch.int64):
         ctx_mask = ctx_mask.to(torch.float32)
     ctx_mask = ctx_mask.contiguous()
@@ -1154,6 +1156,8 @@ class _Film(torch.autograd.Function):
         ldx = _chk(x, "film input")
         n, h, w, _ = x.shape
         ce, te = ce.contiguous().float(), te.contiguous().float()
+        if tuple(ce.shape) != (n, c) or tuple(te.shape) != (n, c):          # the reference's broadcast would raise here too
+            raise RuntimeError(f"film: embeddings {tuple(ce.shape)} / {tuple(te.shape)} do not match the batch ({n}, {c})")
         out = torch.empty_like(x)
         call("dm_film_fwd", _p(x), ldx, _p(ce), _p(te), _p(out), out.stride(2), n, h * w, c, _stream())
         ctx.save_for_backward(x, ce)
@@ -1341,6 +1345,9 @@ LOSS_CFG = dict(hi_t=1.2, mid_t=0.8, hi_w=3.0, mid_w=1.0, lo_w=0.5, fcw=2.0)   #
 def q_sample(x, noise, sqrtab, sqrtmab, ts):
     """x_t as the bf16 NHWC tensor the first conv consumes (new_scripy.py:408-411)."""
     n, c, h, w = x.shape
+    if noise.shape != x.shape or ts.numel() != n or not x.is_cuda:
+        raise RuntimeError(f"q_sample: x {tuple(x.shape)}, noise {tuple(noise.shape)}, timesteps {tuple(ts.shape)} do not match "
+                           "(or are not CUDA tensors: there is no CPU fallback)")
     xt = new_act(n, h, w, c, x.device)
     call("dm_q_sample", _p(x.contiguous()), _p(noise.contiguous()), _p(sqrtab), _p(sqrtmab), _p(ts.contiguous()), _p(xt),
          xt.stride(2), n, c, h, w, _stream())
@@ -1378,6 +1385,11 @@ class _DdpmLoss(torch.autograd.Function):
 def ddpm_loss(pred_nhwc_f32, noise, mask):
     noise = noise.contiguous().float()
     mask = mask.contiguous().float() if mask is not None else None
+    n, h, w, _ = pred_nhwc_f32.shape
+    if noise.dim() != 4 or (noise.shape[0], noise.shape[2], noise.shape[3]) != (n, h, w) or (
+            mask is not None and tuple(mask.shape) != (n, h, w)):
+        raise RuntimeError(f"ddpm_loss: prediction {tuple(pred_nhwc_f32.shape)} (NHWC), noise {tuple(noise.shape)} and attention "
+                           f"mask {None if mask is None else tuple(mask.shape)} do not match")
     return _DdpmLoss.apply(pred_nhwc_f32, noise, mask, LOSS_CFG)
 
 
@@ -1404,6 +1416,8 @@ def cfg_reverse_step_w(eps_nhwc_f32, x, z, coef4, wvec, x_out, xt_out):
     """Graph-capturable reverse step with one guidance scale per trajectory: ``wvec`` [n] fp32 on the device,
     ``coef4[1:]`` = (oneover_sqrta, mab_over_sqrtmab, sqrt_beta)."""
     n, c, h, w = x.shape
+    if eps_nhwc_f32.shape[0] != 2 * n or z.shape != x.shape or wvec.numel() != n or coef4.numel() != 4:
+        raise RuntimeError("cfg_reverse_step_w: eps must hold 2n samples, z match x, one guidance scale per trajectory")
     call("dm_cfg_reverse_step_w", _p(eps_nhwc_f32), eps_nhwc_f32.stride(2), _p(x), _p(z), _p(x_out), _p(xt_out),
          xt_out.stride(2), _p(coef4), _p(wvec), n, c, h, w, _stream())
 

@@ -317,6 +317,8 @@ def test_state_dict_roundtrip_and_fail_loudly(dev):
     ddpm2.load_state_dict(sd)
     with pytest.raises(DmB200Error):
         net(torch.zeros(1, 3, 128, 128), torch.zeros(1, dtype=torch.long), torch.ones(1), torch.ones(1))
+    with pytest.raises(RuntimeError):          # the class list would not cover the batch (new_scripy.py:447-448)
+        ddpm.to(dev).eval().sample(7, (3, 128, 128), dev, guide_w=1.0, steps=1)
 
 
 def test_gemm_native_weight_storage(dev):
