@@ -499,7 +499,7 @@ def test_odd_widths_and_sizes(dev, cfg):
     print(f"F={n_feat} size={size} B={batch}: loss {float(loss):.5f}  kernel-matched oracle {float(lo):.5f}")
     assert abs(float(loss) - float(lo)) < 3e-3 * abs(float(lo))
     g = grads_of(ddpm)
-    assert len(g) > 300 and all(torch.isfinite(v).all() for v in g.values())
+    assert len(g) > 250 and all(torch.isfinite(v).all() for v in g.values())
     ddpm.eval()
     out = ddpm.sample(5, (3, size, size), dev, guide_w=2.0, steps=2)
     assert out.shape == (5, 3, size, size) and torch.isfinite(out).all()
