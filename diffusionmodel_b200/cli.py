@@ -12,7 +12,8 @@ checkpoints as ``{'epoch', 'model_state_dict', 'optimizer_state_dict', 'schedule
 (./cropped_images, VOC XML) is not shipped with it: ``--data DIR`` reads that layout through the device-side batch
 pipeline (data.py), otherwise batches are synthetic road-damage-shaped tensors
 (images in [-1,1], labels, attention map 0.5 / 1.0 lower half / 3.0 box, new_scripy.py:535-546); FID/SSIM
-evaluation (new_scripy.py:1111-1290) is out of scope, ``--no_eval`` is accepted and ignored.
+evaluation (new_scripy.py:1111-1290): ``generate --data DIR`` compares the samples with real images (SSIM / PSNR on the
+device; FID needs a feature network, see metrics.py) and writes ``quality_metrics.json`` like the reference; ``--no_eval`` skips it.
 """
 from __future__ import annotations
 
@@ -131,7 +132,7 @@ def train_model(args):
 
 
 def gen_samples(ckpt, n_samples_per_class=3, guide_scales=(2.0, 4.0), eval_quality=True, n_classes=5, n_feat=Cfg.N_FEAT,
-                img=Cfg.IMG_SIZE, sequential_scales=False):
+                img=Cfg.IMG_SIZE, sequential_scales=False, data=None, feature_fn=None):
     rank, local, world = parallel.init_from_env()
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
@@ -148,6 +149,18 @@ def gen_samples(ckpt, n_samples_per_class=3, guide_scales=(2.0, 4.0), eval_quali
     os.makedirs(Cfg.SAMPLE_DIR, exist_ok=True)
     out = {}
     n_sample = parallel.shard_samples(n_samples_per_class * n_classes, n_classes, rank, world)
+    # real images for the quality assessment (new_scripy.py:1001-1029): n_samples_per_class * min(n_classes, 4) of them, from
+    # the dataset directory if one is given (the reference reads ./cropped_images; nothing is shipped with it)
+    real_images = None
+    if eval_quality and data:
+        from .data import CachedCrackBatches
+        cache = CachedCrackBatches.from_voc_dir(data, img, device)
+        need = min(len(cache), n_samples_per_class * min(n_classes, 4))
+        order = torch.randperm(len(cache), generator=torch.Generator().manual_seed(0))[:need]
+        real_images = cache.batch(order, flips=torch.zeros(need, dtype=torch.int32))[0]
+    elif eval_quality and rank == 0:
+        print("No dataset directory (--data): image-quality assessment skipped")
+    quality_metrics = {}
     # the reference loops over the guidance scales (:1036-1041); here all scales run as ONE trajectory batch unless
     # --sequential_scales asks for the reference's loop (same trajectories, S times the kernel launches)
     groups = [[w] for w in guide_scales] if sequential_scales else [list(guide_scales)]
@@ -158,8 +171,24 @@ def gen_samples(ckpt, n_samples_per_class=3, guide_scales=(2.0, 4.0), eval_quali
         for w, x_gen in zip(ws, xs):
             torch.save(x_gen.cpu(), os.path.join(Cfg.SAMPLE_DIR, f"samples_w{w}_rank{rank}.pt"))
             out[w] = x_gen
+            if real_images is not None and len(real_images) > 0:                 # :1067-1078
+                from . import metrics
+                k = min(len(real_images), len(x_gen))
+                m = metrics.evaluate_batch(real_images[:k], x_gen[:k], feature_fn=feature_fn)
+                quality_metrics[w] = m
+                if rank == 0:
+                    print(f"Image quality metrics (w={w}):")
+                    for name, value in m.items():
+                        print(f"  {name.upper()}: {value:.4f}")
         if rank == 0:
             print(f"guide_w={ws}: {n_sample} samples/rank per scale in {time.time() - t0:.1f}s", flush=True)
+    if quality_metrics and rank == 0:                                            # :1085-1101
+        import json
+        path = os.path.join(Cfg.SAMPLE_DIR, "quality_metrics.json")
+        with open(path, "w") as f:
+            json.dump({str(k): {kk: float(vv) for kk, vv in v.items()} for k, v in quality_metrics.items()}, f, indent=2)
+        print(f"Quality metrics saved to: {path}")
+    out["quality_metrics"] = quality_metrics
     return out
 
 
@@ -195,7 +224,7 @@ def main(argv=None):
             sys.exit(1)
         gen_samples(args.ckpt, n_samples_per_class=args.samples, guide_scales=args.guide_scales,
                     eval_quality=not args.no_eval, n_classes=args.n_classes, n_feat=args.n_feat, img=args.img,
-                    sequential_scales=args.sequential_scales)
+                    sequential_scales=args.sequential_scales, data=args.data)
 
 
 if __name__ == "__main__":
