@@ -319,11 +319,14 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ dy
 // y^2, written without atomics to part[blockIdx.x][2][ld] -- the layout dm_bn_finalize consumes.  Fixed
 // grid + fixed summation order => bit-reproducible statistics (the conv-epilogue variant accumulates
 // through shared-memory atomics and costs ~20% of the GEMM's time in shuffles).
+// blockIdx.z = sample slice (GroupNorm: P pixels per sample, partial rows part[z][blockIdx.x]; BatchNorm: gridDim.z == 1).
 __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ y, int ldy, float* __restrict__ part, int ld,
                                                         unsigned P, int C, int VPB, int R) {
   extern __shared__ float sm[];          // [threads][16]
   const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
   const int c0 = (blockIdx.y * VPB + cvl) * 8;
+  y += (long long)blockIdx.z * P * ldy;
+  part += (long long)blockIdx.z * gridDim.x * 2 * ld;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
@@ -440,6 +443,25 @@ using dm::bf2_to_f2; using dm::f2_to_bf2;
 __device__ __forceinline__ f32x2 coef_pair(const float* __restrict__ p, int c, int C) {
   return pk2(c < C ? __ldg(p + c) : 0.f, c + 1 < C ? __ldg(p + c + 1) : 0.f);
 }
+// Per-channel affine u = A2*y + B2 in front of the activation.  BatchNorm (rows == 0): A2 = invstd*gamma, B2 = beta - mean*A2
+// from the per-channel vectors.  GroupNorm (rows != 0): ``invstd`` / ``mean`` point at the per-(sample, channel) rows
+// sc[n][c] / sh[n][c] that gn_fold_fwd_kernel prepared, sample n = blockIdx.z.
+__device__ __forceinline__ void norm_affine(const float* __restrict__ mean, const float* __restrict__ invstd,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int c0, int C,
+                                            f32x2 (&A2)[4], f32x2 (&B2)[4]) {
+  if (rows) {
+    const long long o = (long long)blockIdx.z * C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { A2[j] = coef_pair(invstd + o, c0 + 2 * j, C); B2[j] = coef_pair(mean + o, c0 + 2 * j, C); }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + 2 * j;
+    A2[j] = mul2(coef_pair(invstd, c, C), coef_pair(gamma, c, C));
+    B2[j] = fma2(mul2(coef_pair(mean, c, C), bc2(-1.0f)), A2[j], coef_pair(beta, c, C));
+  }
+}
 // Streaming skeleton shared by the three kernels below: thread (cvl, r) of block b owns the 8 channels c0..c0+7
 // (one 16-byte vector; pad lanes carry zero coefficients, so they stay zero) of the pixels p0, p0+step, ...;
 // pointers advance by a constant byte stride, rounds of U pixels run without bounds checks except on the
@@ -458,18 +480,14 @@ template <int ACT>
 __global__ void __launch_bounds__(256) bn_fwd_kernel(const bf16* __restrict__ y, int ldy, const float* __restrict__ mean,
                                                       const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, bf16* __restrict__ z, int ldz,
-                                                      unsigned P, int C, int VPB, int R) {
+                                                      unsigned P, int C, int VPB, int R, int rows) {
   const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
   const int c0 = (blockIdx.y * VPB + cvl) * 8;
   PixRun q = pix_run(P, R, r);
   if (c0 >= C || q.n == 0) return;
+  y += (long long)blockIdx.z * P * ldy; z += (long long)blockIdx.z * P * ldz;          // sample slice (GroupNorm)
   f32x2 sc[4], sh[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + 2 * j;
-    sc[j] = mul2(coef_pair(invstd, c, C), coef_pair(gamma, c, C));
-    sh[j] = fma2(mul2(coef_pair(mean, c, C), bc2(-1.0f)), sc[j], coef_pair(beta, c, C));
-  }
+  norm_affine(mean, invstd, gamma, beta, rows, c0, C, sc, sh);
   constexpr int U = 4;
   const char* src = reinterpret_cast<const char*>(y + (long long)q.p0 * ldy + c0);
   char* dst = reinterpret_cast<char*>(z + (long long)q.p0 * ldz + c0);
@@ -517,22 +535,19 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
                                                              int ldy, const float* __restrict__ mean,
                                                              const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* __restrict__ part,
-                                                             unsigned P, int C, int VPB, int R) {
+                                                             unsigned P, int C, int VPB, int R, int rows) {
   extern __shared__ float sm[];          // [threads][16]
   const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
   const int c0 = (blockIdx.y * VPB + cvl) * 8;
+  dz += (long long)blockIdx.z * P * lddz; y += (long long)blockIdx.z * P * ldy;        // sample slice (GroupNorm)
+  part += (long long)blockIdx.z * gridDim.x * 2 * C;
   f32x2 s1[4], s2[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) s1[j] = s2[j] = bc2(0.f);
   PixRun q = pix_run(P, R, r);
   if (c0 < C && q.n > 0) {
     f32x2 A2[4], B2[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = c0 + 2 * j;
-      A2[j] = mul2(coef_pair(invstd, c, C), coef_pair(gamma, c, C));
-      B2[j] = fma2(mul2(coef_pair(mean, c, C), bc2(-1.0f)), A2[j], coef_pair(beta, c, C));
-    }
+    norm_affine(mean, invstd, gamma, beta, rows, c0, C, A2, B2);
     const char* pg = reinterpret_cast<const char*>(dz + (long long)q.p0 * lddz + c0);
     const char* py = reinterpret_cast<const char*>(y + (long long)q.p0 * ldy + c0);
     const long long sg = (long long)q.step * lddz * 2, sy = (long long)q.step * ldy * 2;
@@ -651,17 +666,19 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
                                                             int ldy, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, const float* __restrict__ coef,
-                                                            bf16* __restrict__ dy, int lddy, unsigned P, int C, int VPB, int R) {
+                                                            bf16* __restrict__ dy, int lddy, unsigned P, int C, int VPB, int R,
+                                                            int rows) {
   const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
   const int c0 = (blockIdx.y * VPB + cvl) * 8;
   PixRun q = pix_run(P, R, r);
   if (c0 >= C || q.n == 0) return;
+  dz += (long long)blockIdx.z * P * lddz; y += (long long)blockIdx.z * P * ldy; dy += (long long)blockIdx.z * P * lddy;
+  if (rows) coef += (long long)blockIdx.z * 3 * C;                                       // coef[n][3][C] (GroupNorm)
   f32x2 A2[4], B2[4], k0[4], nK1[4], nK2[4];
+  norm_affine(mean, invstd, gamma, beta, rows, c0, C, A2, B2);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = c0 + 2 * j;
-    A2[j] = mul2(coef_pair(invstd, c, C), coef_pair(gamma, c, C));
-    B2[j] = fma2(mul2(coef_pair(mean, c, C), bc2(-1.0f)), A2[j], coef_pair(beta, c, C));
     k0[j] = coef_pair(coef, c, C); nK1[j] = coef_pair(coef + C, c, C); nK2[j] = coef_pair(coef + 2 * C, c, C);
   }
   extern __shared__ float sm[];
@@ -710,55 +727,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
 }
 
 // ---------------------------------------------------------------------------------- GroupNorm
-// Same streaming structure as the BatchNorm kernels, with one grid.z slice per sample and per-(sample,
-// channel) coefficient rows: the statistics of a (sample, group) fold into rows scale/shift[n][c] once, so
-// the big passes are load -> fma -> activation -> store with the coefficients in registers.
+// The streaming passes ARE the BatchNorm kernels (bn_stats_kernel, bn_fwd_kernel, bn_bwd_reduce_kernel, bn_bwd_apply_kernel)
+// launched with one grid.z slice per sample and ``rows`` = 1: the statistics of a (sample, group) fold into per-(sample,
+// channel) rows scale/shift[n][c] once (gn_fold_fwd_kernel), the backward sums into rows (k0, -K1, -K2)[n][c]
+// (gn_fold_bwd_kernel), so the big passes are load -> fma -> activation -> store with the coefficients in registers.
 //
-// pass 1 (forward): per-block partial sums of x and x^2 for one sample: part[n][blockIdx.x][2][C]
-__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, int ldx, float* __restrict__ part, unsigned HW,
-                                                        int C, int VPB, int R) {
-  extern __shared__ float sm[];          // [threads][16]
-  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
-  const int c0 = (blockIdx.y * VPB + cvl) * 8;
-  const int n = blockIdx.z;
-  x += (long long)n * HW * ldx;
-  float s1[8], s2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  if (c0 < C) {
-    const unsigned step = gridDim.x * R;
-    for (unsigned p = blockIdx.x * R + r; p < HW; p += 4 * step) {
-      uint4 w[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const unsigned pu = p + u * step;
-        w[u] = pu < HW ? dm::ldg16(x + (long long)pu * ldx + c0) : make_uint4(0u, 0u, 0u, 0u);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float v[8];
-        dm::unpack8(w[u], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
-      }
-    }
-  }
-  float* mine = sm + threadIdx.x * 16;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { mine[j] = s1[j]; mine[8 + j] = s2[j]; }
-  __syncthreads();
-  if (r == 0 && c0 < C) {
-    for (int rr = 1; rr < R; ++rr) {
-      const float* o = sm + (rr * VPB + cvl) * 16;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { s1[j] += o[j]; s2[j] += o[8 + j]; }
-    }
-    float* g = part + ((long long)n * gridDim.x + blockIdx.x) * 2 * C;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (c0 + j < C) { g[c0 + j] = s1[j]; g[C + c0 + j] = s2[j]; }
-  }
-}
 // pass 2 (forward): one block per (sample, group): statistics -> mean/rstd and the coefficient rows
 // sc[n][c] = rstd*gamma, sh[n][c] = beta - mean*rstd*gamma
 __global__ void __launch_bounds__(256) gn_fold_fwd_kernel(const float* __restrict__ part, int nblk, int C, int G, double cnt,
@@ -791,97 +764,9 @@ __global__ void __launch_bounds__(256) gn_fold_fwd_kernel(const float* __restric
   }
   (void)sx;
 }
-// pass 3 (forward): z = act(x * sc[n][c] + sh[n][c])
-template <int ACT>
-__global__ void __launch_bounds__(256) gn_apply_fwd_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ sc,
-                                                            const float* __restrict__ sh, bf16* __restrict__ z, int ldz,
-                                                            unsigned HW, int C, int VPB, int R) {
-  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
-  const int c0 = (blockIdx.y * VPB + cvl) * 8;
-  if (c0 >= C) return;
-  const int n = blockIdx.z;
-  x += (long long)n * HW * ldx; z += (long long)n * HW * ldz;
-  float a[8], b[8];
-  ldp8(sc + (long long)n * C, c0, C, a); ldp8(sh + (long long)n * C, c0, C, b);
-  const unsigned step = gridDim.x * R;
-  for (unsigned p = blockIdx.x * R + r; p < HW; p += 2 * step) {
-    const unsigned p1 = p + step;
-    const bool has1 = p1 < HW;
-    float v0[8], v1[8];
-    load8(x + (long long)p * ldx + c0, v0);
-    if (has1) load8(x + (long long)p1 * ldx + c0, v1);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v0[j] = (c0 + j < C) ? dm::act_f(fmaf(v0[j], a[j], b[j]), ACT) : 0.f;
-    store8(z + (long long)p * ldz + c0, v0);
-    if (has1) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v1[j] = (c0 + j < C) ? dm::act_f(fmaf(v1[j], a[j], b[j]), ACT) : 0.f;
-      store8(z + (long long)p1 * ldz + c0, v1);
-    }
-  }
-}
-// backward pass 1: per-block partial sums of g = dz*act'(x*sc+sh) and g*x for one sample: part[n][blk][2][C]
-template <int ACT>
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ x,
-                                                             int ldx, const float* __restrict__ sc, const float* __restrict__ sh,
-                                                             float* __restrict__ part, unsigned HW, int C, int VPB, int R) {
-  extern __shared__ float sm[];          // [threads][8]
-  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
-  const int c0 = (blockIdx.y * VPB + cvl) * 4;
-  const int n = blockIdx.z;
-  dz += (long long)n * HW * lddz; x += (long long)n * HW * ldx;
-  float s1[4], s2[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  if (c0 < C) {
-    float a[4], b[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const bool ok = c0 + j < C;
-      a[j] = ok ? __ldg(sc + (long long)n * C + c0 + j) : 0.f;
-      b[j] = ok ? __ldg(sh + (long long)n * C + c0 + j) : 0.f;
-    }
-    const unsigned step = gridDim.x * R;
-    for (unsigned p = blockIdx.x * R + r; p < HW; p += 2 * step) {
-      const unsigned p1 = p + step;
-      const bool has1 = p1 < HW;
-      float g0[4], v0[4], g1[4], v1[4];
-      dm::load4(dz + (long long)p * lddz + c0, g0);
-      dm::load4(x + (long long)p * ldx + c0, v0);
-      if (has1) { dm::load4(dz + (long long)p1 * lddz + c0, g1); dm::load4(x + (long long)p1 * ldx + c0, v1); }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float gg = g0[j] * dm::act_grad_f(fmaf(v0[j], a[j], b[j]), ACT);
-        s1[j] += gg; s2[j] = fmaf(gg, v0[j], s2[j]);
-      }
-      if (has1) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float gg = g1[j] * dm::act_grad_f(fmaf(v1[j], a[j], b[j]), ACT);
-          s1[j] += gg; s2[j] = fmaf(gg, v1[j], s2[j]);
-        }
-      }
-    }
-  }
-  float* mine = sm + threadIdx.x * 8;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { mine[j] = s1[j]; mine[4 + j] = s2[j]; }
-  __syncthreads();
-  if (r == 0 && c0 < C) {
-    for (int rr = 1; rr < R; ++rr) {
-      const float* o = sm + (rr * VPB + cvl) * 8;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { s1[j] += o[j]; s2[j] += o[4 + j]; }
-    }
-    float* g = part + ((long long)n * gridDim.x + blockIdx.x) * 2 * C;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (c0 + j < C) { g[c0 + j] = s1[j]; g[C + c0 + j] = s2[j]; }
-  }
-}
 // backward pass 2: one block per (sample, group).  With Sg = sum g, Sgx = sum g*x per channel:
 //   m1 = sum_c gamma*Sg / cnt,  m2 = sum_c gamma*rstd*(Sgx - mean*Sg) / cnt
-//   dx = (rstd*gamma)*g - (rstd^2*m2)*x - (rstd*m1 - rstd^2*m2*mean)        -> coef[n][3][C] = (k0, K1, K2)
+//   dx = (rstd*gamma)*g - (rstd^2*m2)*x - (rstd*m1 - rstd^2*m2*mean)        -> coef[n][3][C] = (k0, -K1, -K2)
 //   dgamma[c] += rstd*(Sgx - mean*Sg), dbeta[c] += Sg      (atomic across samples)
 __global__ void __launch_bounds__(256) gn_fold_bwd_kernel(const float* __restrict__ part, int nblk, int C, int G, double cnt,
                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -927,52 +812,9 @@ __global__ void __launch_bounds__(256) gn_fold_bwd_kernel(const float* __restric
   for (int i = threadIdx.x; i < cg; i += blockDim.x) {
     const int c = g * cg + i;
     float* row = coef + (long long)n * 3 * C;
-    row[c] = (float)(rs * (double)gamma[c]);
-    row[C + c] = (float)(rs * m1 - rs * rs * m2 * mu);
-    row[2 * C + c] = (float)(rs * rs * m2);
-  }
-}
-// backward pass 3: dx = k0*g - K2*x - K1
-template <int ACT>
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restrict__ dz, int lddz, const bf16* __restrict__ x,
-                                                            int ldx, const float* __restrict__ sc, const float* __restrict__ sh,
-                                                            const float* __restrict__ coef, bf16* __restrict__ dx, int lddx,
-                                                            unsigned HW, int C, int VPB, int R) {
-  const int cvl = threadIdx.x % VPB, r = threadIdx.x / VPB;
-  const int c0 = (blockIdx.y * VPB + cvl) * 4;
-  if (c0 >= C) return;
-  const int n = blockIdx.z;
-  dz += (long long)n * HW * lddz; x += (long long)n * HW * ldx; dx += (long long)n * HW * lddx;
-  float a[4], b[4], k0[4], K1[4], K2[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const bool ok = c0 + j < C;
-    const long long o = (long long)n * C + c0 + j, o3 = (long long)n * 3 * C + c0 + j;
-    a[j] = ok ? __ldg(sc + o) : 0.f; b[j] = ok ? __ldg(sh + o) : 0.f;
-    k0[j] = ok ? __ldg(coef + o3) : 0.f; K1[j] = ok ? __ldg(coef + o3 + C) : 0.f; K2[j] = ok ? __ldg(coef + o3 + 2 * C) : 0.f;
-  }
-  const unsigned step = gridDim.x * R;
-  for (unsigned p = blockIdx.x * R + r; p < HW; p += 2 * step) {
-    const unsigned p1 = p + step;
-    const bool has1 = p1 < HW;
-    float g0[4], v0[4], g1[4], v1[4];
-    dm::load4(dz + (long long)p * lddz + c0, g0);
-    dm::load4(x + (long long)p * ldx + c0, v0);
-    if (has1) { dm::load4(dz + (long long)p1 * lddz + c0, g1); dm::load4(x + (long long)p1 * ldx + c0, v1); }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float gg = g0[j] * dm::act_grad_f(fmaf(v0[j], a[j], b[j]), ACT);
-      g0[j] = fmaf(k0[j], gg, -fmaf(K2[j], v0[j], K1[j]));
-    }
-    dm::store4(dx + (long long)p * lddx + c0, g0);
-    if (has1) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float gg = g1[j] * dm::act_grad_f(fmaf(v1[j], a[j], b[j]), ACT);
-        g1[j] = fmaf(k0[j], gg, -fmaf(K2[j], v1[j], K1[j]));
-      }
-      dm::store4(dx + (long long)p1 * lddx + c0, g1);
-    }
+    row[c] = (float)(rs * (double)gamma[c]);                 // k0
+    row[C + c] = (float)-(rs * m1 - rs * rs * m2 * mu);       // -K1   (bn_bwd_apply_kernel computes k0*g + (-K2)*x + (-K1))
+    row[2 * C + c] = (float)-(rs * rs * m2);                  // -K2
   }
 }
 
@@ -1592,7 +1434,7 @@ extern "C" int dm_bn_act_fwd(const void* y, int ldy, const float* mean, const fl
   if (P >= (1ll << 31)) { dm_set_error("dm_bn_act_fwd: too many pixels"); return DM_ERR_ARG; }
   const ChanMap m = chan_map(C);
   dim3 grid(chan_grid_x(P, m, 8), m.cvt);
-#define BN_FWD(A) bn_fwd_kernel<A><<<grid, m.threads, 0, ST>>>((const bf16*)y, ldy, mean, invstd, gamma, beta, (bf16*)z, ldz, (unsigned)P, C, m.VPB, m.R)
+#define BN_FWD(A) bn_fwd_kernel<A><<<grid, m.threads, 0, ST>>>((const bf16*)y, ldy, mean, invstd, gamma, beta, (bf16*)z, ldz, (unsigned)P, C, m.VPB, m.R, 0)
   if (act == 1) BN_FWD(1); else if (act == 2) BN_FWD(2); else BN_FWD(0);
 #undef BN_FWD
   DM_CHECK_LAUNCH();
@@ -1620,7 +1462,7 @@ extern "C" int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, c
   float* part = scratch + 3LL * C;          // [nblk][2][C]
   dim3 grid(nblk, m.cvt);
   const size_t smem = (size_t)m.threads * 16 * kRingS * kRingU * 2;       // cp.async ring (>= 64 B per thread for the block reduction)
-#define BN_RED(A) bn_bwd_reduce_kernel<A><<<grid, m.threads, smem, ST>>>((const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, part, (unsigned)P, C, m.VPB, m.R)
+#define BN_RED(A) bn_bwd_reduce_kernel<A><<<grid, m.threads, smem, ST>>>((const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, part, (unsigned)P, C, m.VPB, m.R, 0)
   if (act == 1) BN_RED(1); else if (act == 2) BN_RED(2); else BN_RED(0);
 #undef BN_RED
   DM_CHECK_LAUNCH();
@@ -1628,7 +1470,7 @@ extern "C" int dm_bn_act_bwd(const void* dz, int lddz, const void* y, int ldy, c
                                                          dbias, training);
   DM_CHECK_LAUNCH();
   dim3 grid2(chan_grid_x(P, m, 4), m.cvt);
-#define BN_APP(A) bn_bwd_apply_kernel<A><<<grid2, m.threads, smem, ST>>>((const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, coef, (bf16*)dy, lddy, (unsigned)P, C, m.VPB, m.R)
+#define BN_APP(A) bn_bwd_apply_kernel<A><<<grid2, m.threads, smem, ST>>>((const bf16*)dz, lddz, (const bf16*)y, ldy, mean, invstd, gamma, beta, coef, (bf16*)dy, lddy, (unsigned)P, C, m.VPB, m.R, 0)
   if (act == 1) BN_APP(1); else if (act == 2) BN_APP(2); else BN_APP(0);
 #undef BN_APP
   DM_CHECK_LAUNCH();
@@ -1656,14 +1498,15 @@ extern "C" int dm_gn_act_fwd(const void* x, int ldx, const float* gamma, const f
   float *sc = scratch, *sh = sc + (long long)N * C, *sx = sh + (long long)N * C, *part = scratch + 6LL * N * C;
   const ChanMap m = chan_map(C);
   const int nblk = gn_blocks(N, HW, C, 8);
-  gn_stats_kernel<<<dim3(nblk, m.cvt, N), m.threads, (size_t)m.threads * 16 * sizeof(float), ST>>>((const bf16*)x, ldx, part,
+  bn_stats_kernel<<<dim3(nblk, m.cvt, N), m.threads, (size_t)m.threads * 16 * sizeof(float), ST>>>((const bf16*)x, ldx, part, C,
                                                                                                   (unsigned)HW, C, m.VPB, m.R);
   DM_CHECK_LAUNCH();
   gn_fold_fwd_kernel<<<N * G, 256, 0, ST>>>(part, nblk, C, G, (double)HW * (C / G), eps, gamma, beta, mean, rstd, sc, sh, sx);
   DM_CHECK_LAUNCH();
-  dim3 grid(chan_grid_x(HW, m, 4), m.cvt, N);
+  dim3 grid(chan_grid_x(HW, m, 8), m.cvt, N);
   { int cap = DM_NUM_SMS * 8 / (m.cvt * N); if (cap < 1) cap = 1; if ((int)grid.x > cap) grid.x = cap; }
-#define GN_FWD(A) gn_apply_fwd_kernel<A><<<grid, m.threads, 0, ST>>>((const bf16*)x, ldx, sc, sh, (bf16*)z, ldz, (unsigned)HW, C, m.VPB, m.R)
+  // z = act(x * sc[n][c] + sh[n][c]): the BatchNorm apply kernel on per-sample coefficient rows (rows = 1: invstd -> sc, mean -> sh)
+#define GN_FWD(A) bn_fwd_kernel<A><<<grid, m.threads, 0, ST>>>((const bf16*)x, ldx, sh, sc, nullptr, nullptr, (bf16*)z, ldz, (unsigned)HW, C, m.VPB, m.R, 1)
   if (act == 1) GN_FWD(1); else if (act == 2) GN_FWD(2); else GN_FWD(0);
 #undef GN_FWD
   DM_CHECK_LAUNCH();
@@ -1676,9 +1519,10 @@ extern "C" int dm_gn_act_bwd(const void* dz, int lddz, const void* x, int ldx, c
   REQ8(lddz, "dm_gn_act_bwd"); REQ8(ldx, "dm_gn_act_bwd"); REQ8(lddx, "dm_gn_act_bwd");
   if (N <= 0 || HW <= 0) return DM_OK;
   float *sc = scratch, *sh = sc + (long long)N * C, *coef = scratch + 3LL * N * C, *part = scratch + 6LL * N * C;
-  const ChanMap m = chan_map(C, 4);
-  const int nblk = gn_blocks(N, HW, C, 4);
-#define GN_RED(A) gn_bwd_reduce_kernel<A><<<dim3(nblk, m.cvt, N), m.threads, (size_t)m.threads * 8 * sizeof(float), ST>>>((const bf16*)dz, lddz, (const bf16*)x, ldx, sc, sh, part, (unsigned)HW, C, m.VPB, m.R)
+  const ChanMap m = chan_map(C);
+  const int nblk = gn_blocks(N, HW, C, 8);
+  const size_t smem = (size_t)m.threads * 16 * kRingS * kRingU * 2;       // cp.async ring of the two-operand kernels
+#define GN_RED(A) bn_bwd_reduce_kernel<A><<<dim3(nblk, m.cvt, N), m.threads, smem, ST>>>((const bf16*)dz, lddz, (const bf16*)x, ldx, sh, sc, nullptr, nullptr, part, (unsigned)HW, C, m.VPB, m.R, 1)
   if (act == 1) GN_RED(1); else if (act == 2) GN_RED(2); else GN_RED(0);
 #undef GN_RED
   DM_CHECK_LAUNCH();
@@ -1686,7 +1530,7 @@ extern "C" int dm_gn_act_bwd(const void* dz, int lddz, const void* x, int ldx, c
   DM_CHECK_LAUNCH();
   dim3 grid(chan_grid_x(HW, m, 4), m.cvt, N);
   { int cap = DM_NUM_SMS * 8 / (m.cvt * N); if (cap < 1) cap = 1; if ((int)grid.x > cap) grid.x = cap; }
-#define GN_APP(A) gn_bwd_apply_kernel<A><<<grid, m.threads, 0, ST>>>((const bf16*)dz, lddz, (const bf16*)x, ldx, sc, sh, coef, (bf16*)dx, lddx, (unsigned)HW, C, m.VPB, m.R)
+#define GN_APP(A) bn_bwd_apply_kernel<A><<<grid, m.threads, smem, ST>>>((const bf16*)dz, lddz, (const bf16*)x, ldx, sh, sc, nullptr, nullptr, coef, (bf16*)dx, lddx, (unsigned)HW, C, m.VPB, m.R, 1)
   if (act == 1) GN_APP(1); else if (act == 2) GN_APP(2); else GN_APP(0);
 #undef GN_APP
   DM_CHECK_LAUNCH();
