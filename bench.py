@@ -637,7 +637,7 @@ def run_ours(args):
         ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
         peak = pk["bf16_tflops_sustained"]
         roof = {"bound": "tensor",
-                "kernel": "conv3x3_halo2_kernel (CTA pairs) + conv3x3_halo_kernel + conv_gemm_kernel: fwd + data-gradient implicit GEMMs, all layers of one step",
+                "kernel": "conv3x3_halo2_kernel / conv_gemm2_kernel (CTA pairs) + conv3x3_halo_kernel + conv_gemm_kernel: fwd + data-gradient implicit GEMMs, all layers of one step",
                 "achieved": ach, "peak": peak, "peak_source": f"{src} bf16_tflops_sustained", "unit": "TFLOP/s",
                 "frac": ach / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch on the dominant layer (3x3, 192->192,

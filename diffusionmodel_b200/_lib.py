@@ -177,7 +177,7 @@ def last_kernel():
 
 class kernel_counts:
     """Context manager: ``with kernel_counts() as k: ...; k["conv3x3_halo2"]`` = launches of that variant inside."""
-    NAMES = ("conv_gemm", "conv3x3_halo", "conv3x3_halo2", "wgrad_gemm", "wgrad2_gemm", "wgrad3_pair", "skinny_gemm")
+    NAMES = ("conv_gemm", "conv_gemm2", "conv3x3_halo", "conv3x3_halo2", "wgrad_gemm", "wgrad2_gemm", "wgrad3_pair", "skinny_gemm")
 
     def __enter__(self):
         self._before = {n: kernel_count(n) for n in self.NAMES}

@@ -75,7 +75,13 @@ struct ConvParams {
   // halo kernel (3x3, stride 1): ring of input patches + ring of weight tiles
   int a_stages, base_off_mode;
   CUtensorMap tmB2;             // CTA-pair kernel: half-height weight box (block_n/2 rows)
-  int pair_tiles;               // CTA-pair kernel: number of (two M tiles) x (N tile) work items
+  int pair_tiles;               // CTA-pair kernels: number of (two M tiles) x (N tile) work items
+  int pair_m;                   // CTA-pair kernels: M-tile pairs per phase = ceil(m_tiles / 2)
+  // generic kernels: `phases` > 1 runs that many independent convs of the same geometry in ONE launch (the four output
+  // parities of the stride-2 data gradient): phase f uses taps[f * num_taps ..], weight rows f * phase_rows .. and writes
+  // at out + (f >> 1) * out_ph + (f & 1) * out_pw
+  int phases, phase_rows;
+  long long out_ph, out_pw;
   int ablate;                   // dev: bit0 no MMA issue, bit1 no TMA loads, bit2 no epilogue work (timing decomposition)
   unsigned long long desc_hi_halo;
 };
@@ -310,7 +316,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t bar_
   int it = 0;
   for (int tile = t_first; tile < total_tiles; tile += t_step, ++it) {
     const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
-    const int nt = tile % p.n_tiles, mt = pair_rank < 0 ? tile / p.n_tiles : 2 * (tile / p.n_tiles) + pair_rank;
+    const int nt = tile % p.n_tiles;
+    int mt = tile / p.n_tiles, phs = 0;
+    if (p.phases > 1) { const int per = pair_rank < 0 ? p.m_tiles : p.pair_m; phs = mt / per; mt -= phs * per; }
+    if (pair_rank >= 0) mt = 2 * mt + pair_rank;          // an odd tile count leaves a phantom tile: n >= N below
     const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
     const int w = (tw << p.log_bw) + (row & (bw - 1));
     const int h = (th << p.log_bh) + ((row >> p.log_bw) & (bh - 1));
@@ -319,6 +328,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t bar_
     const int n_base = nt * p.block_n;
     int co0 = n_base;
     long long off = (long long)n * p.sN + (long long)h * p.sH + (long long)w * p.sW;
+    if (p.phases > 1) off += (long long)(phs >> 1) * p.out_ph + (long long)(phs & 1) * p.out_pw;
     if (p.convt_k) {
       const int tap = n_base / p.Cout;
       co0 = n_base - tap * p.Cout;
@@ -411,7 +421,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   const int stage_bytes = kAStage + p.b_stage_bytes;
   const SmemLayout L = carve(smem_raw, p.stages, stage_bytes);
   const int num_kb = p.num_taps * (p.chunks0 + p.chunks1);
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles * (p.phases > 1 ? p.phases : 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(L.full + 8 * s, 1); mbar_init(L.empty + 8 * s, 1); }
@@ -437,16 +447,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
       int stage = 0; uint32_t phase = 0;
       const int chunks = p.chunks0 + p.chunks1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int nt = tile % p.n_tiles;
+        int mt = tile / p.n_tiles, phs = 0;
+        if (p.phases > 1) { phs = mt / p.m_tiles; mt -= phs * p.m_tiles; }
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw << p.log_bw, h0 = th << p.log_bh, n0 = tb << p.log_bn;
-        const int n_base = nt * p.block_n;
+        const int n_base = phs * p.phase_rows + nt * p.block_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(L.empty + 8 * stage, phase ^ 1);
           const uint32_t sa = L.base + stage * stage_bytes, sb = sa + kAStage;
           const uint32_t fb = L.full + 8 * stage;
           const int tap = kb / chunks, ch = kb - tap * chunks;
-          const TapInfo t = p.taps[tap];
+          const TapInfo t = p.taps[phs * p.num_taps + tap];
           int map = t.map, c0 = ch * kBlockK;
           if (p.dual && ch >= p.chunks0) { map = 1; c0 = (ch - p.chunks0) * kBlockK; }
           if (elect_one()) {
@@ -493,6 +505,101 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { __syncwarp(); tc_fence_after(); tc_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------------------ kernel A2
+// CTA-pair version of kernel A (tcgen05.mma.cta_group::2): two M tiles share one weight tile, each CTA stages its own
+// 128-pixel activation box and HALF of the weight rows per K step.  Kernel A moves 16 KB + block_n x 128 B per
+// 128 x block_n x 64 MACs, which at block_n = 256 needs more L2 -> SM bandwidth than the fabric has (the 4x4 stride-2
+// convs and their data gradients ran at 0.6-0.9 PFLOP/s); the pair halves the weight share.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv_gemm2_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int b_half = p.b_stage_bytes >> 1;
+  const int stage_bytes = kAStage + b_half;
+  const SmemLayout L = carve(smem_raw, p.stages, stage_bytes);
+  const int chunks = p.chunks0 + p.chunks1;
+  const int num_kb = p.num_taps * chunks;
+  const int total = p.pair_tiles;
+  const int t_first = blockIdx.x >> 1, t_step = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(L.full + 8 * s, 1); mbar_init(L.empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(L.tfull + 8 * s, 1); mbar_init(L.tempty + 8 * s, 16); }   // 8 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB2); }
+  float* const slab = reinterpret_cast<float*>(smem_raw + (L.stat - smem_u32(smem_raw)));
+  for (int i = threadIdx.x; i < 2 * p.stat_c; i += kConvThreads) slab[i] = 0.0f;
+  if (warp == 1) tc_alloc2(L.tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(L.tmem_slot));
+  const uint32_t l_full = mapa_shared(L.full, 0), l_tempty = mapa_shared(L.tempty, 0);
+
+  if (warp == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int pt = t_first; pt < total; pt += t_step) {
+      const int nt = pt % p.n_tiles;
+      int pm = pt / p.n_tiles, phs = 0;
+      if (p.phases > 1) { phs = pm / p.pair_m; pm -= phs * p.pair_m; }
+      const int mt = 2 * pm + (int)rank;
+      const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+      const int w0 = tw << p.log_bw, h0 = th << p.log_bh, n0 = tb << p.log_bn;     // phantom tile: n0 >= N, zero-filled
+      const int n_row = phs * p.phase_rows + nt * p.block_n + (int)rank * (p.block_n >> 1);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(L.empty + 8 * stage, phase ^ 1);
+        const uint32_t sa = L.base + stage * stage_bytes, sb = sa + kAStage;
+        const int tap = kb / chunks, ch = kb - tap * chunks;
+        const TapInfo t = p.taps[phs * p.num_taps + tap];
+        int map = t.map, c0 = ch * kBlockK;
+        if (p.dual && ch >= p.chunks0) { map = 1; c0 = (ch - p.chunks0) * kBlockK; }
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(L.full + 8 * stage, 2 * stage_bytes);
+          tma_load_4d_2sm(sa, &p.tmA[map], c0, w0 + t.dx, h0 + t.dy, n0, l_full + 8 * stage);
+          tma_load_2d_2sm(sb, &p.tmB2, kb * kBlockK, n_row, l_full + 8 * stage);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int pt = t_first; pt < total; pt += t_step, ++it) {
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(L.tempty + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(L.full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = L.base + stage * stage_bytes, sb = sa + kAStage;
+          const uint64_t adesc = p.desc_hi | (uint64_t)((sa & 0x3FFFFu) >> 4);
+          const uint64_t bdesc = p.desc_hi | (uint64_t)((sb & 0x3FFFFu) >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              tc_mma2_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0);
+            tc_commit2(L.empty + 8 * stage);
+            if (kb == num_kb - 1) tc_commit2(L.tfull + 8 * as);
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    conv_epilogue(p, L.tfull, l_tempty, tmem_base, slab, warp, lane, total, (int)rank);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) { tc_fence_after(); tc_dealloc2(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------------ kernel D
@@ -1215,17 +1322,22 @@ int pick_block_n(int cout) {
 
 // Tile width for a conv with `m_tiles` 128-pixel tiles: the persistent grid runs ceil(tiles / #SMs) rounds of
 // (block_n + fixed) cost each, so for the small-spatial layers (32 M-tiles at 32x32, batch 4) a narrower
-// tile that fills the last round beats the widest one: Cout=1536 -> 9 x 176 (288 tiles, 1.95 rounds)
-// instead of 6 x 256 (192 tiles, 1.3 rounds); Cout=768 -> 4 x 192 instead of 3 x 256.
-int pick_block_n_tiles(int cout, int m_tiles) {
+// tile that fills the last round beats the widest one: Cout=768 -> 4 x 192 instead of 3 x 256.
+// pairs: the 3x3 halo convs run as CTA pairs (two M tiles share one weight tile, half of it staged by each CTA) whenever
+// the width is a multiple of 32 -- a single CTA staging a whole 176-wide weight tile per K step is bound by the
+// L2 -> SM fabric (1.56 GB in 154 us = 10.1 TB/s on 1536 -> 1536 at 32x32, tensor pipe 64 % active), so the pick is made
+// among the pair-capable widths with the pair kernel's own round count.
+int pick_block_n_tiles(int cout, int m_tiles, bool pairs = false) {
   if (g_debug[3] >= 16 && g_debug[3] <= 256 && (g_debug[3] % 16) == 0) return (int)g_debug[3];
   const int widest = pick_block_n(cout);
   if (cout <= 256) return widest;
   int best = widest; double best_cost = 1e30;
-  for (int bn = 256; bn >= 96; bn -= 16) {
+  const int slots = pairs ? g_sm_limit / 2 : g_sm_limit;
+  const long long m_items = pairs ? (m_tiles + 1) / 2 : m_tiles;
+  for (int bn = 256; bn >= 96; bn -= (pairs ? 32 : 16)) {
     const int nt = (cout + bn - 1) / bn;
-    const long long tiles = (long long)m_tiles * nt;
-    const long long rounds = (tiles + g_sm_limit - 1) / g_sm_limit;
+    const long long tiles = m_items * nt;
+    const long long rounds = (tiles + slots - 1) / slots;
     const double cost = (double)rounds * (bn + 48);      // 48 ~ the per-tile share that does not shrink with N
     if (cost < best_cost * 0.98) { best_cost = cost; best = bn; }
   }
@@ -1266,8 +1378,17 @@ long long dm_debug_value(int key) { return (key >= 0 && key < 16) ? g_debug[key]
 // Generic launcher for kernel A.  All geometry is resolved by the typed entry points below.
 static int conv_grid(int tiles) { return tiles < g_sm_limit ? tiles : g_sm_limit; }
 
-static int launch_conv(ConvParams& P, cudaStream_t st) {
-  int stage_bytes = kAStage + P.b_stage_bytes;
+// CTA pairs pay when the M tiles pair up without (much of) a phantom tile
+static bool pair_ok(int m_tiles) { return g_debug[5] != 2 && m_tiles >= 2 && ((m_tiles & 1) == 0 || m_tiles >= 9); }
+
+bool g_attr_a2 = false;
+
+// wpk / w_rows / ktot given: the launch may run as CTA pairs (kernel A2) when the tile width and tile count allow it.
+static int launch_conv(ConvParams& P, cudaStream_t st, const void* wpk = nullptr, long long w_rows = 0, long long ktot = 0) {
+  const int phases = P.phases > 1 ? P.phases : 1;
+  const bool pair = wpk != nullptr && (P.block_n % 32) == 0 && pair_ok(P.m_tiles);
+  const int b_bytes = pair ? P.b_stage_bytes / 2 : P.b_stage_bytes;
+  int stage_bytes = kAStage + b_bytes;
   P.stat_c = P.stats ? (P.n_tiles * P.block_n + 31) / 32 * 32 : 0;   // whole 32-lane chunks
   const int stat_bytes = 8 * P.stat_c;
   if (stat_bytes > kMaxStatBytes) { dm_set_error("conv_gemm: too many output channels for fused BatchNorm statistics"); return DM_ERR_ARG; }
@@ -1278,12 +1399,30 @@ static int launch_conv(ConvParams& P, cudaStream_t st) {
   P.stages = stages;
   P.ablate = (int)g_debug[7] & 4;          // generic kernel: only the epilogue switch
   size_t smem = 1024 + (size_t)stages * stage_bytes + kAuxBytes + stat_bytes;
+  if (pair) {
+    int rc = make_w_map(&P.tmB2, wpk, w_rows, ktot, P.block_n / 2);
+    if (rc) return rc;
+    P.idesc = (P.idesc & ~(0x1Fu << 24)) | ((256u >> 4) << 24);       // M = 256 across the CTA pair
+    P.pair_m = dm::cdiv(P.m_tiles, 2);
+    P.pair_tiles = P.pair_m * P.n_tiles * phases;
+    P.ablate = 0;
+    if (!g_attr_a2) {
+      cudaError_t e = cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+      if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
+      g_attr_a2 = true;
+    }
+    const int clusters = P.pair_tiles < g_sm_limit / 2 ? P.pair_tiles : g_sm_limit / 2;
+    dm_note_kernel("conv_gemm2", P.block_n);
+    conv_gemm2_kernel<<<2 * clusters, kConvThreads, smem, st>>>(P);
+    DM_CHECK_LAUNCH();
+    return DM_OK;
+  }
   if (!g_attr_a) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) { dm_set_error(cudaGetErrorString(e)); return DM_ERR_CUDA; }
     g_attr_a = true;
   }
-  int grid = conv_grid(P.m_tiles * P.n_tiles);
+  int grid = conv_grid(P.m_tiles * P.n_tiles * phases);
   if (!P.stats && g_debug[1] > 0 && g_debug[1] < grid) grid = (int)g_debug[1];
   dm_note_kernel("conv_gemm", P.block_n);
   conv_gemm_kernel<<<grid, kConvThreads, smem, st>>>(P);
@@ -1337,7 +1476,8 @@ static int launch_conv_halo2(ConvParams& P, const void* wpk, long long w_rows, l
   P.desc_hi_halo = kDescHiHalo;
   P.base_off_mode = 0; P.ablate = 0;
   P.idesc = (P.idesc & ~(0x1Fu << 24)) | ((256u >> 4) << 24);       // M = 256 across the CTA pair
-  P.pair_tiles = dm::cdiv(P.m_tiles, 2) * P.n_tiles;
+  P.pair_m = dm::cdiv(P.m_tiles, 2);
+  P.pair_tiles = P.pair_m * P.n_tiles;
   const size_t smem = 1024 + (size_t)P.a_stages * kHaloStage + (size_t)stages * b_half + kAuxBytes + stat_bytes;
   if (!g_attr_e) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
@@ -1381,15 +1521,19 @@ extern "C" int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, in
   const int Ho = (Hin + 2 * pad - kh) / stride + 1, Wo = (Win + 2 * pad - kw) / stride + 1;
   ConvParams P;
   memset(&P, 0, sizeof P);
-  const int block_n = pick_block_n_tiles(Cout, dm::cdiv((long)N * Ho * Wo, kBlockM));
+  // 3x3 / stride 1 / pad 1 on images that tile into 8 x 16 pixel patches: the halo kernel
+  bool halo = kh == 3 && kw == 3 && stride == 1 && pad == 1 && (Win % 8) == 0 && (Hin % 16) == 0;
+  if (g_debug[5] == 1) halo = false;
+  int lbw, lbh, lbn;
+  pick_patch(Wo, Ho, kBlockM, lbw, lbh, lbn);
+  const int m_gen = dm::cdiv(Wo, 1 << lbw) * dm::cdiv(Ho, 1 << lbh) * dm::cdiv(N, 1 << lbn);     // tiles of the generic kernels
+  const int block_n = halo ? pick_block_n_tiles(Cout, dm::cdiv((long)N * Ho * Wo, kBlockM), g_debug[5] != 2)
+                           : pick_block_n_tiles(Cout, m_gen, pair_ok(m_gen));
   fill_common(P, N, Ho, Wo, Cout, block_n);
   P.chunks0 = dm::cdiv(C0, 64);
   P.chunks1 = x1 ? dm::cdiv(C1, 64) : 0;
   P.dual = x1 ? 1 : 0;
   P.num_taps = kh * kw;
-  // 3x3 / stride 1 / pad 1 on images that tile into 8 x 16 pixel patches: the halo kernel
-  bool halo = kh == 3 && kw == 3 && stride == 1 && pad == 1 && (Win % 8) == 0 && (Hin % 16) == 0;
-  if (g_debug[5] == 1) halo = false;
   if (halo) {
     P.log_bw = 3; P.log_bh = 4; P.log_bn = 0;
     P.tiles_w = Wo / 8; P.tiles_h = Ho / 16; P.tiles_b = N;
@@ -1434,7 +1578,7 @@ extern "C" int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, in
   if (stats && (scale || act)) { dm_set_error("dm_conv2d_fwd: statistics are taken of the plain conv output (no scale/act)"); return DM_ERR_ARG; }
   // CTA pairs when the tile width splits into two halves of whole 8-row swizzle groups (always: block_n % 16 == 0)
   if (halo && g_debug[5] != 2 && (block_n % 32) == 0) return launch_conv_halo2(P, wpk, Cout, ktot, (cudaStream_t)stream);
-  return halo ? launch_conv_halo(P, (cudaStream_t)stream) : launch_conv(P, (cudaStream_t)stream);
+  return halo ? launch_conv_halo(P, (cudaStream_t)stream) : launch_conv(P, (cudaStream_t)stream, wpk, Cout, ktot);
 }
 
 // rows of the statistics buffer dm_conv2d_fwd writes: one per CTA of the persistent grid
@@ -1442,11 +1586,13 @@ extern "C" int dm_conv2d_fwd_stat_rows(int N, int Ho, int Wo, int Cout) {
   // one row per CTA; the two tilings (generic 128-pixel patches / 8x16 halo tiles) can differ in tile
   // count, so this is the larger of the two and the kernels zero-fill the rows beyond their grid
   int a, b, c; pick_patch(Wo, Ho, kBlockM, a, b, c);
-  const int nt = dm::cdiv(Cout, pick_block_n_tiles(Cout, dm::cdiv((long)N * Ho * Wo, kBlockM)));
+  const int mt = dm::cdiv((long)N * Ho * Wo, kBlockM);
+  const int bn_a = pick_block_n_tiles(Cout, mt, false), bn_b = pick_block_n_tiles(Cout, mt, true);
+  const int nt = dm::cdiv(Cout, bn_a < bn_b ? bn_a : bn_b);          // whichever kernel runs: the larger tile count
   const int m_generic = dm::cdiv(Wo, 1 << a) * dm::cdiv(Ho, 1 << b) * dm::cdiv(N, 1 << c);
   const int m_halo = dm::cdiv(Wo, 8) * dm::cdiv(Ho, 16) * N;
   const int m = m_generic > m_halo ? m_generic : m_halo;
-  return conv_grid(m * nt + 1);         // +1: the CTA-pair kernel rounds an odd tile count up to whole pairs
+  return conv_grid((m + 1) * nt);       // +1: the CTA-pair kernels round an odd M-tile count up to whole pairs
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1460,31 +1606,37 @@ extern "C" int dm_conv2d_s2_dgrad(const void* dy, int Cout, int lddy, const void
   const int H = 2 * Ho, W = 2 * Wo;
   const int chunks = dm::cdiv(Cout, 64);
   const long long ktot = 4LL * chunks * 64;
+  ConvParams P;
+  memset(&P, 0, sizeof P);
+  int lbw, lbh, lbn;
+  pick_patch(Wo, Ho, kBlockM, lbw, lbh, lbn);
+  const int m_gen = dm::cdiv(Wo, 1 << lbw) * dm::cdiv(Ho, 1 << lbh) * dm::cdiv(N, 1 << lbn);
+  const bool pairs = pair_ok(m_gen);
+  // the four parities are four phases of ONE launch (4x the tiles for the persistent grid to balance)
+  const int block_n = pick_block_n_tiles(Cin, pairs ? 4 * ((m_gen + 1) / 2) * 2 : 4 * m_gen, pairs);
+  fill_common(P, N, Ho, Wo, Cin, block_n);
+  P.chunks0 = chunks; P.num_taps = 4;
+  P.phases = 4; P.phase_rows = Cin;
+  P.out_ph = (long long)W * lddx; P.out_pw = lddx;
+  // row i = 2Y+ph gets dy rows y with r = i + 1 - 2y in [0,3]:  ph=0: (y=Y, r=1), (y=Y-1, r=3);  ph=1: (y=Y+1, r=0), (y=Y, r=2)
+  const int dyo[2][2] = {{0, -1}, {1, 0}};
   for (int ph = 0; ph < 2; ++ph)
-    for (int pw = 0; pw < 2; ++pw) {
-      ConvParams P;
-      memset(&P, 0, sizeof P);
-      const int block_n = pick_block_n_tiles(Cin, dm::cdiv((long)N * Ho * Wo, kBlockM));
-      fill_common(P, N, Ho, Wo, Cin, block_n);
-      P.chunks0 = chunks; P.num_taps = 4;
-      // row i = 2Y+ph gets dy rows y with r = i + 1 - 2y in [0,3]:  ph=0: (y=Y, r=1), (y=Y-1, r=3);  ph=1: (y=Y+1, r=0), (y=Y, r=2)
-      const int dyo[2][2] = {{0, -1}, {1, 0}};
+    for (int pw = 0; pw < 2; ++pw)
       for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 2; ++b) { TapInfo t = {(int8_t)dyo[ph][a], (int8_t)dyo[pw][b], 0, 0}; P.taps[a * 2 + b] = t; }
-      int rc = make_act_map(&P.tmA[0], dy, Cout, Wo, Ho, N, lddy, (long long)Wo * lddy, (long long)Ho * Wo * lddy,
-                            1 << P.log_bw, 1 << P.log_bh, 1 << P.log_bn);
-      if (rc) return rc;
-      const bf16* wbase = reinterpret_cast<const bf16*>(wpk) + (long long)(ph * 2 + pw) * Cin * ktot;
-      rc = make_w_map(&P.tmB, wbase, Cin, ktot, block_n);
-      if (rc) return rc;
-      P.out = reinterpret_cast<bf16*>(dx) + ((long long)ph * W + pw) * lddx;
-      P.out_f32 = 0;
-      P.sN = (long long)H * W * lddx; P.sH = 2LL * W * lddx; P.sW = 2LL * lddx;
-      P.Cout = Cin; P.ldc_pad = lddx;
-      rc = launch_conv(P, (cudaStream_t)stream);
-      if (rc) return rc;
-    }
-  return DM_OK;
+        for (int b = 0; b < 2; ++b) {
+          TapInfo t = {(int8_t)dyo[ph][a], (int8_t)dyo[pw][b], 0, 0};
+          P.taps[(ph * 2 + pw) * 4 + a * 2 + b] = t;
+        }
+  int rc = make_act_map(&P.tmA[0], dy, Cout, Wo, Ho, N, lddy, (long long)Wo * lddy, (long long)Ho * Wo * lddy,
+                        1 << P.log_bw, 1 << P.log_bh, 1 << P.log_bn);
+  if (rc) return rc;
+  rc = make_w_map(&P.tmB, wpk, 4LL * Cin, ktot, block_n);       // [4 phases][Cin] rows
+  if (rc) return rc;
+  P.out = dx;
+  P.out_f32 = 0;
+  P.sN = (long long)H * W * lddx; P.sH = 2LL * W * lddx; P.sW = 2LL * lddx;
+  P.Cout = Cin; P.ldc_pad = lddx;
+  return launch_conv(P, (cudaStream_t)stream, wpk, 4LL * Cin, ktot);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -86,7 +86,7 @@ def _cfg2(dev, training, seed):
         h.remove()
     # the kernel selections the benchmark figure runs on
     print("kernel launches in one cfg2 micro-step:", k.delta)
-    assert k["conv3x3_halo2"] > 0 and k["conv3x3_halo"] > 0 and k["conv_gemm"] > 0
+    assert k["conv3x3_halo2"] > 0 and k["conv3x3_halo"] > 0 and k["conv_gemm"] > 0 and k["conv_gemm2"] > 0
     assert k["wgrad_gemm"] > 0 and k["wgrad2_gemm"] > 0 and k["wgrad3_pair"] > 0 and k["skinny_gemm"] == 1
     tap_name = {"ca1": "down1", "ca2": "down2", "ca3": "down3", "ca4": "down4"}
     return ddpm, sd, inp, float(loss), {tap_name.get(n_, n_): v for n_, v in got.items()}, grads_of(ddpm), n_T
@@ -209,12 +209,12 @@ def test_cfg1_mnist_train_step_at_size(dev):
 
 # N, H, W, Cin (c0 [+ c1]), Cout, k, stride, pad, expected forward kernel, expected weight-gradient kernel
 SHAPE_CLASSES = [
-    ("down4.res 1536->1536 @32^2", 4, 32, 32, (1536,), 1536, 3, 1, 1, "conv3x3_halo", "wgrad3_pair"),
+    ("down4.res 1536->1536 @32^2", 4, 32, 32, (1536,), 1536, 3, 1, 1, "conv3x3_halo2", "wgrad3_pair"),
     ("up1.model.0 3072(dual)->768 @32^2", 4, 32, 32, (1536, 1536), 768, 3, 1, 1, "conv3x3_halo2", "wgrad3_pair"),
-    ("down4.down.4 1536 4x4 s2 32^2->16^2", 4, 32, 32, (1536,), 1536, 4, 2, 1, "conv_gemm", None),
+    ("down4.down.4 1536 4x4 s2 32^2->16^2", 4, 32, 32, (1536,), 1536, 4, 2, 1, "conv_gemm2", None),
     ("up3.model.0 768(dual)->192 @128^2", 4, 128, 128, (384, 384), 192, 3, 1, 1, "conv3x3_halo2", "wgrad2_gemm"),
     ("down1 192->192 @256^2", 4, 256, 256, (192,), 192, 3, 1, 1, "conv3x3_halo2", "wgrad2_gemm"),
-    ("channel_compress 1x1 768->192 @64^2", 4, 64, 64, (768,), 192, 1, 1, 0, "conv_gemm", "wgrad_gemm"),
+    ("channel_compress 1x1 768->192 @64^2", 4, 64, 64, (768,), 192, 1, 1, 0, "conv_gemm2", "wgrad_gemm"),
 ]
 
 
