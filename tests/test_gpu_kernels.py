@@ -52,6 +52,10 @@ CONV_CASES = [
     (1, 128, 128, 192, 192, 3, 1, 1),
     (1, 64, 64, 128, 128, 4, 2, 1),
     (1, 256, 256, 64, 64, 3, 1, 1),
+    # odd M-tile counts (one 128-pixel tile per image): the CTA-pair kernels run a phantom tile in the last pair
+    (9, 8, 16, 64, 64, 1, 1, 0),
+    (9, 16, 32, 64, 96, 4, 2, 1),
+    (11, 16, 8, 32, 64, 3, 1, 1),
 ]
 
 
