@@ -54,6 +54,7 @@ _D = ctypes.c_double
 _SIGS = {
     "dm_conv2d_fwd": "pii pii p p pi pii pi iiiiiiii p",
     "dm_conv2d_fwd_stat_rows": "iiii",
+    "dm_conv2d_fwd_stats_max_cout": "",
     "dm_conv2d_s2_dgrad": "pii p pii iii p",
     "dm_convt_fwd": "pii p p pi iiiii p",
     "dm_conv2d_wgrad": "pii pii pi p iiiiiiii p",

@@ -36,7 +36,7 @@ constexpr int kThreads = 192;        // weight-gradient kernels: TMA warp, MMA w
 constexpr int kConvThreads = 320;    // conv kernel: TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kAuxBytes = 512;                       // barriers + TMEM slot (the BN-statistics slab follows, sized per launch)
-constexpr int kMaxStatBytes = 48 * 1024;
+constexpr int kMaxStatBytes = 56 * 1024;             // fused statistics: 1536 output channels + one tile width of padding
 constexpr int kMaxStages = 8;
 // halo kernel: an 8 x 16 pixel tile's 3x3 neighbourhood = 10 x 18 pixels x 64 channels, loaded ONCE per
 // 64-channel chunk; the nine filter taps are nine shifted views of it (descriptor start + (dy*10+dx) rows,
@@ -291,7 +291,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw, int stages, int stage_
   L.tfull = L.empty + 8 * kMaxStages;
   L.tempty = L.tfull + 16;
   L.tmem_slot = L.tempty + 16;
-  L.stat = aux + kAuxBytes;           // [2][stat_c] floats: per-CTA sum / sum of squares of the outputs
+  L.stat = aux + kAuxBytes;           // [4][2][stat_c] floats: per-CTA sum / sum of squares of the outputs, one copy per lane quarter
   return L;
 }
 
@@ -386,13 +386,21 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t bar_
       }
       if (p.stats != nullptr) {
         // per-channel sum and sum of squares over this warp's 32 rows -> combined over the 4 warps below
+        // ... of the values as stored (bf16-rounded): what the normalisation pass will read back
         float s1[32], s2[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { const float x = valid ? v[j] : 0.0f; s1[j] = x; s2[j] = x * x; }
+        for (int j = 0; j < 32; j += 2) {
+          float x0 = v[j], x1 = v[j + 1];
+          if (!p.out_f32) { const uint32_t u = dm::pack2(x0, x1); x0 = __uint_as_float(u << 16); x1 = __uint_as_float(u & 0xffff0000u); }
+          if (!valid) { x0 = 0.0f; x1 = 0.0f; }
+          s1[j] = x0; s2[j] = x0 * x0; s1[j + 1] = x1; s2[j + 1] = x1 * x1;
+        }
         const float a = warp_colsum32(s1, lane), b2 = warp_colsum32(s2, lane);
-        // accumulated over all of this CTA's tiles in shared memory (atomics: four warps share a column)
-        atomicAdd(slab + n_base + cc + lane, a);
-        atomicAdd(slab + p.stat_c + n_base + cc + lane, b2);
+        // accumulated over all of this CTA's tiles in this lane quarter's own copy of the slab: a column of a copy has
+        // exactly one writer (warp (q, half) owns the chunks of its parity), so plain adds in tile order -- deterministic
+        float* mine = slab + q * 2 * p.stat_c + n_base + cc + lane;
+        mine[0] += a;
+        mine[p.stat_c] += b2;
       }
     }
     tc_fence_before();
@@ -404,9 +412,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, uint32_t bar_
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const int e = threadIdx.x - 64;     // 0..255
     float* g = p.stats + (long long)blockIdx.x * 2 * p.stats_ld;
-    for (int c = e; c < p.Cout; c += 256) {
-      g[c] = slab[c];
-      g[p.stats_ld + c] = slab[p.stat_c + c];
+    const int S = p.stat_c;
+    for (int c = e; c < p.Cout; c += 256) {               // the four quarters' copies in a fixed order
+      g[c] = (slab[c] + slab[2 * S + c]) + (slab[4 * S + c] + slab[6 * S + c]);
+      g[p.stats_ld + c] = (slab[S + c] + slab[3 * S + c]) + (slab[5 * S + c] + slab[7 * S + c]);
     }
     for (int r = blockIdx.x + gridDim.x; r < p.stat_rows; r += gridDim.x) {     // rows no CTA owns: zero
       float* z = p.stats + (long long)r * 2 * p.stats_ld;
@@ -433,7 +442,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_gemm_kernel(const __grid
     tma_prefetch_desc(&p.tmB);
   }
   float* const slab = reinterpret_cast<float*>(smem_raw + (L.stat - smem_u32(smem_raw)));
-  for (int i = threadIdx.x; i < 2 * p.stat_c; i += kConvThreads) slab[i] = 0.0f;
+  for (int i = threadIdx.x; i < 8 * p.stat_c; i += kConvThreads) slab[i] = 0.0f;
   if (warp == 1) tc_alloc(L.tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -532,7 +541,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvParams p) {
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB2); }
   float* const slab = reinterpret_cast<float*>(smem_raw + (L.stat - smem_u32(smem_raw)));
-  for (int i = threadIdx.x; i < 2 * p.stat_c; i += kConvThreads) slab[i] = 0.0f;
+  for (int i = threadIdx.x; i < 8 * p.stat_c; i += kConvThreads) slab[i] = 0.0f;
   if (warp == 1) tc_alloc2(L.tmem_slot, 512);
   tc_fence_before();
   cluster_sync_all();
@@ -628,7 +637,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_halo_kernel(const __g
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB); }
-  for (int i = threadIdx.x; i < 2 * p.stat_c; i += kConvThreads) slab[i] = 0.0f;
+  for (int i = threadIdx.x; i < 8 * p.stat_c; i += kConvThreads) slab[i] = 0.0f;
   if (warp == 1) tc_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -756,7 +765,7 @@ conv3x3_halo2_kernel(const __grid_constant__ ConvParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB2); }
-  for (int i = threadIdx.x; i < 2 * p.stat_c; i += kConvThreads) slab[i] = 0.0f;
+  for (int i = threadIdx.x; i < 8 * p.stat_c; i += kConvThreads) slab[i] = 0.0f;
   if (warp == 1) tc_alloc2(tmem_slot, 512);
   tc_fence_before();
   cluster_sync_all();                      // both CTAs' barriers initialised and TMEM allocated
@@ -1390,7 +1399,7 @@ static int launch_conv(ConvParams& P, cudaStream_t st, const void* wpk = nullptr
   const int b_bytes = pair ? P.b_stage_bytes / 2 : P.b_stage_bytes;
   int stage_bytes = kAStage + b_bytes;
   P.stat_c = P.stats ? (P.n_tiles * P.block_n + 31) / 32 * 32 : 0;   // whole 32-lane chunks
-  const int stat_bytes = 8 * P.stat_c;
+  const int stat_bytes = 32 * P.stat_c;            // [4 lane quarters][2][stat_c] floats
   if (stat_bytes > kMaxStatBytes) { dm_set_error("conv_gemm: too many output channels for fused BatchNorm statistics"); return DM_ERR_ARG; }
   int stages = (kSmemBudget - 1024 - kAuxBytes - stat_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -1436,7 +1445,7 @@ constexpr unsigned long long kDescHiHalo = ((unsigned long long)(kHaloW * 128 / 
 
 static int launch_conv_halo(ConvParams& P, cudaStream_t st) {
   P.stat_c = P.stats ? (P.n_tiles * P.block_n + 31) / 32 * 32 : 0;
-  const int stat_bytes = 8 * P.stat_c;
+  const int stat_bytes = 32 * P.stat_c;            // [4 lane quarters][2][stat_c] floats
   if (stat_bytes > kMaxStatBytes) { dm_set_error("conv_gemm: too many output channels for fused BatchNorm statistics"); return DM_ERR_ARG; }
   P.a_stages = kHaloAStages;
   int stages = (kSmemBudget - 1024 - kAuxBytes - stat_bytes - P.a_stages * kHaloStage) / P.b_stage_bytes;
@@ -1463,7 +1472,7 @@ static int launch_conv_halo(ConvParams& P, cudaStream_t st) {
 bool g_attr_e = false;
 static int launch_conv_halo2(ConvParams& P, const void* wpk, long long w_rows, long long ktot, cudaStream_t st) {
   P.stat_c = P.stats ? (P.n_tiles * P.block_n + 31) / 32 * 32 : 0;
-  const int stat_bytes = 8 * P.stat_c;
+  const int stat_bytes = 32 * P.stat_c;            // [4 lane quarters][2][stat_c] floats
   if (stat_bytes > kMaxStatBytes) { dm_set_error("conv_gemm: too many output channels for fused BatchNorm statistics"); return DM_ERR_ARG; }
   int rc = make_w_map(&P.tmB2, wpk, w_rows, ktot, P.block_n / 2);
   if (rc) return rc;
@@ -1580,6 +1589,9 @@ extern "C" int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, in
   if (halo && g_debug[5] != 2 && (block_n % 32) == 0) return launch_conv_halo2(P, wpk, Cout, ktot, (cudaStream_t)stream);
   return halo ? launch_conv_halo(P, (cudaStream_t)stream) : launch_conv(P, (cudaStream_t)stream, wpk, Cout, ktot);
 }
+
+// widest conv whose epilogue can take the BatchNorm statistics (the slab must fit beside the operand rings)
+extern "C" int dm_conv2d_fwd_stats_max_cout(void) { return kMaxStatBytes / 32 - 256; }
 
 // rows of the statistics buffer dm_conv2d_fwd writes: one per CTA of the persistent grid
 extern "C" int dm_conv2d_fwd_stat_rows(int N, int Ho, int Wo, int Cout) {

@@ -471,6 +471,18 @@ def conv_stat_rows(n, ho, wo, cout):
     return _lib.fn("dm_conv2d_fwd_stat_rows")(n, ho, wo, cout)
 
 
+_stats_max_cout = None
+
+
+def conv_takes_stats(cout):
+    """True when the conv epilogue can also produce the BatchNorm statistics of its output (FUSED_CONV_STATS and the
+    per-CTA slab fits: up to dm_conv2d_fwd_stats_max_cout() = 1536 channels; wider layers keep the dm_bn_stats pass)."""
+    global _stats_max_cout
+    if _stats_max_cout is None:
+        _stats_max_cout = _lib.fn("dm_conv2d_fwd_stats_max_cout")()
+    return FUSED_CONV_STATS and cout <= _stats_max_cout
+
+
 class _Conv2d(torch.autograd.Function):
     """nn.Conv2d (new_scripy.py:184 etc.) on one or two channel-concatenated NHWC sources."""
 
@@ -774,8 +786,11 @@ class _BnAct(torch.autograd.Function):
 
 
 _counters_batched = False     # True while a model forward bumps all num_batches_tracked buffers in one launch
-FUSED_CONV_STATS = False      # True: BatchNorm statistics from the conv epilogue (measured slower: the per-column shuffle
-                              # reduction sits on the epilogue warps' critical path); False: a separate pass over y
+FUSED_CONV_STATS = False      # True: BatchNorm statistics (of the bf16-rounded outputs) from the conv epilogue.  Measured on one box
+                              # against the separate dm_bn_stats pass (tools/ab_micro_step.py): -0.5..-1 % per micro-step with
+                              # shared-memory atomics (run-to-run different last bits), +-0.1 % with the deterministic
+                              # per-lane-quarter slabs that are in the kernel now -- the transposing shuffle reduction
+                              # (62 SHFL + 124 SEL per 32 x 32 chunk) costs what the saved pass over y gains.  Off.
 
 
 class batched_counters:

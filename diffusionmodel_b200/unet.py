@@ -78,7 +78,7 @@ def conv_bn_act(x, seq, act=ACT_GELU, **kw):
         return ops.conv2d_fused_eval(x, cv.weight, _pack_of(cv), shift, scale, act, stride=cv.stride[0],
                                      pad=cv.padding[0], **kw)
     # train mode: batch normalisation cancels the conv bias exactly, so the GEMM epilogue skips it
-    y, stats = conv(x, cv, want_stats=bn.training and ops.FUSED_CONV_STATS, bias_grad_by_norm=cv.bias is not None,
+    y, stats = conv(x, cv, want_stats=bn.training and ops.conv_takes_stats(cv.out_channels), bias_grad_by_norm=cv.bias is not None,
                     add_bias=not bn.training, **kw)
     return ops.bn_act(y, stats, bn, act, conv_bias=cv.bias, bias_outside=bn.training and cv.bias is not None)
 

@@ -45,7 +45,8 @@ int dm_set_workspace(void* ptr, long long bytes);
  * x0 (++ x1 concatenated on channels: replaces torch.cat new_scripy.py:355 / MNIST_script.py:186),
  * wpk = dm_pack_weight() output [Cout][kh*kw][Cin_k]; y bf16 (y_f32=0) or fp32 (y_f32=1, ldy%4==0);
  * stats (nullable): [dm_conv2d_fwd_stat_rows()][2][stats_ld] per-CTA sum / sum-of-squares of y for the
- * train-mode BatchNorm that follows (accumulated across the CTA's tiles in shared memory).
+ * train-mode BatchNorm that follows: of the values as stored (bf16-rounded), accumulated across the CTA's tiles in
+ * shared memory in a fixed order (bit-reproducible).
  * y = act(conv * scale + bias): scale (nullable) and act (0 none, 1 GELU, 2 ReLU) fold an EVAL-mode
  * BatchNorm2d + activation into the epilogue (sampling loop: running statistics are constants).  The data gradient of a stride-1 conv is the same call with the
  * flipped/transposed weight pack and pad' = k-1-pad. */
@@ -53,6 +54,8 @@ int dm_conv2d_fwd(const void* x0, int C0, int ld0, const void* x1, int C1, int l
                   const float* bias, const float* scale, int act, void* y, int ldy, int y_f32, float* stats,
                   int stats_ld, int N, int Hin, int Win, int Cout, int kh, int kw, int stride, int pad, void* stream);
 int dm_conv2d_fwd_stat_rows(int N, int Ho, int Wo, int Cout);
+/* Widest Cout for which dm_conv2d_fwd accepts `stats` (the per-CTA slab must fit beside the operand rings). */
+int dm_conv2d_fwd_stats_max_cout(void);
 /* data gradient of Conv2d(k=4, s=2, p=1) (new_scripy.py:229); wpk = 4 phase packs, see weights.py */
 int dm_conv2d_s2_dgrad(const void* dy, int Cout, int lddy, const void* wpk, void* dx, int Cin, int lddx,
                        int N, int Ho, int Wo, void* stream);
