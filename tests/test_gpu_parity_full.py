@@ -5,6 +5,7 @@
     bf16: GEMM operands rounded to bf16, fp32 accumulate, and a rounding wherever the kernels store bf16 between
     launches; everything else fp32), and the eval-mode forward against the fp32 oracle at the north-star bar (1e-2);
   * cfg1 (configs[0]): MNIST ContextUnet, n_feat 128, batch 128 -- loss and gradients;
+  * cfg5 (configs[4], n_feat 384, 1.41 B parameters): the eval-mode step per block against the oracle executed on the GPU;
   * one convolution per distinct Appendix-A shape class at its true size, each asserting which kernel the dispatcher
     launched (dm_kernel_count / dm_last_kernel);
   * a full 60-step CFG trajectory with injected noise against the fp32 oracle, with the drift curve printed.
@@ -66,10 +67,10 @@ def _oracle_grads(sd, sched, inp, variant, n_T, training, use_map, **kw):
     return float(loss), pred.detach(), {k: v.detach() for k, v in tap.items()}, grads, sd_o
 
 
-def _cfg2(dev, training, seed):
+def _cfg2(dev, training, seed, n_feat=192, batch=4):
     """One cfg2 micro-step (F=192, 3x256x256, B=4, LocalEnhancer fed the attention map) on the GPU with block hooks."""
     from diffusionmodel_b200 import _lib
-    n_feat, size, batch, n_classes, n_T = 192, 256, 4, 5, 700
+    size, n_classes, n_T = 256, 5, 700
     ddpm, sd = build("rdd", n_feat, n_classes, n_T, seed, dev, enhance_with_attn_map=True)
     ddpm.train(training)
     inp = make_inputs("rdd", batch, 3, size, n_classes, n_T, seed)
@@ -85,11 +86,12 @@ def _cfg2(dev, training, seed):
     for h in handles:
         h.remove()
     # the kernel selections the benchmark figure runs on
-    print("kernel launches in one cfg2 micro-step:", k.delta)
-    assert k["conv3x3_halo2"] > 0 and k["conv3x3_halo"] > 0 and k["conv_gemm"] > 0 and k["conv_gemm2"] > 0
-    assert k["wgrad_gemm"] > 0 and k["wgrad2_gemm"] > 0 and k["wgrad3_pair"] > 0 and k["skinny_gemm"] == 1
+    print(f"kernel launches in one micro-step (n_feat {n_feat}, batch {batch}):", k.delta)
+    if n_feat == 192:
+        assert k["conv3x3_halo2"] > 0 and k["conv3x3_halo"] > 0 and k["conv_gemm"] > 0 and k["conv_gemm2"] > 0
+        assert k["wgrad_gemm"] > 0 and k["wgrad2_gemm"] > 0 and k["wgrad3_pair"] > 0 and k["skinny_gemm"] == 1
     tap_name = {"ca1": "down1", "ca2": "down2", "ca3": "down3", "ca4": "down4"}
-    return ddpm, sd, inp, float(loss), {tap_name.get(n_, n_): v for n_, v in got.items()}, grads_of(ddpm), n_T
+    return ddpm, sd, inp, float(loss.detach()), {tap_name.get(n_, n_): v for n_, v in got.items()}, grads_of(ddpm), n_T
 
 
 def _fmt(d):
@@ -163,6 +165,41 @@ def test_cfg2_train_step_vs_kernel_matched_oracle(dev):
     got_bn = torch.cat([ddpm.state_dict()[k_].flatten().cpu() for k_ in bn])
     ref_bn = torch.cat([sd_after[k_].flatten() for k_ in bn])
     assert P.rel_l2(got_bn, ref_bn) < 1e-2
+
+
+def test_cfg5_width_step_vs_oracle_run_on_the_gpu(dev):
+    """cfg5 (BASELINE.json configs[4], the stress shape: n_feat 384, 1.41 B parameters, 3x256x256), batch 2, running-statistics
+    BatchNorm: loss, every block's output and every block's parameter gradients against the fp32 oracle, with the bars of
+    the cfg2 test.  The oracle is the same `ref_port` code, executed here on the GPU in fp32 (TF32 off) through aten / cuDNN --
+    seconds instead of minutes on the host cores; layers up to 3072 -> 3072 and the 6144-channel dual source run only here."""
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ddpm, sd, inp, loss, got, mine, n_T = _cfg2(dev, False, 21, n_feat=384, batch=2)
+        del ddpm
+        torch.cuda.empty_cache()
+        sched = {k_: v.to(dev) for k_, v in P.ddpm_schedules(1e-4, 0.02, n_T).items()}
+        sd_d = {k_: v.to(dev) for k_, v in sd.items()}
+        inp_d = {k_: v.to(dev) for k_, v in inp.items()}
+        l_o, _, tap, g_o, _ = _oracle_grads(sd_d, sched, inp_d, "rdd", n_T, False, True)
+        tap = {k_: v.cpu() for k_, v in tap.items()}
+        g_o = {k_: v.cpu() for k_, v in g_o.items()}
+        _, _, _, g_m, _ = _oracle_grads(sd_d, sched, inp_d, "rdd", n_T, False, True, operand_dtype=torch.bfloat16,
+                                        store_dtype=torch.bfloat16)
+        g_m = {k_: v.cpu() for k_, v in g_m.items()}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    errs = {n_: P.rel_l2(v, tap[n_]) for n_, v in got.items()}
+    gerrs = _block_grad_errors(mine, g_o, RDD_BLOCKS)
+    gmat = _block_grad_errors(g_m, g_o, RDD_BLOCKS)
+    print(f"cfg5 eval-mode loss: ours {loss:.6f}  fp32 oracle (on the GPU) {l_o:.6f}")
+    print("cfg5 eval-mode per-block output rel-L2 vs fp32 oracle:", _fmt(errs))
+    print("cfg5 eval-mode per-block gradient rel-L2 vs fp32 oracle, ours:          ", _fmt(gerrs))
+    print("cfg5 eval-mode per-block gradient rel-L2 vs fp32 oracle, kernel-matched:", _fmt(gmat))
+    assert abs(loss - l_o) < 1e-2 * abs(l_o)
+    assert max(errs.values()) < 1e-2, errs
+    for n_, e in gerrs.items():
+        assert e < max(1e-2, 1.25 * gmat[n_]) and e < 2e-2, (n_, e, gmat[n_])
 
 
 def test_cfg2_eval_forward_vs_fp32_oracle(dev):
