@@ -1,3 +1,5 @@
+"""Dev tool: the CFG reverse step at the benchmarked sampling configuration (n_feat 192, 256 x 256, 15 trajectories): graphed
+ms per step, host enqueue time, and the eager per-entry-point breakdown (ops.enable_profile).  python tools/sample_profile.py"""
 import sys, os, json, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import diffusionmodel_b200 as D
